@@ -1,0 +1,175 @@
+"""ctypes bindings of the C ABI (include/h264recon.h, include/h264synth.h).
+
+Python is only the test/bench harness language here; the product is the C-ABI shared library
+`libh264recon.so` (CUDA engine).  Nothing in this file computes a sample, and nothing here touches oracle/.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_REFS = 32
+COEFFS_PER_MB = 384
+NO_COEFF = 0xFFFFFFFF
+P_SLICE, B_SLICE, I_SLICE = 0, 1, 2
+
+
+class InterInfo(C.Structure):
+    _fields_ = [("sub_mb_type", C.c_uint8 * 4), ("sub_mb_pred_mode", C.c_uint8 * 4)]
+
+
+class MbUnion(C.Union):
+    _fields_ = [("intra_modes", C.c_uint8 * 8), ("inter", InterInfo)]
+
+
+class Mb(C.Structure):
+    _fields_ = [("mb_type", C.c_uint8), ("flags", C.c_uint8), ("slice_idx", C.c_uint16),
+                ("cbp_luma", C.c_uint8), ("cbp_chroma", C.c_uint8), ("qp_y", C.c_int8), ("qp_c", C.c_int8 * 2),
+                ("intra16_mode", C.c_uint8), ("chroma_mode", C.c_uint8), ("reserved0", C.c_uint8),
+                ("cbp_blks", C.c_uint16), ("reserved1", C.c_uint16), ("coeff_slot", C.c_uint32),
+                ("u", MbUnion), ("reserved2", C.c_uint32)]
+
+
+class MbMotion(C.Structure):
+    _fields_ = [("mv", C.c_int16 * 2 * 16 * 2), ("ref_idx", C.c_int8 * 16 * 2), ("ref_pic", C.c_int8 * 16 * 2)]
+
+
+class Slice(C.Structure):
+    _fields_ = [("slice_type", C.c_uint8), ("disable_deblocking_filter_idc", C.c_uint8),
+                ("filter_offset_a", C.c_int8), ("filter_offset_b", C.c_int8),
+                ("luma_log2_weight_denom", C.c_uint8), ("chroma_log2_weight_denom", C.c_uint8),
+                ("weighted_pred_flag", C.c_uint8), ("weighted_bipred_idc", C.c_uint8),
+                ("constrained_intra_pred_flag", C.c_uint8), ("direct_spatial_mv_pred_flag", C.c_uint8),
+                ("num_ref", C.c_uint8 * 2),
+                ("ref_pic_list", C.c_int8 * MAX_REFS * 2),
+                ("wp_weight", C.c_int8 * MAX_REFS * 3 * 2), ("wp_offset", C.c_int8 * MAX_REFS * 3 * 2),
+                ("implicit_w1", C.c_int16 * MAX_REFS * MAX_REFS),
+                ("level_scale_4x4", C.c_uint16 * 16 * 6 * 3 * 2), ("level_scale_8x8", C.c_uint16 * 64 * 6 * 2),
+                ("reserved", C.c_uint8 * 20)]
+
+
+class PicParams(C.Structure):
+    _fields_ = [("num_slices", C.c_int32), ("num_ref_frames", C.c_int32), ("ref_frames", C.c_int32 * MAX_REFS),
+                ("run_deblock", C.c_int32), ("poc", C.c_int32), ("ref_poc", C.c_int32 * MAX_REFS),
+                ("ref_long_term", C.c_uint8 * MAX_REFS)]
+
+
+class SeqParams(C.Structure):
+    _fields_ = [("width_mbs", C.c_int32), ("height_mbs", C.c_int32), ("direct_8x8_inference_flag", C.c_int32),
+                ("max_frames", C.c_int32), ("max_pictures_in_flight", C.c_int32),
+                ("max_slices_per_picture", C.c_int32)]
+
+
+class PicBuffers(C.Structure):
+    _fields_ = [("mbs", C.POINTER(Mb)), ("motion", C.POINTER(MbMotion)), ("slices", C.POINTER(Slice)),
+                ("coeffs", C.POINTER(C.c_int16)), ("coeff_slot_capacity", C.c_uint32)]
+
+
+class PicInfo(C.Structure):
+    _fields_ = [("pic_index", C.c_int32), ("pic_type", C.c_int32), ("used_for_reference", C.c_int32),
+                ("poc", C.c_int32), ("num_refs", C.c_int32), ("ref_pic_index", C.c_int32 * MAX_REFS),
+                ("last_use_of_ref", C.c_int32 * MAX_REFS), ("num_coeff_slots", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("pictures", C.c_uint64), ("macroblocks", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("waves", C.c_uint64)]
+
+
+assert C.sizeof(Mb) == 32 and C.sizeof(MbMotion) == 192 and C.sizeof(Slice) == 5216
+
+_synth = None
+_recon = None
+
+
+def synth_lib():
+    global _synth
+    if _synth is None:
+        L = C.CDLL(os.path.join(HERE, "libh264synth.so"))
+        L.h264s_open.restype = C.c_void_p
+        L.h264s_open.argtypes = [C.c_int] * 5
+        L.h264s_close.argtypes = [C.c_void_p]
+        L.h264s_get_seq.argtypes = [C.c_void_p, C.POINTER(SeqParams), C.POINTER(C.c_int)]
+        L.h264s_next.restype = C.c_int
+        L.h264s_next.argtypes = [C.c_void_p, C.POINTER(PicInfo), C.POINTER(PicParams), C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
+        _synth = L
+    return _synth
+
+
+def recon_lib():
+    """The CUDA engine.  Raises if it is not built: there is no CPU fallback."""
+    global _recon
+    if _recon is None:
+        path = os.path.join(HERE, "libh264recon.so")
+        if not os.path.exists(path):
+            raise RuntimeError("libh264recon.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                               "the engine has no CPU fallback")
+        L = C.CDLL(path)
+        P = C.c_void_p
+        L.h264r_create.restype = C.c_int
+        L.h264r_create.argtypes = [C.POINTER(P), C.c_int, C.POINTER(SeqParams)]
+        L.h264r_destroy.argtypes = [P]
+        L.h264r_frame_alloc.argtypes = [P, C.POINTER(C.c_int32)]
+        L.h264r_frame_release.argtypes = [P, C.c_int32]
+        L.h264r_picture_begin.argtypes = [P, C.c_int32, C.POINTER(PicParams), C.POINTER(PicBuffers)]
+        L.h264r_picture_submit.argtypes = [P, C.c_uint32]
+        L.h264r_flush.argtypes = [P]
+        L.h264r_wait.argtypes = [P, C.c_int32]
+        L.h264r_frame_download.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.h264r_frame_upload.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.h264r_replay_last_flush.argtypes = [P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.h264r_get_stats.argtypes = [P, C.POINTER(Stats)]
+        L.h264r_strerror.restype = C.c_char_p
+        L.h264r_strerror.argtypes = [C.c_int]
+        L.h264r_last_cuda_error.restype = C.c_char_p
+        L.h264r_last_cuda_error.argtypes = [P]
+        L.h264r_device_count.restype = C.c_int
+        _recon = L
+    return _recon
+
+
+class Picture:
+    """One generated picture: owns its host buffers (numpy-free, plain ctypes arrays)."""
+    __slots__ = ("info", "pp", "mbs", "motion", "slices", "coeffs", "nmb")
+
+    def __init__(self, nmb):
+        self.nmb = nmb
+        self.info = PicInfo()
+        self.pp = PicParams()
+        self.mbs = (Mb * nmb)()
+        self.motion = (MbMotion * nmb)()
+        self.slices = (Slice * 4)()
+        self.coeffs = (C.c_int16 * (COEFFS_PER_MB * nmb))()
+
+
+class SynthStream:
+    def __init__(self, config, stream_idx=0, width_mbs=0, height_mbs=0, num_frames=0):
+        self.L = synth_lib()
+        self.h = self.L.h264s_open(config, stream_idx, width_mbs, height_mbs, num_frames)
+        if not self.h:
+            raise ValueError("bad synth config")
+        self.seq = SeqParams()
+        n = C.c_int()
+        self.L.h264s_get_seq(self.h, C.byref(self.seq), C.byref(n))
+        self.num_frames = n.value
+        self.nmb = self.seq.width_mbs * self.seq.height_mbs
+
+    def next(self):
+        pic = Picture(self.nmb)
+        ok = self.L.h264s_next(self.h, C.byref(pic.info), C.byref(pic.pp), pic.mbs, pic.motion, pic.slices, pic.coeffs)
+        return pic if ok else None
+
+    def __iter__(self):
+        while True:
+            p = self.next()
+            if p is None:
+                return
+            yield p
+
+    def close(self):
+        if self.h:
+            self.L.h264s_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

@@ -1,0 +1,220 @@
+/*
+ * h264recon.h -- C ABI of the B200-native H.264 macroblock-reconstruction engine.
+ *
+ * This is the drop-in boundary for the reconstruction path of luuvish/arrow-h264: everything that sits
+ * behind `class vio::h264::Decoder` (reference src/codec/h264/decoder/decoder.h:301-338).  The serial
+ * entropy decoder / slice parser stays on the host and fills, per picture, the flat buffers declared
+ * here (coefficient levels, macroblock headers, motion, slice tables); the GPU reconstructs the whole
+ * picture (dequant + IDCT, motion compensation, intra prediction, deblocking) on `h264r_picture_submit`.
+ *
+ * Plain C, plain pointers and sizes, `int` status codes, no exceptions, no exit().  One context per GPU;
+ * calls on one context must be serialised by the caller (one host thread per GPU), exactly like the
+ * reference's single-threaded decoder loop (core/slice_data.cc:636-661).
+ *
+ * Supported stream subset (anything else returns H264R_ERR_UNSUPPORTED, there is NO CPU fallback):
+ * 8-bit 4:2:0 frame pictures (no PAFF/MBAFF), no transform bypass, no SP/SI slices, no FMO/ASO.
+ *
+ * Every struct below is also the HBM layout: the host fills pinned staging memory laid out exactly as
+ * the device reads it, so submit is a handful of large cudaMemcpyAsync calls.
+ */
+#ifndef H264RECON_H_
+#define H264RECON_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------ */
+/* constants (reference numbering, parser/macroblock.h:36-76, parser/slice.h:25-31)                  */
+
+enum {
+    H264R_P_SLICE = 0, H264R_B_SLICE = 1, H264R_I_SLICE = 2
+};
+enum {                               /* mb_t::mb_type                                                */
+    H264R_MB_SKIP_DIRECT = 0,        /* P_Skip / B_Skip / B_Direct_16x16                              */
+    H264R_MB_16x16 = 1, H264R_MB_16x8 = 2, H264R_MB_8x16 = 3, H264R_MB_8x8 = 4,
+    H264R_SUB_8x4 = 5, H264R_SUB_4x8 = 6, H264R_SUB_4x4 = 7,      /* SubMbType values 4..7, 0=direct */
+    H264R_MB_I4x4 = 8, H264R_MB_I8x8 = 9, H264R_MB_I16x16 = 10, H264R_MB_IPCM = 12
+};
+enum { H264R_PRED_L0 = 0, H264R_PRED_L1 = 1, H264R_PRED_BI = 2 };
+
+#define H264R_MB_FLAG_INTRA   0x01u  /* mb_t::is_intra_block                                          */
+#define H264R_MB_FLAG_T8x8    0x02u  /* mb_t::transform_size_8x8_flag                                 */
+
+#define H264R_NO_COEFF        0xFFFFFFFFu
+#define H264R_MAX_REFS        32     /* entries of one RefPicList (frame decoding uses <= 16)         */
+#define H264R_COEFFS_PER_MB   384    /* 256 Y + 64 Cb + 64 Cr                                         */
+
+/* status codes */
+enum {
+    H264R_OK = 0,
+    H264R_ERR_INVALID = -1,          /* bad argument / bad handle                                     */
+    H264R_ERR_UNSUPPORTED = -2,      /* stream feature outside the supported subset                   */
+    H264R_ERR_NOMEM = -3,            /* frame pool / staging exhausted or cudaMalloc failed           */
+    H264R_ERR_CUDA = -4,             /* CUDA runtime error (h264r_last_cuda_error gives the text)     */
+    H264R_ERR_STATE = -5,            /* call order violated (e.g. submit without begin)               */
+    H264R_ERR_NODEVICE = -6          /* no CUDA device: the engine never falls back to the CPU        */
+};
+
+/* ------------------------------------------------------------------------------------------------ */
+/* per-macroblock header: 32 bytes.  Snapshot of the mb_t fields the reconstruction path reads       */
+/* (parser/macroblock.h:78-135; list extracted in SURVEY.md §8a row TY).                             */
+
+typedef struct h264r_mb {
+    uint8_t  mb_type;                /* mb_t::mb_type                                                 */
+    uint8_t  flags;                  /* H264R_MB_FLAG_*                                               */
+    uint16_t slice_idx;              /* index into the picture's slice table == mb_t::slice_nr        */
+    uint8_t  cbp_luma;               /* CodedBlockPatternLuma   (bit b = 8x8 block b)                 */
+    uint8_t  cbp_chroma;             /* CodedBlockPatternChroma (0, 1 = DC only, 2 = DC + AC)         */
+    int8_t   qp_y;                   /* QpY      (== qp_scaled[0] at 8 bit)                           */
+    int8_t   qp_c[2];                /* QpC[0,1] (== qp_scaled[1,2]), from update_qp, interpret_mb.cc:784 */
+    uint8_t  intra16_mode;           /* Intra16x16PredMode                                            */
+    uint8_t  chroma_mode;            /* intra_chroma_pred_mode                                        */
+    uint8_t  reserved0;
+    uint16_t cbp_blks;               /* cbp_blks[0] bits 0..15: 4x4 block (by*4+bx) has luma AC levels
+                                        (transform.cc:433-436; 0xFFFF for I_PCM, interpret_mb.cc:421) */
+    uint16_t reserved1;
+    uint32_t coeff_slot;             /* index of this MB's 384-int16 slot in the coefficient buffer,
+                                        H264R_NO_COEFF when the MB received no level and is not I16x16/I_PCM */
+    union {
+        uint8_t intra_modes[8];      /* 16 nibbles, low nibble first: Intra4x4PredMode[luma4x4BlkIdx]
+                                        (I_4x4) or Intra8x8PredMode[0..3] in nibbles 0..3 (I_8x8)     */
+        struct {
+            uint8_t sub_mb_type[4];      /* SubMbType[mbPartIdx]  (== mb_type for non-8x8 MBs)        */
+            uint8_t sub_mb_pred_mode[4]; /* SubMbPredMode[mbPartIdx] after direct-mode resolution     */
+        } inter;
+    } u;
+    uint32_t reserved2;
+} h264r_mb;
+
+/* per-macroblock motion: 192 bytes.  The 16 pic_motion_params (framebuf/picture.h:66-71) of the MB,   */
+/* 4x4 blocks in raster order (by*4+bx).  Only read for non-intra MBs.                                */
+typedef struct h264r_mb_motion {
+    int16_t mv[2][16][2];            /* [list][blk][x,y] quarter-pel                                   */
+    int8_t  ref_idx[2][16];          /* pic_motion_params::ref_idx (may be 0 for an unused list, quirk 2) */
+    int8_t  ref_pic[2][16];          /* identity of pic_motion_params::ref_pic: index into
+                                        h264r_pic_params::ref_frames, -1 == nullptr                    */
+} h264r_mb_motion;
+
+/* per-slice table.  Fields of shr_t / pps_t read by the path plus the tables the reference builds per
+ * slice header (Decoder::assign_quant_params -> Transform::init, transform.cc:173-302).              */
+typedef struct h264r_slice {
+    uint8_t  slice_type;                         /* H264R_{P,B,I}_SLICE                                */
+    uint8_t  disable_deblocking_filter_idc;
+    int8_t   filter_offset_a;                    /* shr.FilterOffsetA                                  */
+    int8_t   filter_offset_b;
+    uint8_t  luma_log2_weight_denom;
+    uint8_t  chroma_log2_weight_denom;
+    uint8_t  weighted_pred_flag;                 /* pps                                                */
+    uint8_t  weighted_bipred_idc;                /* pps                                                */
+    uint8_t  constrained_intra_pred_flag;        /* pps                                                */
+    uint8_t  direct_spatial_mv_pred_flag;
+    uint8_t  num_ref[2];                         /* slice_t::RefPicSize                                */
+    int8_t   ref_pic_list[2][H264R_MAX_REFS];    /* RefPicList[list][ref_idx] -> index into ref_frames  */
+    int8_t   wp_weight[2][3][H264R_MAX_REFS];    /* pred_weight_l[list][plane][ref_idx].weight (int8!)  */
+    int8_t   wp_offset[2][3][H264R_MAX_REFS];
+    int16_t  implicit_w1[H264R_MAX_REFS][H264R_MAX_REFS]; /* weighted_bipred_idc==2: weight1 for
+                                                    (ref_idx0, ref_idx1); weight0 = 64 - weight1
+                                                    (inter_prediction.cc:112-139, host precomputes)    */
+    uint16_t level_scale_4x4[2][3][6][16];       /* [0 intra / 1 inter][plane][qp%6][j*4+i]             */
+    uint16_t level_scale_8x8[2][6][64];          /* [0 intra / 1 inter][qp%6][j*8+i] (luma only, 4:2:0) */
+    uint8_t  reserved[20];
+} h264r_slice;
+
+/* per-picture parameters */
+typedef int32_t h264r_frame;                     /* frame-pool id, >= 0                                */
+
+typedef struct h264r_pic_params {
+    int32_t     num_slices;
+    int32_t     num_ref_frames;                  /* distinct reference pictures used by this picture   */
+    h264r_frame ref_frames[H264R_MAX_REFS];      /* pool ids; motion.ref_pic / ref_pic_list index this  */
+    int32_t     run_deblock;                     /* reference: some slice has idc != 1 and
+                                                    used_for_reference in {0,1} (deblock.cc:631-643)   */
+    int32_t     poc;                             /* informational (implicit weights are precomputed)   */
+    int32_t     ref_poc[H264R_MAX_REFS];         /* informational: POC of ref_frames[i]                */
+    uint8_t     ref_long_term[H264R_MAX_REFS];   /* informational                                      */
+} h264r_pic_params;
+
+/* sequence parameters (sps_t) */
+typedef struct h264r_seq_params {
+    int32_t width_mbs;                           /* PicWidthInMbs                                      */
+    int32_t height_mbs;                          /* FrameHeightInMbs                                   */
+    int32_t direct_8x8_inference_flag;
+    int32_t max_frames;                          /* frame pool capacity                                */
+    int32_t max_pictures_in_flight;              /* staging slots that can be filled before a flush    */
+    int32_t max_slices_per_picture;
+} h264r_seq_params;
+
+/* host staging pointers handed out by h264r_picture_begin (pinned memory owned by the context) */
+typedef struct h264r_pic_buffers {
+    h264r_mb*        mbs;                        /* [width_mbs*height_mbs], raster order               */
+    h264r_mb_motion* motion;                     /* [width_mbs*height_mbs]                             */
+    h264r_slice*     slices;                     /* [max_slices_per_picture]                           */
+    int16_t*         coeffs;                     /* [coeff_slot_capacity][384] raw levels at raster
+                                                    positions: Y 16x16 (256), Cb 8x8 (64), Cr 8x8 (64);
+                                                    I_PCM: the 384 samples.  Slots must be zero where no
+                                                    level was written (begin hands them out zeroed).   */
+    uint32_t         coeff_slot_capacity;        /* == number of MBs                                   */
+} h264r_pic_buffers;
+
+typedef struct h264r_ctx h264r_ctx;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* entry points                                                                                       */
+
+/* replaces: slice_t owning a `Decoder decoder` (parser/slice.h:173) + storable_picture allocation     */
+int  h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp);
+void h264r_destroy(h264r_ctx* ctx);
+
+/* replaces: new storable_picture(...) planes (framebuf/picture.cc:15-83); device Y/Cb/Cr, uint8        */
+int  h264r_frame_alloc(h264r_ctx* ctx, h264r_frame* out);
+int  h264r_frame_release(h264r_ctx* ctx, h264r_frame f);
+
+/* replaces: init_picture + Decoder::init (core/slice_data.cc:149-313, 618).  Reserves a staging slot. */
+int  h264r_picture_begin(h264r_ctx* ctx, h264r_frame dst, const h264r_pic_params* pp, h264r_pic_buffers* out);
+/* replaces: Decoder::deblock_filter at exit_picture (framebuf/picture.cc:253): the picture is complete
+ * on the host side; it is queued.  `num_coeff_slots` = slots actually used.                           */
+int  h264r_picture_submit(h264r_ctx* ctx, uint32_t num_coeff_slots);
+/* launches everything queued: pictures are grouped into dependency waves (a picture whose references
+ * are produced by a queued picture goes to a later wave); every wave is one batched launch sequence.  */
+int  h264r_flush(h264r_ctx* ctx);
+/* blocks until frame `f` (or everything, f < 0) is reconstructed                                      */
+int  h264r_wait(h264r_ctx* ctx, h264r_frame f);
+
+/* replaces: write_out_picture reading imgY/imgUV (framebuf/output.cc:109-227)                          */
+int  h264r_frame_download(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb, uint8_t* cr,
+                          int pitch_y, int pitch_c);
+/* test/seed helper: set a frame's samples (e.g. an externally decoded reference picture)               */
+int  h264r_frame_upload(h264r_ctx* ctx, h264r_frame f, const uint8_t* y, const uint8_t* cb, const uint8_t* cr,
+                        int pitch_y, int pitch_c);
+
+/* Device-resident replay for benchmarking: keeps the already-uploaded descriptions of the last flush in
+ * HBM and re-runs only the kernels (no H2D).  Returns the CUDA-event time of the replay in milliseconds. */
+int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, float* ms_total, float* ms_kernels);
+
+/* host helper restating inter_prediction.cc:112-139 (implicit bi-prediction weights)                   */
+void h264r_implicit_weights(int cur_poc, int poc0, int poc1, int long_term0, int long_term1, int* w0, int* w1);
+/* host helper restating transform.cc:265-302 (set_quant) for 8-bit 4:2:0: qmatrix[0..5] 4x4 lists
+ * (Intra Y,Cb,Cr, Inter Y,Cb,Cr) and qmatrix[6..7] 8x8 lists (Intra Y, Inter Y), raster order          */
+void h264r_build_level_scale(h264r_slice* s, const int* const qmatrix4x4[6], const int* const qmatrix8x8[2]);
+
+/* counters / diagnostics */
+typedef struct h264r_stats {
+    uint64_t kernel_launches;        /* number of kernels launched by this context so far              */
+    uint64_t pictures;               /* pictures reconstructed                                         */
+    uint64_t macroblocks;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t waves;                  /* batched launch sequences                                       */
+} h264r_stats;
+int         h264r_get_stats(h264r_ctx* ctx, h264r_stats* out);
+const char* h264r_strerror(int code);
+const char* h264r_last_cuda_error(h264r_ctx* ctx);
+int         h264r_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H264RECON_H_ */
