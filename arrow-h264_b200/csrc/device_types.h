@@ -1,0 +1,46 @@
+// Device-side view of one queued picture and the launch interface between engine.cu (host runtime) and
+// kernels.cu (sm_100a kernels).
+#ifndef H264R_DEVICE_TYPES_H_
+#define H264R_DEVICE_TYPES_H_
+
+#include "h264recon.h"
+#include <cuda_runtime.h>
+
+namespace h264r {
+
+// Frame in HBM: one allocation, planes at fixed offsets, unpadded (kernels clamp coordinates, which is
+// bit-identical to the reference's padded planes + block pre-clamp, SURVEY.md §8a derived facts).
+struct FrameGeom {
+    int width_mbs, height_mbs;
+    int pitch_y, pitch_c;            // bytes; multiples of 128
+    size_t off_cb, off_cr, bytes;    // plane offsets inside the allocation
+};
+
+struct DevPicture {
+    const h264r_mb*        mbs;
+    const h264r_mb_motion* motion;
+    const h264r_slice*     slices;
+    const int16_t*         coeffs;
+    uint8_t*               dst;                       // frame base
+    const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]
+    int*                   row_progress;              // [2][height_mbs]: intra wavefront, deblock wavefront
+    int                    run_deblock;
+    int                    has_intra;                 // any intra MB in the picture (host-side hint)
+    int                    has_inter;
+    int                    pad;
+};
+
+struct WaveLaunch {
+    const DevPicture* pics;          // device array
+    int   num_pics;
+    int*  tickets;                   // device: [2] work-ticket counters (intra, deblock), zeroed per wave
+    FrameGeom geom;
+    int   direct8x8;
+    int   any_inter, any_intra, any_deblock;
+};
+
+// Launches the reconstruction kernels of one wave on `stream`; returns the number of kernels launched.
+int launch_wave(const WaveLaunch& w, cudaStream_t stream);
+
+} // namespace h264r
+#endif

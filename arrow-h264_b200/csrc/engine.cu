@@ -1,0 +1,423 @@
+// Host runtime behind the C ABI of include/h264recon.h: frame pool, pinned staging slots, dependency waves,
+// batched launches.  C++ host code + CUDA runtime only (no PyTorch, no NCCL: streams/GOPs are independent).
+#include "device_types.h"
+
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+
+using namespace h264r;
+
+static_assert(sizeof(h264r_mb) == 32, "h264r_mb must be 32 bytes");
+static_assert(sizeof(h264r_mb_motion) == 192, "h264r_mb_motion must be 192 bytes");
+static_assert(sizeof(h264r_slice) % 16 == 0, "h264r_slice must keep 16-byte alignment in arrays");
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Frame {
+    uint8_t* dev = nullptr;
+    bool used = false;
+    int write_wave = -1, read_wave = -1;      // bookkeeping inside one flush
+};
+
+enum SlotState { SLOT_FREE = 0, SLOT_FILLING, SLOT_QUEUED, SLOT_INFLIGHT };
+
+struct Slot {
+    uint8_t* host = nullptr;                  // pinned
+    uint8_t* dev = nullptr;
+    SlotState state = SLOT_FREE;
+    h264r_pic_params pp;
+    h264r_frame dst = -1;
+    uint32_t used_slots = 0;
+    int has_intra = 0, has_inter = 0;
+    int wave = 0;
+};
+
+struct WaveRecord {
+    WaveLaunch launch;
+    size_t progress_bytes;
+};
+
+} // namespace
+
+struct h264r_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    h264r_seq_params seq;
+    FrameGeom geom;
+    int nmb = 0;
+    size_t off_mbs = 0, off_motion = 0, off_slices = 0, off_coeffs = 0, slot_bytes = 0;
+    std::vector<Frame> frames;
+    std::vector<Slot> slots;
+    std::vector<int> queue;                   // slot indexes in submission order
+    int filling = -1;
+    DevPicture* h_pics = nullptr;             // pinned, [max_pictures_in_flight]
+    DevPicture* d_pics = nullptr;
+    int* d_sync = nullptr;                    // [2 tickets (padded to 64 ints)] + per picture [2][H] progress
+    size_t sync_ints_per_pic = 0;
+    std::vector<WaveRecord> last_waves;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    h264r_stats stats;
+    char cuda_err[256];
+};
+
+namespace {
+
+int cuda_fail(h264r_ctx* c, cudaError_t e, const char* what)
+{
+    snprintf(c->cuda_err, sizeof(c->cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return H264R_ERR_CUDA;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+bool frame_ok(const h264r_ctx* c, h264r_frame f) { return f >= 0 && f < (int)c->frames.size() && c->frames[f].used; }
+
+} // namespace
+
+extern "C" {
+
+int h264r_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* h264r_strerror(int code)
+{
+    switch (code) {
+    case H264R_OK: return "ok";
+    case H264R_ERR_INVALID: return "invalid argument";
+    case H264R_ERR_UNSUPPORTED: return "unsupported stream feature (8-bit 4:2:0 frame pictures only)";
+    case H264R_ERR_NOMEM: return "out of frames, staging slots or device memory";
+    case H264R_ERR_CUDA: return "CUDA runtime error";
+    case H264R_ERR_STATE: return "call order violated";
+    case H264R_ERR_NODEVICE: return "no CUDA device (this engine has no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+
+const char* h264r_last_cuda_error(h264r_ctx* ctx) { return ctx ? ctx->cuda_err : ""; }
+
+int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
+{
+    if (!out || !sp || sp->width_mbs <= 0 || sp->height_mbs <= 0 || sp->max_frames <= 0 ||
+        sp->max_pictures_in_flight <= 0 || sp->max_slices_per_picture <= 0) return H264R_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return H264R_ERR_NODEVICE;
+    if (device < 0 || device >= ndev) return H264R_ERR_INVALID;
+    h264r_ctx* ctx = new h264r_ctx();
+    ctx->device = device; ctx->seq = *sp; ctx->cuda_err[0] = 0;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e != cudaSuccess) { delete ctx; return H264R_ERR_CUDA; }
+
+    FrameGeom& g = ctx->geom;
+    g.width_mbs = sp->width_mbs; g.height_mbs = sp->height_mbs;
+    g.pitch_y = (int)align_up((size_t)sp->width_mbs * 16, 128);
+    g.pitch_c = (int)align_up((size_t)sp->width_mbs * 8, 128);
+    g.off_cb = align_up((size_t)g.pitch_y * sp->height_mbs * 16, 256);
+    g.off_cr = g.off_cb + align_up((size_t)g.pitch_c * sp->height_mbs * 8, 256);
+    g.bytes  = g.off_cr + align_up((size_t)g.pitch_c * sp->height_mbs * 8, 256);
+    ctx->nmb = sp->width_mbs * sp->height_mbs;
+
+    ctx->off_mbs = 0;
+    ctx->off_motion = align_up(ctx->off_mbs + sizeof(h264r_mb) * ctx->nmb, 256);
+    ctx->off_slices = align_up(ctx->off_motion + sizeof(h264r_mb_motion) * ctx->nmb, 256);
+    ctx->off_coeffs = align_up(ctx->off_slices + sizeof(h264r_slice) * sp->max_slices_per_picture, 256);
+    ctx->slot_bytes = align_up(ctx->off_coeffs + sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)ctx->nmb, 256);
+
+    ctx->frames.resize(sp->max_frames);
+    ctx->slots.resize(sp->max_pictures_in_flight);
+    // one pinned and one device arena for all staging slots
+    uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr;
+    const size_t arena = ctx->slot_bytes * sp->max_pictures_in_flight;
+    e = cudaHostAlloc((void**)&h_arena, arena, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_arena, arena);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * sp->max_pictures_in_flight, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * sp->max_pictures_in_flight);
+    ctx->sync_ints_per_pic = align_up((size_t)2 * sp->height_mbs, 32);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_sync, sizeof(int) * (64 + ctx->sync_ints_per_pic * sp->max_pictures_in_flight));
+    if (e != cudaSuccess) {
+        snprintf(ctx->cuda_err, sizeof(ctx->cuda_err), "allocation: %s", cudaGetErrorString(e));
+        if (h_arena) cudaFreeHost(h_arena);
+        if (d_arena) cudaFree(d_arena);
+        if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
+        if (ctx->d_pics) cudaFree(ctx->d_pics);
+        if (ctx->d_sync) cudaFree(ctx->d_sync);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return H264R_ERR_NOMEM;
+    }
+    for (int i = 0; i < sp->max_pictures_in_flight; ++i) {
+        ctx->slots[i].host = h_arena + ctx->slot_bytes * i;
+        ctx->slots[i].dev = d_arena + ctx->slot_bytes * i;
+    }
+    *out = ctx;
+    return H264R_OK;
+}
+
+void h264r_destroy(h264r_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (Frame& f : ctx->frames) if (f.dev) cudaFree(f.dev);
+    if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); }
+    cudaFreeHost(ctx->h_pics); cudaFree(ctx->d_pics); cudaFree(ctx->d_sync);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int h264r_frame_alloc(h264r_ctx* ctx, h264r_frame* out)
+{
+    if (!ctx || !out) return H264R_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    for (size_t i = 0; i < ctx->frames.size(); ++i)
+        if (!ctx->frames[i].used) {
+            if (!ctx->frames[i].dev) CU(cudaMalloc((void**)&ctx->frames[i].dev, ctx->geom.bytes));
+            ctx->frames[i].used = true;
+            *out = (h264r_frame)i;
+            return H264R_OK;
+        }
+    return H264R_ERR_NOMEM;
+}
+
+int h264r_frame_release(h264r_ctx* ctx, h264r_frame f)
+{
+    if (!ctx || !frame_ok(ctx, f)) return H264R_ERR_INVALID;
+    ctx->frames[f].used = false;               // memory is kept for reuse; queued work that references it stays valid
+    return H264R_OK;
+}
+
+int h264r_picture_begin(h264r_ctx* ctx, h264r_frame dst, const h264r_pic_params* pp, h264r_pic_buffers* out)
+{
+    if (!ctx || !pp || !out || !frame_ok(ctx, dst)) return H264R_ERR_INVALID;
+    if (ctx->filling >= 0) return H264R_ERR_STATE;
+    if (pp->num_slices <= 0 || pp->num_slices > ctx->seq.max_slices_per_picture) return H264R_ERR_INVALID;
+    if (pp->num_ref_frames < 0 || pp->num_ref_frames > H264R_MAX_REFS) return H264R_ERR_INVALID;
+    for (int i = 0; i < pp->num_ref_frames; ++i)
+        if (pp->ref_frames[i] < 0 || pp->ref_frames[i] >= (int)ctx->frames.size() || !ctx->frames[pp->ref_frames[i]].dev)
+            return H264R_ERR_INVALID;
+    int s = -1;
+    for (int attempt = 0; attempt < 2 && s < 0; ++attempt) {
+        for (size_t i = 0; i < ctx->slots.size(); ++i) if (ctx->slots[i].state == SLOT_FREE) { s = (int)i; break; }
+        if (s < 0 && attempt == 0) {
+            // staging of flushed pictures is reusable once their H2D copies have drained
+            cudaSetDevice(ctx->device);
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (Slot& t : ctx->slots) if (t.state == SLOT_INFLIGHT) t.state = SLOT_FREE;
+        }
+    }
+    if (s < 0) return H264R_ERR_NOMEM;
+    Slot& sl = ctx->slots[s];
+    sl.state = SLOT_FILLING; sl.pp = *pp; sl.dst = dst; sl.used_slots = 0;
+    ctx->filling = s;
+    out->mbs = reinterpret_cast<h264r_mb*>(sl.host + ctx->off_mbs);
+    out->motion = reinterpret_cast<h264r_mb_motion*>(sl.host + ctx->off_motion);
+    out->slices = reinterpret_cast<h264r_slice*>(sl.host + ctx->off_slices);
+    out->coeffs = reinterpret_cast<int16_t*>(sl.host + ctx->off_coeffs);
+    out->coeff_slot_capacity = (uint32_t)ctx->nmb;
+    return H264R_OK;
+}
+
+int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_coeff_slots)
+{
+    if (!ctx) return H264R_ERR_INVALID;
+    if (ctx->filling < 0) return H264R_ERR_STATE;
+    if (num_coeff_slots > (uint32_t)ctx->nmb) return H264R_ERR_INVALID;
+    Slot& sl = ctx->slots[ctx->filling];
+    sl.used_slots = num_coeff_slots;
+    // validate what would otherwise become an out-of-bounds access on the device
+    const h264r_mb* mbs = reinterpret_cast<const h264r_mb*>(sl.host + ctx->off_mbs);
+    int has_intra = 0, has_inter = 0, bad = 0, unsupported = 0;
+    for (int i = 0; i < ctx->nmb; ++i) {
+        const h264r_mb& m = mbs[i];
+        if (m.flags & H264R_MB_FLAG_INTRA) has_intra = 1; else has_inter = 1;
+        if (m.slice_idx >= sl.pp.num_slices) bad = 1;
+        if (m.coeff_slot != H264R_NO_COEFF && m.coeff_slot >= num_coeff_slots) bad = 1;
+        if ((m.mb_type == H264R_MB_I16x16 || m.mb_type == H264R_MB_IPCM) && m.coeff_slot == H264R_NO_COEFF) bad = 1;
+        if (m.mb_type > H264R_MB_IPCM || m.mb_type == 11) unsupported = 1;        // SI and friends
+        if (!(m.flags & H264R_MB_FLAG_INTRA) && m.mb_type > H264R_MB_8x8) bad = 1;
+        if (m.qp_y < 0 || m.qp_y > 51 || m.qp_c[0] < 0 || m.qp_c[0] > 51 || m.qp_c[1] < 0 || m.qp_c[1] > 51) bad = 1;
+    }
+    const h264r_slice* slices = reinterpret_cast<const h264r_slice*>(sl.host + ctx->off_slices);
+    for (int k = 0; k < sl.pp.num_slices; ++k) {
+        if (slices[k].slice_type > H264R_I_SLICE) unsupported = 1;               // SP / SI
+        for (int list = 0; list < 2; ++list)
+            for (int i = 0; i < H264R_MAX_REFS; ++i)
+                if (slices[k].ref_pic_list[list][i] >= sl.pp.num_ref_frames) bad = 1;
+    }
+    if (bad || unsupported) {
+        sl.state = SLOT_FREE; ctx->filling = -1;
+        return unsupported ? H264R_ERR_UNSUPPORTED : H264R_ERR_INVALID;
+    }
+    sl.has_intra = has_intra; sl.has_inter = has_inter;
+    sl.state = SLOT_QUEUED;
+    ctx->queue.push_back(ctx->filling);
+    ctx->filling = -1;
+    return H264R_OK;
+}
+
+int h264r_flush(h264r_ctx* ctx)
+{
+    if (!ctx) return H264R_ERR_INVALID;
+    if (ctx->filling >= 0) return H264R_ERR_STATE;
+    if (ctx->queue.empty()) return H264R_OK;
+    cudaSetDevice(ctx->device);
+
+    // ---- dependency waves: RAW on reference frames, WAR/WAW on the destination frame ----
+    for (Frame& f : ctx->frames) { f.write_wave = -1; f.read_wave = -1; }
+    int num_waves = 0;
+    for (int qi : ctx->queue) {
+        Slot& s = ctx->slots[qi];
+        int w = 0;
+        for (int i = 0; i < s.pp.num_ref_frames; ++i) w = std::max(w, ctx->frames[s.pp.ref_frames[i]].write_wave + 1);
+        Frame& d = ctx->frames[s.dst];
+        w = std::max(w, std::max(d.write_wave, d.read_wave) + 1);
+        if (d.write_wave < 0 && d.read_wave < 0) w = std::max(w, 0);
+        s.wave = w;
+        d.write_wave = w;
+        for (int i = 0; i < s.pp.num_ref_frames; ++i) {
+            Frame& r = ctx->frames[s.pp.ref_frames[i]];
+            r.read_wave = std::max(r.read_wave, w);
+        }
+        num_waves = std::max(num_waves, w + 1);
+    }
+    std::vector<int> order(ctx->queue);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->slots[a].wave < ctx->slots[b].wave; });
+
+    // ---- device picture table (one upload for all waves) ----
+    const int H = ctx->geom.height_mbs;
+    ctx->last_waves.clear();
+    std::vector<int> wave_begin(num_waves + 1, 0);
+    for (size_t k = 0; k < order.size(); ++k) wave_begin[ctx->slots[order[k]].wave + 1] = (int)k + 1;
+    for (int w = 1; w <= num_waves; ++w) wave_begin[w] = std::max(wave_begin[w], wave_begin[w - 1]);
+    for (size_t k = 0; k < order.size(); ++k) {
+        Slot& s = ctx->slots[order[k]];
+        DevPicture& p = ctx->h_pics[k];
+        memset(&p, 0, sizeof(p));
+        p.mbs = reinterpret_cast<const h264r_mb*>(s.dev + ctx->off_mbs);
+        p.motion = reinterpret_cast<const h264r_mb_motion*>(s.dev + ctx->off_motion);
+        p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
+        p.coeffs = reinterpret_cast<const int16_t*>(s.dev + ctx->off_coeffs);
+        p.dst = ctx->frames[s.dst].dev;
+        for (int i = 0; i < H264R_MAX_REFS; ++i)
+            p.ref[i] = i < s.pp.num_ref_frames ? ctx->frames[s.pp.ref_frames[i]].dev : ctx->frames[s.dst].dev;
+        const int pos_in_wave = (int)k - wave_begin[s.wave];
+        p.row_progress = ctx->d_sync + 64 + ctx->sync_ints_per_pic * pos_in_wave;
+        p.run_deblock = s.pp.run_deblock; p.has_intra = s.has_intra; p.has_inter = s.has_inter;
+    }
+    CU(cudaMemcpyAsync(ctx->d_pics, ctx->h_pics, sizeof(DevPicture) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += sizeof(DevPicture) * order.size();
+
+    // ---- per wave: H2D of the picture descriptions, then the batched kernels ----
+    for (int w = 0; w < num_waves; ++w) {
+        const int b = wave_begin[w], e = wave_begin[w + 1];
+        if (e <= b) continue;
+        WaveRecord rec;
+        WaveLaunch& L = rec.launch;
+        L.pics = ctx->d_pics + b; L.num_pics = e - b; L.tickets = ctx->d_sync; L.geom = ctx->geom;
+        L.direct8x8 = ctx->seq.direct_8x8_inference_flag;
+        L.any_inter = L.any_intra = L.any_deblock = 0;
+        for (int k = b; k < e; ++k) {
+            Slot& s = ctx->slots[order[k]];
+            const size_t bytes = ctx->off_coeffs + sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)s.used_slots;
+            CU(cudaMemcpyAsync(s.dev, s.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->stats.h2d_bytes += bytes;
+            L.any_inter |= s.has_inter; L.any_intra |= s.has_intra; L.any_deblock |= s.pp.run_deblock;
+            ctx->stats.pictures += 1; ctx->stats.macroblocks += (uint64_t)ctx->nmb;
+        }
+        rec.progress_bytes = sizeof(int) * (64 + ctx->sync_ints_per_pic * (size_t)L.num_pics);
+        CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
+        ctx->stats.kernel_launches += (uint64_t)launch_wave(L, ctx->stream);
+        CU(cudaGetLastError());
+        ctx->stats.waves += 1;
+        ctx->last_waves.push_back(rec);
+    }
+    (void)H;
+    for (int qi : ctx->queue) ctx->slots[qi].state = SLOT_INFLIGHT;   // reusable once the stream has drained (h264r_wait)
+    ctx->queue.clear();
+    return H264R_OK;
+}
+
+int h264r_wait(h264r_ctx* ctx, h264r_frame f)
+{
+    if (!ctx) return H264R_ERR_INVALID;
+    (void)f;                                                      // single in-order stream: waiting for one waits for all
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (Slot& t : ctx->slots) if (t.state == SLOT_INFLIGHT) t.state = SLOT_FREE;
+    return H264R_OK;
+}
+
+int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, float* ms_total, float* ms_kernels)
+{
+    if (!ctx || iterations <= 0) return H264R_ERR_INVALID;
+    if (ctx->last_waves.empty()) return H264R_ERR_STATE;
+    cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int it = 0; it < iterations; ++it)
+        for (WaveRecord& rec : ctx->last_waves) {
+            CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
+            ctx->stats.kernel_launches += (uint64_t)launch_wave(rec.launch, ctx->stream);
+        }
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaGetLastError());
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ms_total) *ms_total = ms;
+    if (ms_kernels) *ms_kernels = ms;
+    return H264R_OK;
+}
+
+int h264r_frame_download(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb, uint8_t* cr, int pitch_y, int pitch_c)
+{
+    if (!ctx || f < 0 || f >= (int)ctx->frames.size() || !ctx->frames[f].dev || !y || !cb || !cr) return H264R_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const FrameGeom& g = ctx->geom;
+    const int w = g.width_mbs * 16, h = g.height_mbs * 16;
+    if (pitch_y < w || pitch_c < w / 2) return H264R_ERR_INVALID;
+    const uint8_t* d = ctx->frames[f].dev;
+    CU(cudaMemcpy2DAsync(y, pitch_y, d, g.pitch_y, w, h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpy2DAsync(cb, pitch_c, d + g.off_cb, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpy2DAsync(cr, pitch_c, d + g.off_cr, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (uint64_t)w * h * 3 / 2;
+    return H264R_OK;
+}
+
+int h264r_frame_upload(h264r_ctx* ctx, h264r_frame f, const uint8_t* y, const uint8_t* cb, const uint8_t* cr, int pitch_y, int pitch_c)
+{
+    if (!ctx || !frame_ok(ctx, f) || !y || !cb || !cr) return H264R_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const FrameGeom& g = ctx->geom;
+    const int w = g.width_mbs * 16, h = g.height_mbs * 16;
+    if (pitch_y < w || pitch_c < w / 2) return H264R_ERR_INVALID;
+    uint8_t* d = ctx->frames[f].dev;
+    CU(cudaMemcpy2DAsync(d, g.pitch_y, y, pitch_y, w, h, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(d + g.off_cb, g.pitch_c, cb, pitch_c, w / 2, h / 2, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(d + g.off_cr, g.pitch_c, cr, pitch_c, w / 2, h / 2, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes += (uint64_t)w * h * 3 / 2;
+    return H264R_OK;
+}
+
+int h264r_get_stats(h264r_ctx* ctx, h264r_stats* out)
+{
+    if (!ctx || !out) return H264R_ERR_INVALID;
+    *out = ctx->stats;
+    return H264R_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,1036 @@
+// sm_100a kernels of the H.264 macroblock-reconstruction path.
+//
+//   recon_inter_kernel   : one warp per inter macroblock, all pictures of a wave in one grid
+//                          (motion compensation + weighted prediction + dequant/IDCT + reconstruction)
+//   recon_intra_kernel   : one warp per macroblock ROW; rows of a picture form a 2:1 wavefront
+//                          (MB(x,y) needs (x-1,y), (x-1,y-1), (x,y-1), (x+1,y-1)); progress counters in HBM
+//   deblock_kernel       : same row wavefront; per MB bS derivation, vertical then horizontal edges, in place
+//
+// Arithmetic follows the reference (src/codec/h264/decoder/{transform,inter_prediction,intra_prediction,
+// deblock}.cc); the line-by-line citations live in the CPU restatement oracle/port_recon.c, whose structure
+// these kernels mirror.  All sample arithmetic is int32; results are bit-exact by construction.
+#include "device_types.h"
+
+#include <stdint.h>
+
+namespace h264r {
+
+constexpr int kWarpsPerCta = 4;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers
+
+__device__ __forceinline__ int clip3i(int lo, int hi, int v) { return min(max(v, lo), hi); }
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+
+__device__ __forceinline__ uint32_t ldcg_u32(const void* p) { return __ldcg(reinterpret_cast<const unsigned int*>(p)); }
+__device__ __forceinline__ uint8_t  ldcg_u8(const uint8_t* p) { return __ldcg(p); }
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+struct MbHdr {
+    int mb_type, flags, slice_idx, cbp_luma, cbp_chroma, qp_y, qp_c[2], i16mode, cmode, cbp_blks;
+    uint32_t coeff_slot, u0, u1;          // u0/u1: the 8-byte union (intra modes | sub_mb_type, sub_mb_pred_mode)
+    __device__ __forceinline__ bool intra() const { return flags & H264R_MB_FLAG_INTRA; }
+    __device__ __forceinline__ bool t8() const { return flags & H264R_MB_FLAG_T8x8; }
+};
+
+__device__ __forceinline__ MbHdr load_hdr(const h264r_mb* mbs, int addr)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(mbs + addr);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    MbHdr h;
+    h.mb_type = a.x & 0xFF; h.flags = (a.x >> 8) & 0xFF; h.slice_idx = a.x >> 16;
+    h.cbp_luma = a.y & 0xFF; h.cbp_chroma = (a.y >> 8) & 0xFF;
+    h.qp_y = (int)(int8_t)(a.y >> 16); h.qp_c[0] = (int)(int8_t)(a.y >> 24);
+    h.qp_c[1] = (int)(int8_t)(a.z & 0xFF); h.i16mode = (a.z >> 8) & 0xFF; h.cmode = (a.z >> 16) & 0xFF;
+    h.cbp_blks = a.w & 0xFFFF;
+    h.coeff_slot = b.x; h.u0 = b.y; h.u1 = b.z;
+    return h;
+}
+// first word only: mb_type | flags << 8 | slice_idx << 16
+__device__ __forceinline__ uint32_t load_hdr_word0(const h264r_mb* mbs, int addr)
+{
+    return __ldg(reinterpret_cast<const unsigned int*>(mbs + addr));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// residual: dequantisation + DC Hadamard + inverse transform, whole MB by one warp into res[384] (int32,
+// Y 16x16 stride 16 | Cb 8x8 | Cr 8x8).  Uncoded parts come out as 0, so reconstruction is always
+// clip(pred + res) (equal to the reference's "copy prediction" branches, transform.cc:926-934, 1070-1073).
+
+__device__ __forceinline__ void idct4_inplace(int* d, int s)
+{
+    int f[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int d0 = d[i * s], d1 = d[i * s + 1], d2 = d[i * s + 2], d3 = d[i * s + 3];
+        int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+        f[i][0] = e0 + e3; f[i][1] = e1 + e2; f[i][2] = e1 - e2; f[i][3] = e0 - e3;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        int f0 = f[0][j], f1 = f[1][j], f2 = f[2][j], f3 = f[3][j];
+        int g0 = f0 + f2, g1 = f0 - f2, g2 = (f1 >> 1) - f3, g3 = f1 + (f3 >> 1);
+        d[0 * s + j] = (g0 + g3 + 32) >> 6;
+        d[1 * s + j] = (g1 + g2 + 32) >> 6;
+        d[2 * s + j] = (g1 - g2 + 32) >> 6;
+        d[3 * s + j] = (g0 - g3 + 32) >> 6;
+    }
+}
+
+__device__ __forceinline__ void idct8_1d(int* p, int stride, bool final_pass)
+{
+    int d0 = p[0], d1 = p[stride], d2 = p[2 * stride], d3 = p[3 * stride];
+    int d4 = p[4 * stride], d5 = p[5 * stride], d6 = p[6 * stride], d7 = p[7 * stride];
+    int e0 = d0 + d4;
+    int e1 = -d3 + d5 - d7 - (d7 >> 1);
+    int e2 = d0 - d4;
+    int e3 = d1 + d7 - d3 - (d3 >> 1);
+    int e4 = (d2 >> 1) - d6;
+    int e5 = -d1 + d7 + d5 + (d5 >> 1);
+    int e6 = d2 + (d6 >> 1);
+    int e7 = d3 + d5 + d1 + (d1 >> 1);
+    int f0 = e0 + e6, f1 = e1 + (e7 >> 2), f2 = e2 + e4, f3 = e3 + (e5 >> 2);
+    int f4 = e2 - e4, f5 = (e3 >> 2) - e5, f6 = e0 - e6, f7 = e7 - (e1 >> 2);
+    int o0 = f0 + f7, o1 = f2 + f5, o2 = f4 + f3, o3 = f6 + f1, o4 = f6 - f1, o5 = f4 - f3, o6 = f2 - f5, o7 = f0 - f7;
+    if (final_pass) {
+        o0 = (o0 + 32) >> 6; o1 = (o1 + 32) >> 6; o2 = (o2 + 32) >> 6; o3 = (o3 + 32) >> 6;
+        o4 = (o4 + 32) >> 6; o5 = (o5 + 32) >> 6; o6 = (o6 + 32) >> 6; o7 = (o7 + 32) >> 6;
+    }
+    p[0] = o0; p[stride] = o1; p[2 * stride] = o2; p[3 * stride] = o3;
+    p[4 * stride] = o4; p[5 * stride] = o5; p[6 * stride] = o6; p[7 * stride] = o7;
+}
+
+__device__ void mb_residual(const MbHdr& h, const h264r_slice* __restrict__ sl, const int16_t* __restrict__ coeffs,
+                            int* res, int lane)
+{
+    if (h.coeff_slot == H264R_NO_COEFF) {
+        for (int i = lane; i < 384; i += 32) res[i] = 0;
+        __syncwarp();
+        return;
+    }
+    const int inter = h.intra() ? 0 : 1;
+    const bool t8 = h.t8();
+    const bool i16 = h.mb_type == H264R_MB_I16x16;
+    const int per = h.qp_y / 6, rem = h.qp_y - per * 6;
+    const uint16_t* ls4y = sl->level_scale_4x4[inter][0][rem];
+    const uint16_t* ls8  = sl->level_scale_8x8[inter][rem];
+    const uint4* src = reinterpret_cast<const uint4*>(coeffs + (size_t)h.coeff_slot * H264R_COEFFS_PER_MB);
+
+    for (int v = lane; v < 48; v += 32) {
+        uint4 q = __ldg(src + v);
+        uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int l = (int)(int16_t)(w[k >> 1] >> ((k & 1) * 16));
+            int p = v * 8 + k, val = 0;
+            if (p < 256) {
+                int x = p & 15, y = p >> 4;
+                if (i16) {
+                    if (((x | y) & 3) == 0) val = l;                                    // DC level, transformed below
+                    else if (l) val = ((l * (int)__ldg(&ls4y[(y & 3) * 4 + (x & 3)])) * (1 << per) + 8) >> 4;
+                } else if (l && ((h.cbp_luma >> ((y >> 3) * 2 + (x >> 3))) & 1)) {
+                    if (t8) val = ((l * (int)__ldg(&ls8[(y & 7) * 8 + (x & 7)])) * (1 << per) + 32) >> 6;
+                    else    val = ((l * (int)__ldg(&ls4y[(y & 3) * 4 + (x & 3)])) * (1 << per) + 8) >> 4;
+                }
+            } else if (h.cbp_chroma) {
+                int c = p - 256, pl = c >> 6, x = c & 7, y = (c >> 3) & 7;
+                if (((x | y) & 3) == 0) val = l;
+                else if (l) {
+                    int qc = h.qp_c[pl], cper = qc / 6, crem = qc - cper * 6;
+                    val = ((l * (int)__ldg(&sl->level_scale_4x4[inter][pl + 1][crem][(y & 3) * 4 + (x & 3)])) * (1 << cper) + 8) >> 4;
+                }
+            }
+            res[p] = val;
+        }
+    }
+    __syncwarp();
+
+    // DC transforms (transform_luma_dc / transform_chroma_dc)
+    if (i16 && lane == 0) {
+        int c[4][4], e[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[i][j] = res[i * 64 + j * 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int a0 = c[i][0] + c[i][2], a1 = c[i][0] - c[i][2], a2 = c[i][1] - c[i][3], a3 = c[i][1] + c[i][3];
+            e[i][0] = a0 + a3; e[i][1] = a1 + a2; e[i][2] = a1 - a2; e[i][3] = a0 - a3;
+        }
+        const int scale = (int)__ldg(&sl->level_scale_4x4[0][0][rem][0]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int a0 = e[0][j] + e[2][j], a1 = e[0][j] - e[2][j], a2 = e[1][j] - e[3][j], a3 = e[1][j] + e[3][j];
+            int f[4] = { a0 + a3, a1 + a2, a1 - a2, a0 - a3 };
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                res[i * 64 + j * 4] = h.qp_y >= 36 ? (f[i] * scale) * (1 << (per - 6))
+                                                   : (f[i] * scale + (1 << (5 - per))) >> (6 - per);
+        }
+    }
+    if (h.cbp_chroma && (lane == 1 || lane == 2)) {
+        const int pl = lane - 1, qc = h.qp_c[pl], cper = qc / 6, crem = qc - cper * 6;
+        int* c = res + 256 + pl * 64;
+        int c00 = c[0], c01 = c[4], c10 = c[32], c11 = c[36];
+        int e00 = c00 + c01, e01 = c00 - c01, e10 = c10 + c11, e11 = c10 - c11;
+        const int scale = (int)__ldg(&sl->level_scale_4x4[inter][pl + 1][crem][0]);
+        c[0]  = (((e00 + e10) * scale) * (1 << cper)) >> 5;
+        c[4]  = (((e01 + e11) * scale) * (1 << cper)) >> 5;
+        c[32] = (((e00 - e10) * scale) * (1 << cper)) >> 5;
+        c[36] = (((e01 - e11) * scale) * (1 << cper)) >> 5;
+    }
+    __syncwarp();
+
+    // inverse transforms
+    if (t8) {
+        const int b = lane >> 3, i = lane & 7;
+        int* blk = res + (b >> 1) * 128 + (b & 1) * 8;
+        idct8_1d(blk + i * 16, 1, false);
+        __syncwarp();
+        idct8_1d(blk + i, 16, true);
+        if (lane < 8) idct4_inplace(res + 256 + (lane >> 2) * 64 + ((lane >> 1) & 1) * 32 + (lane & 1) * 4, 8);
+    } else if (lane < 16) {
+        idct4_inplace(res + (lane >> 2) * 64 + (lane & 3) * 4, 16);
+    } else if (lane < 24) {
+        const int c = lane - 16;
+        idct4_inplace(res + 256 + (c >> 2) * 64 + ((c >> 1) & 1) * 32 + (c & 1) * 4, 8);
+    }
+    __syncwarp();
+}
+
+// out = clip(pred + res) for the whole MB, stored to the frame with 16-byte (luma) / 8-byte (chroma) row stores.
+// pred: 384 bytes (Y 16x16 | Cb 8x8 | Cr 8x8) in shared memory, 16-byte aligned.
+__device__ __forceinline__ void store_mb(const uint8_t* pred, const int* res, uint8_t* dst, const FrameGeom& g,
+                                         int mbx, int mby, int lane)
+{
+    if (lane < 16) {
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(pred + lane * 16);
+        const int* r = res + lane * 16;
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t p = pw[k];
+            o[k] = (uint32_t)clip255((int)(p & 0xFF) + r[k * 4])
+                 | (uint32_t)clip255((int)((p >> 8) & 0xFF) + r[k * 4 + 1]) << 8
+                 | (uint32_t)clip255((int)((p >> 16) & 0xFF) + r[k * 4 + 2]) << 16
+                 | (uint32_t)clip255((int)(p >> 24) + r[k * 4 + 3]) << 24;
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        const int c = lane - 16, pl = c >> 3, row = c & 7;
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(pred + 256 + pl * 64 + row * 8);
+        const int* r = res + 256 + pl * 64 + row * 8;
+        uint32_t o[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            uint32_t p = pw[k];
+            o[k] = (uint32_t)clip255((int)(p & 0xFF) + r[k * 4])
+                 | (uint32_t)clip255((int)((p >> 8) & 0xFF) + r[k * 4 + 1]) << 8
+                 | (uint32_t)clip255((int)((p >> 16) & 0xFF) + r[k * 4 + 2]) << 16
+                 | (uint32_t)clip255((int)(p >> 24) + r[k * 4 + 3]) << 24;
+        }
+        uint8_t* base = dst + (pl ? g.off_cr : g.off_cb);
+        *reinterpret_cast<uint2*>(base + (size_t)(mby * 8 + row) * g.pitch_c + mbx * 8) = make_uint2(o[0], o[1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inter prediction
+
+__constant__ int8_t c_block_step[8][2] = { {0,0}, {4,4}, {4,2}, {2,4}, {2,2}, {2,1}, {1,2}, {1,1} };
+
+// Decoder::mb_pred_inter partition walk (decoder.cc:217-262) for 4x4 block `blk`: returns the block whose
+// motion entry the reference reads (partition origin) and the prediction direction.
+__device__ __forceinline__ void partition_of_block(const MbHdr& h, const h264r_slice* sl, const h264r_mb_motion* m,
+                                                   int direct8x8, int blk, int& origin, int& dir)
+{
+    const int bx = blk & 3, by = blk >> 2;
+    const bool is_b = __ldg(&sl->slice_type) == H264R_B_SLICE;
+    int sh0 = c_block_step[h.mb_type & 7][0], sv0 = c_block_step[h.mb_type & 7][1];
+    if (h.mb_type == 0) sh0 = sv0 = is_b ? 2 : 4;
+    const int i0 = bx & ~(sh0 - 1), j0 = by & ~(sv0 - 1);
+    const int b8 = 2 * (j0 >> 1) + (i0 >> 1);
+    const int mode = (h.u0 >> (8 * b8)) & 0xFF;
+    int pd = (h.u1 >> (8 * b8)) & 0xFF;
+    int sh4 = c_block_step[mode & 7][0], sv4 = c_block_step[mode & 7][1];
+    if (mode == 0) sh4 = sv4 = direct8x8 ? 2 : 1;
+    if (is_b && h.mb_type == H264R_MB_8x8 && __ldg(&sl->direct_spatial_mv_pred_flag)) {
+        const int b = j0 * 4 + i0;
+        pd = m->ref_idx[1][b] < 0 ? 0 : (m->ref_idx[0][b] < 0 ? 1 : 2);
+    }
+    // partitions tile the (i0, j0) block from its origin in steps (sh4, sv4)
+    const int i = i0 + ((bx - i0) / sh4) * sh4, j = j0 + ((by - j0) / sv4) * sv4;
+    origin = j * 4 + i;
+    dir = pd;
+}
+
+// Luma interpolation of rows r0, r0+1 (4 samples each) of a 4x4 block from its 9x9 window (window origin =
+// integer position - 2).  get_block_luma, inter_prediction.cc:158-340.
+__device__ __forceinline__ void luma_half_block(const uint8_t* w, int xf, int yf, int r0, int out[8])
+{
+#define WIN(x, y) ((int)w[((y) + 2) * 9 + (x) + 2])
+    if ((xf | yf) == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) out[r * 4 + x] = WIN(x, r0 + r);
+        return;
+    }
+    if (yf == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int y = r0 + r;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                int b = clip255((tap6(WIN(x - 2, y), WIN(x - 1, y), WIN(x, y), WIN(x + 1, y), WIN(x + 2, y), WIN(x + 3, y)) + 16) >> 5);
+                out[r * 4 + x] = xf == 2 ? b : (WIN(x + (xf == 3), y) + b + 1) >> 1;
+            }
+        }
+        return;
+    }
+    if (xf == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int y = r0 + r;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                int hh = clip255((tap6(WIN(x, y - 2), WIN(x, y - 1), WIN(x, y), WIN(x, y + 1), WIN(x, y + 2), WIN(x, y + 3)) + 16) >> 5);
+                out[r * 4 + x] = yf == 2 ? hh : (WIN(x, y + (yf == 3)) + hh + 1) >> 1;
+            }
+        }
+        return;
+    }
+    if ((xf & 1) && (yf & 1)) {
+        const int dy = yf == 3, dx = xf == 3;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int y = r0 + r;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                int b = clip255((tap6(WIN(x - 2, y + dy), WIN(x - 1, y + dy), WIN(x, y + dy), WIN(x + 1, y + dy), WIN(x + 2, y + dy), WIN(x + 3, y + dy)) + 16) >> 5);
+                int hh = clip255((tap6(WIN(x + dx, y - 2), WIN(x + dx, y - 1), WIN(x + dx, y), WIN(x + dx, y + 1), WIN(x + dx, y + 2), WIN(x + dx, y + 3)) + 16) >> 5);
+                out[r * 4 + x] = (b + hh + 1) >> 1;
+            }
+        }
+        return;
+    }
+    // centre sample j (and f, q / i, k): horizontal 6-tap on 7 rows, then vertical 6-tap on the unrounded sums
+    int b1[7][4];
+#pragma unroll
+    for (int rr = 0; rr < 7; ++rr) {
+        const int y = r0 - 2 + rr;
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            b1[rr][x] = tap6(WIN(x - 2, y), WIN(x - 1, y), WIN(x, y), WIN(x + 1, y), WIN(x + 2, y), WIN(x + 3, y));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int y = r0 + r;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            int j = clip255((tap6(b1[r][x], b1[r + 1][x], b1[r + 2][x], b1[r + 3][x], b1[r + 4][x], b1[r + 5][x]) + 512) >> 10);
+            int v = j;
+            if (xf == 2 && yf != 2) {
+                int q = clip255(((yf == 3 ? b1[r + 3][x] : b1[r + 2][x]) + 16) >> 5);
+                v = (j + q + 1) >> 1;
+            } else if (yf == 2 && xf != 2) {
+                const int dx = xf == 3;
+                int q = clip255((tap6(WIN(x + dx, y - 2), WIN(x + dx, y - 1), WIN(x + dx, y), WIN(x + dx, y + 1), WIN(x + dx, y + 2), WIN(x + dx, y + 3)) + 16) >> 5);
+                v = (j + q + 1) >> 1;
+            }
+            out[r * 4 + x] = v;
+        }
+    }
+#undef WIN
+}
+
+struct InterSmem {
+    int      res[384];
+    uint8_t  pred[384];
+    h264r_mb_motion motion;                       // 192 B
+    uint8_t  win[16][84];                         // 9x9 luma window per 4x4 block (81, padded)
+    uint8_t  cwin[16][2][12];                     // 3x3 chroma window per block and plane (9, padded)
+};
+
+__device__ __forceinline__ int rshift_rnd(int x, int a) { return a > 0 ? (x + (1 << (a - 1))) >> a : x; }
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g, int direct8x8)
+{
+    __shared__ __align__(16) InterSmem smem_all[kWarpsPerCta];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nmb = g.width_mbs * g.height_mbs;
+    const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (gw >= (long long)num_pics * nmb) return;
+    const int pic_i = (int)(gw / nmb), addr = (int)(gw - (long long)pic_i * nmb);
+    const DevPicture& pic = pics[pic_i];
+    if (!pic.has_inter) return;
+    const MbHdr h = load_hdr(pic.mbs, addr);
+    if (h.intra()) return;
+    InterSmem& sm = smem_all[warp];
+    const h264r_slice* sl = pic.slices + h.slice_idx;
+    const int mbx = addr % g.width_mbs, mby = addr / g.width_mbs;
+    const int wY = g.width_mbs * 16, hY = g.height_mbs * 16, wC = wY >> 1, hC = hY >> 1;
+
+    // motion -> shared (192 B = 12 x uint4)
+    if (lane < 12) reinterpret_cast<uint4*>(&sm.motion)[lane] = __ldg(reinterpret_cast<const uint4*>(pic.motion + addr) + lane);
+    __syncwarp();
+
+    const int blk = lane >> 1, half = lane & 1;
+    const int bx = blk & 3, by = blk >> 2;
+    int origin, pd;
+    partition_of_block(h, sl, &sm.motion, direct8x8, blk, origin, pd);
+
+    int luma[2][8], chroma[2][4], refidx[2] = { 0, 0 };
+    for (int k = 0; k < 2; ++k) {
+        const bool active = k == 0 || pd == 2;
+        const int list = pd == 2 ? k : pd;
+        int vx = 0, vy = 0;
+        const uint8_t* rbase = nullptr;
+        if (active) {
+            refidx[k] = sm.motion.ref_idx[list][origin];
+            const int slot = (int)(int8_t)__ldg(&sl->ref_pic_list[list][refidx[k] & 31]);
+            rbase = pic.ref[slot & 31];
+            vx = (mbx * 4 + bx) * 16 + sm.motion.mv[list][origin][0];
+            vy = (mby * 4 + by) * 16 + sm.motion.mv[list][origin][1];
+            // luma window: rows half, half+2, ... of the 9x9 window
+            const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2;
+            for (int wy = half; wy < 9; wy += 2) {
+                const uint8_t* row = rbase + (size_t)clip3i(0, hY - 1, y0 + wy) * g.pitch_y;
+#pragma unroll
+                for (int wx = 0; wx < 9; ++wx) sm.win[blk][wy * 9 + wx] = __ldg(row + clip3i(0, wC * 2 - 1, x0 + wx));
+            }
+            // chroma window of plane `half`
+            const uint8_t* cb = rbase + (half ? g.off_cr : g.off_cb);
+            const int cx0 = vx >> 3, cy0 = vy >> 3;
+#pragma unroll
+            for (int wy = 0; wy < 3; ++wy) {
+                const uint8_t* row = cb + (size_t)clip3i(0, hC - 1, cy0 + wy) * g.pitch_c;
+#pragma unroll
+                for (int wx = 0; wx < 3; ++wx) sm.cwin[blk][half][wy * 3 + wx] = __ldg(row + clip3i(0, wC - 1, cx0 + wx));
+            }
+        }
+        __syncwarp();
+        if (active) {
+            luma_half_block(sm.win[blk], vx & 3, vy & 3, half * 2, luma[k]);
+            const uint8_t* cw = sm.cwin[blk][half];
+            const int xf = vx & 7, yf = vy & 7;
+#pragma unroll
+            for (int y = 0; y < 2; ++y)
+#pragma unroll
+                for (int x = 0; x < 2; ++x)
+                    chroma[k][y * 2 + x] = ((8 - xf) * (8 - yf) * cw[y * 3 + x] + xf * (8 - yf) * cw[y * 3 + x + 1] +
+                                            (8 - xf) * yf * cw[(y + 1) * 3 + x] + xf * yf * cw[(y + 1) * 3 + x + 1] + 32) >> 6;
+        }
+        __syncwarp();
+    }
+
+    // weighted sample prediction (mc_prediction / bi_prediction, inter_prediction.cc:53-156)
+    {
+        const bool is_b = __ldg(&sl->slice_type) == H264R_B_SLICE;
+        const int wp_flag = __ldg(&sl->weighted_pred_flag), bipred_idc = __ldg(&sl->weighted_bipred_idc);
+        const bool uni_weighted = (wp_flag && !is_b) || (bipred_idc == 1 && is_b);
+        for (int part = 0; part < 2; ++part) {            // 0: luma (this lane's 8 samples), 1: chroma plane `half` (4 samples)
+            const int pl = part ? 1 + half : 0;
+            const int n = part ? 4 : 8;
+            const int denom = pl ? __ldg(&sl->chroma_log2_weight_denom) : __ldg(&sl->luma_log2_weight_denom);
+            int w0 = 0, w1 = 0, o0 = 0, o1 = 0;
+            int mode;                                      // 0 copy, 1 uni weighted, 2 bi average, 3 bi weighted
+            if (pd != 2) {
+                mode = uni_weighted ? 1 : 0;
+                if (uni_weighted) {
+                    w0 = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][refidx[0] & 31]);
+                    o0 = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][refidx[0] & 31]);
+                }
+            } else if (bipred_idc == 0) mode = 2;
+            else {
+                mode = 3;
+                if (bipred_idc == 1) {
+                    w0 = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][refidx[0] & 31]); w1 = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][refidx[1] & 31]);
+                    o0 = (int)(int8_t)__ldg(&sl->wp_offset[0][pl][refidx[0] & 31]); o1 = (int)(int8_t)__ldg(&sl->wp_offset[1][pl][refidx[1] & 31]);
+                } else {
+                    w1 = (int)__ldg(&sl->implicit_w1[refidx[0] & 31][refidx[1] & 31]); w0 = 64 - w1;
+                }
+            }
+            for (int i = 0; i < n; ++i) {
+                const int s0 = part ? chroma[0][i] : luma[0][i];
+                const int s1 = part ? chroma[1][i] : luma[1][i];
+                int v;
+                if (mode == 0) v = s0;
+                else if (mode == 1) v = clip255(rshift_rnd(w0 * s0, denom) + o0);
+                else if (mode == 2) v = (s0 + s1 + 1) >> 1;
+                else v = clip255(rshift_rnd(w0 * s0 + w1 * s1, denom + 1) + ((o0 + o1 + 1) >> 1));
+                if (part == 0) sm.pred[(by * 4 + half * 2 + (i >> 2)) * 16 + bx * 4 + (i & 3)] = (uint8_t)v;
+                else           sm.pred[256 + half * 64 + (by * 2 + (i >> 1)) * 8 + bx * 2 + (i & 1)] = (uint8_t)v;
+            }
+        }
+    }
+
+    mb_residual(h, sl, pic.coeffs, sm.res, lane);          // ends with __syncwarp: pred + res visible
+    store_mb(sm.pred, sm.res, pic.dst, g, mbx, mby, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row wavefront plumbing
+
+// Wait until the row above has completed at least `need` macroblocks.
+__device__ __forceinline__ void wait_row(const int* progress_above, int need, int lane)
+{
+    if (lane == 0) {
+        while (ld_acquire(progress_above) < need) __nanosleep(64);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void publish_row(int* progress, int done, int lane, bool wrote_pixels)
+{
+    __syncwarp();
+    if (lane == 0) {
+        if (wrote_pixels) __threadfence();
+        st_release(progress, done);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// intra prediction (wavefront)
+
+// luma tile: rows -1..15, cols -4..27 -> index (y+1)*32 + (x+4); 17 rows x 32 B
+// chroma tile per plane: rows -1..7, cols -4..11 -> index (y+1)*16 + (x+4); 9 rows x 16 B
+struct IntraSmem {
+    int      res[384];
+    __align__(16) uint8_t ty[17 * 32];
+    __align__(16) uint8_t tc[2][9 * 16];
+    uint8_t  ft[20], fl[12];                     // Intra8x8 filtered reference samples: ft[i+1] = p'(i,-1), fl[i+1] = p'(-1,i)
+};
+
+#define TY(x, y) sm.ty[((y) + 1) * 32 + (x) + 4]
+#define TC(pl, x, y) sm.tc[pl][((y) + 1) * 16 + (x) + 4]
+
+__device__ __forceinline__ bool nb_avail(const h264r_mb* mbs, int W, int H, int cur, uint32_t cur_w0, int nx, int ny, bool need_intra)
+{
+    if (nx < 0 || nx >= W || ny < 0 || ny >= H) return false;
+    const int nb = ny * W + nx;
+    if (nb >= cur) return false;
+    const uint32_t w0 = load_hdr_word0(mbs, nb);
+    if ((w0 >> 16) != (cur_w0 >> 16)) return false;
+    if (need_intra && !((w0 >> 8) & H264R_MB_FLAG_INTRA)) return false;
+    return true;
+}
+
+// One of the nine directional predictors at sample (x, y) of an n x n block.  T(i), L(i): reference samples
+// with T(-1) == L(-1) the corner; tmax = last valid top index (2n-1, or n-1 when C is substituted).
+template <typename TF, typename LF>
+__device__ __forceinline__ int pred_dir_sample(int mode, int n, int x, int y, int dcv, TF T, LF L)
+{
+    switch (mode) {
+    case 0: return T(x);
+    case 1: return L(y);
+    case 2: return dcv;
+    case 3:
+        if (x == n - 1 && y == n - 1) return (T(x + y) + 3 * T(x + y + 1) + 2) >> 2;
+        return (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
+    case 4:
+        if (x > y) return (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
+        if (x < y) return (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
+        return (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
+    case 5: {
+        const int z = 2 * x - y;
+        if (z >= 0 && (z & 1) == 0) return (T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 1) >> 1;
+        if (z >= 0) return (T(x - (y >> 1) - 2) + 2 * T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 2) >> 2;
+        if (z == -1) return (L(0) + 2 * T(-1) + T(0) + 2) >> 2;
+        return (L(y - 2 * x - 1) + 2 * L(y - 2 * x - 2) + L(y - 2 * x - 3) + 2) >> 2; }
+    case 6: {
+        const int z = 2 * y - x;
+        if (z >= 0 && (z & 1) == 0) return (L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 1) >> 1;
+        if (z >= 0) return (L(y - (x >> 1) - 2) + 2 * L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 2) >> 2;
+        if (z == -1) return (L(0) + 2 * T(-1) + T(0) + 2) >> 2;
+        return (T(x - 2 * y - 1) + 2 * T(x - 2 * y - 2) + T(x - 2 * y - 3) + 2) >> 2; }
+    case 7:
+        if ((y & 1) == 0) return (T(x + (y >> 1)) + T(x + (y >> 1) + 1) + 1) >> 1;
+        return (T(x + (y >> 1)) + 2 * T(x + (y >> 1) + 1) + T(x + (y >> 1) + 2) + 2) >> 2;
+    default: {
+        const int z = x + 2 * y, m = 2 * n - 3;
+        if (z < m && (z & 1) == 0) return (L(y + (x >> 1)) + L(y + (x >> 1) + 1) + 1) >> 1;
+        if (z < m) return (L(y + (x >> 1)) + 2 * L(y + (x >> 1) + 1) + L(y + (x >> 1) + 2) + 2) >> 2;
+        if (z == m) return (L(n - 2) + 3 * L(n - 1) + 2) >> 2;
+        return L(n - 1); }
+    }
+}
+
+// Intra16x16 / chroma whole-plane predictors (intra_prediction.cc:668-735, 798-894) at sample (x, y).
+// mode numbering here: 0 V, 1 H, 2 DC, 3 plane.  T/L as above, n = 16 or 8.
+template <typename TF, typename LF>
+__device__ __forceinline__ void plane_params(int n, bool chroma, TF T, LF L, int& a, int& b, int& c)
+{
+    const int hn = n >> 1;
+    int Hs = 0, Vs = 0;
+    for (int i = 0; i < hn; ++i) {
+        Hs += (i + 1) * (T(hn + i) - T(hn - 2 - i));
+        Vs += (i + 1) * (L(hn + i) - L(hn - 2 - i));
+    }
+    a = 16 * (L(n - 1) + T(n - 1));
+    b = chroma ? (34 * Hs + 32) >> 6 : (5 * Hs + 32) >> 6;
+    c = chroma ? (34 * Vs + 32) >> 6 : (5 * Vs + 32) >> 6;
+}
+
+template <typename TF, typename LF>
+__device__ __forceinline__ int dc_value(int n, int log2n, bool a, bool b, TF T, LF L)
+{
+    if (!a && !b) return 128;
+    int sum = 0;
+    if (a) for (int y = 0; y < n; ++y) sum += L(y);
+    if (b) for (int x = 0; x < n; ++x) sum += T(x);
+    const int shift = log2n - 1 + (a ? 1 : 0) + (b ? 1 : 0);
+    const int round = (a ? n >> 1 : 0) + (b ? n >> 1 : 0);
+    return (sum + round) >> shift;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
+{
+    __shared__ __align__(16) IntraSmem smem_all[kWarpsPerCta];
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[0], 1);
+    __syncthreads();
+    const int W = g.width_mbs, H = g.height_mbs;
+    const int groups = (H + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int pic_i = s_ticket / groups, rg = s_ticket - pic_i * groups;
+    if (pic_i >= num_pics) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mby = rg * kWarpsPerCta + warp;
+    if (mby >= H) return;
+    const DevPicture& pic = pics[pic_i];
+    if (!pic.has_intra) return;
+    IntraSmem& sm = smem_all[warp];
+    int* progress = pic.row_progress;                    // [0][H]
+    uint8_t* const dY = pic.dst;
+    uint8_t* const dC[2] = { pic.dst + g.off_cb, pic.dst + g.off_cr };
+
+    for (int mbx = 0; mbx < W; ++mbx) {
+        const int addr = mby * W + mbx;
+        const MbHdr h = load_hdr(pic.mbs, addr);
+        if (!h.intra()) { publish_row(progress + mby, mbx + 1, lane, false); continue; }
+        if (mby > 0) wait_row(progress + mby - 1, min(mbx + 2, W), lane);
+
+        const h264r_slice* sl = pic.slices + h.slice_idx;
+        const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
+
+        if (h.mb_type == H264R_MB_IPCM) {                 // mb_pred_ipcm, decoder.cc:149-168
+            const int16_t* c = pic.coeffs + (size_t)h.coeff_slot * H264R_COEFFS_PER_MB;
+            for (int p = lane; p < 256; p += 32) dY[(size_t)(py + (p >> 4)) * g.pitch_y + px + (p & 15)] = (uint8_t)__ldg(c + p);
+            for (int p = lane; p < 128; p += 32) {
+                const int pl = p >> 6, q = p & 63;
+                dC[pl][(size_t)(cy + (q >> 3)) * g.pitch_c + cx + (q & 7)] = (uint8_t)__ldg(c + 256 + p);
+            }
+            publish_row(progress + mby, mbx + 1, lane, true);
+            continue;
+        }
+
+        // availability of the four neighbouring MBs (neighbour.cc:123-175 + slice_nr + constrained intra)
+        const uint32_t w0 = (uint32_t)h.mb_type | (uint32_t)h.flags << 8 | (uint32_t)h.slice_idx << 16;
+        const bool ci = __ldg(&sl->constrained_intra_pred_flag) != 0;
+        const bool aL  = nb_avail(pic.mbs, W, H, addr, w0, mbx - 1, mby, ci);
+        const bool aT  = nb_avail(pic.mbs, W, H, addr, w0, mbx, mby - 1, ci);
+        const bool aTL = nb_avail(pic.mbs, W, H, addr, w0, mbx - 1, mby - 1, ci);
+        const bool aTR = nb_avail(pic.mbs, W, H, addr, w0, mbx + 1, mby - 1, ci);
+
+        // neighbour samples of the current, unfiltered picture -> tiles (L1-bypassing loads: other SMs wrote them)
+        if (mby > 0) {
+            if (lane < 8) {                                // luma top row, cols -4..27
+                const int x = px - 4 + lane * 4;
+                uint32_t v = 0;
+                if (x >= 0 && x < W * 16) v = ldcg_u32(dY + (size_t)(py - 1) * g.pitch_y + x);
+                reinterpret_cast<uint32_t*>(sm.ty)[lane] = v;
+            } else if (lane < 16) {                        // chroma top rows, cols -4..11
+                const int c = lane - 8, pl = c >> 2, x = cx - 4 + (c & 3) * 4;
+                uint32_t v = 0;
+                if (x >= 0 && x < W * 8) v = ldcg_u32(dC[pl] + (size_t)(cy - 1) * g.pitch_c + x);
+                reinterpret_cast<uint32_t*>(sm.tc[pl])[c & 3] = v;
+            }
+        }
+        if (mbx > 0) {
+            if (lane < 16) TY(-1, lane) = ldcg_u8(dY + (size_t)(py + lane) * g.pitch_y + px - 1);
+            else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = ldcg_u8(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx - 1); }
+        }
+        mb_residual(h, sl, pic.coeffs, sm.res, lane);      // ends with __syncwarp (tiles visible too)
+
+        // ---- luma ----
+        if (h.mb_type == H264R_MB_I16x16) {
+            auto T = [&](int i) { return (int)TY(i, -1); };
+            auto L = [&](int i) { return (int)TY(-1, i); };
+            const int y = lane >> 1, x0 = (lane & 1) * 8;
+            int pa = 0, pb = 0, pc = 0, dcv = 0;
+            if (h.i16mode == 3) plane_params(16, false, T, L, pa, pb, pc);
+            else if (h.i16mode == 2) dcv = dc_value(16, 4, aL, aT, T, L);
+            int v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int x = x0 + i;
+                int p;
+                if (h.i16mode == 0) p = T(x);
+                else if (h.i16mode == 1) p = L(y);
+                else if (h.i16mode == 2) p = dcv;
+                else p = clip255((pa + pb * (x - 7) + pc * (y - 7) + 16) >> 5);
+                v[i] = clip255(p + sm.res[y * 16 + x]);
+            }
+            __syncwarp();                                  // all lanes have read the border before the tile is written
+#pragma unroll
+            for (int i = 0; i < 8; ++i) TY(x0 + i, y) = (uint8_t)v[i];
+        } else {
+            const bool is8 = h.mb_type == H264R_MB_I8x8;
+            const int n = is8 ? 8 : 4, nblk = is8 ? 4 : 16;
+            for (int k = 0; k < nblk; ++k) {
+                int xO, yO;
+                if (is8) { xO = (k & 1) * 8; yO = (k >> 1) * 8; }
+                else { xO = ((k >> 2) & 1) * 8 + (k & 1) * 4; yO = (k >> 3) * 8 + ((k >> 1) & 1) * 4; }
+                const int mode = ((k < 8 ? h.u0 >> (4 * k) : h.u1 >> (4 * (k - 8)))) & 15;
+                const bool avA = xO > 0 ? true : aL;
+                const bool avB = yO > 0 ? true : aT;
+                const bool avD = (xO > 0 && yO > 0) ? true : (xO > 0 ? aT : (yO > 0 ? aL : aTL));
+                bool avC;
+                if (yO == 0) avC = (xO + n < 16) ? aT : aTR;
+                else avC = xO + n < 16;
+                if (!is8 && xO == 4 && (yO == 4 || yO == 12)) avC = false;
+                if (is8 && xO == 8 && yO == 8) avC = false;
+                const int tmax = avC ? 2 * n - 1 : n - 1;  // C substitution: p(x,-1) = p(n-1,-1) for x >= n
+
+                if (!is8) {
+                    auto T = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
+                    auto L = [&](int i) { return (int)TY(xO - 1, yO + i); };
+                    int v = 0;
+                    const int x = lane & 3, y = (lane >> 2) & 3;
+                    if (lane < 16) {
+                        const int dcv = mode == 2 ? dc_value(4, 2, avA, avB, T, L) : 0;
+                        v = clip255(pred_dir_sample(mode, 4, x, y, dcv, T, L) + sm.res[(yO + y) * 16 + xO + x]);
+                    }
+                    __syncwarp();
+                    if (lane < 16) TY(xO + x, yO + y) = (uint8_t)v;
+                    __syncwarp();
+                } else {
+                    // reference sample filtering (Intra8x8::filtering, intra_prediction.cc:413-447)
+                    auto To = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
+                    auto Lo = [&](int i) { return (int)TY(xO - 1, yO + i); };
+                    if (lane < 16) {                       // p'(lane, -1)
+                        int f = 0;
+                        if (avB) {
+                            if (lane == 0) f = avD ? (To(-1) + 2 * To(0) + To(1) + 2) >> 2 : (3 * To(0) + To(1) + 2) >> 2;
+                            else if (lane == 15) f = (To(14) + 3 * To(15) + 2) >> 2;
+                            else f = (To(lane - 1) + 2 * To(lane) + To(lane + 1) + 2) >> 2;
+                        }
+                        sm.ft[lane + 1] = (uint8_t)f;
+                    } else if (lane < 24) {                // p'(-1, i)
+                        const int i = lane - 16;
+                        int f = 0;
+                        if (avA) {
+                            if (i == 0) f = avD ? (Lo(-1) + 2 * Lo(0) + Lo(1) + 2) >> 2 : (3 * Lo(0) + Lo(1) + 2) >> 2;
+                            else if (i == 7) f = (Lo(6) + 3 * Lo(7) + 2) >> 2;
+                            else f = (Lo(i - 1) + 2 * Lo(i) + Lo(i + 1) + 2) >> 2;
+                        }
+                        sm.fl[i + 1] = (uint8_t)f;
+                    } else if (lane == 24) {               // p'(-1, -1)
+                        int f = 0;
+                        if (avD) {
+                            const int c = To(-1);
+                            if (avA && avB) f = (To(0) + 2 * c + Lo(0) + 2) >> 2;
+                            else if (avB) f = (3 * c + To(0) + 2) >> 2;
+                            else if (avA) f = (3 * c + Lo(0) + 2) >> 2;
+                            else f = c;
+                        }
+                        sm.ft[0] = sm.fl[0] = (uint8_t)f;
+                    }
+                    __syncwarp();
+                    auto T = [&](int i) { return (int)sm.ft[i + 1]; };
+                    auto L = [&](int i) { return (int)sm.fl[i + 1]; };
+                    const int dcv = mode == 2 ? dc_value(8, 3, avA, avB, T, L) : 0;
+                    const int y = lane >> 2, x0 = (lane & 3) * 2;
+                    int v[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        v[i] = clip255(pred_dir_sample(mode, 8, x0 + i, y, dcv, T, L) + sm.res[(yO + y) * 16 + xO + x0 + i]);
+                    __syncwarp();
+                    TY(xO + x0, yO + y) = (uint8_t)v[0]; TY(xO + x0 + 1, yO + y) = (uint8_t)v[1];
+                    __syncwarp();
+                }
+            }
+        }
+
+        // ---- chroma: lanes 0..15 Cb, 16..31 Cr; 4 samples per lane ----
+        {
+            const int pl = lane >> 4, l16 = lane & 15, y = l16 >> 1, x0 = (l16 & 1) * 4;
+            auto T = [&](int i) { return (int)TC(pl, i, -1); };
+            auto L = [&](int i) { return (int)TC(pl, -1, i); };
+            const int m = h.cmode;                         // 0 DC, 1 H, 2 V, 3 plane
+            int pa = 0, pb = 0, pc = 0, dcv = 0;
+            if (m == 3) plane_params(8, true, T, L, pa, pb, pc);
+            else if (m == 0) {                             // DC of this lane's 4x4 block (intra_prediction.cc:825-849)
+                const int xO = x0, yO = y & 4;
+                bool a, b;
+                if ((xO == 0 && yO == 0) || (xO > 0 && yO > 0)) { a = aL; b = aT; }
+                else if (xO > 0) { a = aT ? false : aL; b = aT; }
+                else { a = aL; b = aL ? false : aT; }
+                auto T4 = [&](int i) { return T(xO + i); };
+                auto L4 = [&](int i) { return L(yO + i); };
+                dcv = dc_value(4, 2, a, b, T4, L4);
+            }
+            int v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = x0 + i;
+                int p;
+                if (m == 0) p = dcv;
+                else if (m == 1) p = L(y);
+                else if (m == 2) p = T(x);
+                else p = clip255((pa + pb * (x - 3) + pc * (y - 3) + 16) >> 5);
+                v[i] = clip255(p + sm.res[256 + pl * 64 + y * 8 + x]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) TC(pl, x0 + i, y) = (uint8_t)v[i];
+        }
+        __syncwarp();
+
+        // ---- store the reconstructed MB ----
+        if (lane < 16) {
+            const uint32_t* r = reinterpret_cast<const uint32_t*>(&TY(0, lane));
+            *reinterpret_cast<uint4*>(dY + (size_t)(py + lane) * g.pitch_y + px) = make_uint4(r[0], r[1], r[2], r[3]);
+        } else {
+            const int c = lane - 16, pl = c >> 3, y = c & 7;
+            const uint32_t* r = reinterpret_cast<const uint32_t*>(&TC(pl, 0, y));
+            *reinterpret_cast<uint2*>(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx) = make_uint2(r[0], r[1]);
+        }
+        publish_row(progress + mby, mbx + 1, lane, true);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// deblocking (wavefront)
+
+__constant__ uint8_t c_alpha[52] = {
+    0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,4,4,5,6,7,8,9,10,12,13,15,17,20,22,25,28,32,36,40,45,50,56,63,71,80,90,101,113,127,144,162,182,203,226,255,255 };
+__constant__ uint8_t c_beta[52] = {
+    0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,2,2,2,3,3,3,3,4,4,4,6,6,7,7,8,8,9,9,10,10,11,11,12,12,13,13,14,14,15,15,16,16,17,17,18,18 };
+__constant__ uint8_t c_tc0[52][3] = {
+    {0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},{0,0,0},
+    {0,0,1},{0,0,1},{0,0,1},{0,0,1},{0,1,1},{0,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,1},{1,1,2},{1,1,2},{1,1,2},{1,1,2},{1,2,3},{1,2,3},{2,2,3},
+    {2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6},{4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},
+    {10,13,20},{11,15,23},{13,17,25} };
+
+// luma tile: rows -4..15, cols -4..15 -> index (y+4)*32 + (x+4); chroma tile per plane: rows -4..7, cols -4..7 -> (y+4)*16 + (x+4)
+struct DeblockSmem {
+    __align__(16) uint8_t ty[20 * 32];
+    __align__(16) uint8_t tc[2][12 * 16];
+    uint8_t bs[2][4][4];                          // [dir][edge][4-sample group]
+};
+#define DY(x, y) sm.ty[((y) + 4) * 32 + (x) + 4]
+#define DC_(pl, x, y) sm.tc[pl][((y) + 4) * 16 + (x) + 4]
+
+__device__ __forceinline__ int mv_differs(const h264r_mb_motion* a, int ba, int la, const h264r_mb_motion* b, int bb, int lb)
+{
+    const int ax = __ldg(&a->mv[la][ba][0]), ay = __ldg(&a->mv[la][ba][1]);
+    const int bx = __ldg(&b->mv[lb][bb][0]), by = __ldg(&b->mv[lb][bb][1]);
+    return (abs(ax - bx) >= 4) | (abs(ay - by) >= 4);
+}
+// bs_compare_mvs, deblock.cc:35-75
+__device__ __forceinline__ int bs_compare(const h264r_mb_motion* mp, int bp, const h264r_mb_motion* mq, int bq)
+{
+    const int p0 = (int8_t)__ldg(&mp->ref_pic[0][bp]), p1 = (int8_t)__ldg(&mp->ref_pic[1][bp]);
+    const int q0 = (int8_t)__ldg(&mq->ref_pic[0][bq]), q1 = (int8_t)__ldg(&mq->ref_pic[1][bq]);
+    if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;
+    if (p0 != p1) {
+        if (p0 == q0) return mv_differs(mp, bp, 0, mq, bq, 0) | mv_differs(mp, bp, 1, mq, bq, 1);
+        return mv_differs(mp, bp, 0, mq, bq, 1) | mv_differs(mp, bp, 1, mq, bq, 0);
+    }
+    return (mv_differs(mp, bp, 0, mq, bq, 0) | mv_differs(mp, bp, 1, mq, bq, 1)) &
+           (mv_differs(mp, bp, 0, mq, bq, 1) | mv_differs(mp, bp, 1, mq, bq, 0));
+}
+
+// filter_strong / filter_normal (deblock.cc:327-415) across one edge in a shared-memory tile; pix -> q0
+__device__ __forceinline__ void filter_samples(uint8_t* pix, int step, int bS, int alpha, int beta, int tc0, bool chroma)
+{
+    const int p0 = pix[-step], p1 = pix[-2 * step], q0 = pix[0], q1 = pix[step];
+    if (!(abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta)) return;
+    const int p2 = chroma ? 0 : pix[-3 * step], q2 = chroma ? 0 : pix[2 * step];
+    const int ap = abs(p2 - p0), aq = abs(q2 - q0);
+    if (bS == 4) {
+        const bool small = abs(p0 - q0) < (alpha >> 2) + 2;
+        if (!chroma && ap < beta && small) {
+            const int p3 = pix[-4 * step];
+            pix[-step]     = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+            pix[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+            pix[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+        } else pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+        if (!chroma && aq < beta && small) {
+            const int q3 = pix[3 * step];
+            pix[0]        = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+            pix[step]     = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+            pix[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+        } else pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+        return;
+    }
+    const int tc = chroma ? tc0 + 1 : tc0 + (ap < beta) + (aq < beta);
+    const int delta = clip3i(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
+    pix[-step] = (uint8_t)clip255(p0 + delta);
+    pix[0]     = (uint8_t)clip255(q0 - delta);
+    if (!chroma && ap < beta) pix[-2 * step] = (uint8_t)(p1 + clip3i(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 * 2)) >> 1));
+    if (!chroma && aq < beta) pix[step]      = (uint8_t)(q1 + clip3i(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 * 2)) >> 1));
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
+{
+    __shared__ __align__(16) DeblockSmem smem_all[kWarpsPerCta];
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[1], 1);
+    __syncthreads();
+    const int W = g.width_mbs, H = g.height_mbs;
+    const int groups = (H + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int pic_i = s_ticket / groups, rg = s_ticket - pic_i * groups;
+    if (pic_i >= num_pics) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mby = rg * kWarpsPerCta + warp;
+    if (mby >= H) return;
+    const DevPicture& pic = pics[pic_i];
+    if (!pic.run_deblock) return;
+    DeblockSmem& sm = smem_all[warp];
+    int* progress = pic.row_progress + H;                // [1][H]
+    uint8_t* const dY = pic.dst;
+    uint8_t* const dC[2] = { pic.dst + g.off_cb, pic.dst + g.off_cr };
+
+    for (int mbx = 0; mbx < W; ++mbx) {
+        const int q = mby * W + mbx;
+        const MbHdr Q = load_hdr(pic.mbs, q);
+        const h264r_slice* sl = pic.slices + Q.slice_idx;
+        const int idc = __ldg(&sl->disable_deblocking_filter_idc);
+        if (idc == 1) { publish_row(progress + mby, mbx + 1, lane, false); continue; }
+        if (mby > 0) wait_row(progress + mby - 1, min(mbx + 2, W), lane);
+
+        bool left = mbx > 0, top = mby > 0;
+        MbHdr PL = Q, PT = Q;
+        if (left) { PL = load_hdr(pic.mbs, q - 1); if (idc == 2 && PL.slice_idx != Q.slice_idx) left = false; }
+        if (top)  { PT = load_hdr(pic.mbs, q - W); if (idc == 2 && PT.slice_idx != Q.slice_idx) top = false; }
+        const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
+
+        // ---- load the MB and its 4-sample left / top borders into the tiles (words, L1-bypassing) ----
+        for (int i = lane; i < 100; i += 32) {             // luma: 20 rows x 5 words
+            const int r = i / 5, wq = i - r * 5, y = r - 4, x = wq * 4 - 4;
+            uint32_t v = 0;
+            if ((y >= 0 || mby > 0) && (x >= 0 || mbx > 0) && !(y < 0 && x < 0))
+                v = ldcg_u32(dY + (size_t)(py + y) * g.pitch_y + px + x);
+            reinterpret_cast<uint32_t*>(sm.ty)[r * 8 + wq] = v;
+        }
+        for (int i = lane; i < 72; i += 32) {              // chroma: 2 planes x 12 rows x 3 words
+            const int pl = i / 36, j = i - pl * 36, r = j / 3, wq = j - r * 3, y = r - 4, x = wq * 4 - 4;
+            uint32_t v = 0;
+            if ((y >= 0 || mby > 0) && (x >= 0 || mbx > 0) && !(y < 0 && x < 0))
+                v = ldcg_u32(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx + x);
+            reinterpret_cast<uint32_t*>(sm.tc[pl])[r * 4 + wq] = v;
+        }
+
+        // ---- boundary strengths: lane = dir*16 + edge*4 + group (deblock.cc:78-228) ----
+        {
+            const int dir = lane >> 4, e = (lane >> 2) & 3, k4 = lane & 3;
+            const bool mbedge = dir == 0 ? left : top;
+            const bool luma_on = e == 0 ? mbedge : !(Q.t8() && (e & 1));
+            int s = 0;
+            if (luma_on) {
+                const MbHdr& P = e ? Q : (dir == 0 ? PL : PT);
+                const int pidx = e ? q : (dir == 0 ? q - 1 : q - W);
+                if (e > 0 && __ldg(&sl->slice_type) == H264R_P_SLICE && Q.mb_type == 0) s = 0;
+                else if (P.intra() || Q.intra()) s = e == 0 ? 4 : 3;
+                else {
+                    const int blkQ = dir == 0 ? k4 * 4 + e : e * 4 + k4;
+                    const int blkP = dir == 0 ? k4 * 4 + (e ? e - 1 : 3) : (e ? e - 1 : 3) * 4 + k4;
+                    if (((Q.cbp_blks >> blkQ) & 1) || ((P.cbp_blks >> blkP) & 1)) s = 2;
+                    else if (e > 0 && (Q.mb_type == 1 || Q.mb_type == (dir == 0 ? 2 : 3))) s = 0;
+                    else s = bs_compare(pic.motion + pidx, blkP, pic.motion + q, blkQ);
+                }
+            }
+            sm.bs[dir][e][k4] = (uint8_t)s;
+        }
+        __syncwarp();
+
+        // ---- filtering: dir 0 (vertical edges) then dir 1 (horizontal); lanes 0..15 luma line, 16..31 chroma line ----
+        const int foa = (int)(int8_t)__ldg(&sl->filter_offset_a), fob = (int)(int8_t)__ldg(&sl->filter_offset_b);
+        for (int dir = 0; dir < 2; ++dir) {
+            const bool mbedge = dir == 0 ? left : top;
+            const MbHdr& PN = dir == 0 ? PL : PT;
+            if (lane < 16) {
+                const int step = dir == 0 ? 1 : 32;
+                for (int e = 0; e < 4; ++e) {
+                    const bool on = e == 0 ? mbedge : !(Q.t8() && (e & 1));
+                    const int s = sm.bs[dir][e][lane >> 2];
+                    if (!on || !s) continue;
+                    const int qPav = ((e ? Q.qp_y : PN.qp_y) + Q.qp_y + 1) >> 1;
+                    const int ia = clip3i(0, 51, qPav + foa), ib = clip3i(0, 51, qPav + fob);
+                    uint8_t* pix = dir == 0 ? &DY(e * 4, lane) : &DY(lane, e * 4);
+                    filter_samples(pix, step, s, c_alpha[ia], c_beta[ib], s < 4 ? c_tc0[ia][s - 1] : 0, false);
+                }
+            } else {
+                const int c = lane - 16, pl = c >> 3, line = c & 7;
+                const int step = dir == 0 ? 1 : 16;
+                for (int e = 0; e < 2; ++e) {
+                    const bool on = e == 0 ? mbedge : true;
+                    const int s = sm.bs[dir][e * 2][line >> 1];     // chroma edge e uses luma edge 2e, sample 2*line
+                    if (!on || !s) continue;
+                    const int qPav = ((e ? Q.qp_c[pl] : PN.qp_c[pl]) + Q.qp_c[pl] + 1) >> 1;
+                    const int ia = clip3i(0, 51, qPav + foa), ib = clip3i(0, 51, qPav + fob);
+                    uint8_t* pix = dir == 0 ? &DC_(pl, e * 4, line) : &DC_(pl, line, e * 4);
+                    filter_samples(pix, step, s, c_alpha[ia], c_beta[ib], s < 4 ? c_tc0[ia][s - 1] : 0, true);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- write back: own MB, left 4 columns (if filtered), top 4 rows (if filtered) ----
+        for (int i = lane; i < 100; i += 32) {
+            const int r = i / 5, wq = i - r * 5, y = r - 4, x = wq * 4 - 4;
+            if ((y < 0 && !top) || (x < 0 && !left) || (y < 0 && x < 0)) continue;
+            *reinterpret_cast<uint32_t*>(dY + (size_t)(py + y) * g.pitch_y + px + x) = reinterpret_cast<const uint32_t*>(sm.ty)[r * 8 + wq];
+        }
+        for (int i = lane; i < 72; i += 32) {
+            const int pl = i / 36, j = i - pl * 36, r = j / 3, wq = j - r * 3, y = r - 4, x = wq * 4 - 4;
+            if ((y < 0 && !top) || (x < 0 && !left) || (y < 0 && x < 0)) continue;
+            *reinterpret_cast<uint32_t*>(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx + x) = reinterpret_cast<const uint32_t*>(sm.tc[pl])[r * 4 + wq];
+        }
+        publish_row(progress + mby, mbx + 1, lane, true);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+
+int launch_wave(const WaveLaunch& w, cudaStream_t stream)
+{
+    int launches = 0;
+    const int nmb = w.geom.width_mbs * w.geom.height_mbs;
+    const int threads = kWarpsPerCta * 32;
+    if (w.any_inter) {
+        const long long warps = (long long)w.num_pics * nmb;
+        const int blocks = (int)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
+        recon_inter_kernel<<<blocks, threads, 0, stream>>>(w.pics, w.num_pics, w.geom, w.direct8x8);
+        ++launches;
+    }
+    const int groups = (w.geom.height_mbs + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (w.any_intra) {
+        recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
+        ++launches;
+    }
+    if (w.any_deblock) {
+        deblock_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
+        ++launches;
+    }
+    return launches;
+}
+
+} // namespace h264r

@@ -173,3 +173,85 @@ class SynthStream:
 
     def __del__(self):
         self.close()
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """Thin object wrapper over the C ABI of libh264recon.so (one context == one GPU)."""
+
+    def __init__(self, seq, device=0, max_frames=8, max_pictures=4, max_slices=4):
+        self.L = recon_lib()
+        sp = SeqParams.from_buffer_copy(seq)
+        sp.max_frames, sp.max_pictures_in_flight, sp.max_slices_per_picture = max_frames, max_pictures, max_slices
+        self.seq = sp
+        self.nmb = sp.width_mbs * sp.height_mbs
+        self.w, self.h = sp.width_mbs * 16, sp.height_mbs * 16
+        self.ctx = C.c_void_p()
+        self._check(self.L.h264r_create(C.byref(self.ctx), device, C.byref(sp)), "h264r_create")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            detail = self.L.h264r_last_cuda_error(self.ctx).decode() if self.ctx else ""
+            raise EngineError(f"{what}: {self.L.h264r_strerror(rc).decode()} ({rc}) {detail}")
+
+    def frame_alloc(self):
+        f = C.c_int32()
+        self._check(self.L.h264r_frame_alloc(self.ctx, C.byref(f)), "h264r_frame_alloc")
+        return f.value
+
+    def frame_release(self, f):
+        self._check(self.L.h264r_frame_release(self.ctx, f), "h264r_frame_release")
+
+    def submit(self, pic, dst, ref_frames):
+        """picture_begin + fill the pinned staging from a generated Picture + picture_submit."""
+        pp = PicParams.from_buffer_copy(pic.pp)
+        for i, f in enumerate(ref_frames):
+            pp.ref_frames[i] = f
+        bufs = PicBuffers()
+        self._check(self.L.h264r_picture_begin(self.ctx, dst, C.byref(pp), C.byref(bufs)), "h264r_picture_begin")
+        n = self.nmb
+        C.memmove(bufs.mbs, pic.mbs, C.sizeof(Mb) * n)
+        C.memmove(bufs.motion, pic.motion, C.sizeof(MbMotion) * n)
+        C.memmove(bufs.slices, pic.slices, C.sizeof(Slice) * pp.num_slices)
+        C.memmove(bufs.coeffs, pic.coeffs, 2 * COEFFS_PER_MB * pic.info.num_coeff_slots)
+        self._check(self.L.h264r_picture_submit(self.ctx, pic.info.num_coeff_slots), "h264r_picture_submit")
+
+    def flush(self):
+        self._check(self.L.h264r_flush(self.ctx), "h264r_flush")
+
+    def wait(self, f=-1):
+        self._check(self.L.h264r_wait(self.ctx, f), "h264r_wait")
+
+    def download(self, f):
+        y = (C.c_uint8 * (self.w * self.h))()
+        cb = (C.c_uint8 * (self.w * self.h // 4))()
+        cr = (C.c_uint8 * (self.w * self.h // 4))()
+        self._check(self.L.h264r_frame_download(self.ctx, f, y, cb, cr, self.w, self.w // 2), "h264r_frame_download")
+        return bytes(y), bytes(cb), bytes(cr)
+
+    def upload(self, f, y, cb, cr):
+        self._check(self.L.h264r_frame_upload(self.ctx, f, y, cb, cr, self.w, self.w // 2), "h264r_frame_upload")
+
+    def replay(self, iterations=1):
+        t, k = C.c_float(), C.c_float()
+        self._check(self.L.h264r_replay_last_flush(self.ctx, iterations, C.byref(t), C.byref(k)), "h264r_replay_last_flush")
+        return t.value
+
+    def stats(self):
+        s = Stats()
+        self._check(self.L.h264r_get_stats(self.ctx, C.byref(s)), "h264r_get_stats")
+        return s
+
+    def close(self):
+        if self.ctx:
+            self.L.h264r_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
