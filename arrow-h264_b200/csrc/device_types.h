@@ -39,8 +39,10 @@ struct WaveLaunch {
     int   any_inter, any_intra, any_deblock;
 };
 
-// Launches the reconstruction kernels of one wave on `stream`; returns the number of kernels launched.
-int launch_wave(const WaveLaunch& w, cudaStream_t stream);
+// Kernel launchers of one wave (kernels.cu).  which: 0 inter, 1 intra wavefront, 2 deblock wavefront.
+// Returns true if a kernel was launched (false when the wave has no work of that kind).
+enum { KERNEL_INTER = 0, KERNEL_INTRA = 1, KERNEL_DEBLOCK = 2, KERNEL_KINDS = 3 };
+bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);
 
 } // namespace h264r
 #endif

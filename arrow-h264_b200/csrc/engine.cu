@@ -21,6 +21,7 @@ struct Frame {
     uint8_t* dev = nullptr;
     bool used = false;
     int write_wave = -1, read_wave = -1;      // bookkeeping inside one flush
+    cudaEvent_t ready = nullptr;              // ev_done of the wave that last wrote this frame (owned by the pool)
 };
 
 enum SlotState { SLOT_FREE = 0, SLOT_FILLING, SLOT_QUEUED, SLOT_INFLIGHT };
@@ -36,16 +37,25 @@ struct Slot {
     int wave = 0;
 };
 
+struct WaveCopy { int slot; size_t bytes; };
+
 struct WaveRecord {
     WaveLaunch launch;
     size_t progress_bytes;
+    std::vector<WaveCopy> copies;             // H2D copies of the picture descriptions of this wave
+    cudaEvent_t ev_h2d = nullptr;             // recorded on the H2D stream after the wave's copies
+    cudaEvent_t ev_done = nullptr;            // recorded on the compute stream after the wave's kernels
 };
 
 } // namespace
 
 struct h264r_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;            // compute
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> event_pool;      // reused across flushes
+    size_t events_used = 0;
+    std::vector<cudaEvent_t> timer_events;    // H264R_REPLAY_TIME_KERNELS
     h264r_seq_params seq;
     FrameGeom geom;
     int nmb = 0;
@@ -54,8 +64,10 @@ struct h264r_ctx {
     std::vector<Slot> slots;
     std::vector<int> queue;                   // slot indexes in submission order
     int filling = -1;
-    DevPicture* h_pics = nullptr;             // pinned, [max_pictures_in_flight]
+    DevPicture* h_pics = nullptr;             // pinned, [2][max_pictures_in_flight]: alternating halves per flush
     DevPicture* d_pics = nullptr;
+    cudaEvent_t table_ev[2] = { nullptr, nullptr };   // end of the flush that last used each half
+    int table_idx = 0;
     int* d_sync = nullptr;                    // [2 tickets (padded to 64 ints)] + per picture [2][H] progress
     size_t sync_ints_per_pic = 0;
     std::vector<WaveRecord> last_waves;
@@ -74,6 +86,72 @@ int cuda_fail(h264r_ctx* c, cudaError_t e, const char* what)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
 
 bool frame_ok(const h264r_ctx* c, h264r_frame f) { return f >= 0 && f < (int)c->frames.size() && c->frames[f].used; }
+
+cudaEvent_t take_event(h264r_ctx* c)
+{
+    if (c->events_used == c->event_pool.size()) {
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        c->event_pool.push_back(ev);
+    }
+    return c->event_pool[c->events_used++];
+}
+
+// Runs the recorded waves of the last flush.  H2D copies go to their own stream and are joined per wave; a wave's
+// copies also wait for the previous run of the same wave (its staging in HBM is being overwritten).
+int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int* launches)
+{
+    size_t timer_used = 0;
+    struct Pending { int kind; size_t ev; };
+    std::vector<Pending> pend;
+    for (WaveRecord& rec : ctx->last_waves) {
+        if (h2d) {
+            CU(cudaStreamWaitEvent(ctx->s_h2d, rec.ev_done, 0));          // no-op before the first record
+            for (const WaveCopy& c : rec.copies) {
+                Slot& s = ctx->slots[c.slot];
+                CU(cudaMemcpyAsync(s.dev, s.host, c.bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+                ctx->stats.h2d_bytes += c.bytes;
+            }
+            CU(cudaEventRecord(rec.ev_h2d, ctx->s_h2d));
+            CU(cudaStreamWaitEvent(ctx->stream, rec.ev_h2d, 0));
+        }
+        CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
+        for (int kind = 0; kind < KERNEL_KINDS; ++kind) {
+            if (time_kernels) {
+                while (ctx->timer_events.size() < timer_used + 2) {
+                    cudaEvent_t ev = nullptr;
+                    CU(cudaEventCreate(&ev));
+                    ctx->timer_events.push_back(ev);
+                }
+                CU(cudaEventRecord(ctx->timer_events[timer_used], ctx->stream));
+            }
+            const bool launched = launch_wave_kernel(rec.launch, kind, ctx->stream);
+            if (launched) {
+                ctx->stats.kernel_launches += 1;
+                if (launches) launches[kind + 1] += 1;
+                if (time_kernels) {
+                    CU(cudaEventRecord(ctx->timer_events[timer_used + 1], ctx->stream));
+                    pend.push_back({ kind, timer_used });
+                    timer_used += 2;
+                }
+            }
+        }
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(rec.ev_done, ctx->stream));
+        ctx->stats.waves += 1;
+        ctx->stats.pictures += (uint64_t)rec.launch.num_pics;
+        ctx->stats.macroblocks += (uint64_t)rec.launch.num_pics * ctx->nmb;
+    }
+    if (time_kernels && ms_kernel) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (const Pending& p : pend) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, ctx->timer_events[p.ev], ctx->timer_events[p.ev + 1]));
+            ms_kernel[p.kind + 1] += ms;
+        }
+    }
+    return H264R_OK;
+}
 
 } // namespace
 
@@ -115,6 +193,8 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
     if (e != cudaSuccess) { delete ctx; return H264R_ERR_CUDA; }
@@ -141,8 +221,9 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     const size_t arena = ctx->slot_bytes * sp->max_pictures_in_flight;
     e = cudaHostAlloc((void**)&h_arena, arena, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_arena, arena);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * sp->max_pictures_in_flight, cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * sp->max_pictures_in_flight);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
     ctx->sync_ints_per_pic = align_up((size_t)2 * sp->height_mbs, 32);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_sync, sizeof(int) * (64 + ctx->sync_ints_per_pic * sp->max_pictures_in_flight));
     if (e != cudaSuccess) {
@@ -168,12 +249,15 @@ void h264r_destroy(h264r_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
     for (Frame& f : ctx->frames) if (f.dev) cudaFree(f.dev);
     if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); }
     cudaFreeHost(ctx->h_pics); cudaFree(ctx->d_pics); cudaFree(ctx->d_sync);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-    cudaStreamDestroy(ctx->stream);
+    for (int i = 0; i < 2; ++i) if (ctx->table_ev[i]) cudaEventDestroy(ctx->table_ev[i]);
+    for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->timer_events) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
     delete ctx;
 }
 
@@ -301,9 +385,16 @@ int h264r_flush(h264r_ctx* ctx)
     std::vector<int> wave_begin(num_waves + 1, 0);
     for (size_t k = 0; k < order.size(); ++k) wave_begin[ctx->slots[order[k]].wave + 1] = (int)k + 1;
     for (int w = 1; w <= num_waves; ++w) wave_begin[w] = std::max(wave_begin[w], wave_begin[w - 1]);
+    // the picture table alternates between two halves so that this flush never overwrites what the previous
+    // (possibly still running) flush reads
+    ctx->table_idx ^= 1;
+    const size_t table_off = (size_t)ctx->table_idx * ctx->seq.max_pictures_in_flight;
+    CU(cudaEventSynchronize(ctx->table_ev[ctx->table_idx]));
+    DevPicture* const h_table = ctx->h_pics + table_off;
+    DevPicture* const d_table = ctx->d_pics + table_off;
     for (size_t k = 0; k < order.size(); ++k) {
         Slot& s = ctx->slots[order[k]];
-        DevPicture& p = ctx->h_pics[k];
+        DevPicture& p = h_table[k];
         memset(&p, 0, sizeof(p));
         p.mbs = reinterpret_cast<const h264r_mb*>(s.dev + ctx->off_mbs);
         p.motion = reinterpret_cast<const h264r_mb_motion*>(s.dev + ctx->off_motion);
@@ -316,68 +407,93 @@ int h264r_flush(h264r_ctx* ctx)
         p.row_progress = ctx->d_sync + 64 + ctx->sync_ints_per_pic * pos_in_wave;
         p.run_deblock = s.pp.run_deblock; p.has_intra = s.has_intra; p.has_inter = s.has_inter;
     }
-    CU(cudaMemcpyAsync(ctx->d_pics, ctx->h_pics, sizeof(DevPicture) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_table, h_table, sizeof(DevPicture) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += sizeof(DevPicture) * order.size();
 
-    // ---- per wave: H2D of the picture descriptions, then the batched kernels ----
+    // ---- per wave: record what to copy and what to launch, then run it (H2D stream || compute stream) ----
+    ctx->events_used = 0;
     for (int w = 0; w < num_waves; ++w) {
         const int b = wave_begin[w], e = wave_begin[w + 1];
         if (e <= b) continue;
         WaveRecord rec;
         WaveLaunch& L = rec.launch;
-        L.pics = ctx->d_pics + b; L.num_pics = e - b; L.tickets = ctx->d_sync; L.geom = ctx->geom;
+        L.pics = d_table + b; L.num_pics = e - b; L.tickets = ctx->d_sync; L.geom = ctx->geom;
         L.direct8x8 = ctx->seq.direct_8x8_inference_flag;
         L.any_inter = L.any_intra = L.any_deblock = 0;
         for (int k = b; k < e; ++k) {
             Slot& s = ctx->slots[order[k]];
-            const size_t bytes = ctx->off_coeffs + sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)s.used_slots;
-            CU(cudaMemcpyAsync(s.dev, s.host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-            ctx->stats.h2d_bytes += bytes;
+            rec.copies.push_back({ order[k], ctx->off_coeffs + sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)s.used_slots });
             L.any_inter |= s.has_inter; L.any_intra |= s.has_intra; L.any_deblock |= s.pp.run_deblock;
-            ctx->stats.pictures += 1; ctx->stats.macroblocks += (uint64_t)ctx->nmb;
         }
         rec.progress_bytes = sizeof(int) * (64 + ctx->sync_ints_per_pic * (size_t)L.num_pics);
-        CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
-        ctx->stats.kernel_launches += (uint64_t)launch_wave(L, ctx->stream);
-        CU(cudaGetLastError());
-        ctx->stats.waves += 1;
+        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx);
+        if (!rec.ev_h2d || !rec.ev_done) return H264R_ERR_CUDA;
+        for (int k = b; k < e; ++k) ctx->frames[ctx->slots[order[k]].dst].ready = rec.ev_done;
         ctx->last_waves.push_back(rec);
     }
-    (void)H;
-    for (int qi : ctx->queue) ctx->slots[qi].state = SLOT_INFLIGHT;   // reusable once the stream has drained (h264r_wait)
+    for (int qi : ctx->queue) ctx->slots[qi].state = SLOT_INFLIGHT;   // reusable once the streams have drained (h264r_wait)
     ctx->queue.clear();
-    return H264R_OK;
+    const int rc = run_waves(ctx, true, false, nullptr, nullptr);
+    if (rc == H264R_OK) CU(cudaEventRecord(ctx->table_ev[ctx->table_idx], ctx->stream));
+    return rc;
 }
 
 int h264r_wait(h264r_ctx* ctx, h264r_frame f)
 {
     if (!ctx) return H264R_ERR_INVALID;
-    (void)f;                                                      // single in-order stream: waiting for one waits for all
+    (void)f;                                                      // in-order streams: waiting for one waits for all
     cudaSetDevice(ctx->device);
+    CU(cudaStreamSynchronize(ctx->s_h2d));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->s_d2h));
     for (Slot& t : ctx->slots) if (t.state == SLOT_INFLIGHT) t.state = SLOT_FREE;
     return H264R_OK;
 }
 
-int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, float* ms_total, float* ms_kernels)
+int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[4], int launches_out[4])
 {
     if (!ctx || iterations <= 0) return H264R_ERR_INVALID;
-    if (ctx->last_waves.empty()) return H264R_ERR_STATE;
+    if (ctx->last_waves.empty() || ctx->filling >= 0 || !ctx->queue.empty()) return H264R_ERR_STATE;
     cudaSetDevice(ctx->device);
-    CU(cudaStreamSynchronize(ctx->stream));
+    int rc = h264r_wait(ctx, -1);
+    if (rc != H264R_OK) return rc;
+    float ms[4] = { 0.f, 0.f, 0.f, 0.f };
+    int launches[4] = { 0, 0, 0, 0 };
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int it = 0; it < iterations; ++it)
-        for (WaveRecord& rec : ctx->last_waves) {
-            CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
-            ctx->stats.kernel_launches += (uint64_t)launch_wave(rec.launch, ctx->stream);
-        }
+    for (int it = 0; it < iterations; ++it) {
+        rc = run_waves(ctx, (flags & H264R_REPLAY_H2D) != 0, (flags & H264R_REPLAY_TIME_KERNELS) != 0, ms, launches);
+        if (rc != H264R_OK) return rc;
+    }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     CU(cudaEventSynchronize(ctx->ev1));
     CU(cudaGetLastError());
-    float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    if (ms_total) *ms_total = ms;
-    if (ms_kernels) *ms_kernels = ms;
+    CU(cudaEventElapsedTime(&ms[0], ctx->ev0, ctx->ev1));
+    if (ms_out) for (int i = 0; i < 4; ++i) ms_out[i] = ms[i];
+    if (launches_out) for (int i = 0; i < 4; ++i) launches_out[i] = launches[i];
+    return H264R_OK;
+}
+
+void* h264r_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void h264r_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int h264r_frame_download_async(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb, uint8_t* cr, int pitch_y, int pitch_c)
+{
+    if (!ctx || f < 0 || f >= (int)ctx->frames.size() || !ctx->frames[f].dev || !y || !cb || !cr) return H264R_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const FrameGeom& g = ctx->geom;
+    const int w = g.width_mbs * 16, h = g.height_mbs * 16;
+    if (pitch_y < w || pitch_c < w / 2) return H264R_ERR_INVALID;
+    const uint8_t* d = ctx->frames[f].dev;
+    if (ctx->frames[f].ready) CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->frames[f].ready, 0));
+    CU(cudaMemcpy2DAsync(y, pitch_y, d, g.pitch_y, w, h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU(cudaMemcpy2DAsync(cb, pitch_c, d + g.off_cb, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU(cudaMemcpy2DAsync(cr, pitch_c, d + g.off_cr, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    ctx->stats.d2h_bytes += (uint64_t)w * h * 3 / 2;
     return H264R_OK;
 }
 

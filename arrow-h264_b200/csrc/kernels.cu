@@ -16,7 +16,6 @@
 namespace h264r {
 
 constexpr int kWarpsPerCta = 4;
-constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------------------------
 // small helpers
@@ -1010,27 +1009,26 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
 
 // ---------------------------------------------------------------------------------------------------
 
-int launch_wave(const WaveLaunch& w, cudaStream_t stream)
+bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
 {
-    int launches = 0;
     const int nmb = w.geom.width_mbs * w.geom.height_mbs;
     const int threads = kWarpsPerCta * 32;
-    if (w.any_inter) {
+    const int groups = (w.geom.height_mbs + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (which == KERNEL_INTER) {
+        if (!w.any_inter) return false;
         const long long warps = (long long)w.num_pics * nmb;
         const int blocks = (int)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
         recon_inter_kernel<<<blocks, threads, 0, stream>>>(w.pics, w.num_pics, w.geom, w.direct8x8);
-        ++launches;
+        return true;
     }
-    const int groups = (w.geom.height_mbs + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (w.any_intra) {
+    if (which == KERNEL_INTRA) {
+        if (!w.any_intra) return false;
         recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
-        ++launches;
+        return true;
     }
-    if (w.any_deblock) {
-        deblock_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
-        ++launches;
-    }
-    return launches;
+    if (!w.any_deblock) return false;
+    deblock_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
+    return true;
 }
 
 } // namespace h264r

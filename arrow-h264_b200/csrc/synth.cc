@@ -713,4 +713,25 @@ int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264
     return 1;
 }
 
+void h264s_account(const h264r_mb* mbs, const h264r_slice* slices, int nmb, int run_deblock, uint64_t out[8])
+{
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    for (int a = 0; a < nmb; ++a) {
+        const h264r_mb& m = mbs[a];
+        const bool intra = (m.flags & H264R_MB_FLAG_INTRA) != 0;
+        uint64_t b = 32 + 384;
+        if (m.coeff_slot != H264R_NO_COEFF) { b += 768; out[6] += 1; }
+        if (!intra) {
+            b += 192;
+            for (int q = 0; q < 4; ++q) b += (m.u.inter.sub_mb_pred_mode[q] == H264R_PRED_BI ? 2 : 1) * 96;
+            out[1] += b; out[4] += 1;
+        } else { out[2] += b; out[5] += 1; }
+        out[0] += b;
+        if (run_deblock && slices[m.slice_idx].disable_deblocking_filter_idc != 1) {
+            out[3] += 32 + 384 + 384 + (intra ? 0 : 192);
+            out[7] += 1;
+        }
+    }
+}
+
 } // extern "C"

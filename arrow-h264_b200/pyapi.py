@@ -92,6 +92,7 @@ def synth_lib():
         L.h264s_next.restype = C.c_int
         L.h264s_next.argtypes = [C.c_void_p, C.POINTER(PicInfo), C.POINTER(PicParams), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
+        L.h264s_account.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         _synth = L
     return _synth
 
@@ -117,7 +118,11 @@ def recon_lib():
         L.h264r_wait.argtypes = [P, C.c_int32]
         L.h264r_frame_download.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.h264r_frame_upload.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-        L.h264r_replay_last_flush.argtypes = [P, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.h264r_replay_last_flush.argtypes = [P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.h264r_frame_download_async.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.h264r_host_alloc.restype = C.c_void_p
+        L.h264r_host_alloc.argtypes = [C.c_size_t]
+        L.h264r_host_free.argtypes = [C.c_void_p]
         L.h264r_get_stats.argtypes = [P, C.POINTER(Stats)]
         L.h264r_strerror.restype = C.c_char_p
         L.h264r_strerror.argtypes = [C.c_int]
@@ -235,10 +240,36 @@ class Engine:
     def upload(self, f, y, cb, cr):
         self._check(self.L.h264r_frame_upload(self.ctx, f, y, cb, cr, self.w, self.w // 2), "h264r_frame_upload")
 
-    def replay(self, iterations=1):
-        t, k = C.c_float(), C.c_float()
-        self._check(self.L.h264r_replay_last_flush(self.ctx, iterations, C.byref(t), C.byref(k)), "h264r_replay_last_flush")
-        return t.value
+    REPLAY_H2D, REPLAY_TIME_KERNELS = 1, 2
+
+    def replay(self, iterations=1, flags=0):
+        """Re-runs the last flush; returns (ms[total, inter, intra, deblock], launches[_, inter, intra, deblock])."""
+        ms = (C.c_float * 4)()
+        n = (C.c_int * 4)()
+        self._check(self.L.h264r_replay_last_flush(self.ctx, iterations, flags, ms, n), "h264r_replay_last_flush")
+        return list(ms), list(n)
+
+    def host_alloc(self, nbytes):
+        p = self.L.h264r_host_alloc(nbytes)
+        if not p:
+            raise EngineError("h264r_host_alloc failed")
+        return p
+
+    def host_free(self, p):
+        self.L.h264r_host_free(p)
+
+    def download_async(self, f, y_ptr, cb_ptr, cr_ptr):
+        self._check(self.L.h264r_frame_download_async(self.ctx, f, y_ptr, cb_ptr, cr_ptr, self.w, self.w // 2),
+                    "h264r_frame_download_async")
+
+    def begin(self, dst, pp):
+        """picture_begin only: returns the staging buffers so a producer can write into pinned memory directly."""
+        bufs = PicBuffers()
+        self._check(self.L.h264r_picture_begin(self.ctx, dst, C.byref(pp), C.byref(bufs)), "h264r_picture_begin")
+        return bufs
+
+    def submit_filled(self, num_coeff_slots):
+        self._check(self.L.h264r_picture_submit(self.ctx, num_coeff_slots), "h264r_picture_submit")
 
     def stats(self):
         s = Stats()

@@ -155,8 +155,9 @@ typedef struct h264r_pic_buffers {
     h264r_slice*     slices;                     /* [max_slices_per_picture]                           */
     int16_t*         coeffs;                     /* [coeff_slot_capacity][384] raw levels at raster
                                                     positions: Y 16x16 (256), Cb 8x8 (64), Cr 8x8 (64);
-                                                    I_PCM: the 384 samples.  Slots must be zero where no
-                                                    level was written (begin hands them out zeroed).   */
+                                                    I_PCM: the 384 samples.  A slot must be zero where no
+                                                    level was written: the producer clears a slot when it
+                                                    takes it (staging memory is recycled, not cleared).  */
     uint32_t         coeff_slot_capacity;        /* == number of MBs                                   */
 } h264r_pic_buffers;
 
@@ -191,9 +192,23 @@ int  h264r_frame_download(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb
 int  h264r_frame_upload(h264r_ctx* ctx, h264r_frame f, const uint8_t* y, const uint8_t* cb, const uint8_t* cr,
                         int pitch_y, int pitch_c);
 
-/* Device-resident replay for benchmarking: keeps the already-uploaded descriptions of the last flush in
- * HBM and re-runs only the kernels (no H2D).  Returns the CUDA-event time of the replay in milliseconds. */
-int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, float* ms_total, float* ms_kernels);
+/* Asynchronous variant: the copy is ordered after the wave that produces `f` and runs on the engine's D2H
+ * stream, overlapping later waves; destination should be pinned (h264r_host_alloc).  h264r_wait(ctx, -1) joins. */
+int  h264r_frame_download_async(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb, uint8_t* cr,
+                                int pitch_y, int pitch_c);
+/* pinned host memory for download destinations */
+void* h264r_host_alloc(size_t bytes);
+void  h264r_host_free(void* p);
+
+/* Re-runs the last flush (benchmark support; the staging slots and device copies of the last flush must not have
+ * been refilled since).  flags: H264R_REPLAY_H2D re-issues the host->device copies of every picture description
+ * from the pinned staging (end-to-end path); without it only the kernels run on the HBM-resident inputs.
+ * H264R_REPLAY_TIME_KERNELS brackets every kernel with CUDA events (serialises nothing, costs a few us each).
+ * ms_out[0] = whole replay (CUDA events on the compute stream), [1] inter, [2] intra, [3] deblock kernel time;
+ * launches_out[1..3] = number of launches of each kernel. */
+#define H264R_REPLAY_H2D           1
+#define H264R_REPLAY_TIME_KERNELS  2
+int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[4], int launches_out[4]);
 
 /* host helper restating inter_prediction.cc:112-139 (implicit bi-prediction weights)                   */
 void h264r_implicit_weights(int cur_poc, int poc0, int poc1, int long_term0, int long_term1, int* w0, int* w1);

@@ -52,6 +52,16 @@ void          h264s_get_seq(const h264s_stream* s, h264r_seq_params* sp, int* nu
 int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264r_mb* mbs,
                h264r_mb_motion* motion, h264r_slice* slices, int16_t* coeffs);
 
+/* Algorithmic (compulsory) HBM bytes of one picture, SURVEY.md §8d: every input byte read once, every output byte
+ * written once, ideal reference fetch without halo.
+ *   out[0] whole path : per MB 32 (header) + 768 (levels, if the MB owns a slot) + 192 (motion, inter MBs)
+ *                       + 96 per used prediction list and 8x8 quadrant (= 384 per list and MB) + 384 (output)
+ *   out[1] inter kernel: the above restricted to inter MBs
+ *   out[2] intra kernel: the above restricted to intra MBs
+ *   out[3] deblock kernel (its own pass): per filtered MB 32 + 384 read + 384 written (+192 motion if inter)
+ *   out[4] inter MBs, out[5] intra MBs, out[6] MBs owning a coefficient slot, out[7] filtered MBs */
+void h264s_account(const h264r_mb* mbs, const h264r_slice* slices, int nmb, int run_deblock, uint64_t out[8]);
+
 #ifdef __cplusplus
 }
 #endif

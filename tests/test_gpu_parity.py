@@ -110,6 +110,7 @@ def test_gpu_batched_multi_stream_waves():
         assert d == want[s][idx], f"stream {s} picture {idx} differs"
     # device-resident replay (the bench's kernel-only path) must reproduce the same frames
     eng.replay(2)
+    eng.replay(1, pyapi.Engine.REPLAY_H2D | pyapi.Engine.REPLAY_TIME_KERNELS)
     for s, idx, dst in order:
         d = hashlib.md5(b"".join(eng.download(dst))).hexdigest()
         assert d == want[s][idx], f"after replay: stream {s} picture {idx} differs"
