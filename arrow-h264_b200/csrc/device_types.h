@@ -16,6 +16,13 @@ struct FrameGeom {
     size_t off_cb, off_cr, bytes;    // plane offsets inside the allocation
 };
 
+// Output of the parallel deblock pre-pass, input of the deblock wavefront: 32 bytes per MB.
+struct DeblockDesc {
+    uint32_t bs[3];                  // bit planes of bS; bit index = dir*16 + edge*4 + 4-sample group
+    uint8_t  ia[9], ib[9];           // indexA / indexB for [left MB edge, internal, top MB edge] x [Y, Cb, Cr]
+    uint8_t  pad[2];
+};
+
 struct DevPicture {
     const h264r_mb*        mbs;
     const h264r_mb_motion* motion;
@@ -24,6 +31,7 @@ struct DevPicture {
     uint8_t*               dst;                       // frame base
     const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]
     int*                   row_progress;              // [2][height_mbs]: intra wavefront, deblock wavefront
+    DeblockDesc*           desc;                      // [nmb], device only
     int                    run_deblock;
     int                    has_intra;                 // any intra MB in the picture (host-side hint)
     int                    has_inter;
@@ -39,9 +47,9 @@ struct WaveLaunch {
     int   any_inter, any_intra, any_deblock;
 };
 
-// Kernel launchers of one wave (kernels.cu).  which: 0 inter, 1 intra wavefront, 2 deblock wavefront.
+// Kernel launchers of one wave (kernels.cu).  which: 0 inter, 1 intra wavefront, 2 deblock descriptors (parallel), 3 deblock wavefront.
 // Returns true if a kernel was launched (false when the wave has no work of that kind).
-enum { KERNEL_INTER = 0, KERNEL_INTRA = 1, KERNEL_DEBLOCK = 2, KERNEL_KINDS = 3 };
+enum { KERNEL_INTER = 0, KERNEL_INTRA = 1, KERNEL_DBPREP = 2, KERNEL_DEBLOCK = 3, KERNEL_KINDS = 4 };
 bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);
 
 } // namespace h264r

@@ -11,6 +11,7 @@ using namespace h264r;
 
 static_assert(sizeof(h264r_mb) == 32, "h264r_mb must be 32 bytes");
 static_assert(sizeof(h264r_mb_motion) == 192, "h264r_mb_motion must be 192 bytes");
+static_assert(sizeof(DeblockDesc) == 32, "DeblockDesc must be 32 bytes");
 static_assert(sizeof(h264r_slice) % 16 == 0, "h264r_slice must keep 16-byte alignment in arrays");
 
 namespace {
@@ -29,6 +30,7 @@ enum SlotState { SLOT_FREE = 0, SLOT_FILLING, SLOT_QUEUED, SLOT_INFLIGHT };
 struct Slot {
     uint8_t* host = nullptr;                  // pinned
     uint8_t* dev = nullptr;
+    DeblockDesc* dev_desc = nullptr;          // device only: output of the deblock pre-pass
     SlotState state = SLOT_FREE;
     h264r_pic_params pp;
     h264r_frame dst = -1;
@@ -86,6 +88,25 @@ int cuda_fail(h264r_ctx* c, cudaError_t e, const char* what)
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
 
 bool frame_ok(const h264r_ctx* c, h264r_frame f) { return f >= 0 && f < (int)c->frames.size() && c->frames[f].used; }
+
+// device frame -> host planes on `stream`: one copy when the destination is one tight contiguous block
+int copy_frame_d2h(h264r_ctx* ctx, cudaStream_t stream, const uint8_t* d, uint8_t* y, uint8_t* cb, uint8_t* cr, int pitch_y, int pitch_c)
+{
+    const FrameGeom& g = ctx->geom;
+    const int w = g.width_mbs * 16, h = g.height_mbs * 16;
+    const size_t ny = (size_t)w * h, nc = ny / 4;
+    if (pitch_y == w && pitch_c == w / 2) {
+        if (cb == y + ny && cr == cb + nc) { CU(cudaMemcpyAsync(y, d, ny + 2 * nc, cudaMemcpyDeviceToHost, stream)); return H264R_OK; }
+        CU(cudaMemcpyAsync(y, d, ny, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(cb, d + g.off_cb, nc, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(cr, d + g.off_cr, nc, cudaMemcpyDeviceToHost, stream));
+        return H264R_OK;
+    }
+    CU(cudaMemcpy2DAsync(y, pitch_y, d, g.pitch_y, w, h, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpy2DAsync(cb, pitch_c, d + g.off_cb, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpy2DAsync(cr, pitch_c, d + g.off_cr, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, stream));
+    return H264R_OK;
+}
 
 cudaEvent_t take_event(h264r_ctx* c)
 {
@@ -201,11 +222,11 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
 
     FrameGeom& g = ctx->geom;
     g.width_mbs = sp->width_mbs; g.height_mbs = sp->height_mbs;
-    g.pitch_y = (int)align_up((size_t)sp->width_mbs * 16, 128);
-    g.pitch_c = (int)align_up((size_t)sp->width_mbs * 8, 128);
-    g.off_cb = align_up((size_t)g.pitch_y * sp->height_mbs * 16, 256);
-    g.off_cr = g.off_cb + align_up((size_t)g.pitch_c * sp->height_mbs * 8, 256);
-    g.bytes  = g.off_cr + align_up((size_t)g.pitch_c * sp->height_mbs * 8, 256);
+    g.pitch_y = sp->width_mbs * 16;            // tight: a whole frame is one contiguous 1.5*W*H block
+    g.pitch_c = sp->width_mbs * 8;
+    g.off_cb = (size_t)g.pitch_y * sp->height_mbs * 16;
+    g.off_cr = g.off_cb + (size_t)g.pitch_c * sp->height_mbs * 8;
+    g.bytes  = align_up(g.off_cr + (size_t)g.pitch_c * sp->height_mbs * 8, 256);
     ctx->nmb = sp->width_mbs * sp->height_mbs;
 
     ctx->off_mbs = 0;
@@ -217,10 +238,11 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     ctx->frames.resize(sp->max_frames);
     ctx->slots.resize(sp->max_pictures_in_flight);
     // one pinned and one device arena for all staging slots
-    uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr;
+    uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr;
     const size_t arena = ctx->slot_bytes * sp->max_pictures_in_flight;
     e = cudaHostAlloc((void**)&h_arena, arena, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_arena, arena);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_desc, sizeof(DeblockDesc) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
@@ -230,6 +252,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         snprintf(ctx->cuda_err, sizeof(ctx->cuda_err), "allocation: %s", cudaGetErrorString(e));
         if (h_arena) cudaFreeHost(h_arena);
         if (d_arena) cudaFree(d_arena);
+        if (d_desc) cudaFree(d_desc);
         if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
         if (ctx->d_pics) cudaFree(ctx->d_pics);
         if (ctx->d_sync) cudaFree(ctx->d_sync);
@@ -240,6 +263,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     for (int i = 0; i < sp->max_pictures_in_flight; ++i) {
         ctx->slots[i].host = h_arena + ctx->slot_bytes * i;
         ctx->slots[i].dev = d_arena + ctx->slot_bytes * i;
+        ctx->slots[i].dev_desc = d_desc + (size_t)ctx->nmb * i;
     }
     *out = ctx;
     return H264R_OK;
@@ -251,7 +275,7 @@ void h264r_destroy(h264r_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
     for (Frame& f : ctx->frames) if (f.dev) cudaFree(f.dev);
-    if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); }
+    if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); }
     cudaFreeHost(ctx->h_pics); cudaFree(ctx->d_pics); cudaFree(ctx->d_sync);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) if (ctx->table_ev[i]) cudaEventDestroy(ctx->table_ev[i]);
@@ -401,6 +425,7 @@ int h264r_flush(h264r_ctx* ctx)
         p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
         p.coeffs = reinterpret_cast<const int16_t*>(s.dev + ctx->off_coeffs);
         p.dst = ctx->frames[s.dst].dev;
+        p.desc = s.dev_desc;
         for (int i = 0; i < H264R_MAX_REFS; ++i)
             p.ref[i] = i < s.pp.num_ref_frames ? ctx->frames[s.pp.ref_frames[i]].dev : ctx->frames[s.dst].dev;
         const int pos_in_wave = (int)k - wave_begin[s.wave];
@@ -450,15 +475,15 @@ int h264r_wait(h264r_ctx* ctx, h264r_frame f)
     return H264R_OK;
 }
 
-int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[4], int launches_out[4])
+int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[5], int launches_out[5])
 {
     if (!ctx || iterations <= 0) return H264R_ERR_INVALID;
     if (ctx->last_waves.empty() || ctx->filling >= 0 || !ctx->queue.empty()) return H264R_ERR_STATE;
     cudaSetDevice(ctx->device);
     int rc = h264r_wait(ctx, -1);
     if (rc != H264R_OK) return rc;
-    float ms[4] = { 0.f, 0.f, 0.f, 0.f };
-    int launches[4] = { 0, 0, 0, 0 };
+    float ms[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
+    int launches[5] = { 0, 0, 0, 0, 0 };
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int it = 0; it < iterations; ++it) {
         rc = run_waves(ctx, (flags & H264R_REPLAY_H2D) != 0, (flags & H264R_REPLAY_TIME_KERNELS) != 0, ms, launches);
@@ -468,8 +493,8 @@ int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_
     CU(cudaEventSynchronize(ctx->ev1));
     CU(cudaGetLastError());
     CU(cudaEventElapsedTime(&ms[0], ctx->ev0, ctx->ev1));
-    if (ms_out) for (int i = 0; i < 4; ++i) ms_out[i] = ms[i];
-    if (launches_out) for (int i = 0; i < 4; ++i) launches_out[i] = launches[i];
+    if (ms_out) for (int i = 0; i < 5; ++i) ms_out[i] = ms[i];
+    if (launches_out) for (int i = 0; i < 5; ++i) launches_out[i] = launches[i];
     return H264R_OK;
 }
 
@@ -490,9 +515,7 @@ int h264r_frame_download_async(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_
     if (pitch_y < w || pitch_c < w / 2) return H264R_ERR_INVALID;
     const uint8_t* d = ctx->frames[f].dev;
     if (ctx->frames[f].ready) CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->frames[f].ready, 0));
-    CU(cudaMemcpy2DAsync(y, pitch_y, d, g.pitch_y, w, h, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CU(cudaMemcpy2DAsync(cb, pitch_c, d + g.off_cb, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CU(cudaMemcpy2DAsync(cr, pitch_c, d + g.off_cr, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    { const int rc = copy_frame_d2h(ctx, ctx->s_d2h, d, y, cb, cr, pitch_y, pitch_c); if (rc != H264R_OK) return rc; }
     ctx->stats.d2h_bytes += (uint64_t)w * h * 3 / 2;
     return H264R_OK;
 }
@@ -505,9 +528,7 @@ int h264r_frame_download(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb,
     const int w = g.width_mbs * 16, h = g.height_mbs * 16;
     if (pitch_y < w || pitch_c < w / 2) return H264R_ERR_INVALID;
     const uint8_t* d = ctx->frames[f].dev;
-    CU(cudaMemcpy2DAsync(y, pitch_y, d, g.pitch_y, w, h, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpy2DAsync(cb, pitch_c, d + g.off_cb, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpy2DAsync(cr, pitch_c, d + g.off_cr, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->stream));
+    { const int rc = copy_frame_d2h(ctx, ctx->stream, d, y, cb, cr, pitch_y, pitch_c); if (rc != H264R_OK) return rc; }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stats.d2h_bytes += (uint64_t)w * h * 3 / 2;
     return H264R_OK;

@@ -493,13 +493,22 @@ __device__ __forceinline__ void wait_row(const int* progress_above, int need, in
     }
     __syncwarp();
 }
+// st.release.gpu orders this warp's earlier stores (cumulative over the __syncwarp) before the counter update
 __device__ __forceinline__ void publish_row(int* progress, int done, int lane, bool wrote_pixels)
 {
+    (void)wrote_pixels;
     __syncwarp();
-    if (lane == 0) {
-        if (wrote_pixels) __threadfence();
-        st_release(progress, done);
+    if (lane == 0) st_release(progress, done);
+}
+// Progress of the row above as last observed by this warp (monotonic): polls only when the cached value is not enough.
+__device__ __forceinline__ void wait_row_cached(const int* progress_above, int need, int& known)
+{
+    if (known >= need) return;
+    int v = 0;
+    if ((threadIdx.x & 31) == 0) {
+        while ((v = ld_acquire(progress_above)) < need) __nanosleep(40);
     }
+    known = __shfl_sync(0xFFFFFFFFu, v, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -596,7 +605,7 @@ __device__ __forceinline__ int dc_value(int n, int log2n, bool a, bool b, TF T, 
     return (sum + round) >> shift;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
 {
     __shared__ __align__(16) IntraSmem smem_all[kWarpsPerCta];
@@ -617,11 +626,35 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
     uint8_t* const dY = pic.dst;
     uint8_t* const dC[2] = { pic.dst + g.off_cb, pic.dst + g.off_cr };
 
-    for (int mbx = 0; mbx < W; ++mbx) {
+    int known = mby > 0 ? 0 : 0x7FFFFFFF;                 // progress of the row above as last observed
+    // Rows are walked in super-chunks of 256 MBs: the intra MBs of the super-chunk are found up front (8 coalesced
+    // header-word loads + ballots), so that after every intra MB the row can publish the position of its NEXT
+    // intra MB -- everything before it is complete (inter MBs were reconstructed by recon_inter_kernel).
+    for (int x0 = 0; x0 < W; x0 += 256) {
+      unsigned masks[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+          const int x = x0 + c * 32 + lane;
+          masks[c] = __ballot_sync(0xFFFFFFFFu, x < W && ((load_hdr_word0(pic.mbs, mby * W + x) >> 8) & H264R_MB_FLAG_INTRA));
+      }
+      const int xend = min(x0 + 256, W);
+      // position of the first intra MB at or after chunk c0 (xend if none)
+      auto next_intra = [&](int c0) {
+          int nx = xend;
+#pragma unroll
+          for (int c = 7; c >= 0; --c) if (c >= c0 && masks[c]) nx = x0 + c * 32 + __ffs(masks[c]) - 1;
+          return nx;
+      };
+      { const int first = next_intra(0); if (first > x0) publish_row(progress + mby, first, lane, false); }
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+       while (masks[c]) {
+        const int mbx = x0 + c * 32 + __ffs(masks[c]) - 1;
+        masks[c] &= masks[c] - 1;
+        const int done_to = next_intra(c);                 // published after this MB: the next intra MB of the row
         const int addr = mby * W + mbx;
         const MbHdr h = load_hdr(pic.mbs, addr);
-        if (!h.intra()) { publish_row(progress + mby, mbx + 1, lane, false); continue; }
-        if (mby > 0) wait_row(progress + mby - 1, min(mbx + 2, W), lane);
+        if (mby > 0) wait_row_cached(progress + mby - 1, min(mbx + 2, W), known);
 
         const h264r_slice* sl = pic.slices + h.slice_idx;
         const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
@@ -633,8 +666,8 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
                 const int pl = p >> 6, q = p & 63;
                 dC[pl][(size_t)(cy + (q >> 3)) * g.pitch_c + cx + (q & 7)] = (uint8_t)__ldg(c + 256 + p);
             }
-            publish_row(progress + mby, mbx + 1, lane, true);
-            continue;
+            publish_row(progress + mby, done_to, lane, true);
+            continue;                                      // next intra MB of the chunk
         }
 
         // availability of the four neighbouring MBs (neighbour.cc:123-175 + slice_nr + constrained intra)
@@ -809,7 +842,9 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
             const uint32_t* r = reinterpret_cast<const uint32_t*>(&TC(pl, 0, y));
             *reinterpret_cast<uint2*>(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx) = make_uint2(r[0], r[1]);
         }
-        publish_row(progress + mby, mbx + 1, lane, true);
+        publish_row(progress + mby, done_to, lane, true);
+       }
+      }
     }
 }
 
@@ -826,14 +861,7 @@ __constant__ uint8_t c_tc0[52][3] = {
     {2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6},{4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},
     {10,13,20},{11,15,23},{13,17,25} };
 
-// luma tile: rows -4..15, cols -4..15 -> index (y+4)*32 + (x+4); chroma tile per plane: rows -4..7, cols -4..7 -> (y+4)*16 + (x+4)
-struct DeblockSmem {
-    __align__(16) uint8_t ty[20 * 32];
-    __align__(16) uint8_t tc[2][12 * 16];
-    uint8_t bs[2][4][4];                          // [dir][edge][4-sample group]
-};
-#define DY(x, y) sm.ty[((y) + 4) * 32 + (x) + 4]
-#define DC_(pl, x, y) sm.tc[pl][((y) + 4) * 16 + (x) + 4]
+// ---- pass 1 (fully parallel): per-MB deblock descriptor = boundary strengths + alpha/beta table indexes ----
 
 __device__ __forceinline__ int mv_differs(const h264r_mb_motion* a, int ba, int la, const h264r_mb_motion* b, int bb, int lb)
 {
@@ -855,22 +883,115 @@ __device__ __forceinline__ int bs_compare(const h264r_mb_motion* mp, int bp, con
            (mv_differs(mp, bp, 0, mq, bq, 1) | mv_differs(mp, bp, 1, mq, bq, 0));
 }
 
-// filter_strong / filter_normal (deblock.cc:327-415) across one edge in a shared-memory tile; pix -> q0
+// Deblock::strength (deblock.cc:78-289) + the qPav/indexA/indexB part of filter_edge (deblock.cc:469-474).
+// One THREAD per MB (the work is scalar: 32 strengths and 18 table indexes out of three MB headers).
+struct HdrLite { int mb_type, flags, slice_idx, qp_y, qp_c[2], cbp_blks; };
+__device__ __forceinline__ HdrLite load_hdr_lite(const h264r_mb* mbs, int addr)
+{
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(mbs + addr));
+    HdrLite h;
+    h.mb_type = a.x & 0xFF; h.flags = (a.x >> 8) & 0xFF; h.slice_idx = a.x >> 16;
+    h.qp_y = (int)(int8_t)(a.y >> 16); h.qp_c[0] = (int)(int8_t)(a.y >> 24); h.qp_c[1] = (int)(int8_t)(a.z & 0xFF);
+    h.cbp_blks = a.w & 0xFFFF;
+    return h;
+}
+
+__global__ void __launch_bounds__(128)
+deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g)
+{
+    const int W = g.width_mbs, nmb = W * g.height_mbs;
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= (long long)num_pics * nmb) return;
+    const int pic_i = (int)(gi / nmb), q = (int)(gi - (long long)pic_i * nmb);
+    const DevPicture& pic = pics[pic_i];
+    if (!pic.run_deblock) return;
+    const int mbx = q % W, mby = q / W;
+    const HdrLite Q = load_hdr_lite(pic.mbs, q);
+    const h264r_slice* sl = pic.slices + Q.slice_idx;
+    const int idc = __ldg(&sl->disable_deblocking_filter_idc);
+    uint4* out = reinterpret_cast<uint4*>(pic.desc + q);
+    if (idc == 1) { out[0] = make_uint4(0, 0, 0, 0); out[1] = make_uint4(0, 0, 0, 0); return; }
+
+    bool left = mbx > 0, top = mby > 0;
+    HdrLite PL = Q, PT = Q;
+    if (left) { PL = load_hdr_lite(pic.mbs, q - 1); if (idc == 2 && PL.slice_idx != Q.slice_idx) left = false; }
+    if (top)  { PT = load_hdr_lite(pic.mbs, q - W); if (idc == 2 && PT.slice_idx != Q.slice_idx) top = false; }
+    const bool q_intra = Q.flags & H264R_MB_FLAG_INTRA, t8 = Q.flags & H264R_MB_FLAG_T8x8;
+    const bool p_skip = __ldg(&sl->slice_type) == H264R_P_SLICE && Q.mb_type == 0;
+
+    uint32_t b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+    for (int dir = 0; dir < 2; ++dir) {
+        const bool mbedge = dir == 0 ? left : top;
+        const HdrLite& PN = dir == 0 ? PL : PT;
+        const int pn_idx = dir == 0 ? q - 1 : q - W;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const bool on = e == 0 ? mbedge : !(t8 && (e & 1));
+            if (!on) continue;
+            if (e > 0 && p_skip) continue;
+            const bool p_intra = e ? q_intra : (PN.flags & H264R_MB_FLAG_INTRA) != 0;
+            if (p_intra || q_intra) {
+                const uint32_t m = 0xFu << (dir * 16 + e * 4);
+                if (e == 0) b2 |= m; else { b0 |= m; b1 |= m; }        // 4 = 100b, 3 = 011b
+                continue;
+            }
+            const int pcbp = e ? Q.cbp_blks : PN.cbp_blks;
+            const int pidx = e ? q : pn_idx;
+            const bool same_part = e > 0 && (Q.mb_type == 1 || Q.mb_type == (dir == 0 ? 2 : 3));
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const int blkQ = dir == 0 ? k4 * 4 + e : e * 4 + k4;
+                const int blkP = dir == 0 ? k4 * 4 + (e ? e - 1 : 3) : (e ? e - 1 : 3) * 4 + k4;
+                const int bit = dir * 16 + e * 4 + k4;
+                if (((Q.cbp_blks >> blkQ) & 1) || ((pcbp >> blkP) & 1)) b1 |= 1u << bit;          // 2
+                else if (!same_part && bs_compare(pic.motion + pidx, blkP, pic.motion + q, blkQ)) b0 |= 1u << bit;   // 1
+            }
+        }
+    }
+    // table indexes: combo = type*3 + plane, type 0 = left MB edge, 1 = internal edge, 2 = top MB edge
+    const int foa = (int)(int8_t)__ldg(&sl->filter_offset_a), fob = (int)(int8_t)__ldg(&sl->filter_offset_b);
+    uint32_t w[5] = { 0, 0, 0, 0, 0 };
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        const int t = c / 3, pl = c % 3;
+        const HdrLite& P = t == 0 ? PL : (t == 2 ? PT : Q);
+        const int qp_p = pl ? P.qp_c[pl - 1] : P.qp_y, qp_q = pl ? Q.qp_c[pl - 1] : Q.qp_y;
+        const int qPav = (qp_p + qp_q + 1) >> 1;
+        const uint32_t ia = (uint32_t)clip3i(0, 51, qPav + foa), ib = (uint32_t)clip3i(0, 51, qPav + fob);
+        const int ba = c, bb = 9 + c;                       // byte positions inside words 3..7
+        w[ba >> 2] |= ia << ((ba & 3) * 8);
+        w[bb >> 2] |= ib << ((bb & 3) * 8);
+    }
+    out[0] = make_uint4(b0, b1, b2, w[0]);
+    out[1] = make_uint4(w[1], w[2], w[3], w[4]);
+}
+
+// ---- pass 2 (row wavefront): filtering, in place ----
+//
+// Tile layout per warp (bytes): luma rows -4..15: index (y+4)*32 + (x+16), x in -4..15 (own 16 samples 16-byte aligned);
+// chroma plane pl at 640 + pl*192: rows -4..7: index (y+4)*16 + (x+8), x in -4..7.
+struct DeblockSmem {
+    __align__(16) uint8_t t[640 + 2 * 192];
+};
+
+// filter_strong / filter_normal (deblock.cc:327-415) across one edge in the shared-memory tile; pix -> q0.
+// One instruction stream for luma and chroma lanes (chroma is data, not control flow).
 __device__ __forceinline__ void filter_samples(uint8_t* pix, int step, int bS, int alpha, int beta, int tc0, bool chroma)
 {
     const int p0 = pix[-step], p1 = pix[-2 * step], q0 = pix[0], q1 = pix[step];
     if (!(abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta)) return;
-    const int p2 = chroma ? 0 : pix[-3 * step], q2 = chroma ? 0 : pix[2 * step];
-    const int ap = abs(p2 - p0), aq = abs(q2 - q0);
+    const int p2 = pix[-3 * step], q2 = pix[2 * step];
+    const bool ap = !chroma && abs(p2 - p0) < beta, aq = !chroma && abs(q2 - q0) < beta;
     if (bS == 4) {
         const bool small = abs(p0 - q0) < (alpha >> 2) + 2;
-        if (!chroma && ap < beta && small) {
+        if (ap && small) {
             const int p3 = pix[-4 * step];
             pix[-step]     = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
             pix[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
             pix[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
         } else pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
-        if (!chroma && aq < beta && small) {
+        if (aq && small) {
             const int q3 = pix[3 * step];
             pix[0]        = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
             pix[step]     = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
@@ -878,15 +999,15 @@ __device__ __forceinline__ void filter_samples(uint8_t* pix, int step, int bS, i
         } else pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
         return;
     }
-    const int tc = chroma ? tc0 + 1 : tc0 + (ap < beta) + (aq < beta);
+    const int tc = chroma ? tc0 + 1 : tc0 + (ap ? 1 : 0) + (aq ? 1 : 0);
     const int delta = clip3i(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
     pix[-step] = (uint8_t)clip255(p0 + delta);
     pix[0]     = (uint8_t)clip255(q0 - delta);
-    if (!chroma && ap < beta) pix[-2 * step] = (uint8_t)(p1 + clip3i(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 * 2)) >> 1));
-    if (!chroma && aq < beta) pix[step]      = (uint8_t)(q1 + clip3i(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 * 2)) >> 1));
+    if (ap) pix[-2 * step] = (uint8_t)(p1 + clip3i(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 * 2)) >> 1));
+    if (aq) pix[step]      = (uint8_t)(q1 + clip3i(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 * 2)) >> 1));
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8)
 deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
 {
     __shared__ __align__(16) DeblockSmem smem_all[kWarpsPerCta];
@@ -902,106 +1023,120 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
     if (mby >= H) return;
     const DevPicture& pic = pics[pic_i];
     if (!pic.run_deblock) return;
-    DeblockSmem& sm = smem_all[warp];
+    uint8_t* const T = smem_all[warp].t;
     int* progress = pic.row_progress + H;                // [1][H]
     uint8_t* const dY = pic.dst;
-    uint8_t* const dC[2] = { pic.dst + g.off_cb, pic.dst + g.off_cr };
+    const size_t off_c[2] = { g.off_cb, g.off_cr };
+    const uint32_t* desc = reinterpret_cast<const uint32_t*>(pic.desc + (size_t)mby * W);
+
+    // per-lane line geometry: lanes 0..15 = luma line, 16..31 = chroma line (plane, line)
+    const bool is_c = lane >= 16;
+    const int cpl = (lane >> 3) & 1, line = is_c ? (lane & 7) : lane;
+    const int tile_base = is_c ? 640 + cpl * 192 : 0;
+    const int tstride = is_c ? 16 : 32, tx0 = is_c ? 8 : 16;
+    const int nedges = is_c ? 2 : 4;
+
+    int known = mby > 0 ? 0 : 0x7FFFFFFF;                 // progress of the row above as last observed
+    const int* const prog_above = progress + mby - 1;
+    bool top_pref = false;                                // top border of the coming MB already in registers
+    uint4 topY = make_uint4(0, 0, 0, 0); uint2 topC = make_uint2(0, 0);
+    // lanes 0..3: luma rows -4..-1; lanes 4..7: chroma rows -2..-1 of both planes
+    const int tpl = (lane >> 1) & 1, tr = lane & 1;
+
+    // prefetch: descriptor word (lanes 0..7) and the MB's own samples of MB 0
+    uint32_t dnext = lane < 8 ? __ldg(desc + lane) : 0;
+    uint4 ownY = make_uint4(0, 0, 0, 0); uint2 ownC = make_uint2(0, 0);
+    {
+        if (!is_c) ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (size_t)(mby * 16 + line) * g.pitch_y));
+        else ownC = __ldcg(reinterpret_cast<const uint2*>(dY + off_c[cpl] + (size_t)(mby * 8 + line) * g.pitch_c));
+    }
 
     for (int mbx = 0; mbx < W; ++mbx) {
-        const int q = mby * W + mbx;
-        const MbHdr Q = load_hdr(pic.mbs, q);
-        const h264r_slice* sl = pic.slices + Q.slice_idx;
-        const int idc = __ldg(&sl->disable_deblocking_filter_idc);
-        if (idc == 1) { publish_row(progress + mby, mbx + 1, lane, false); continue; }
-        if (mby > 0) wait_row(progress + mby - 1, min(mbx + 2, W), lane);
-
-        bool left = mbx > 0, top = mby > 0;
-        MbHdr PL = Q, PT = Q;
-        if (left) { PL = load_hdr(pic.mbs, q - 1); if (idc == 2 && PL.slice_idx != Q.slice_idx) left = false; }
-        if (top)  { PT = load_hdr(pic.mbs, q - W); if (idc == 2 && PT.slice_idx != Q.slice_idx) top = false; }
+        const uint32_t dcur = dnext;
+        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, dcur, 0), b1 = __shfl_sync(0xFFFFFFFFu, dcur, 1), b2 = __shfl_sync(0xFFFFFFFFu, dcur, 2);
+        const uint32_t any = b0 | b1 | b2;
         const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
 
-        // ---- load the MB and its 4-sample left / top borders into the tiles (words, L1-bypassing) ----
-        for (int i = lane; i < 100; i += 32) {             // luma: 20 rows x 5 words
-            const int r = i / 5, wq = i - r * 5, y = r - 4, x = wq * 4 - 4;
-            uint32_t v = 0;
-            if ((y >= 0 || mby > 0) && (x >= 0 || mbx > 0) && !(y < 0 && x < 0))
-                v = ldcg_u32(dY + (size_t)(py + y) * g.pitch_y + px + x);
-            reinterpret_cast<uint32_t*>(sm.ty)[r * 8 + wq] = v;
+        // carry: the previous MB's last 4 columns become this MB's left border; then drop in this MB's own samples
+        if (mbx > 0) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(T + tile_base + (line + 4) * tstride + tx0 + (is_c ? 4 : 12));
+            __syncwarp();
+            *reinterpret_cast<uint32_t*>(T + tile_base + (line + 4) * tstride + tx0 - 4) = v;
         }
-        for (int i = lane; i < 72; i += 32) {              // chroma: 2 planes x 12 rows x 3 words
-            const int pl = i / 36, j = i - pl * 36, r = j / 3, wq = j - r * 3, y = r - 4, x = wq * 4 - 4;
-            uint32_t v = 0;
-            if ((y >= 0 || mby > 0) && (x >= 0 || mbx > 0) && !(y < 0 && x < 0))
-                v = ldcg_u32(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx + x);
-            reinterpret_cast<uint32_t*>(sm.tc[pl])[r * 4 + wq] = v;
-        }
+        if (!is_c) *reinterpret_cast<uint4*>(T + (line + 4) * 32 + 16) = ownY;
+        else *reinterpret_cast<uint2*>(T + tile_base + (line + 4) * 16 + 8) = ownC;
 
-        // ---- boundary strengths: lane = dir*16 + edge*4 + group (deblock.cc:78-228) ----
-        {
-            const int dir = lane >> 4, e = (lane >> 2) & 3, k4 = lane & 3;
-            const bool mbedge = dir == 0 ? left : top;
-            const bool luma_on = e == 0 ? mbedge : !(Q.t8() && (e & 1));
-            int s = 0;
-            if (luma_on) {
-                const MbHdr& P = e ? Q : (dir == 0 ? PL : PT);
-                const int pidx = e ? q : (dir == 0 ? q - 1 : q - W);
-                if (e > 0 && __ldg(&sl->slice_type) == H264R_P_SLICE && Q.mb_type == 0) s = 0;
-                else if (P.intra() || Q.intra()) s = e == 0 ? 4 : 3;
-                else {
-                    const int blkQ = dir == 0 ? k4 * 4 + e : e * 4 + k4;
-                    const int blkP = dir == 0 ? k4 * 4 + (e ? e - 1 : 3) : (e ? e - 1 : 3) * 4 + k4;
-                    if (((Q.cbp_blks >> blkQ) & 1) || ((P.cbp_blks >> blkP) & 1)) s = 2;
-                    else if (e > 0 && (Q.mb_type == 1 || Q.mb_type == (dir == 0 ? 2 : 3))) s = 0;
-                    else s = bs_compare(pic.motion + pidx, blkP, pic.motion + q, blkQ);
-                }
+        // prefetch the next MB (descriptor + own samples): independent of every other MB of this kernel
+        if (mbx + 1 < W) {
+            if (lane < 8) dnext = __ldg(desc + (mbx + 1) * 8 + lane);
+            if (!is_c) ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (size_t)(py + line) * g.pitch_y + px + 16));
+            else ownC = __ldcg(reinterpret_cast<const uint2*>(dY + off_c[cpl] + (size_t)(cy + line) * g.pitch_c + cx + 8));
+        }
+        const bool top = (any >> 16) & 0xF, left = any & 0xF;
+        const bool have_top = top_pref;
+        const uint4 curTopY = topY; const uint2 curTopC = topC;
+        // top border of the next MB, if the row above is already known to be far enough
+        top_pref = false;
+        if (mby > 0 && mbx + 1 < W && known >= min(mbx + 3, W)) {
+            top_pref = true;
+            if (lane < 4) topY = __ldcg(reinterpret_cast<const uint4*>(dY + (size_t)(py - 4 + lane) * g.pitch_y + px + 16));
+            else if (lane < 8) topC = __ldcg(reinterpret_cast<const uint2*>(dY + off_c[tpl] + (size_t)(cy - 2 + tr) * g.pitch_c + cx + 8));
+        }
+        if (!any) { publish_row(progress + mby, mbx + 1, lane, false); continue; }
+
+        if (top) {
+            if (have_top) {
+                if (lane < 4) *reinterpret_cast<uint4*>(T + lane * 32 + 16) = curTopY;
+                else if (lane < 8) *reinterpret_cast<uint2*>(T + 640 + tpl * 192 + (2 + tr) * 16 + 8) = curTopC;
+            } else {
+                wait_row_cached(prog_above, min(mbx + 2, W), known);
+                if (lane < 4)
+                    *reinterpret_cast<uint4*>(T + lane * 32 + 16) = __ldcg(reinterpret_cast<const uint4*>(dY + (size_t)(py - 4 + lane) * g.pitch_y + px));
+                else if (lane < 8)
+                    *reinterpret_cast<uint2*>(T + 640 + tpl * 192 + (2 + tr) * 16 + 8) =
+                        __ldcg(reinterpret_cast<const uint2*>(dY + off_c[tpl] + (size_t)(cy - 2 + tr) * g.pitch_c + cx));
             }
-            sm.bs[dir][e][k4] = (uint8_t)s;
         }
         __syncwarp();
 
-        // ---- filtering: dir 0 (vertical edges) then dir 1 (horizontal); lanes 0..15 luma line, 16..31 chroma line ----
-        const int foa = (int)(int8_t)__ldg(&sl->filter_offset_a), fob = (int)(int8_t)__ldg(&sl->filter_offset_b);
+        // index tables = bytes 12..29 of the descriptor (words 3..7, held by lanes 3..7)
+        uint32_t dw[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) dw[k] = __shfl_sync(0xFFFFFFFFu, dcur, 3 + k);
+        // ---- dir 0: vertical edges; dir 1: horizontal edges ----
+#pragma unroll
         for (int dir = 0; dir < 2; ++dir) {
-            const bool mbedge = dir == 0 ? left : top;
-            const MbHdr& PN = dir == 0 ? PL : PT;
-            if (lane < 16) {
-                const int step = dir == 0 ? 1 : 32;
-                for (int e = 0; e < 4; ++e) {
-                    const bool on = e == 0 ? mbedge : !(Q.t8() && (e & 1));
-                    const int s = sm.bs[dir][e][lane >> 2];
-                    if (!on || !s) continue;
-                    const int qPav = ((e ? Q.qp_y : PN.qp_y) + Q.qp_y + 1) >> 1;
-                    const int ia = clip3i(0, 51, qPav + foa), ib = clip3i(0, 51, qPav + fob);
-                    uint8_t* pix = dir == 0 ? &DY(e * 4, lane) : &DY(lane, e * 4);
-                    filter_samples(pix, step, s, c_alpha[ia], c_beta[ib], s < 4 ? c_tc0[ia][s - 1] : 0, false);
-                }
-            } else {
-                const int c = lane - 16, pl = c >> 3, line = c & 7;
-                const int step = dir == 0 ? 1 : 16;
-                for (int e = 0; e < 2; ++e) {
-                    const bool on = e == 0 ? mbedge : true;
-                    const int s = sm.bs[dir][e * 2][line >> 1];     // chroma edge e uses luma edge 2e, sample 2*line
-                    if (!on || !s) continue;
-                    const int qPav = ((e ? Q.qp_c[pl] : PN.qp_c[pl]) + Q.qp_c[pl] + 1) >> 1;
-                    const int ia = clip3i(0, 51, qPav + foa), ib = clip3i(0, 51, qPav + fob);
-                    uint8_t* pix = dir == 0 ? &DC_(pl, e * 4, line) : &DC_(pl, line, e * 4);
-                    filter_samples(pix, step, s, c_alpha[ia], c_beta[ib], s < 4 ? c_tc0[ia][s - 1] : 0, true);
+            const int step = dir == 0 ? 1 : tstride;
+            uint8_t* linep = T + tile_base + (dir == 0 ? (line + 4) * tstride + tx0 : 4 * tstride + tx0 + line);
+            for (int e = 0; e < nedges; ++e) {
+                const int E = is_c ? 2 * e : e;
+                const int bit = dir * 16 + E * 4 + (is_c ? line >> 1 : line >> 2);
+                const int s = ((b0 >> bit) & 1) | (((b1 >> bit) & 1) << 1) | (((b2 >> bit) & 1) << 2);
+                if (s) {
+                    const int combo = (e == 0 ? (dir == 0 ? 0 : 2) : 1) * 3 + (is_c ? 1 + cpl : 0);
+                    const int ba = 12 + combo, bb = 21 + combo;
+                    const int ia = (dw[(ba >> 2) - 3] >> ((ba & 3) * 8)) & 0xFF;
+                    const int ib = (dw[(bb >> 2) - 3] >> ((bb & 3) * 8)) & 0xFF;
+                    filter_samples(linep + e * 4 * step, step, s, c_alpha[ia], c_beta[ib], s < 4 ? c_tc0[ia][s - 1] : 0, is_c);
                 }
             }
             __syncwarp();
         }
 
-        // ---- write back: own MB, left 4 columns (if filtered), top 4 rows (if filtered) ----
-        for (int i = lane; i < 100; i += 32) {
-            const int r = i / 5, wq = i - r * 5, y = r - 4, x = wq * 4 - 4;
-            if ((y < 0 && !top) || (x < 0 && !left) || (y < 0 && x < 0)) continue;
-            *reinterpret_cast<uint32_t*>(dY + (size_t)(py + y) * g.pitch_y + px + x) = reinterpret_cast<const uint32_t*>(sm.ty)[r * 8 + wq];
+        // ---- write back: own samples, left 4 columns (if that edge was filtered), top rows (ditto) ----
+        if (!is_c) *reinterpret_cast<uint4*>(dY + (size_t)(py + line) * g.pitch_y + px) = *reinterpret_cast<const uint4*>(T + (line + 4) * 32 + 16);
+        else *reinterpret_cast<uint2*>(dY + off_c[cpl] + (size_t)(cy + line) * g.pitch_c + cx) = *reinterpret_cast<const uint2*>(T + tile_base + (line + 4) * 16 + 8);
+        if (left) {
+            if (!is_c) *reinterpret_cast<uint32_t*>(dY + (size_t)(py + line) * g.pitch_y + px - 4) = *reinterpret_cast<const uint32_t*>(T + (line + 4) * 32 + 12);
+            else *reinterpret_cast<uint32_t*>(dY + off_c[cpl] + (size_t)(cy + line) * g.pitch_c + cx - 4) = *reinterpret_cast<const uint32_t*>(T + tile_base + (line + 4) * 16 + 4);
         }
-        for (int i = lane; i < 72; i += 32) {
-            const int pl = i / 36, j = i - pl * 36, r = j / 3, wq = j - r * 3, y = r - 4, x = wq * 4 - 4;
-            if ((y < 0 && !top) || (x < 0 && !left) || (y < 0 && x < 0)) continue;
-            *reinterpret_cast<uint32_t*>(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx + x) = reinterpret_cast<const uint32_t*>(sm.tc[pl])[r * 4 + wq];
+        if (top) {
+            if (lane >= 1 && lane < 4)
+                *reinterpret_cast<uint4*>(dY + (size_t)(py - 4 + lane) * g.pitch_y + px) = *reinterpret_cast<const uint4*>(T + lane * 32 + 16);
+            else if (lane == 4 || lane == 5) {
+                const int pl = lane & 1;
+                *reinterpret_cast<uint2*>(dY + off_c[pl] + (size_t)(cy - 1) * g.pitch_c + cx) = *reinterpret_cast<const uint2*>(T + 640 + pl * 192 + 3 * 16 + 8);
+            }
         }
         publish_row(progress + mby, mbx + 1, lane, true);
     }
@@ -1027,6 +1162,11 @@ bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
         return true;
     }
     if (!w.any_deblock) return false;
+    if (which == KERNEL_DBPREP) {
+        const long long total = (long long)w.num_pics * nmb;
+        deblock_prep_kernel<<<(int)((total + 127) / 128), 128, 0, stream>>>(w.pics, w.num_pics, w.geom);
+        return true;
+    }
     deblock_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
     return true;
 }

@@ -243,9 +243,9 @@ class Engine:
     REPLAY_H2D, REPLAY_TIME_KERNELS = 1, 2
 
     def replay(self, iterations=1, flags=0):
-        """Re-runs the last flush; returns (ms[total, inter, intra, deblock], launches[_, inter, intra, deblock])."""
-        ms = (C.c_float * 4)()
-        n = (C.c_int * 4)()
+        """Re-runs the last flush; returns (ms[total, inter, intra, dbprep, deblock], launches[_, ...same])."""
+        ms = (C.c_float * 5)()
+        n = (C.c_int * 5)()
         self._check(self.L.h264r_replay_last_flush(self.ctx, iterations, flags, ms, n), "h264r_replay_last_flush")
         return list(ms), list(n)
 

@@ -178,7 +178,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     first = rank * streams
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex:
         all_pics = list(ex.map(generate_stream, [(first + s, frames) for s in range(streams)]))
-    acct = [0] * 8
+    acct = [0] * 9
     frames_of = [dict() for _ in range(streams)]
     out_frames = []
     for i in range(frames):                       # picture i of every stream, decode order
@@ -190,7 +190,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
             out_frames.append(dst)
             a = (C.c_uint64 * 8)()
             pyapi.synth_lib().h264s_account(pic.mbs, pic.slices, nmb, pic.pp.run_deblock, a)
-            acct = [x + y for x, y in zip(acct, a)]
+            acct = [x + y for x, y in zip(acct, list(a) + [a[7] * (32 + 32) + a[4] * 192])]
             all_pics[s][i] = None                 # the pinned staging now owns the data
     del all_pics
     gen_s = time.time() - t0
@@ -266,9 +266,9 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     value = world * total_mb * args.steps / t_dev
     e2e_value = world * total_mb * args.steps / t_e2e
     peak, peak_src = peaks()
-    names = ["inter", "intra", "deblock"]
-    k_bytes = [acct[1], acct[2], acct[3]]
-    dom = max(range(3), key=lambda i: kms[i + 1])
+    names = ["inter", "intra", "deblock_prep", "deblock"]
+    k_bytes = [acct[1], acct[2], acct[8], acct[3]]
+    dom = max(range(4), key=lambda i: kms[i + 1])
     dom_ms_per_launch = kms[dom + 1] / max(1, kn[dom + 1])
     dom_bytes_per_launch = k_bytes[dom] / max(1, kn[dom + 1])
     achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0

@@ -204,11 +204,11 @@ void  h264r_host_free(void* p);
  * been refilled since).  flags: H264R_REPLAY_H2D re-issues the host->device copies of every picture description
  * from the pinned staging (end-to-end path); without it only the kernels run on the HBM-resident inputs.
  * H264R_REPLAY_TIME_KERNELS brackets every kernel with CUDA events (serialises nothing, costs a few us each).
- * ms_out[0] = whole replay (CUDA events on the compute stream), [1] inter, [2] intra, [3] deblock kernel time;
- * launches_out[1..3] = number of launches of each kernel. */
+ * ms_out[0] = whole replay (CUDA events on the compute stream), [1] inter, [2] intra wavefront, [3] deblock
+ * pre-pass, [4] deblock wavefront kernel time; launches_out[1..4] = number of launches of each kernel. */
 #define H264R_REPLAY_H2D           1
 #define H264R_REPLAY_TIME_KERNELS  2
-int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[4], int launches_out[4]);
+int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[5], int launches_out[5]);
 
 /* host helper restating inter_prediction.cc:112-139 (implicit bi-prediction weights)                   */
 void h264r_implicit_weights(int cur_poc, int poc0, int poc1, int long_term0, int long_term1, int* w0, int* w1);
