@@ -27,7 +27,8 @@ struct DevPicture {
     const h264r_mb*        mbs;
     const h264r_mb_motion* motion;
     const h264r_slice*     slices;
-    const int16_t*         coeffs;
+    const h264r_level*     levels;
+    int16_t*               resid;                     // [nmb][384] residual plane, device only (residual_kernel)
     uint8_t*               dst;                       // frame base
     const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]
     int*                   row_progress;              // [2][height_mbs]: intra wavefront, deblock wavefront
@@ -47,9 +48,9 @@ struct WaveLaunch {
     int   any_inter, any_intra, any_deblock;
 };
 
-// Kernel launchers of one wave (kernels.cu).  which: 0 inter, 1 intra wavefront, 2 deblock descriptors (parallel), 3 deblock wavefront.
+// Kernel launchers of one wave (kernels.cu).  which: 0 residual (parallel), 1 inter (parallel), 2 intra wavefront, 3 deblock descriptors (parallel), 4 deblock wavefront.
 // Returns true if a kernel was launched (false when the wave has no work of that kind).
-enum { KERNEL_INTER = 0, KERNEL_INTRA = 1, KERNEL_DBPREP = 2, KERNEL_DEBLOCK = 3, KERNEL_KINDS = 4 };
+enum { KERNEL_RESID = 0, KERNEL_INTER = 1, KERNEL_INTRA = 2, KERNEL_DBPREP = 3, KERNEL_DEBLOCK = 4, KERNEL_KINDS = 5 };
 bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);
 
 } // namespace h264r

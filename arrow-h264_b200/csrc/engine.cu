@@ -31,10 +31,11 @@ struct Slot {
     uint8_t* host = nullptr;                  // pinned
     uint8_t* dev = nullptr;
     DeblockDesc* dev_desc = nullptr;          // device only: output of the deblock pre-pass
+    int16_t* dev_resid = nullptr;             // device only: residual plane [nmb][384]
     SlotState state = SLOT_FREE;
     h264r_pic_params pp;
     h264r_frame dst = -1;
-    uint32_t used_slots = 0;
+    uint32_t used_levels = 0;
     int has_intra = 0, has_inter = 0;
     int wave = 0;
 };
@@ -61,7 +62,8 @@ struct h264r_ctx {
     h264r_seq_params seq;
     FrameGeom geom;
     int nmb = 0;
-    size_t off_mbs = 0, off_motion = 0, off_slices = 0, off_coeffs = 0, slot_bytes = 0;
+    size_t off_mbs = 0, off_motion = 0, off_slices = 0, off_levels = 0, slot_bytes = 0;
+    uint32_t level_capacity = 0;
     std::vector<Frame> frames;
     std::vector<Slot> slots;
     std::vector<int> queue;                   // slot indexes in submission order
@@ -232,17 +234,20 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     ctx->off_mbs = 0;
     ctx->off_motion = align_up(ctx->off_mbs + sizeof(h264r_mb) * ctx->nmb, 256);
     ctx->off_slices = align_up(ctx->off_motion + sizeof(h264r_mb_motion) * ctx->nmb, 256);
-    ctx->off_coeffs = align_up(ctx->off_slices + sizeof(h264r_slice) * sp->max_slices_per_picture, 256);
-    ctx->slot_bytes = align_up(ctx->off_coeffs + sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)ctx->nmb, 256);
+    ctx->off_levels = align_up(ctx->off_slices + sizeof(h264r_slice) * sp->max_slices_per_picture, 256);
+    ctx->level_capacity = sp->max_levels_per_picture > 0 ? (uint32_t)sp->max_levels_per_picture
+                                                          : (uint32_t)H264R_COEFFS_PER_MB * (uint32_t)ctx->nmb;
+    ctx->slot_bytes = align_up(ctx->off_levels + sizeof(h264r_level) * (size_t)ctx->level_capacity, 256);
 
     ctx->frames.resize(sp->max_frames);
     ctx->slots.resize(sp->max_pictures_in_flight);
     // one pinned and one device arena for all staging slots
-    uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr;
+    uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr; int16_t* d_resid = nullptr;
     const size_t arena = ctx->slot_bytes * sp->max_pictures_in_flight;
     e = cudaHostAlloc((void**)&h_arena, arena, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_arena, arena);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_desc, sizeof(DeblockDesc) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_resid, sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
@@ -253,6 +258,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         if (h_arena) cudaFreeHost(h_arena);
         if (d_arena) cudaFree(d_arena);
         if (d_desc) cudaFree(d_desc);
+        if (d_resid) cudaFree(d_resid);
         if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
         if (ctx->d_pics) cudaFree(ctx->d_pics);
         if (ctx->d_sync) cudaFree(ctx->d_sync);
@@ -264,6 +270,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         ctx->slots[i].host = h_arena + ctx->slot_bytes * i;
         ctx->slots[i].dev = d_arena + ctx->slot_bytes * i;
         ctx->slots[i].dev_desc = d_desc + (size_t)ctx->nmb * i;
+        ctx->slots[i].dev_resid = d_resid + (size_t)H264R_COEFFS_PER_MB * ctx->nmb * i;
     }
     *out = ctx;
     return H264R_OK;
@@ -275,7 +282,7 @@ void h264r_destroy(h264r_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
     for (Frame& f : ctx->frames) if (f.dev) cudaFree(f.dev);
-    if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); }
+    if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); cudaFree(ctx->slots[0].dev_resid); }
     cudaFreeHost(ctx->h_pics); cudaFree(ctx->d_pics); cudaFree(ctx->d_sync);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) if (ctx->table_ev[i]) cudaEventDestroy(ctx->table_ev[i]);
@@ -327,23 +334,23 @@ int h264r_picture_begin(h264r_ctx* ctx, h264r_frame dst, const h264r_pic_params*
     }
     if (s < 0) return H264R_ERR_NOMEM;
     Slot& sl = ctx->slots[s];
-    sl.state = SLOT_FILLING; sl.pp = *pp; sl.dst = dst; sl.used_slots = 0;
+    sl.state = SLOT_FILLING; sl.pp = *pp; sl.dst = dst; sl.used_levels = 0;
     ctx->filling = s;
     out->mbs = reinterpret_cast<h264r_mb*>(sl.host + ctx->off_mbs);
     out->motion = reinterpret_cast<h264r_mb_motion*>(sl.host + ctx->off_motion);
     out->slices = reinterpret_cast<h264r_slice*>(sl.host + ctx->off_slices);
-    out->coeffs = reinterpret_cast<int16_t*>(sl.host + ctx->off_coeffs);
-    out->coeff_slot_capacity = (uint32_t)ctx->nmb;
+    out->levels = reinterpret_cast<h264r_level*>(sl.host + ctx->off_levels);
+    out->level_capacity = ctx->level_capacity;
     return H264R_OK;
 }
 
-int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_coeff_slots)
+int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels)
 {
     if (!ctx) return H264R_ERR_INVALID;
     if (ctx->filling < 0) return H264R_ERR_STATE;
-    if (num_coeff_slots > (uint32_t)ctx->nmb) return H264R_ERR_INVALID;
+    if (num_levels > ctx->level_capacity) return H264R_ERR_INVALID;
     Slot& sl = ctx->slots[ctx->filling];
-    sl.used_slots = num_coeff_slots;
+    sl.used_levels = num_levels;
     // validate what would otherwise become an out-of-bounds access on the device
     const h264r_mb* mbs = reinterpret_cast<const h264r_mb*>(sl.host + ctx->off_mbs);
     int has_intra = 0, has_inter = 0, bad = 0, unsupported = 0;
@@ -351,8 +358,7 @@ int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_coeff_slots)
         const h264r_mb& m = mbs[i];
         if (m.flags & H264R_MB_FLAG_INTRA) has_intra = 1; else has_inter = 1;
         if (m.slice_idx >= sl.pp.num_slices) bad = 1;
-        if (m.coeff_slot != H264R_NO_COEFF && m.coeff_slot >= num_coeff_slots) bad = 1;
-        if ((m.mb_type == H264R_MB_I16x16 || m.mb_type == H264R_MB_IPCM) && m.coeff_slot == H264R_NO_COEFF) bad = 1;
+        if (m.coeff_count && ((uint64_t)m.coeff_offset + m.coeff_count > num_levels)) bad = 1;   // positions are checked on the device
         if (m.mb_type > H264R_MB_IPCM || m.mb_type == 11) unsupported = 1;        // SI and friends
         if (!(m.flags & H264R_MB_FLAG_INTRA) && m.mb_type > H264R_MB_8x8) bad = 1;
         if (m.qp_y < 0 || m.qp_y > 51 || m.qp_c[0] < 0 || m.qp_c[0] > 51 || m.qp_c[1] < 0 || m.qp_c[1] > 51) bad = 1;
@@ -423,7 +429,8 @@ int h264r_flush(h264r_ctx* ctx)
         p.mbs = reinterpret_cast<const h264r_mb*>(s.dev + ctx->off_mbs);
         p.motion = reinterpret_cast<const h264r_mb_motion*>(s.dev + ctx->off_motion);
         p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
-        p.coeffs = reinterpret_cast<const int16_t*>(s.dev + ctx->off_coeffs);
+        p.levels = reinterpret_cast<const h264r_level*>(s.dev + ctx->off_levels);
+        p.resid = s.dev_resid;
         p.dst = ctx->frames[s.dst].dev;
         p.desc = s.dev_desc;
         for (int i = 0; i < H264R_MAX_REFS; ++i)
@@ -447,7 +454,7 @@ int h264r_flush(h264r_ctx* ctx)
         L.any_inter = L.any_intra = L.any_deblock = 0;
         for (int k = b; k < e; ++k) {
             Slot& s = ctx->slots[order[k]];
-            rec.copies.push_back({ order[k], ctx->off_coeffs + sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)s.used_slots });
+            rec.copies.push_back({ order[k], ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels });
             L.any_inter |= s.has_inter; L.any_intra |= s.has_intra; L.any_deblock |= s.pp.run_deblock;
         }
         rec.progress_bytes = sizeof(int) * (64 + ctx->sync_ints_per_pic * (size_t)L.num_pics);
@@ -475,15 +482,15 @@ int h264r_wait(h264r_ctx* ctx, h264r_frame f)
     return H264R_OK;
 }
 
-int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[5], int launches_out[5])
+int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[6], int launches_out[6])
 {
     if (!ctx || iterations <= 0) return H264R_ERR_INVALID;
     if (ctx->last_waves.empty() || ctx->filling >= 0 || !ctx->queue.empty()) return H264R_ERR_STATE;
     cudaSetDevice(ctx->device);
     int rc = h264r_wait(ctx, -1);
     if (rc != H264R_OK) return rc;
-    float ms[5] = { 0.f, 0.f, 0.f, 0.f, 0.f };
-    int launches[5] = { 0, 0, 0, 0, 0 };
+    float ms[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+    int launches[6] = { 0, 0, 0, 0, 0, 0 };
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int it = 0; it < iterations; ++it) {
         rc = run_waves(ctx, (flags & H264R_REPLAY_H2D) != 0, (flags & H264R_REPLAY_TIME_KERNELS) != 0, ms, launches);
@@ -493,8 +500,8 @@ int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_
     CU(cudaEventSynchronize(ctx->ev1));
     CU(cudaGetLastError());
     CU(cudaEventElapsedTime(&ms[0], ctx->ev0, ctx->ev1));
-    if (ms_out) for (int i = 0; i < 5; ++i) ms_out[i] = ms[i];
-    if (launches_out) for (int i = 0; i < 5; ++i) launches_out[i] = launches[i];
+    if (ms_out) for (int i = 0; i < 6; ++i) ms_out[i] = ms[i];
+    if (launches_out) for (int i = 0; i < 6; ++i) launches_out[i] = launches[i];
     return H264R_OK;
 }
 

@@ -40,9 +40,12 @@ __device__ __forceinline__ void st_release(int* p, int v)
 
 struct MbHdr {
     int mb_type, flags, slice_idx, cbp_luma, cbp_chroma, qp_y, qp_c[2], i16mode, cmode, cbp_blks;
-    uint32_t coeff_slot, u0, u1;          // u0/u1: the 8-byte union (intra modes | sub_mb_type, sub_mb_pred_mode)
+    uint32_t coeff_offset, u0, u1;        // u0/u1: the 8-byte union (intra modes | sub_mb_type, sub_mb_pred_mode)
+    int coeff_count;
     __device__ __forceinline__ bool intra() const { return flags & H264R_MB_FLAG_INTRA; }
     __device__ __forceinline__ bool t8() const { return flags & H264R_MB_FLAG_T8x8; }
+    // a residual plane exists for this MB (written by residual_kernel)
+    __device__ __forceinline__ bool has_resid() const { return coeff_count > 0 && mb_type != H264R_MB_IPCM; }
 };
 
 __device__ __forceinline__ MbHdr load_hdr(const h264r_mb* mbs, int addr)
@@ -54,8 +57,8 @@ __device__ __forceinline__ MbHdr load_hdr(const h264r_mb* mbs, int addr)
     h.cbp_luma = a.y & 0xFF; h.cbp_chroma = (a.y >> 8) & 0xFF;
     h.qp_y = (int)(int8_t)(a.y >> 16); h.qp_c[0] = (int)(int8_t)(a.y >> 24);
     h.qp_c[1] = (int)(int8_t)(a.z & 0xFF); h.i16mode = (a.z >> 8) & 0xFF; h.cmode = (a.z >> 16) & 0xFF;
-    h.cbp_blks = a.w & 0xFFFF;
-    h.coeff_slot = b.x; h.u0 = b.y; h.u1 = b.z;
+    h.cbp_blks = a.w & 0xFFFF; h.coeff_count = a.w >> 16;
+    h.coeff_offset = b.x; h.u0 = b.y; h.u1 = b.z;
     return h;
 }
 // first word only: mb_type | flags << 8 | slice_idx << 16
@@ -112,137 +115,136 @@ __device__ __forceinline__ void idct8_1d(int* p, int stride, bool final_pass)
     p[4 * stride] = o4; p[5 * stride] = o5; p[6 * stride] = o6; p[7 * stride] = o7;
 }
 
-__device__ void mb_residual(const MbHdr& h, const h264r_slice* __restrict__ sl, const int16_t* __restrict__ coeffs,
-                            int* res, int lane)
+// residual_kernel: one warp per MB that received levels.  Scatters the dequantised levels into shared memory,
+// runs the DC Hadamards and the inverse transforms, and writes the MB's 384 residual samples (int16, clamped to
+// [-255, 255]: clip(pred + res) cannot tell the difference) to the picture's residual plane.
+struct __align__(16) ResidSmem { int cof[384]; unsigned nz; };
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+residual_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g)
 {
-    if (h.coeff_slot == H264R_NO_COEFF) {
-        for (int i = lane; i < 384; i += 32) res[i] = 0;
-        __syncwarp();
-        return;
-    }
+    __shared__ __align__(16) ResidSmem smem_all[kWarpsPerCta];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nmb = g.width_mbs * g.height_mbs;
+    const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (gw >= (long long)num_pics * nmb) return;
+    const int pic_i = (int)(gw / nmb), addr = (int)(gw - (long long)pic_i * nmb);
+    const DevPicture& pic = pics[pic_i];
+    const MbHdr h = load_hdr(pic.mbs, addr);
+    if (!h.has_resid()) return;
+    ResidSmem& sm = smem_all[warp];
+    int* res = sm.cof;
+    const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
     const int inter = h.intra() ? 0 : 1;
     const bool t8 = h.t8();
     const bool i16 = h.mb_type == H264R_MB_I16x16;
     const int per = h.qp_y / 6, rem = h.qp_y - per * 6;
-    const uint16_t* ls4y = sl->level_scale_4x4[inter][0][rem];
-    const uint16_t* ls8  = sl->level_scale_8x8[inter][rem];
-    const uint4* src = reinterpret_cast<const uint4*>(coeffs + (size_t)h.coeff_slot * H264R_COEFFS_PER_MB);
 
-    for (int v = lane; v < 48; v += 32) {
-        uint4 q = __ldg(src + v);
-        uint32_t w[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            int l = (int)(int16_t)(w[k >> 1] >> ((k & 1) * 16));
-            int p = v * 8 + k, val = 0;
-            if (p < 256) {
-                int x = p & 15, y = p >> 4;
-                if (i16) {
-                    if (((x | y) & 3) == 0) val = l;                                    // DC level, transformed below
-                    else if (l) val = ((l * (int)__ldg(&ls4y[(y & 3) * 4 + (x & 3)])) * (1 << per) + 8) >> 4;
-                } else if (l && ((h.cbp_luma >> ((y >> 3) * 2 + (x >> 3))) & 1)) {
-                    if (t8) val = ((l * (int)__ldg(&ls8[(y & 7) * 8 + (x & 7)])) * (1 << per) + 32) >> 6;
-                    else    val = ((l * (int)__ldg(&ls4y[(y & 3) * 4 + (x & 3)])) * (1 << per) + 8) >> 4;
-                }
-            } else if (h.cbp_chroma) {
-                int c = p - 256, pl = c >> 6, x = c & 7, y = (c >> 3) & 7;
-                if (((x | y) & 3) == 0) val = l;
-                else if (l) {
-                    int qc = h.qp_c[pl], cper = qc / 6, crem = qc - cper * 6;
-                    val = ((l * (int)__ldg(&sl->level_scale_4x4[inter][pl + 1][crem][(y & 3) * 4 + (x & 3)])) * (1 << cper) + 8) >> 4;
-                }
-            }
-            res[p] = val;
-        }
-    }
+    for (int k = 0; k < 3; ++k) reinterpret_cast<int4*>(res)[lane + 32 * k] = make_int4(0, 0, 0, 0);
+    if (lane == 0) sm.nz = 0;
     __syncwarp();
 
-    // DC transforms (transform_luma_dc / transform_chroma_dc)
-    if (i16 && lane == 0) {
-        int c[4][4], e[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) c[i][j] = res[i * 64 + j * 4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int a0 = c[i][0] + c[i][2], a1 = c[i][0] - c[i][2], a2 = c[i][1] - c[i][3], a3 = c[i][1] + c[i][3];
-            e[i][0] = a0 + a3; e[i][1] = a1 + a2; e[i][2] = a1 - a2; e[i][3] = a0 - a3;
+    // scatter: dequantise at coeff_luma_ac / coeff_chroma_ac time (transform.cc:394-456); DC levels stay raw
+    const h264r_level* __restrict__ lv = pic.levels + h.coeff_offset;
+    unsigned nz = 0;                                         // bit b: 4x4 block b (0..15 luma raster, 16..23 chroma) has a level
+    for (int i = lane; i < h.coeff_count; i += 32) {
+        const uint32_t e = __ldg(lv + i);
+        const int p = (int)(e & 0xFFFFu), l = (int)(int16_t)(e >> 16);
+        if (p >= 384 || l == 0) continue;
+        int val = 0;
+        if (p < 256) {
+            const int x = p & 15, y = p >> 4;
+            if (i16) {
+                if (((x | y) & 3) == 0) val = l;
+                else val = ((l * (int)__ldg(&sl->level_scale_4x4[0][0][rem][(y & 3) * 4 + (x & 3)])) * (1 << per) + 8) >> 4;
+            } else if ((h.cbp_luma >> ((y >> 3) * 2 + (x >> 3))) & 1) {                      // quirk 6
+                if (t8) val = ((l * (int)__ldg(&sl->level_scale_8x8[inter][rem][(y & 7) * 8 + (x & 7)])) * (1 << per) + 32) >> 6;
+                else    val = ((l * (int)__ldg(&sl->level_scale_4x4[inter][0][rem][(y & 3) * 4 + (x & 3)])) * (1 << per) + 8) >> 4;
+            }
+            nz |= 1u << ((y >> 2) * 4 + (x >> 2));
+        } else if (h.cbp_chroma) {
+            const int c = p - 256, pl = c >> 6, x = c & 7, y = (c >> 3) & 7;
+            if (((x | y) & 3) == 0) val = l;
+            else {
+                const int qc = h.qp_c[pl], cper = qc / 6, crem = qc - cper * 6;
+                val = ((l * (int)__ldg(&sl->level_scale_4x4[inter][pl + 1][crem][(y & 3) * 4 + (x & 3)])) * (1 << cper) + 8) >> 4;
+            }
+            nz |= 1u << (16 + pl * 4 + (y >> 2) * 2 + (x >> 2));
         }
-        const int scale = (int)__ldg(&sl->level_scale_4x4[0][0][rem][0]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int a0 = e[0][j] + e[2][j], a1 = e[0][j] - e[2][j], a2 = e[1][j] - e[3][j], a3 = e[1][j] + e[3][j];
-            int f[4] = { a0 + a3, a1 + a2, a1 - a2, a0 - a3 };
+        res[p] = val;
+    }
+    nz = __reduce_or_sync(0xFFFFFFFFu, nz);
+    __syncwarp();
+
+    // DC transforms (transform_luma_dc :825-856, transform_chroma_dc :858-910)
+    if (i16) {
+        if (lane == 0) {
+            int c[4][4], e[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                res[i * 64 + j * 4] = h.qp_y >= 36 ? (f[i] * scale) * (1 << (per - 6))
-                                                   : (f[i] * scale + (1 << (5 - per))) >> (6 - per);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[i][j] = res[i * 64 + j * 4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int a0 = c[i][0] + c[i][2], a1 = c[i][0] - c[i][2], a2 = c[i][1] - c[i][3], a3 = c[i][1] + c[i][3];
+                e[i][0] = a0 + a3; e[i][1] = a1 + a2; e[i][2] = a1 - a2; e[i][3] = a0 - a3;
+            }
+            const int scale = (int)__ldg(&sl->level_scale_4x4[0][0][rem][0]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int a0 = e[0][j] + e[2][j], a1 = e[0][j] - e[2][j], a2 = e[1][j] - e[3][j], a3 = e[1][j] + e[3][j];
+                int f[4] = { a0 + a3, a1 + a2, a1 - a2, a0 - a3 };
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    res[i * 64 + j * 4] = h.qp_y >= 36 ? (f[i] * scale) * (1 << (per - 6))
+                                                       : (f[i] * scale + (1 << (5 - per))) >> (6 - per);
+            }
         }
+        nz |= 0xFFFFu;                                       // the DC Hadamard spreads into every luma block
     }
-    if (h.cbp_chroma && (lane == 1 || lane == 2)) {
-        const int pl = lane - 1, qc = h.qp_c[pl], cper = qc / 6, crem = qc - cper * 6;
-        int* c = res + 256 + pl * 64;
-        int c00 = c[0], c01 = c[4], c10 = c[32], c11 = c[36];
-        int e00 = c00 + c01, e01 = c00 - c01, e10 = c10 + c11, e11 = c10 - c11;
-        const int scale = (int)__ldg(&sl->level_scale_4x4[inter][pl + 1][crem][0]);
-        c[0]  = (((e00 + e10) * scale) * (1 << cper)) >> 5;
-        c[4]  = (((e01 + e11) * scale) * (1 << cper)) >> 5;
-        c[32] = (((e00 - e10) * scale) * (1 << cper)) >> 5;
-        c[36] = (((e01 - e11) * scale) * (1 << cper)) >> 5;
+    if (h.cbp_chroma && (nz >> 16)) {
+        if (lane == 1 || lane == 2) {
+            const int pl = lane - 1, qc = h.qp_c[pl], cper = qc / 6, crem = qc - cper * 6;
+            int* c = res + 256 + pl * 64;
+            int c00 = c[0], c01 = c[4], c10 = c[32], c11 = c[36];
+            int e00 = c00 + c01, e01 = c00 - c01, e10 = c10 + c11, e11 = c10 - c11;
+            const int scale = (int)__ldg(&sl->level_scale_4x4[inter][pl + 1][crem][0]);
+            c[0]  = (((e00 + e10) * scale) * (1 << cper)) >> 5;
+            c[4]  = (((e01 + e11) * scale) * (1 << cper)) >> 5;
+            c[32] = (((e00 - e10) * scale) * (1 << cper)) >> 5;
+            c[36] = (((e01 - e11) * scale) * (1 << cper)) >> 5;
+        }
+        nz |= 0xFF0000u;
     }
     __syncwarp();
 
-    // inverse transforms
+    // inverse transforms, only where something is non-zero
     if (t8) {
         const int b = lane >> 3, i = lane & 7;
         int* blk = res + (b >> 1) * 128 + (b & 1) * 8;
-        idct8_1d(blk + i * 16, 1, false);
+        const unsigned m8 = 0x33u << ((b >> 1) * 8 + (b & 1) * 2);          // the four 4x4 blocks of 8x8 block b
+        if (nz & m8) idct8_1d(blk + i * 16, 1, false);
         __syncwarp();
-        idct8_1d(blk + i, 16, true);
-        if (lane < 8) idct4_inplace(res + 256 + (lane >> 2) * 64 + ((lane >> 1) & 1) * 32 + (lane & 1) * 4, 8);
+        if (nz & m8) idct8_1d(blk + i, 16, true);
+        if (lane < 8 && ((nz >> (16 + lane)) & 1)) idct4_inplace(res + 256 + (lane >> 2) * 64 + ((lane >> 1) & 1) * 32 + (lane & 1) * 4, 8);
     } else if (lane < 16) {
-        idct4_inplace(res + (lane >> 2) * 64 + (lane & 3) * 4, 16);
+        if ((nz >> lane) & 1) idct4_inplace(res + (lane >> 2) * 64 + (lane & 3) * 4, 16);
     } else if (lane < 24) {
         const int c = lane - 16;
-        idct4_inplace(res + 256 + (c >> 2) * 64 + ((c >> 1) & 1) * 32 + (c & 1) * 4, 8);
+        if ((nz >> lane) & 1) idct4_inplace(res + 256 + (c >> 2) * 64 + ((c >> 1) & 1) * 32 + (c & 1) * 4, 8);
     }
     __syncwarp();
-}
 
-// out = clip(pred + res) for the whole MB, stored to the frame with 16-byte (luma) / 8-byte (chroma) row stores.
-// pred: 384 bytes (Y 16x16 | Cb 8x8 | Cr 8x8) in shared memory, 16-byte aligned.
-__device__ __forceinline__ void store_mb(const uint8_t* pred, const int* res, uint8_t* dst, const FrameGeom& g,
-                                         int mbx, int mby, int lane)
-{
-    if (lane < 16) {
-        const uint32_t* pw = reinterpret_cast<const uint32_t*>(pred + lane * 16);
-        const int* r = res + lane * 16;
-        uint32_t o[4];
+    // 384 x int16 = 48 x 16 B
+    uint4* out = reinterpret_cast<uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
+    for (int v = lane; v < 48; v += 32) {
+        const int* r = res + v * 8;
+        uint32_t w[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t p = pw[k];
-            o[k] = (uint32_t)clip255((int)(p & 0xFF) + r[k * 4])
-                 | (uint32_t)clip255((int)((p >> 8) & 0xFF) + r[k * 4 + 1]) << 8
-                 | (uint32_t)clip255((int)((p >> 16) & 0xFF) + r[k * 4 + 2]) << 16
-                 | (uint32_t)clip255((int)(p >> 24) + r[k * 4 + 3]) << 24;
-        }
-        *reinterpret_cast<uint4*>(dst + (size_t)(mby * 16 + lane) * g.pitch_y + mbx * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-    } else {
-        const int c = lane - 16, pl = c >> 3, row = c & 7;
-        const uint32_t* pw = reinterpret_cast<const uint32_t*>(pred + 256 + pl * 64 + row * 8);
-        const int* r = res + 256 + pl * 64 + row * 8;
-        uint32_t o[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            uint32_t p = pw[k];
-            o[k] = (uint32_t)clip255((int)(p & 0xFF) + r[k * 4])
-                 | (uint32_t)clip255((int)((p >> 8) & 0xFF) + r[k * 4 + 1]) << 8
-                 | (uint32_t)clip255((int)((p >> 16) & 0xFF) + r[k * 4 + 2]) << 16
-                 | (uint32_t)clip255((int)(p >> 24) + r[k * 4 + 3]) << 24;
-        }
-        uint8_t* base = dst + (pl ? g.off_cr : g.off_cb);
-        *reinterpret_cast<uint2*>(base + (size_t)(mby * 8 + row) * g.pitch_c + mbx * 8) = make_uint2(o[0], o[1]);
+        for (int k = 0; k < 4; ++k)
+            w[k] = (uint32_t)(uint16_t)(int16_t)clip3i(-255, 255, r[2 * k]) | (uint32_t)(uint16_t)(int16_t)clip3i(-255, 255, r[2 * k + 1]) << 16;
+        out[v] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -251,13 +253,13 @@ __device__ __forceinline__ void store_mb(const uint8_t* pred, const int* res, ui
 
 __constant__ int8_t c_block_step[8][2] = { {0,0}, {4,4}, {4,2}, {2,4}, {2,2}, {2,1}, {1,2}, {1,1} };
 
-// Decoder::mb_pred_inter partition walk (decoder.cc:217-262) for 4x4 block `blk`: returns the block whose
-// motion entry the reference reads (partition origin) and the prediction direction.
-__device__ __forceinline__ void partition_of_block(const MbHdr& h, const h264r_slice* sl, const h264r_mb_motion* m,
-                                                   int direct8x8, int blk, int& origin, int& dir)
+// Decoder::mb_pred_inter partition walk (decoder.cc:217-262) for 4x4 block `blk`: returns the block whose motion
+// entry the reference reads (partition origin), the prediction direction, and whether the partition covers the
+// whole 8x8 quadrant of the block.
+__device__ __forceinline__ void partition_of_block(const MbHdr& h, int is_b, int direct_spatial, const h264r_mb_motion* m,
+                                                   int direct8x8, int blk, int& origin, int& dir, bool& covers8x8)
 {
     const int bx = blk & 3, by = blk >> 2;
-    const bool is_b = __ldg(&sl->slice_type) == H264R_B_SLICE;
     int sh0 = c_block_step[h.mb_type & 7][0], sv0 = c_block_step[h.mb_type & 7][1];
     if (h.mb_type == 0) sh0 = sv0 = is_b ? 2 : 4;
     const int i0 = bx & ~(sh0 - 1), j0 = by & ~(sv0 - 1);
@@ -266,107 +268,136 @@ __device__ __forceinline__ void partition_of_block(const MbHdr& h, const h264r_s
     int pd = (h.u1 >> (8 * b8)) & 0xFF;
     int sh4 = c_block_step[mode & 7][0], sv4 = c_block_step[mode & 7][1];
     if (mode == 0) sh4 = sv4 = direct8x8 ? 2 : 1;
-    if (is_b && h.mb_type == H264R_MB_8x8 && __ldg(&sl->direct_spatial_mv_pred_flag)) {
+    if (is_b && h.mb_type == H264R_MB_8x8 && direct_spatial) {
         const int b = j0 * 4 + i0;
         pd = m->ref_idx[1][b] < 0 ? 0 : (m->ref_idx[0][b] < 0 ? 1 : 2);
     }
-    // partitions tile the (i0, j0) block from its origin in steps (sh4, sv4)
-    const int i = i0 + ((bx - i0) / sh4) * sh4, j = j0 + ((by - j0) / sv4) * sv4;
+    const int i = bx & ~(sh4 - 1), j = by & ~(sv4 - 1);   // partitions are aligned to their own size
     origin = j * 4 + i;
     dir = pd;
+    covers8x8 = sh4 >= 2 && sv4 >= 2;
 }
 
-// Luma interpolation of rows r0, r0+1 (4 samples each) of a 4x4 block from its 9x9 window (window origin =
-// integer position - 2).  get_block_luma, inter_prediction.cc:158-340.
-__device__ __forceinline__ void luma_half_block(const uint8_t* w, int xf, int yf, int r0, int out[8])
+// Luma interpolation of a 4x2 patch (get_block_luma, inter_prediction.cc:158-340).  w points at the window byte of
+// integer sample (0, 0) of the patch; the window holds 2 more samples to the left/top and 3 to the right/bottom.
+// Results are 8-bit samples, packed little-endian: out0 = row 0, out1 = row 1.  One copy of this code per kernel.
+__device__ __noinline__ void luma_patch_4x2(const uint8_t* w, int pitch, int xf, int yf, uint32_t& out0, uint32_t& out1)
 {
-#define WIN(x, y) ((int)w[((y) + 2) * 9 + (x) + 2])
+#define WIN(x, y) ((int)w[(y) * pitch + (x)])
+    int o[8];
     if ((xf | yf) == 0) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int y = 0; y < 2; ++y)
 #pragma unroll
-            for (int x = 0; x < 4; ++x) out[r * 4 + x] = WIN(x, r0 + r);
-        return;
-    }
-    if (yf == 0) {
+            for (int x = 0; x < 4; ++x) o[y * 4 + x] = WIN(x, y);
+    } else if (yf == 0 || ((xf & 1) && (yf & 1))) {
+        // horizontal half sample b (row + dy), alone, averaged with an integer sample, or with the vertical half sample h
+        const int dy = (yf == 3), dx = (xf == 3);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int y = r0 + r;
+        for (int y = 0; y < 2; ++y) {
+            int r[9];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                int b = clip255((tap6(WIN(x - 2, y), WIN(x - 1, y), WIN(x, y), WIN(x + 1, y), WIN(x + 2, y), WIN(x + 3, y)) + 16) >> 5);
-                out[r * 4 + x] = xf == 2 ? b : (WIN(x + (xf == 3), y) + b + 1) >> 1;
-            }
-        }
-        return;
-    }
-    if (xf == 0) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int y = r0 + r;
+            for (int x = 0; x < 9; ++x) r[x] = WIN(x - 2, y + dy);
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                int hh = clip255((tap6(WIN(x, y - 2), WIN(x, y - 1), WIN(x, y), WIN(x, y + 1), WIN(x, y + 2), WIN(x, y + 3)) + 16) >> 5);
-                out[r * 4 + x] = yf == 2 ? hh : (WIN(x, y + (yf == 3)) + hh + 1) >> 1;
+                int b = clip255((tap6(r[x], r[x + 1], r[x + 2], r[x + 3], r[x + 4], r[x + 5]) + 16) >> 5);
+                if (yf == 0) o[y * 4 + x] = xf == 2 ? b : ((dx ? r[x + 3] : r[x + 2]) + b + 1) >> 1;
+                else o[y * 4 + x] = b;
             }
         }
-        return;
-    }
-    if ((xf & 1) && (yf & 1)) {
-        const int dy = yf == 3, dx = xf == 3;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int y = r0 + r;
+        if (yf != 0) {
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
-                int b = clip255((tap6(WIN(x - 2, y + dy), WIN(x - 1, y + dy), WIN(x, y + dy), WIN(x + 1, y + dy), WIN(x + 2, y + dy), WIN(x + 3, y + dy)) + 16) >> 5);
-                int hh = clip255((tap6(WIN(x + dx, y - 2), WIN(x + dx, y - 1), WIN(x + dx, y), WIN(x + dx, y + 1), WIN(x + dx, y + 2), WIN(x + dx, y + 3)) + 16) >> 5);
-                out[r * 4 + x] = (b + hh + 1) >> 1;
+                int c[7];
+#pragma unroll
+                for (int y = 0; y < 7; ++y) c[y] = WIN(x + dx, y - 2);
+#pragma unroll
+                for (int y = 0; y < 2; ++y) {
+                    int hh = clip255((tap6(c[y], c[y + 1], c[y + 2], c[y + 3], c[y + 4], c[y + 5]) + 16) >> 5);
+                    o[y * 4 + x] = (o[y * 4 + x] + hh + 1) >> 1;
+                }
             }
         }
-        return;
-    }
-    // centre sample j (and f, q / i, k): horizontal 6-tap on 7 rows, then vertical 6-tap on the unrounded sums
-    int b1[7][4];
-#pragma unroll
-    for (int rr = 0; rr < 7; ++rr) {
-        const int y = r0 - 2 + rr;
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-            b1[rr][x] = tap6(WIN(x - 2, y), WIN(x - 1, y), WIN(x, y), WIN(x + 1, y), WIN(x + 2, y), WIN(x + 3, y));
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int y = r0 + r;
+    } else if (xf == 0) {
+        const int dy = yf == 3;
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
-            int j = clip255((tap6(b1[r][x], b1[r + 1][x], b1[r + 2][x], b1[r + 3][x], b1[r + 4][x], b1[r + 5][x]) + 512) >> 10);
-            int v = j;
-            if (xf == 2 && yf != 2) {
-                int q = clip255(((yf == 3 ? b1[r + 3][x] : b1[r + 2][x]) + 16) >> 5);
-                v = (j + q + 1) >> 1;
-            } else if (yf == 2 && xf != 2) {
-                const int dx = xf == 3;
-                int q = clip255((tap6(WIN(x + dx, y - 2), WIN(x + dx, y - 1), WIN(x + dx, y), WIN(x + dx, y + 1), WIN(x + dx, y + 2), WIN(x + dx, y + 3)) + 16) >> 5);
-                v = (j + q + 1) >> 1;
+            int c[7];
+#pragma unroll
+            for (int y = 0; y < 7; ++y) c[y] = WIN(x, y - 2);
+#pragma unroll
+            for (int y = 0; y < 2; ++y) {
+                int hh = clip255((tap6(c[y], c[y + 1], c[y + 2], c[y + 3], c[y + 4], c[y + 5]) + 16) >> 5);
+                o[y * 4 + x] = yf == 2 ? hh : ((dy ? c[y + 3] : c[y + 2]) + hh + 1) >> 1;
             }
-            out[r * 4 + x] = v;
         }
+    } else {
+        // centre sample j (and f, q / i, k): horizontal 6-tap on 7 rows, then vertical 6-tap on the unrounded sums
+        int b1[7][4];
+#pragma unroll
+        for (int rr = 0; rr < 7; ++rr) {
+            int r[9];
+#pragma unroll
+            for (int x = 0; x < 9; ++x) r[x] = WIN(x - 2, rr - 2);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) b1[rr][x] = tap6(r[x], r[x + 1], r[x + 2], r[x + 3], r[x + 4], r[x + 5]);
+        }
+#pragma unroll
+        for (int y = 0; y < 2; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                int j = clip255((tap6(b1[y][x], b1[y + 1][x], b1[y + 2][x], b1[y + 3][x], b1[y + 4][x], b1[y + 5][x]) + 512) >> 10);
+                int v = j;
+                if (xf == 2 && yf != 2) {
+                    int q = clip255(((yf == 3 ? b1[y + 3][x] : b1[y + 2][x]) + 16) >> 5);
+                    v = (j + q + 1) >> 1;
+                } else if (yf == 2 && xf != 2) {
+                    const int dx = xf == 3;
+                    int q = clip255((tap6(WIN(x + dx, y - 2), WIN(x + dx, y - 1), WIN(x + dx, y), WIN(x + dx, y + 1), WIN(x + dx, y + 2), WIN(x + dx, y + 3)) + 16) >> 5);
+                    v = (j + q + 1) >> 1;
+                }
+                o[y * 4 + x] = v;
+            }
     }
 #undef WIN
+    out0 = (uint32_t)o[0] | (uint32_t)o[1] << 8 | (uint32_t)o[2] << 16 | (uint32_t)o[3] << 24;
+    out1 = (uint32_t)o[4] | (uint32_t)o[5] << 8 | (uint32_t)o[6] << 16 | (uint32_t)o[7] << 24;
 }
 
-struct InterSmem {
-    int      res[384];
-    uint8_t  pred[384];
-    h264r_mb_motion motion;                       // 192 B
-    uint8_t  win[16][84];                         // 9x9 luma window per 4x4 block (81, padded)
-    uint8_t  cwin[16][2][12];                     // 3x3 chroma window per block and plane (9, padded)
+// Reference window: rows [y0, y0+nrows) x bytes [x0, x0+ncols) of a plane go to shared memory with row pitch `wp`.
+// Interior windows are fetched as aligned 32-bit words (the sample x0 then sits at byte offset x0 & 3 of a window
+// row); windows touching the picture border are fetched sample by sample with clamped coordinates (== the
+// reference's padded planes) and start at byte offset 0.
+__device__ __forceinline__ bool window_interior(int x0, int y0, int ncols, int nrows, int W, int H)
+{
+    const int xa = x0 & ~3;
+    return xa >= 0 && xa + (((x0 - xa) + ncols + 3) & ~3) <= W && y0 >= 0 && y0 + nrows <= H;
+}
+__device__ __forceinline__ void load_window_row(uint8_t* win_row, const uint8_t* __restrict__ plane, int pitch, int W, int H,
+                                                int x0, int y, int ncols, bool interior)
+{
+    if (interior) {
+        const int xa = x0 & ~3, nwords = ((x0 - xa) + ncols + 3) >> 2;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(plane + (size_t)y * pitch + xa);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(win_row);
+        for (int k = 0; k < nwords; ++k) dst[k] = __ldg(src + k);
+    } else {
+        const uint8_t* src = plane + (size_t)clip3i(0, H - 1, y) * pitch;
+        for (int c = 0; c < ncols; ++c) win_row[c] = __ldg(src + clip3i(0, W - 1, x0 + c));
+    }
+}
+
+// per-warp scratch: 4 quadrants x { luma window, chroma windows }.  uniform quadrant: luma 13 rows x 16 B,
+// chroma 2 planes x 5 rows x 8 B; split quadrant: 4 blocks x (9 rows x 12 B) luma, 4 blocks x 2 planes x (3 rows x 8 B)
+struct __align__(16) InterSmem {
+    __align__(16) uint8_t luma[4][448];
+    __align__(16) uint8_t chroma[4][192];
+    h264r_mb_motion motion;
 };
 
 __device__ __forceinline__ int rshift_rnd(int x, int a) { return a > 0 ? (x + (1 << (a - 1))) >> a : x; }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 6)
 recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g, int direct8x8)
 {
     __shared__ __align__(16) InterSmem smem_all[kWarpsPerCta];
@@ -380,106 +411,153 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
     const MbHdr h = load_hdr(pic.mbs, addr);
     if (h.intra()) return;
     InterSmem& sm = smem_all[warp];
-    const h264r_slice* sl = pic.slices + h.slice_idx;
+    const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
     const int mbx = addr % g.width_mbs, mby = addr / g.width_mbs;
     const int wY = g.width_mbs * 16, hY = g.height_mbs * 16, wC = wY >> 1, hC = hY >> 1;
 
-    // motion -> shared (192 B = 12 x uint4)
     if (lane < 12) reinterpret_cast<uint4*>(&sm.motion)[lane] = __ldg(reinterpret_cast<const uint4*>(pic.motion + addr) + lane);
+    // slice-level parameters (one 12-byte read, broadcast)
+    const uint32_t s0 = __ldg(reinterpret_cast<const uint32_t*>(sl)), s1 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 1),
+                   s2 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 2);
+    const bool is_b = (s0 & 0xFF) == H264R_B_SLICE;
+    const int denom_y = s1 & 0xFF, denom_c = (s1 >> 8) & 0xFF, wp_flag = (s1 >> 16) & 0xFF, bipred_idc = (s1 >> 24) & 0xFF;
+    const int direct_spatial = (s2 >> 8) & 0xFF;
     __syncwarp();
 
-    const int blk = lane >> 1, half = lane & 1;
-    const int bx = blk & 3, by = blk >> 2;
-    int origin, pd;
-    partition_of_block(h, sl, &sm.motion, direct8x8, blk, origin, pd);
+    // lanes 8q..8q+7 work on 8x8 quadrant q: lane r = 4x4 block sb = r>>1 of the quadrant, luma rows 2*(r&1)..+1 (a 4x2
+    // patch) and the block's 2x2 chroma patch of plane r&1.  If one partition covers the quadrant ("uniform") the eight
+    // lanes share one 13x13 luma / 5x5 chroma window; otherwise every block has its own 9x9 / 3x3 window.
+    const int q = lane >> 3, r = lane & 7, qx = q & 1, qy = q >> 1;
+    const int sb = r >> 1, half = r & 1;
+    const int blk = (qy * 2 + (sb >> 1)) * 4 + qx * 2 + (sb & 1);
+    int origin, pd; bool uni;
+    partition_of_block(h, is_b, direct_spatial, &sm.motion, direct8x8, qy * 8 + qx * 2, origin, pd, uni);
+    if (!uni) { bool dummy; partition_of_block(h, is_b, direct_spatial, &sm.motion, direct8x8, blk, origin, pd, dummy); }
 
-    int luma[2][8], chroma[2][4], refidx[2] = { 0, 0 };
+    // residual of this lane's samples (issued early; consumed at the end)
+    const int lx = (blk & 3) * 4, ly = (blk >> 2) * 4 + half * 2;          // luma position in the MB
+    const int cxx = (blk & 3) * 2, cyy = (blk >> 2) * 2;                    // chroma position in the MB (plane `half`)
+    uint2 resY0 = make_uint2(0, 0), resY1 = make_uint2(0, 0); uint32_t resC0 = 0, resC1 = 0;
+    if (h.has_resid()) {
+        const int16_t* __restrict__ rs = pic.resid + (size_t)addr * H264R_COEFFS_PER_MB;
+        resY0 = __ldg(reinterpret_cast<const uint2*>(rs + ly * 16 + lx));
+        resY1 = __ldg(reinterpret_cast<const uint2*>(rs + (ly + 1) * 16 + lx));
+        resC0 = __ldg(reinterpret_cast<const uint32_t*>(rs + 256 + half * 64 + cyy * 8 + cxx));
+        resC1 = __ldg(reinterpret_cast<const uint32_t*>(rs + 256 + half * 64 + (cyy + 1) * 8 + cxx));
+    }
+
+    // samples of the (up to) two lists, packed bytes: cur = last list done, prev = the one before
+    uint32_t curY0 = 0, curY1 = 0, curC = 0, prevY0 = 0, prevY1 = 0, prevC = 0;
+    int ref_cur = 0, ref_prev = 0;
+#pragma unroll 1
     for (int k = 0; k < 2; ++k) {
         const bool active = k == 0 || pd == 2;
         const int list = pd == 2 ? k : pd;
-        int vx = 0, vy = 0;
-        const uint8_t* rbase = nullptr;
+        int vx = 0, vy = 0, refidx = 0;
+        const uint8_t* wl = nullptr; const uint8_t* wc = nullptr;
+        int wpitch = 16;
         if (active) {
-            refidx[k] = sm.motion.ref_idx[list][origin];
-            const int slot = (int)(int8_t)__ldg(&sl->ref_pic_list[list][refidx[k] & 31]);
-            rbase = pic.ref[slot & 31];
-            vx = (mbx * 4 + bx) * 16 + sm.motion.mv[list][origin][0];
-            vy = (mby * 4 + by) * 16 + sm.motion.mv[list][origin][1];
-            // luma window: rows half, half+2, ... of the 9x9 window
-            const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2;
-            for (int wy = half; wy < 9; wy += 2) {
-                const uint8_t* row = rbase + (size_t)clip3i(0, hY - 1, y0 + wy) * g.pitch_y;
-#pragma unroll
-                for (int wx = 0; wx < 9; ++wx) sm.win[blk][wy * 9 + wx] = __ldg(row + clip3i(0, wC * 2 - 1, x0 + wx));
-            }
-            // chroma window of plane `half`
-            const uint8_t* cb = rbase + (half ? g.off_cr : g.off_cb);
-            const int cx0 = vx >> 3, cy0 = vy >> 3;
-#pragma unroll
-            for (int wy = 0; wy < 3; ++wy) {
-                const uint8_t* row = cb + (size_t)clip3i(0, hC - 1, cy0 + wy) * g.pitch_c;
-#pragma unroll
-                for (int wx = 0; wx < 3; ++wx) sm.cwin[blk][half][wy * 3 + wx] = __ldg(row + clip3i(0, wC - 1, cx0 + wx));
+            refidx = sm.motion.ref_idx[list][origin];
+            const int slot = (int)(int8_t)__ldg(&sl->ref_pic_list[list][refidx & 31]);
+            const uint8_t* __restrict__ rbase = pic.ref[slot & 31];
+            const int mvx = sm.motion.mv[list][origin][0], mvy = sm.motion.mv[list][origin][1];
+            vx = (mbx * 16 + lx) * 4 + mvx; vy = (mby * 16 + (blk >> 2) * 4) * 4 + mvy;        // this block's position
+            if (uni) {
+                const int qvx = (mbx * 16 + qx * 8) * 4 + mvx, qvy = (mby * 16 + qy * 8) * 4 + mvy;
+                const int x0 = (qvx >> 2) - 2, y0 = (qvy >> 2) - 2, cx0 = qvx >> 3, cy0 = qvy >> 3;
+                const bool in_y = window_interior(x0, y0, 13, 13, wY, hY), in_c = window_interior(cx0, cy0, 5, 5, wC, hC);
+                for (int row = r; row < 13; row += 8)
+                    load_window_row(sm.luma[q] + row * 16, rbase, g.pitch_y, wY, hY, x0, y0 + row, 13, in_y);
+                for (int i = r; i < 10; i += 8) {               // chroma: 2 planes x 5 rows over 8 lanes
+                    const int pl = i >= 5, row = i - pl * 5;
+                    load_window_row(sm.chroma[q] + pl * 96 + row * 8, rbase + (pl ? g.off_cr : g.off_cb), g.pitch_c, wC, hC,
+                                    cx0, cy0 + row, 5, in_c);
+                }
+                wl = sm.luma[q] + ((sb >> 1) * 4 + half * 2 + 2) * 16 + (sb & 1) * 4 + 2 + (in_y ? x0 & 3 : 0);
+                wc = sm.chroma[q] + half * 96 + (sb >> 1) * 2 * 8 + (sb & 1) * 2 + (in_c ? cx0 & 3 : 0);
+            } else {
+                const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2, cx0 = vx >> 3, cy0 = vy >> 3;
+                const bool in_y = window_interior(x0, y0, 9, 9, wY, hY), in_c = window_interior(cx0, cy0, 3, 3, wC, hC);
+                for (int row = half; row < 9; row += 2)
+                    load_window_row(sm.luma[q] + sb * 108 + row * 12, rbase, g.pitch_y, wY, hY, x0, y0 + row, 9, in_y);
+                for (int row = 0; row < 3; ++row)
+                    load_window_row(sm.chroma[q] + sb * 48 + half * 24 + row * 8, rbase + (half ? g.off_cr : g.off_cb), g.pitch_c, wC, hC,
+                                    cx0, cy0 + row, 3, in_c);
+                wl = sm.luma[q] + sb * 108 + (half * 2 + 2) * 12 + 2 + (in_y ? x0 & 3 : 0);
+                wc = sm.chroma[q] + sb * 48 + half * 24 + (in_c ? cx0 & 3 : 0);
+                wpitch = 12;
             }
         }
         __syncwarp();
         if (active) {
-            luma_half_block(sm.win[blk], vx & 3, vy & 3, half * 2, luma[k]);
-            const uint8_t* cw = sm.cwin[blk][half];
+            prevY0 = curY0; prevY1 = curY1; prevC = curC; ref_prev = ref_cur; ref_cur = refidx;
+            luma_patch_4x2(wl, wpitch, vx & 3, vy & 3, curY0, curY1);
             const int xf = vx & 7, yf = vy & 7;
+            curC = 0;
 #pragma unroll
             for (int y = 0; y < 2; ++y)
 #pragma unroll
-                for (int x = 0; x < 2; ++x)
-                    chroma[k][y * 2 + x] = ((8 - xf) * (8 - yf) * cw[y * 3 + x] + xf * (8 - yf) * cw[y * 3 + x + 1] +
-                                            (8 - xf) * yf * cw[(y + 1) * 3 + x] + xf * yf * cw[(y + 1) * 3 + x + 1] + 32) >> 6;
+                for (int x = 0; x < 2; ++x) {
+                    const int v = ((8 - xf) * (8 - yf) * wc[y * 8 + x] + xf * (8 - yf) * wc[y * 8 + x + 1] +
+                                   (8 - xf) * yf * wc[(y + 1) * 8 + x] + xf * yf * wc[(y + 1) * 8 + x + 1] + 32) >> 6;
+                    curC |= (uint32_t)v << ((y * 2 + x) * 8);
+                }
         }
         __syncwarp();
     }
 
-    // weighted sample prediction (mc_prediction / bi_prediction, inter_prediction.cc:53-156)
-    {
-        const bool is_b = __ldg(&sl->slice_type) == H264R_B_SLICE;
-        const int wp_flag = __ldg(&sl->weighted_pred_flag), bipred_idc = __ldg(&sl->weighted_bipred_idc);
-        const bool uni_weighted = (wp_flag && !is_b) || (bipred_idc == 1 && is_b);
-        for (int part = 0; part < 2; ++part) {            // 0: luma (this lane's 8 samples), 1: chroma plane `half` (4 samples)
-            const int pl = part ? 1 + half : 0;
-            const int n = part ? 4 : 8;
-            const int denom = pl ? __ldg(&sl->chroma_log2_weight_denom) : __ldg(&sl->luma_log2_weight_denom);
-            int w0 = 0, w1 = 0, o0 = 0, o1 = 0;
-            int mode;                                      // 0 copy, 1 uni weighted, 2 bi average, 3 bi weighted
-            if (pd != 2) {
-                mode = uni_weighted ? 1 : 0;
-                if (uni_weighted) {
-                    w0 = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][refidx[0] & 31]);
-                    o0 = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][refidx[0] & 31]);
-                }
-            } else if (bipred_idc == 0) mode = 2;
-            else {
-                mode = 3;
-                if (bipred_idc == 1) {
-                    w0 = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][refidx[0] & 31]); w1 = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][refidx[1] & 31]);
-                    o0 = (int)(int8_t)__ldg(&sl->wp_offset[0][pl][refidx[0] & 31]); o1 = (int)(int8_t)__ldg(&sl->wp_offset[1][pl][refidx[1] & 31]);
-                } else {
-                    w1 = (int)__ldg(&sl->implicit_w1[refidx[0] & 31][refidx[1] & 31]); w0 = 64 - w1;
-                }
+    // weighted sample prediction (mc_prediction / bi_prediction, inter_prediction.cc:53-156), residual, store
+    const bool uni_weighted = (wp_flag && !is_b) || (bipred_idc == 1 && is_b);
+    const int ref0 = pd == 2 ? ref_prev : ref_cur, ref1 = ref_cur;
+    uint32_t outw[3] = { 0, 0, 0 };                            // 4x2 luma + 2x2 chroma bytes
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const int pl = part ? 1 + half : 0;
+        const int denom = part ? denom_c : denom_y;
+        int w0 = 0, w1 = 0, o0 = 0, o1 = 0, mode;              // mode 0 copy, 1 uni weighted, 2 bi average, 3 bi weighted
+        if (pd != 2) {
+            mode = uni_weighted ? 1 : 0;
+            if (uni_weighted) {
+                w0 = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][ref0 & 31]);
+                o0 = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][ref0 & 31]);
             }
-            for (int i = 0; i < n; ++i) {
-                const int s0 = part ? chroma[0][i] : luma[0][i];
-                const int s1 = part ? chroma[1][i] : luma[1][i];
-                int v;
-                if (mode == 0) v = s0;
-                else if (mode == 1) v = clip255(rshift_rnd(w0 * s0, denom) + o0);
-                else if (mode == 2) v = (s0 + s1 + 1) >> 1;
-                else v = clip255(rshift_rnd(w0 * s0 + w1 * s1, denom + 1) + ((o0 + o1 + 1) >> 1));
-                if (part == 0) sm.pred[(by * 4 + half * 2 + (i >> 2)) * 16 + bx * 4 + (i & 3)] = (uint8_t)v;
-                else           sm.pred[256 + half * 64 + (by * 2 + (i >> 1)) * 8 + bx * 2 + (i & 1)] = (uint8_t)v;
+        } else if (bipred_idc == 0) mode = 2;
+        else {
+            mode = 3;
+            if (bipred_idc == 1) {
+                w0 = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][ref0 & 31]); w1 = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][ref1 & 31]);
+                o0 = (int)(int8_t)__ldg(&sl->wp_offset[0][pl][ref0 & 31]); o1 = (int)(int8_t)__ldg(&sl->wp_offset[1][pl][ref1 & 31]);
+            } else {
+                w1 = (int)__ldg(&sl->implicit_w1[ref0 & 31][ref1 & 31]); w0 = 64 - w1;
             }
         }
+        const int n = part ? 4 : 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i >= n) break;
+            // sample i of list 0 / list 1 and its residual
+            const uint32_t a0 = part ? (pd == 2 ? prevC : curC) : (i < 4 ? (pd == 2 ? prevY0 : curY0) : (pd == 2 ? prevY1 : curY1));
+            const uint32_t a1 = part ? curC : (i < 4 ? curY0 : curY1);
+            const int s0v = (a0 >> ((i & 3) * 8)) & 0xFF, s1v = (a1 >> ((i & 3) * 8)) & 0xFF;
+            uint32_t rw;
+            if (part) rw = (i < 2 ? resC0 : resC1) >> ((i & 1) * 16);
+            else rw = (i < 4 ? (i < 2 ? resY0.x : resY0.y) : (i < 6 ? resY1.x : resY1.y)) >> ((i & 1) * 16);
+            int v;
+            if (mode == 0) v = s0v;
+            else if (mode == 1) v = clip255(rshift_rnd(w0 * s0v, denom) + o0);
+            else if (mode == 2) v = (s0v + s1v + 1) >> 1;
+            else v = clip255(rshift_rnd(w0 * s0v + w1 * s1v, denom + 1) + ((o0 + o1 + 1) >> 1));
+            v = clip255(v + (int)(int16_t)(rw & 0xFFFF));
+            if (part == 0) outw[i >> 2] |= (uint32_t)v << ((i & 3) * 8);
+            else outw[2] |= (uint32_t)v << (i * 8);
+        }
     }
-
-    mb_residual(h, sl, pic.coeffs, sm.res, lane);          // ends with __syncwarp: pred + res visible
-    store_mb(sm.pred, sm.res, pic.dst, g, mbx, mby, lane);
+    uint8_t* dY = pic.dst + (size_t)(mby * 16 + ly) * g.pitch_y + mbx * 16 + lx;
+    uint8_t* dC = pic.dst + (half ? g.off_cr : g.off_cb) + (size_t)(mby * 8 + cyy) * g.pitch_c + mbx * 8 + cxx;
+    *reinterpret_cast<uint32_t*>(dY) = outw[0];
+    *reinterpret_cast<uint32_t*>(dY + g.pitch_y) = outw[1];
+    *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(outw[2] & 0xFFFF);
+    *reinterpret_cast<uint16_t*>(dC + g.pitch_c) = (uint16_t)(outw[2] >> 16);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -516,8 +594,8 @@ __device__ __forceinline__ void wait_row_cached(const int* progress_above, int n
 
 // luma tile: rows -1..15, cols -4..27 -> index (y+1)*32 + (x+4); 17 rows x 32 B
 // chroma tile per plane: rows -1..7, cols -4..11 -> index (y+1)*16 + (x+4); 9 rows x 16 B
-struct IntraSmem {
-    int      res[384];
+struct __align__(16) IntraSmem {
+    __align__(16) int16_t res[384];              // this MB's residual (zero when it has none)
     __align__(16) uint8_t ty[17 * 32];
     __align__(16) uint8_t tc[2][9 * 16];
     uint8_t  ft[20], fl[12];                     // Intra8x8 filtered reference samples: ft[i+1] = p'(i,-1), fl[i+1] = p'(-1,i)
@@ -660,11 +738,15 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
         const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
 
         if (h.mb_type == H264R_MB_IPCM) {                 // mb_pred_ipcm, decoder.cc:149-168
-            const int16_t* c = pic.coeffs + (size_t)h.coeff_slot * H264R_COEFFS_PER_MB;
-            for (int p = lane; p < 256; p += 32) dY[(size_t)(py + (p >> 4)) * g.pitch_y + px + (p & 15)] = (uint8_t)__ldg(c + p);
-            for (int p = lane; p < 128; p += 32) {
-                const int pl = p >> 6, q = p & 63;
-                dC[pl][(size_t)(cy + (q >> 3)) * g.pitch_c + cx + (q & 7)] = (uint8_t)__ldg(c + 256 + p);
+            const h264r_level* __restrict__ lv = pic.levels + h.coeff_offset;
+            for (int i = lane; i < h.coeff_count; i += 32) {
+                const uint32_t e = __ldg(lv + i);
+                const int p = (int)(e & 0xFFFFu), v = (int)(e >> 16) & 0xFF;
+                if (p < 256) dY[(size_t)(py + (p >> 4)) * g.pitch_y + px + (p & 15)] = (uint8_t)v;
+                else if (p < 384) {
+                    const int pl = (p - 256) >> 6, q = (p - 256) & 63;
+                    dC[pl][(size_t)(cy + (q >> 3)) * g.pitch_c + cx + (q & 7)] = (uint8_t)v;
+                }
             }
             publish_row(progress + mby, done_to, lane, true);
             continue;                                      // next intra MB of the chunk
@@ -696,7 +778,13 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
             if (lane < 16) TY(-1, lane) = ldcg_u8(dY + (size_t)(py + lane) * g.pitch_y + px - 1);
             else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = ldcg_u8(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx - 1); }
         }
-        mb_residual(h, sl, pic.coeffs, sm.res, lane);      // ends with __syncwarp (tiles visible too)
+        {   // residual plane written by residual_kernel (48 x 16 B), or zeros
+            const uint4* rsrc = reinterpret_cast<const uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
+            const bool has = h.has_resid();
+            for (int v = lane; v < 48; v += 32)
+                reinterpret_cast<uint4*>(sm.res)[v] = has ? __ldg(rsrc + v) : make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();                                      // tiles and residual visible
 
         // ---- luma ----
         if (h.mb_type == H264R_MB_I16x16) {
@@ -1149,6 +1237,11 @@ bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     const int nmb = w.geom.width_mbs * w.geom.height_mbs;
     const int threads = kWarpsPerCta * 32;
     const int groups = (w.geom.height_mbs + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (which == KERNEL_RESID) {
+        const long long warps = (long long)w.num_pics * nmb;
+        residual_kernel<<<(int)((warps + kWarpsPerCta - 1) / kWarpsPerCta), threads, 0, stream>>>(w.pics, w.num_pics, w.geom);
+        return true;
+    }
     if (which == KERNEL_INTER) {
         if (!w.any_inter) return false;
         const long long warps = (long long)w.num_pics * nmb;

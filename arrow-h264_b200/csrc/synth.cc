@@ -129,8 +129,11 @@ struct Gen {
     h264r_mb* mbs;
     h264r_mb_motion* motion;
     h264r_slice* slices;
-    int16_t* coeffs;
-    uint32_t n_slots;
+    int16_t dense[H264R_COEFFS_PER_MB];   // the current MB's levels at raster positions (scratch)
+    bool     dense_used;
+    h264r_level* levels;
+    uint32_t n_levels, level_capacity;
+    bool     overflow;
     int num_slices;
     int slice_first_mb[4];
     int qp;                           // running QpY
@@ -204,10 +207,27 @@ bool fill_block8x8(Gen& g, int16_t* dst, int stride, int qp)
     return any;
 }
 
-int16_t* take_slot(Gen& g, h264r_mb& mb)
+int16_t* take_slot(Gen& g, h264r_mb&)
 {
-    if (mb.coeff_slot == H264R_NO_COEFF) mb.coeff_slot = g.n_slots++;
-    return g.coeffs + (size_t)mb.coeff_slot * H264R_COEFFS_PER_MB;
+    if (!g.dense_used) { memset(g.dense, 0, sizeof(g.dense)); g.dense_used = true; }
+    return g.dense;
+}
+
+// what the residual parser hands over: one entry per non-zero level (every sample for I_PCM)
+void emit_levels(Gen& g, h264r_mb& mb)
+{
+    mb.coeff_offset = g.n_levels; mb.coeff_count = 0;
+    if (!g.dense_used) return;
+    const bool pcm = mb.mb_type == H264R_MB_IPCM;
+    int n = 0;
+    for (int p = 0; p < H264R_COEFFS_PER_MB; ++p) {
+        if (!pcm && g.dense[p] == 0) continue;
+        if (g.n_levels + n >= g.level_capacity) { g.overflow = true; break; }
+        g.levels[g.n_levels + n] = H264R_LEVEL(p, g.dense[p]);
+        ++n;
+    }
+    mb.coeff_count = (uint16_t)n;
+    g.n_levels += n;
 }
 
 // residual for a non-I16x16, non-PCM MB.  Sets cbp_luma/cbp_chroma/cbp_blks and writes levels.
@@ -632,12 +652,12 @@ void h264s_get_seq(const h264s_stream* s, h264r_seq_params* sp, int* num_frames)
     memset(sp, 0, sizeof(*sp));
     sp->width_mbs = s->W; sp->height_mbs = s->H;
     sp->direct_8x8_inference_flag = 1;
-    sp->max_frames = 8; sp->max_pictures_in_flight = 4; sp->max_slices_per_picture = 4;
+    sp->max_frames = 8; sp->max_pictures_in_flight = 4; sp->max_slices_per_picture = 4; sp->max_levels_per_picture = 0;
     if (num_frames) *num_frames = s->num_frames;
 }
 
 int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264r_mb* mbs,
-               h264r_mb_motion* motion, h264r_slice* slices, int16_t* coeffs)
+               h264r_mb_motion* motion, h264r_slice* slices, h264r_level* levels, uint32_t level_capacity)
 {
     if (s->next_pic >= s->num_frames) return 0;
     const int pic_idx = s->next_pic++;
@@ -647,9 +667,9 @@ int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264
 
     Gen g;
     g.s = s; g.rng = &r; g.W = W; g.H = H; g.plan = &plan;
-    g.mbs = mbs; g.motion = motion; g.slices = slices; g.coeffs = coeffs; g.n_slots = 0;
+    g.mbs = mbs; g.motion = motion; g.slices = slices;
+    g.levels = levels; g.n_levels = 0; g.level_capacity = level_capacity; g.overflow = false; g.dense_used = false;
     memset(mbs, 0, sizeof(h264r_mb) * (size_t)nmb);
-    memset(coeffs, 0, sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)nmb);
 
     // distinct reference pictures of this picture -> slots
     memset(info, 0, sizeof(*info));
@@ -687,7 +707,7 @@ int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264
     for (int addr = 0; addr < nmb; ++addr) {
         h264r_mb& mb = mbs[addr];
         mb.slice_idx = (uint16_t)((g.num_slices > 1 && addr >= g.slice_first_mb[1]) ? 1 : 0);
-        mb.coeff_slot = H264R_NO_COEFF;
+        g.dense_used = false;
         g.qp = clip3(s->qp_lo, s->qp_hi, g.qp + r.range(-2, 2));
         mb.qp_y = (int8_t)g.qp;
         for (int i = 0; i < 2; ++i)
@@ -708,9 +728,10 @@ int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264
         } else {
             gen_inter_mb(g, addr);
         }
+        emit_levels(g, mb);
     }
-    info->num_coeff_slots = g.n_slots;
-    return 1;
+    info->num_levels = g.n_levels;
+    return g.overflow ? -1 : 1;
 }
 
 void h264s_account(const h264r_mb* mbs, const h264r_slice* slices, int nmb, int run_deblock, uint64_t out[8])
@@ -720,7 +741,7 @@ void h264s_account(const h264r_mb* mbs, const h264r_slice* slices, int nmb, int 
         const h264r_mb& m = mbs[a];
         const bool intra = (m.flags & H264R_MB_FLAG_INTRA) != 0;
         uint64_t b = 32 + 384;
-        if (m.coeff_slot != H264R_NO_COEFF) { b += 768; out[6] += 1; }
+        if (m.coeff_count) { b += 4 * (uint64_t)m.coeff_count; out[6] += 1; }
         if (!intra) {
             b += 192;
             for (int q = 0; q < 4; ++q) b += (m.u.inter.sub_mb_pred_mode[q] == H264R_PRED_BI ? 2 : 1) * 96;

@@ -9,7 +9,6 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 MAX_REFS = 32
 COEFFS_PER_MB = 384
-NO_COEFF = 0xFFFFFFFF
 P_SLICE, B_SLICE, I_SLICE = 0, 1, 2
 
 
@@ -25,7 +24,7 @@ class Mb(C.Structure):
     _fields_ = [("mb_type", C.c_uint8), ("flags", C.c_uint8), ("slice_idx", C.c_uint16),
                 ("cbp_luma", C.c_uint8), ("cbp_chroma", C.c_uint8), ("qp_y", C.c_int8), ("qp_c", C.c_int8 * 2),
                 ("intra16_mode", C.c_uint8), ("chroma_mode", C.c_uint8), ("reserved0", C.c_uint8),
-                ("cbp_blks", C.c_uint16), ("reserved1", C.c_uint16), ("coeff_slot", C.c_uint32),
+                ("cbp_blks", C.c_uint16), ("coeff_count", C.c_uint16), ("coeff_offset", C.c_uint32),
                 ("u", MbUnion), ("reserved2", C.c_uint32)]
 
 
@@ -56,18 +55,18 @@ class PicParams(C.Structure):
 class SeqParams(C.Structure):
     _fields_ = [("width_mbs", C.c_int32), ("height_mbs", C.c_int32), ("direct_8x8_inference_flag", C.c_int32),
                 ("max_frames", C.c_int32), ("max_pictures_in_flight", C.c_int32),
-                ("max_slices_per_picture", C.c_int32)]
+                ("max_slices_per_picture", C.c_int32), ("max_levels_per_picture", C.c_int32)]
 
 
 class PicBuffers(C.Structure):
     _fields_ = [("mbs", C.POINTER(Mb)), ("motion", C.POINTER(MbMotion)), ("slices", C.POINTER(Slice)),
-                ("coeffs", C.POINTER(C.c_int16)), ("coeff_slot_capacity", C.c_uint32)]
+                ("levels", C.POINTER(C.c_uint32)), ("level_capacity", C.c_uint32)]
 
 
 class PicInfo(C.Structure):
     _fields_ = [("pic_index", C.c_int32), ("pic_type", C.c_int32), ("used_for_reference", C.c_int32),
                 ("poc", C.c_int32), ("num_refs", C.c_int32), ("ref_pic_index", C.c_int32 * MAX_REFS),
-                ("last_use_of_ref", C.c_int32 * MAX_REFS), ("num_coeff_slots", C.c_uint32)]
+                ("last_use_of_ref", C.c_int32 * MAX_REFS), ("num_levels", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -91,7 +90,7 @@ def synth_lib():
         L.h264s_get_seq.argtypes = [C.c_void_p, C.POINTER(SeqParams), C.POINTER(C.c_int)]
         L.h264s_next.restype = C.c_int
         L.h264s_next.argtypes = [C.c_void_p, C.POINTER(PicInfo), C.POINTER(PicParams), C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p]
+                                 C.c_void_p, C.c_void_p, C.c_uint32]
         L.h264s_account.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
         _synth = L
     return _synth
@@ -135,16 +134,16 @@ def recon_lib():
 
 class Picture:
     """One generated picture: owns its host buffers (numpy-free, plain ctypes arrays)."""
-    __slots__ = ("info", "pp", "mbs", "motion", "slices", "coeffs", "nmb")
+    __slots__ = ("info", "pp", "mbs", "motion", "slices", "levels", "nmb")
 
-    def __init__(self, nmb):
+    def __init__(self, nmb, scratch_levels=None):
         self.nmb = nmb
         self.info = PicInfo()
         self.pp = PicParams()
         self.mbs = (Mb * nmb)()
         self.motion = (MbMotion * nmb)()
         self.slices = (Slice * 4)()
-        self.coeffs = (C.c_int16 * (COEFFS_PER_MB * nmb))()
+        self.levels = scratch_levels          # replaced by a right-sized copy after generation
 
 
 class SynthStream:
@@ -158,11 +157,21 @@ class SynthStream:
         self.L.h264s_get_seq(self.h, C.byref(self.seq), C.byref(n))
         self.num_frames = n.value
         self.nmb = self.seq.width_mbs * self.seq.height_mbs
+        self._scratch = None
 
     def next(self):
-        pic = Picture(self.nmb)
-        ok = self.L.h264s_next(self.h, C.byref(pic.info), C.byref(pic.pp), pic.mbs, pic.motion, pic.slices, pic.coeffs)
-        return pic if ok else None
+        cap = COEFFS_PER_MB * self.nmb
+        if self._scratch is None:
+            self._scratch = (C.c_uint32 * cap)()
+        pic = Picture(self.nmb, self._scratch)
+        ok = self.L.h264s_next(self.h, C.byref(pic.info), C.byref(pic.pp), pic.mbs, pic.motion, pic.slices,
+                               self._scratch, cap)
+        if ok <= 0:
+            return None
+        n = pic.info.num_levels
+        pic.levels = (C.c_uint32 * max(n, 1))()
+        C.memmove(pic.levels, self._scratch, 4 * n)
+        return pic
 
     def __iter__(self):
         while True:
@@ -187,10 +196,11 @@ class EngineError(RuntimeError):
 class Engine:
     """Thin object wrapper over the C ABI of libh264recon.so (one context == one GPU)."""
 
-    def __init__(self, seq, device=0, max_frames=8, max_pictures=4, max_slices=4):
+    def __init__(self, seq, device=0, max_frames=8, max_pictures=4, max_slices=4, max_levels=0):
         self.L = recon_lib()
         sp = SeqParams.from_buffer_copy(seq)
         sp.max_frames, sp.max_pictures_in_flight, sp.max_slices_per_picture = max_frames, max_pictures, max_slices
+        sp.max_levels_per_picture = max_levels
         self.seq = sp
         self.nmb = sp.width_mbs * sp.height_mbs
         self.w, self.h = sp.width_mbs * 16, sp.height_mbs * 16
@@ -221,8 +231,10 @@ class Engine:
         C.memmove(bufs.mbs, pic.mbs, C.sizeof(Mb) * n)
         C.memmove(bufs.motion, pic.motion, C.sizeof(MbMotion) * n)
         C.memmove(bufs.slices, pic.slices, C.sizeof(Slice) * pp.num_slices)
-        C.memmove(bufs.coeffs, pic.coeffs, 2 * COEFFS_PER_MB * pic.info.num_coeff_slots)
-        self._check(self.L.h264r_picture_submit(self.ctx, pic.info.num_coeff_slots), "h264r_picture_submit")
+        if pic.info.num_levels > bufs.level_capacity:
+            raise EngineError("level list larger than the staging capacity (max_levels_per_picture)")
+        C.memmove(bufs.levels, pic.levels, 4 * pic.info.num_levels)
+        self._check(self.L.h264r_picture_submit(self.ctx, pic.info.num_levels), "h264r_picture_submit")
 
     def flush(self):
         self._check(self.L.h264r_flush(self.ctx), "h264r_flush")
@@ -243,9 +255,9 @@ class Engine:
     REPLAY_H2D, REPLAY_TIME_KERNELS = 1, 2
 
     def replay(self, iterations=1, flags=0):
-        """Re-runs the last flush; returns (ms[total, inter, intra, dbprep, deblock], launches[_, ...same])."""
-        ms = (C.c_float * 5)()
-        n = (C.c_int * 5)()
+        """Re-runs the last flush; returns (ms[total, resid, inter, intra, dbprep, deblock], launches[_, ...same])."""
+        ms = (C.c_float * 6)()
+        n = (C.c_int * 6)()
         self._check(self.L.h264r_replay_last_flush(self.ctx, iterations, flags, ms, n), "h264r_replay_last_flush")
         return list(ms), list(n)
 
@@ -268,8 +280,8 @@ class Engine:
         self._check(self.L.h264r_picture_begin(self.ctx, dst, C.byref(pp), C.byref(bufs)), "h264r_picture_begin")
         return bufs
 
-    def submit_filled(self, num_coeff_slots):
-        self._check(self.L.h264r_picture_submit(self.ctx, num_coeff_slots), "h264r_picture_submit")
+    def submit_filled(self, num_levels):
+        self._check(self.L.h264r_picture_submit(self.ctx, num_levels), "h264r_picture_submit")
 
     def stats(self):
         s = Stats()

@@ -171,14 +171,14 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     seq, nmb = st.seq, st.nmb
     st.close()
     npics = streams * frames
-    eng = pyapi.Engine(seq, device=local_rank, max_frames=npics, max_pictures=npics, max_slices=4)
+    eng = pyapi.Engine(seq, device=local_rank, max_frames=npics, max_pictures=npics, max_slices=4, max_levels=args.max_levels)
 
     # ---- generate (threads; the generator releases the GIL) and stage every picture in pinned memory ----
     t0 = time.time()
     first = rank * streams
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex:
         all_pics = list(ex.map(generate_stream, [(first + s, frames) for s in range(streams)]))
-    acct = [0] * 9
+    acct = [0] * 10
     frames_of = [dict() for _ in range(streams)]
     out_frames = []
     for i in range(frames):                       # picture i of every stream, decode order
@@ -190,7 +190,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
             out_frames.append(dst)
             a = (C.c_uint64 * 8)()
             pyapi.synth_lib().h264s_account(pic.mbs, pic.slices, nmb, pic.pp.run_deblock, a)
-            acct = [x + y for x, y in zip(acct, list(a) + [a[7] * (32 + 32) + a[4] * 192])]
+            acct = [x + y for x, y in zip(acct, list(a) + [a[7] * (32 + 32) + a[4] * 192, 4 * pic.info.num_levels + a[6] * (32 + 768)])]
             all_pics[s][i] = None                 # the pinned staging now owns the data
     del all_pics
     gen_s = time.time() - t0
@@ -266,9 +266,11 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     value = world * total_mb * args.steps / t_dev
     e2e_value = world * total_mb * args.steps / t_e2e
     peak, peak_src = peaks()
-    names = ["inter", "intra", "deblock_prep", "deblock"]
-    k_bytes = [acct[1], acct[2], acct[8], acct[3]]
-    dom = max(range(4), key=lambda i: kms[i + 1])
+    names = ["residual", "inter", "intra", "deblock_prep", "deblock"]
+    # algorithmic bytes of each kernel's own pass: residual = levels in + 768 B residual plane out per coded MB;
+    # inter/intra = SURVEY 8d formula restricted to their MBs; deblock_prep = headers + motion in, 32 B out
+    k_bytes = [acct[9], acct[1], acct[2], acct[8], acct[3]]
+    dom = max(range(5), key=lambda i: kms[i + 1])
     dom_ms_per_launch = kms[dom + 1] / max(1, kn[dom + 1])
     dom_bytes_per_launch = k_bytes[dom] / max(1, kn[dom + 1])
     achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0
@@ -280,7 +282,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
         "config": {"workload": f"{streams} independent 1080p (120x68 MB) High-profile I/P/B streams x {frames} pictures per GPU "
                                "(BASELINE configs[4]; 8x8 transform, intra 8x8, bi-pred, weighted prediction, 2 slices on odd pictures)",
                    "streams_per_gpu": streams, "pictures_per_step_per_gpu": npics, "macroblocks_per_step_per_gpu": total_mb,
-                   "l2_policy": "inputs larger than L2 (6.6 GB of picture descriptions + 3.2 GB of frames per step)",
+                   "l2_policy": "inputs larger than L2 (GBs of picture descriptions + 3.2 GB of frames per step)",
                    "frames_per_s": value / nmb, "output_bytes_per_s": value * 384},
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((s3.h2d_bytes - s2.h2d_bytes) // args.steps),
@@ -319,6 +321,7 @@ def main():
     ap.add_argument("--streams", type=int, default=64, help="independent streams per GPU")
     ap.add_argument("--frames", type=int, default=16, help="pictures per stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-levels", type=int, default=8160 * 96, help="staging capacity of one picture's level list")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

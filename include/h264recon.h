@@ -44,9 +44,16 @@ enum { H264R_PRED_L0 = 0, H264R_PRED_L1 = 1, H264R_PRED_BI = 2 };
 #define H264R_MB_FLAG_INTRA   0x01u  /* mb_t::is_intra_block                                          */
 #define H264R_MB_FLAG_T8x8    0x02u  /* mb_t::transform_size_8x8_flag                                 */
 
-#define H264R_NO_COEFF        0xFFFFFFFFu
 #define H264R_MAX_REFS        32     /* entries of one RefPicList (frame decoding uses <= 16)         */
 #define H264R_COEFFS_PER_MB   384    /* 256 Y + 64 Cb + 64 Cr                                         */
+
+/* One transmitted coefficient level: what one Decoder::coeff_* call carries (decoder.h:312-315).
+ * pos = raster position inside the MB's 384 samples (Y 16x16: y*16+x; Cb: 256 + y*8+x; Cr: 320 + y*8+x) after
+ * the inverse scan; level = the raw (not yet dequantised) level.  I_PCM: 384 entries, level = the sample. */
+typedef uint32_t h264r_level;
+#define H264R_LEVEL(pos, level)   ((uint32_t)(uint16_t)(pos) | ((uint32_t)(uint16_t)(int16_t)(level) << 16))
+#define H264R_LEVEL_POS(e)        ((int)((e) & 0xFFFFu))
+#define H264R_LEVEL_VALUE(e)      ((int)(int16_t)((e) >> 16))
 
 /* status codes */
 enum {
@@ -76,9 +83,8 @@ typedef struct h264r_mb {
     uint8_t  reserved0;
     uint16_t cbp_blks;               /* cbp_blks[0] bits 0..15: 4x4 block (by*4+bx) has luma AC levels
                                         (transform.cc:433-436; 0xFFFF for I_PCM, interpret_mb.cc:421) */
-    uint16_t reserved1;
-    uint32_t coeff_slot;             /* index of this MB's 384-int16 slot in the coefficient buffer,
-                                        H264R_NO_COEFF when the MB received no level and is not I16x16/I_PCM */
+    uint16_t coeff_count;            /* number of h264r_level entries of this MB (0 = no residual)     */
+    uint32_t coeff_offset;           /* index of the MB's first entry in the picture's level list       */
     union {
         uint8_t intra_modes[8];      /* 16 nibbles, low nibble first: Intra4x4PredMode[luma4x4BlkIdx]
                                         (I_4x4) or Intra8x8PredMode[0..3] in nibbles 0..3 (I_8x8)     */
@@ -146,6 +152,8 @@ typedef struct h264r_seq_params {
     int32_t max_frames;                          /* frame pool capacity                                */
     int32_t max_pictures_in_flight;              /* staging slots that can be filled before a flush    */
     int32_t max_slices_per_picture;
+    int32_t max_levels_per_picture;              /* staging capacity of the level list; 0 = worst case
+                                                    (384 per MB)                                       */
 } h264r_seq_params;
 
 /* host staging pointers handed out by h264r_picture_begin (pinned memory owned by the context) */
@@ -153,12 +161,9 @@ typedef struct h264r_pic_buffers {
     h264r_mb*        mbs;                        /* [width_mbs*height_mbs], raster order               */
     h264r_mb_motion* motion;                     /* [width_mbs*height_mbs]                             */
     h264r_slice*     slices;                     /* [max_slices_per_picture]                           */
-    int16_t*         coeffs;                     /* [coeff_slot_capacity][384] raw levels at raster
-                                                    positions: Y 16x16 (256), Cb 8x8 (64), Cr 8x8 (64);
-                                                    I_PCM: the 384 samples.  A slot must be zero where no
-                                                    level was written: the producer clears a slot when it
-                                                    takes it (staging memory is recycled, not cleared).  */
-    uint32_t         coeff_slot_capacity;        /* == number of MBs                                   */
+    h264r_level*     levels;                     /* [level_capacity] level list of the picture; the
+                                                    entries of one MB are contiguous (any order)        */
+    uint32_t         level_capacity;             /* h264r_seq_params::max_levels_per_picture            */
 } h264r_pic_buffers;
 
 typedef struct h264r_ctx h264r_ctx;
@@ -177,8 +182,8 @@ int  h264r_frame_release(h264r_ctx* ctx, h264r_frame f);
 /* replaces: init_picture + Decoder::init (core/slice_data.cc:149-313, 618).  Reserves a staging slot. */
 int  h264r_picture_begin(h264r_ctx* ctx, h264r_frame dst, const h264r_pic_params* pp, h264r_pic_buffers* out);
 /* replaces: Decoder::deblock_filter at exit_picture (framebuf/picture.cc:253): the picture is complete
- * on the host side; it is queued.  `num_coeff_slots` = slots actually used.                           */
-int  h264r_picture_submit(h264r_ctx* ctx, uint32_t num_coeff_slots);
+ * on the host side; it is queued.  `num_levels` = entries of the level list actually used.           */
+int  h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels);
 /* launches everything queued: pictures are grouped into dependency waves (a picture whose references
  * are produced by a queued picture goes to a later wave); every wave is one batched launch sequence.  */
 int  h264r_flush(h264r_ctx* ctx);
@@ -204,11 +209,11 @@ void  h264r_host_free(void* p);
  * been refilled since).  flags: H264R_REPLAY_H2D re-issues the host->device copies of every picture description
  * from the pinned staging (end-to-end path); without it only the kernels run on the HBM-resident inputs.
  * H264R_REPLAY_TIME_KERNELS brackets every kernel with CUDA events (serialises nothing, costs a few us each).
- * ms_out[0] = whole replay (CUDA events on the compute stream), [1] inter, [2] intra wavefront, [3] deblock
- * pre-pass, [4] deblock wavefront kernel time; launches_out[1..4] = number of launches of each kernel. */
+ * ms_out[0] = whole replay (CUDA events on the compute stream), [1] residual, [2] inter, [3] intra wavefront,
+ * [4] deblock pre-pass, [5] deblock wavefront kernel time; launches_out[1..5] = launches of each kernel. */
 #define H264R_REPLAY_H2D           1
 #define H264R_REPLAY_TIME_KERNELS  2
-int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[5], int launches_out[5]);
+int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[6], int launches_out[6]);
 
 /* host helper restating inter_prediction.cc:112-139 (implicit bi-prediction weights)                   */
 void h264r_implicit_weights(int cur_poc, int poc0, int poc1, int long_term0, int long_term1, int* w0, int* w1);

@@ -38,7 +38,7 @@ typedef struct h264s_pic_info {
     int32_t num_refs;                /* == pic_params.num_ref_frames                                   */
     int32_t ref_pic_index[H264R_MAX_REFS]; /* decode-order index of pic_params.ref_frames[i]           */
     int32_t last_use_of_ref[H264R_MAX_REFS]; /* 1 if no later picture of the stream references it       */
-    uint32_t num_coeff_slots;
+    uint32_t num_levels;             /* entries written to the level list                                */
 } h264s_pic_info;
 
 /* width_mbs/height_mbs/num_frames <= 0 select the config's own values */
@@ -46,20 +46,21 @@ h264s_stream* h264s_open(int config, int stream_idx, int width_mbs, int height_m
 void          h264s_close(h264s_stream* s);
 void          h264s_get_seq(const h264s_stream* s, h264r_seq_params* sp, int* num_frames);
 
-/* Generates the next picture.  Buffers must hold width_mbs*height_mbs entries (coeffs: that many slots,
- * zero-filled by this call where unused); slices: at least 4.  pp->ref_frames[] is left as -1: the caller
- * maps info->ref_pic_index[] to frame handles.  Returns 1 if a picture was produced, 0 at end of stream. */
+/* Generates the next picture.  mbs/motion must hold width_mbs*height_mbs entries, slices at least 4, levels
+ * `level_capacity` entries (384 per MB always suffices).  pp->ref_frames[] is left as -1: the caller maps
+ * info->ref_pic_index[] to frame handles.  Returns 1 if a picture was produced, 0 at end of stream, -1 if the
+ * level list overflowed. */
 int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264r_mb* mbs,
-               h264r_mb_motion* motion, h264r_slice* slices, int16_t* coeffs);
+               h264r_mb_motion* motion, h264r_slice* slices, h264r_level* levels, uint32_t level_capacity);
 
 /* Algorithmic (compulsory) HBM bytes of one picture, SURVEY.md §8d: every input byte read once, every output byte
  * written once, ideal reference fetch without halo.
- *   out[0] whole path : per MB 32 (header) + 768 (levels, if the MB owns a slot) + 192 (motion, inter MBs)
+ *   out[0] whole path : per MB 32 (header) + 4 per transmitted level + 192 (motion, inter MBs)
  *                       + 96 per used prediction list and 8x8 quadrant (= 384 per list and MB) + 384 (output)
  *   out[1] inter kernel: the above restricted to inter MBs
  *   out[2] intra kernel: the above restricted to intra MBs
  *   out[3] deblock kernel (its own pass): per filtered MB 32 + 384 read + 384 written (+192 motion if inter)
- *   out[4] inter MBs, out[5] intra MBs, out[6] MBs owning a coefficient slot, out[7] filtered MBs */
+ *   out[4] inter MBs, out[5] intra MBs, out[6] MBs with at least one level, out[7] filtered MBs */
 void h264s_account(const h264r_mb* mbs, const h264r_slice* slices, int nmb, int run_deblock, uint64_t out[8]);
 
 #ifdef __cplusplus

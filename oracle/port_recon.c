@@ -39,7 +39,7 @@ typedef struct {
     const h264r_slice* slices;
     const h264r_mb* mbs;
     const h264r_mb_motion* motion;
-    const int16_t* coeffs;
+    const h264r_level* levels;
     frame_t* dst;
 } pic_t;
 
@@ -140,7 +140,18 @@ static void mb_residual(const pic_t* p, const h264r_mb* mb, int res[3][256], int
     const h264r_slice* sl = &p->slices[mb->slice_idx];
     const int intra = (mb->flags & H264R_MB_FLAG_INTRA) != 0;
     const int t8 = (mb->flags & H264R_MB_FLAG_T8x8) != 0;
-    const int16_t* lev = mb->coeff_slot != H264R_NO_COEFF ? p->coeffs + (size_t)mb->coeff_slot * H264R_COEFFS_PER_MB : NULL;
+    /* the MB's transmitted levels, placed at their raster positions (what Transform::cof holds after the
+       residual parser ran, transform.cc:425-456, before dequantisation) */
+    int16_t dense[H264R_COEFFS_PER_MB];
+    const int16_t* lev = NULL;
+    if (mb->coeff_count) {
+        memset(dense, 0, sizeof(dense));
+        for (int i = 0; i < mb->coeff_count; ++i) {
+            h264r_level e = p->levels[mb->coeff_offset + i];
+            dense[H264R_LEVEL_POS(e)] = (int16_t)H264R_LEVEL_VALUE(e);
+        }
+        lev = dense;
+    }
     int cof[256];
     memset(res[0], 0, sizeof(int) * 256); memset(res[1], 0, sizeof(int) * 256); memset(res[2], 0, sizeof(int) * 256);
     has[0] = has[1] = 0;
@@ -578,7 +589,12 @@ static void reconstruct_mb(const pic_t* p, int cur)
     const int sY = W * 16, sC = W * 8;
 
     if (mb->mb_type == H264R_MB_IPCM) {                             /* mb_pred_ipcm, decoder.cc:149-168 */
-        const int16_t* c = p->coeffs + (size_t)mb->coeff_slot * H264R_COEFFS_PER_MB;
+        int16_t c[H264R_COEFFS_PER_MB];
+        memset(c, 0, sizeof(c));
+        for (int i = 0; i < mb->coeff_count; ++i) {
+            h264r_level e = p->levels[mb->coeff_offset + i];
+            c[H264R_LEVEL_POS(e)] = (int16_t)H264R_LEVEL_VALUE(e);
+        }
         for (int y = 0; y < 16; ++y) for (int x = 0; x < 16; ++x) Y[(mby * 16 + y) * sY + mbx * 16 + x] = (uint8_t)c[y * 16 + x];
         for (int pl = 1; pl <= 2; ++pl)
             for (int y = 0; y < 8; ++y) for (int x = 0; x < 8; ++x)
@@ -771,9 +787,9 @@ static double now_sec(void)
 
 int port_reconstruct(port_dec* d, int dst, const h264r_pic_params* pp, int used_for_reference,
                      const h264r_slice* slices, const h264r_mb* mbs, const h264r_mb_motion* motion,
-                     const int16_t* coeffs, double* sec_decode, double* sec_deblock)
+                     const h264r_level* levels, double* sec_decode, double* sec_deblock)
 {
-    pic_t p = { d, pp, slices, mbs, motion, coeffs, &d->fr[dst] };
+    pic_t p = { d, pp, slices, mbs, motion, levels, &d->fr[dst] };
     const int nmb = d->W * d->H;
     (void)used_for_reference;
     double t0 = now_sec();

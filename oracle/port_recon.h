@@ -15,7 +15,7 @@ void      port_frame_get(port_dec* d, int id, uint8_t* y, uint8_t* cb, uint8_t* 
 void      port_frame_set(port_dec* d, int id, const uint8_t* y, const uint8_t* cb, const uint8_t* cr);
 int       port_reconstruct(port_dec* d, int dst, const h264r_pic_params* pp, int used_for_reference,
                            const h264r_slice* slices, const h264r_mb* mbs, const h264r_mb_motion* motion,
-                           const int16_t* coeffs, double* sec_decode, double* sec_deblock);
+                           const h264r_level* levels, double* sec_decode, double* sec_deblock);
 #ifdef __cplusplus
 }
 #endif

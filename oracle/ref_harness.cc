@@ -129,7 +129,7 @@ void ref_frame_set(ref_dec* d, int id, const uint8_t* y, const uint8_t* cb, cons
 // description's -- a consistency check of the generator/facade, not of the reconstruction.
 int ref_reconstruct(ref_dec* d, int dst, const h264r_pic_params* pp, int used_for_reference,
                     const h264r_slice* slices, const h264r_mb* mbs, const h264r_mb_motion* motion,
-                    const int16_t* coeffs, double* sec_decode, double* sec_deblock)
+                    const h264r_level* levels, double* sec_decode, double* sec_deblock)
 {
     VideoParameters* vid = d->vid;
     const int W = d->W, H = d->H, nmb = W * H;
@@ -264,8 +264,13 @@ int ref_reconstruct(ref_dec* d, int dst, const h264r_pic_params* pp, int used_fo
         }
         // coefficients: mb_t::init zeroes Transform::cof (core/slice_data.cc:496-503)
         memset(dec.transform->cof, 0, sizeof(dec.transform->cof));
-        if (hm.coeff_slot != H264R_NO_COEFF) {
-            const int16_t* c = coeffs + (size_t)hm.coeff_slot * H264R_COEFFS_PER_MB;
+        if (hm.coeff_count) {
+            int16_t c[H264R_COEFFS_PER_MB];
+            memset(c, 0, sizeof(c));
+            for (int i = 0; i < hm.coeff_count; ++i) {
+                const h264r_level e = levels[hm.coeff_offset + i];
+                c[H264R_LEVEL_POS(e)] = (int16_t)H264R_LEVEL_VALUE(e);
+            }
             if (hm.mb_type == H264R_MB_IPCM) {                          // parse_i_pcm, interpret_mb.cc:405-470
                 for (int y = 0; y < 16; ++y) for (int x = 0; x < 16; ++x) dec.transform->cof[0][y][x] = c[y * 16 + x];
                 for (int pl = 0; pl < 2; ++pl)

@@ -53,7 +53,7 @@ class CpuDecoder:
             pp.ref_frames[i] = f
         t0, t1 = C.c_double(), C.c_double()
         rc = self._recon(self.h, dst, C.byref(pp), pic.info.used_for_reference, pic.slices, pic.mbs, pic.motion,
-                         pic.coeffs, C.byref(t0), C.byref(t1))
+                         pic.levels, C.byref(t0), C.byref(t1))
         self.sec_decode += t0.value
         self.sec_deblock += t1.value
         return rc

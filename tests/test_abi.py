@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(pyapi.Mb) == 32
     assert C.sizeof(pyapi.MbMotion) == 192
     assert C.sizeof(pyapi.Slice) == 5216
-    assert pyapi.Mb.coeff_slot.offset == 16 and pyapi.Mb.u.offset == 20 and pyapi.Mb.cbp_blks.offset == 12
+    assert pyapi.Mb.coeff_offset.offset == 16 and pyapi.Mb.coeff_count.offset == 14 and pyapi.Mb.u.offset == 20 and pyapi.Mb.cbp_blks.offset == 12
 
 
 @pytest.mark.skipif(not os.path.exists(LIB), reason="libh264recon.so not built yet")
