@@ -33,6 +33,12 @@ __device__ __forceinline__ int ld_acquire(const int* p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release(int* p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -584,7 +590,10 @@ __device__ __forceinline__ void wait_row_cached(const int* progress_above, int n
     if (known >= need) return;
     int v = 0;
     if ((threadIdx.x & 31) == 0) {
-        while ((v = ld_acquire(progress_above)) < need) __nanosleep(40);
+        // poll with relaxed loads (no L1 invalidation per poll) and exponential back-off; one acquire load at the end
+        unsigned ns = 32;
+        while (ld_relaxed(progress_above) < need) { __nanosleep(ns); if (ns < 512) ns *= 2; }
+        v = ld_acquire(progress_above);
     }
     known = __shfl_sync(0xFFFFFFFFu, v, 0);
 }
@@ -692,8 +701,10 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
     __syncthreads();
     const int W = g.width_mbs, H = g.height_mbs;
     const int groups = (H + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int pic_i = s_ticket / groups, rg = s_ticket - pic_i * groups;
-    if (pic_i >= num_pics) return;
+    // tickets run row-group-major over the pictures of the wave: a CTA's predecessor (same picture, previous
+    // row group) took its ticket num_pics tickets earlier, so it is normally far ahead and nobody spins
+    const int rg = s_ticket / num_pics, pic_i = s_ticket - rg * num_pics;
+    if (rg >= groups) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mby = rg * kWarpsPerCta + warp;
     if (mby >= H) return;
@@ -1104,8 +1115,8 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
     __syncthreads();
     const int W = g.width_mbs, H = g.height_mbs;
     const int groups = (H + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int pic_i = s_ticket / groups, rg = s_ticket - pic_i * groups;
-    if (pic_i >= num_pics) return;
+    const int rg = s_ticket / num_pics, pic_i = s_ticket - rg * num_pics;      // row-group-major, see recon_intra_kernel
+    if (rg >= groups) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mby = rg * kWarpsPerCta + warp;
     if (mby >= H) return;
