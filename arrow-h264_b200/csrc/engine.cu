@@ -487,7 +487,15 @@ int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_
     if (!ctx || iterations <= 0) return H264R_ERR_INVALID;
     if (ctx->last_waves.empty() || ctx->filling >= 0 || !ctx->queue.empty()) return H264R_ERR_STATE;
     cudaSetDevice(ctx->device);
-    int rc = h264r_wait(ctx, -1);
+    int rc;
+    if (flags & H264R_REPLAY_ASYNC) {
+        for (int it = 0; it < iterations; ++it) {
+            rc = run_waves(ctx, (flags & H264R_REPLAY_H2D) != 0, false, nullptr, nullptr);
+            if (rc != H264R_OK) return rc;
+        }
+        return H264R_OK;
+    }
+    rc = h264r_wait(ctx, -1);
     if (rc != H264R_OK) return rc;
     float ms[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
     int launches[6] = { 0, 0, 0, 0, 0, 0 };

@@ -252,7 +252,7 @@ class Engine:
     def upload(self, f, y, cb, cr):
         self._check(self.L.h264r_frame_upload(self.ctx, f, y, cb, cr, self.w, self.w // 2), "h264r_frame_upload")
 
-    REPLAY_H2D, REPLAY_TIME_KERNELS = 1, 2
+    REPLAY_H2D, REPLAY_TIME_KERNELS, REPLAY_ASYNC = 1, 2, 4
 
     def replay(self, iterations=1, flags=0):
         """Re-runs the last flush; returns (ms[total, resid, inter, intra, dbprep, deblock], launches[_, ...same])."""

@@ -235,20 +235,35 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     barrier()
 
     # ---- K timed steps end to end: H2D of every description + kernels + D2H of every frame ----
+    E2E = pyapi.Engine.REPLAY_H2D | pyapi.Engine.REPLAY_ASYNC      # enqueue like h264r_flush: nothing blocks the host
     for _ in range(max(1, args.warmup // 2)):
-        eng.replay(1, pyapi.Engine.REPLAY_H2D)
+        eng.replay(1, E2E)
         download_all()
         eng.wait()
     barrier()
     s2 = eng.stats()
     t_start = time.perf_counter()
     for _ in range(args.steps):
-        eng.replay(1, pyapi.Engine.REPLAY_H2D)
+        eng.replay(1, E2E)
         download_all()
         eng.wait()
     t_e2e = time.perf_counter() - t_start
     s3 = eng.stats()
     barrier()
+
+    if args.diag:
+        def timed(fn, n=3):
+            eng.wait(); t0 = time.perf_counter()
+            for _ in range(n): fn()
+            eng.wait(); return (time.perf_counter() - t0) / n * 1e3
+        def f_h2d_only(): eng.replay(1, pyapi.Engine.REPLAY_H2D)
+        def f_k_d2h(): eng.replay(1, 0); download_all()
+        def f_d2h_only(): download_all()
+        def f_all(): eng.replay(1, E2E); download_all()
+        print(f"[diag] kernels {timed(lambda: eng.replay(1, 0)):.1f} ms | h2d+kernels {timed(f_h2d_only):.1f} | "
+              f"kernels+d2h {timed(f_k_d2h):.1f} | d2h only {timed(f_d2h_only):.1f} | all {timed(f_all):.1f}", file=sys.stderr)
+        t0 = time.perf_counter(); download_all(); t_issue = (time.perf_counter() - t0) * 1e3; eng.wait()
+        print(f"[diag] host time to issue {npics} async downloads: {t_issue:.1f} ms", file=sys.stderr)
 
     # ---- per-kernel times (separate pass: the events sit between kernels) ----
     kms, kn = eng.replay(1, pyapi.Engine.REPLAY_TIME_KERNELS)
@@ -321,6 +336,7 @@ def main():
     ap.add_argument("--streams", type=int, default=64, help="independent streams per GPU")
     ap.add_argument("--frames", type=int, default=16, help="pictures per stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--diag", action="store_true", help="print a transfer/kernel time breakdown to stderr")
     ap.add_argument("--max-levels", type=int, default=8160 * 96, help="staging capacity of one picture's level list")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

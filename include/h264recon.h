@@ -213,6 +213,8 @@ void  h264r_host_free(void* p);
  * [4] deblock pre-pass, [5] deblock wavefront kernel time; launches_out[1..5] = launches of each kernel. */
 #define H264R_REPLAY_H2D           1
 #define H264R_REPLAY_TIME_KERNELS  2
+#define H264R_REPLAY_ASYNC         4   /* enqueue only (like h264r_flush): no host synchronisation, no timings;
+                                          the caller joins with h264r_wait.  Lets downloads overlap the kernels. */
 int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[6], int launches_out[6]);
 
 /* host helper restating inter_prediction.cc:112-139 (implicit bi-prediction weights)                   */
