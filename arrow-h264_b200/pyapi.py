@@ -298,3 +298,11 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+def streams_of_rank(rank, world, streams_per_gpu):
+    """Stream sharding: streams are independent units, no exchange step.  Weak scaling: every
+    rank owns `streams_per_gpu` streams; global stream ids are contiguous per rank, so seeds differ across GPUs."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return list(range(rank * streams_per_gpu, (rank + 1) * streams_per_gpu))

@@ -175,9 +175,9 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
 
     # ---- generate (threads; the generator releases the GIL) and stage every picture in pinned memory ----
     t0 = time.time()
-    first = rank * streams
+    my_streams = pyapi.streams_of_rank(rank, world, streams)
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex:
-        all_pics = list(ex.map(generate_stream, [(first + s, frames) for s in range(streams)]))
+        all_pics = list(ex.map(generate_stream, [(sid, frames) for sid in my_streams]))
     acct = [0] * 10
     frames_of = [dict() for _ in range(streams)]
     out_frames = []
