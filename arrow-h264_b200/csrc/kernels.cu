@@ -10,8 +10,10 @@
 // deblock}.cc); the line-by-line citations live in the CPU restatement oracle/port_recon.c, whose structure
 // these kernels mirror.  All sample arithmetic is int32; results are bit-exact by construction.
 #include "device_types.h"
+#include "mc_core.cuh"
 
 #include <stdint.h>
+#include <stddef.h>
 
 namespace h264r {
 
@@ -257,22 +259,21 @@ residual_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g)
 // ---------------------------------------------------------------------------------------------------
 // inter prediction
 
-__constant__ int8_t c_block_step[8][2] = { {0,0}, {4,4}, {4,2}, {2,4}, {2,2}, {2,1}, {1,2}, {1,1} };
-
 // Decoder::mb_pred_inter partition walk (decoder.cc:217-262) for 4x4 block `blk`: returns the block whose motion
 // entry the reference reads (partition origin), the prediction direction, and whether the partition covers the
-// whole 8x8 quadrant of the block.
+// whole 8x8 quadrant of the block.  Partition steps in 4x4 units per type 0..7 ({0,0},{4,4},{4,2},{2,4},{2,2},{2,1},
+// {1,2},{1,1}) are nibbles of two constants.
 __device__ __forceinline__ void partition_of_block(const MbHdr& h, int is_b, int direct_spatial, const h264r_mb_motion* m,
                                                    int direct8x8, int blk, int& origin, int& dir, bool& covers8x8)
 {
     const int bx = blk & 3, by = blk >> 2;
-    int sh0 = c_block_step[h.mb_type & 7][0], sv0 = c_block_step[h.mb_type & 7][1];
+    int sh0 = (0x11222440u >> (4 * (h.mb_type & 7))) & 7, sv0 = (0x12124240u >> (4 * (h.mb_type & 7))) & 7;
     if (h.mb_type == 0) sh0 = sv0 = is_b ? 2 : 4;
     const int i0 = bx & ~(sh0 - 1), j0 = by & ~(sv0 - 1);
     const int b8 = 2 * (j0 >> 1) + (i0 >> 1);
     const int mode = (h.u0 >> (8 * b8)) & 0xFF;
     int pd = (h.u1 >> (8 * b8)) & 0xFF;
-    int sh4 = c_block_step[mode & 7][0], sv4 = c_block_step[mode & 7][1];
+    int sh4 = (0x11222440u >> (4 * (mode & 7))) & 7, sv4 = (0x12124240u >> (4 * (mode & 7))) & 7;
     if (mode == 0) sh4 = sv4 = direct8x8 ? 2 : 1;
     if (is_b && h.mb_type == H264R_MB_8x8 && direct_spatial) {
         const int b = j0 * 4 + i0;
@@ -284,126 +285,42 @@ __device__ __forceinline__ void partition_of_block(const MbHdr& h, int is_b, int
     covers8x8 = sh4 >= 2 && sv4 >= 2;
 }
 
-// Luma interpolation of a 4x2 patch (get_block_luma, inter_prediction.cc:158-340).  w points at the window byte of
-// integer sample (0, 0) of the patch; the window holds 2 more samples to the left/top and 3 to the right/bottom.
-// Results are 8-bit samples, packed little-endian: out0 = row 0, out1 = row 1.  One copy of this code per kernel.
-__device__ __noinline__ void luma_patch_4x2(const uint8_t* w, int pitch, int xf, int yf, uint32_t& out0, uint32_t& out1)
-{
-#define WIN(x, y) ((int)w[(y) * pitch + (x)])
-    int o[8];
-    if ((xf | yf) == 0) {
-#pragma unroll
-        for (int y = 0; y < 2; ++y)
-#pragma unroll
-            for (int x = 0; x < 4; ++x) o[y * 4 + x] = WIN(x, y);
-    } else if (yf == 0 || ((xf & 1) && (yf & 1))) {
-        // horizontal half sample b (row + dy), alone, averaged with an integer sample, or with the vertical half sample h
-        const int dy = (yf == 3), dx = (xf == 3);
-#pragma unroll
-        for (int y = 0; y < 2; ++y) {
-            int r[9];
-#pragma unroll
-            for (int x = 0; x < 9; ++x) r[x] = WIN(x - 2, y + dy);
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                int b = clip255((tap6(r[x], r[x + 1], r[x + 2], r[x + 3], r[x + 4], r[x + 5]) + 16) >> 5);
-                if (yf == 0) o[y * 4 + x] = xf == 2 ? b : ((dx ? r[x + 3] : r[x + 2]) + b + 1) >> 1;
-                else o[y * 4 + x] = b;
-            }
-        }
-        if (yf != 0) {
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                int c[7];
-#pragma unroll
-                for (int y = 0; y < 7; ++y) c[y] = WIN(x + dx, y - 2);
-#pragma unroll
-                for (int y = 0; y < 2; ++y) {
-                    int hh = clip255((tap6(c[y], c[y + 1], c[y + 2], c[y + 3], c[y + 4], c[y + 5]) + 16) >> 5);
-                    o[y * 4 + x] = (o[y * 4 + x] + hh + 1) >> 1;
-                }
-            }
-        }
-    } else if (xf == 0) {
-        const int dy = yf == 3;
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            int c[7];
-#pragma unroll
-            for (int y = 0; y < 7; ++y) c[y] = WIN(x, y - 2);
-#pragma unroll
-            for (int y = 0; y < 2; ++y) {
-                int hh = clip255((tap6(c[y], c[y + 1], c[y + 2], c[y + 3], c[y + 4], c[y + 5]) + 16) >> 5);
-                o[y * 4 + x] = yf == 2 ? hh : ((dy ? c[y + 3] : c[y + 2]) + hh + 1) >> 1;
-            }
-        }
-    } else {
-        // centre sample j (and f, q / i, k): horizontal 6-tap on 7 rows, then vertical 6-tap on the unrounded sums
-        int b1[7][4];
-#pragma unroll
-        for (int rr = 0; rr < 7; ++rr) {
-            int r[9];
-#pragma unroll
-            for (int x = 0; x < 9; ++x) r[x] = WIN(x - 2, rr - 2);
-#pragma unroll
-            for (int x = 0; x < 4; ++x) b1[rr][x] = tap6(r[x], r[x + 1], r[x + 2], r[x + 3], r[x + 4], r[x + 5]);
-        }
-#pragma unroll
-        for (int y = 0; y < 2; ++y)
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                int j = clip255((tap6(b1[y][x], b1[y + 1][x], b1[y + 2][x], b1[y + 3][x], b1[y + 4][x], b1[y + 5][x]) + 512) >> 10);
-                int v = j;
-                if (xf == 2 && yf != 2) {
-                    int q = clip255(((yf == 3 ? b1[y + 3][x] : b1[y + 2][x]) + 16) >> 5);
-                    v = (j + q + 1) >> 1;
-                } else if (yf == 2 && xf != 2) {
-                    const int dx = xf == 3;
-                    int q = clip255((tap6(WIN(x + dx, y - 2), WIN(x + dx, y - 1), WIN(x + dx, y), WIN(x + dx, y + 1), WIN(x + dx, y + 2), WIN(x + dx, y + 3)) + 16) >> 5);
-                    v = (j + q + 1) >> 1;
-                }
-                o[y * 4 + x] = v;
-            }
-    }
-#undef WIN
-    out0 = (uint32_t)o[0] | (uint32_t)o[1] << 8 | (uint32_t)o[2] << 16 | (uint32_t)o[3] << 24;
-    out1 = (uint32_t)o[4] | (uint32_t)o[5] << 8 | (uint32_t)o[6] << 16 | (uint32_t)o[7] << 24;
-}
-
-// Reference window: rows [y0, y0+nrows) x bytes [x0, x0+ncols) of a plane go to shared memory with row pitch `wp`.
-// Interior windows are fetched as aligned 32-bit words (the sample x0 then sits at byte offset x0 & 3 of a window
-// row); windows touching the picture border are fetched sample by sample with clamped coordinates (== the
-// reference's padded planes) and start at byte offset 0.
+// Reference window: rows [y0, y0+nrows) x bytes [x0, x0+ncols) of a plane go to shared memory.  Interior windows are
+// fetched as aligned 32-bit words (the sample x0 then sits at byte offset x0 & 3 of a window row); windows touching the
+// picture border are fetched sample by sample with clamped coordinates (== the reference's padded planes)
+// and start at byte offset 0.
 __device__ __forceinline__ bool window_interior(int x0, int y0, int ncols, int nrows, int W, int H)
 {
     const int xa = x0 & ~3;
     return xa >= 0 && xa + (((x0 - xa) + ncols + 3) & ~3) <= W && y0 >= 0 && y0 + nrows <= H;
 }
-__device__ __forceinline__ void load_window_row(uint8_t* win_row, const uint8_t* __restrict__ plane, int pitch, int W, int H,
+__device__ __forceinline__ void load_window_row(uint32_t* win_row, const uint8_t* __restrict__ plane, int pitch, int W, int H,
                                                 int x0, int y, int ncols, bool interior)
 {
     if (interior) {
         const int xa = x0 & ~3, nwords = ((x0 - xa) + ncols + 3) >> 2;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(plane + (size_t)y * pitch + xa);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(win_row);
-        for (int k = 0; k < nwords; ++k) dst[k] = __ldg(src + k);
+        for (int k = 0; k < nwords; ++k) win_row[k] = __ldg(src + k);
     } else {
         const uint8_t* src = plane + (size_t)clip3i(0, H - 1, y) * pitch;
-        for (int c = 0; c < ncols; ++c) win_row[c] = __ldg(src + clip3i(0, W - 1, x0 + c));
+        uint8_t* dst = reinterpret_cast<uint8_t*>(win_row);
+        for (int c = 0; c < ncols; ++c) dst[c] = __ldg(src + clip3i(0, W - 1, x0 + c));
     }
 }
 
-// per-warp scratch: 4 quadrants x { luma window, chroma windows }.  uniform quadrant: luma 13 rows x 16 B,
-// chroma 2 planes x 5 rows x 8 B; split quadrant: 4 blocks x (9 rows x 12 B) luma, 4 blocks x 2 planes x (3 rows x 8 B)
+// per-warp scratch, in 32-bit words.  Per 8x8 quadrant: luma 114 words = uniform quadrant 13 rows x 4 words | split
+// quadrant 4 blocks x (9 rows x 3 words); chroma 50 words = uniform 2 planes x (5 rows x 2 words) | split 4 blocks x
+// 2 planes x (3 rows x 2 words), + 1 word the funnel shifts may touch.  114 = 2 (mod 8): the four quadrant groups of a
+// warp read disjoint banks.
+constexpr int kLumaQ = 114, kChromaQ = 50;
 struct __align__(16) InterSmem {
-    __align__(16) uint8_t luma[4][448];
-    __align__(16) uint8_t chroma[4][192];
+    uint32_t luma[4 * kLumaQ + 2];
+    uint32_t chroma[4 * kChromaQ + 2];
     h264r_mb_motion motion;
 };
+static_assert(sizeof(InterSmem) % 16 == 0 && offsetof(InterSmem, motion) % 16 == 0, "InterSmem alignment");
 
-__device__ __forceinline__ int rshift_rnd(int x, int a) { return a > 0 ? (x + (1 << (a - 1))) >> a : x; }
-
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 6)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 5)
 recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g, int direct8x8)
 {
     __shared__ __align__(16) InterSmem smem_all[kWarpsPerCta];
@@ -437,8 +354,7 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
     const int sb = r >> 1, half = r & 1;
     const int blk = (qy * 2 + (sb >> 1)) * 4 + qx * 2 + (sb & 1);
     int origin, pd; bool uni;
-    partition_of_block(h, is_b, direct_spatial, &sm.motion, direct8x8, qy * 8 + qx * 2, origin, pd, uni);
-    if (!uni) { bool dummy; partition_of_block(h, is_b, direct_spatial, &sm.motion, direct8x8, blk, origin, pd, dummy); }
+    partition_of_block(h, is_b, direct_spatial, &sm.motion, direct8x8, blk, origin, pd, uni);
 
     // residual of this lane's samples (issued early; consumed at the end)
     const int lx = (blk & 3) * 4, ly = (blk >> 2) * 4 + half * 2;          // luma position in the MB
@@ -452,6 +368,9 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
         resC1 = __ldg(reinterpret_cast<const uint32_t*>(rs + 256 + half * 64 + (cyy + 1) * 8 + cxx));
     }
 
+    uint32_t* const lq = sm.luma + q * kLumaQ;
+    uint32_t* const cq = sm.chroma + q * kChromaQ;
+
     // samples of the (up to) two lists, packed bytes: cur = last list done, prev = the one before
     uint32_t curY0 = 0, curY1 = 0, curC = 0, prevY0 = 0, prevY1 = 0, prevC = 0;
     int ref_cur = 0, ref_prev = 0;
@@ -460,54 +379,49 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
         const bool active = k == 0 || pd == 2;
         const int list = pd == 2 ? k : pd;
         int vx = 0, vy = 0, refidx = 0;
-        const uint8_t* wl = nullptr; const uint8_t* wc = nullptr;
-        int wpitch = 16;
+        const uint32_t* wl = lq; const uint32_t* wc = cq;
+        int lpitch = 4, loff = 2, coff = 0;
         if (active) {
             refidx = sm.motion.ref_idx[list][origin];
             const int slot = (int)(int8_t)__ldg(&sl->ref_pic_list[list][refidx & 31]);
             const uint8_t* __restrict__ rbase = pic.ref[slot & 31];
             const int mvx = sm.motion.mv[list][origin][0], mvy = sm.motion.mv[list][origin][1];
-            vx = (mbx * 16 + lx) * 4 + mvx; vy = (mby * 16 + (blk >> 2) * 4) * 4 + mvy;        // this block's position
+            vx = (mbx * 16 + (blk & 3) * 4) * 4 + mvx; vy = (mby * 16 + (blk >> 2) * 4) * 4 + mvy;   // this block's position
             if (uni) {
                 const int qvx = (mbx * 16 + qx * 8) * 4 + mvx, qvy = (mby * 16 + qy * 8) * 4 + mvy;
                 const int x0 = (qvx >> 2) - 2, y0 = (qvy >> 2) - 2, cx0 = qvx >> 3, cy0 = qvy >> 3;
                 const bool in_y = window_interior(x0, y0, 13, 13, wY, hY), in_c = window_interior(cx0, cy0, 5, 5, wC, hC);
                 for (int row = r; row < 13; row += 8)
-                    load_window_row(sm.luma[q] + row * 16, rbase, g.pitch_y, wY, hY, x0, y0 + row, 13, in_y);
+                    load_window_row(lq + row * 4, rbase, g.pitch_y, wY, hY, x0, y0 + row, 13, in_y);
                 for (int i = r; i < 10; i += 8) {               // chroma: 2 planes x 5 rows over 8 lanes
                     const int pl = i >= 5, row = i - pl * 5;
-                    load_window_row(sm.chroma[q] + pl * 96 + row * 8, rbase + (pl ? g.off_cr : g.off_cb), g.pitch_c, wC, hC,
+                    load_window_row(cq + pl * 10 + row * 2, rbase + (pl ? g.off_cr : g.off_cb), g.pitch_c, wC, hC,
                                     cx0, cy0 + row, 5, in_c);
                 }
-                wl = sm.luma[q] + ((sb >> 1) * 4 + half * 2 + 2) * 16 + (sb & 1) * 4 + 2 + (in_y ? x0 & 3 : 0);
-                wc = sm.chroma[q] + half * 96 + (sb >> 1) * 2 * 8 + (sb & 1) * 2 + (in_c ? cx0 & 3 : 0);
+                wl = lq + ((sb >> 1) * 4 + half * 2) * 4;
+                loff = 2 + (sb & 1) * 4 + (in_y ? x0 & 3 : 0);
+                wc = cq + half * 10 + (sb >> 1) * 2 * 2;
+                coff = (sb & 1) * 2 + (in_c ? cx0 & 3 : 0);
             } else {
                 const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2, cx0 = vx >> 3, cy0 = vy >> 3;
                 const bool in_y = window_interior(x0, y0, 9, 9, wY, hY), in_c = window_interior(cx0, cy0, 3, 3, wC, hC);
                 for (int row = half; row < 9; row += 2)
-                    load_window_row(sm.luma[q] + sb * 108 + row * 12, rbase, g.pitch_y, wY, hY, x0, y0 + row, 9, in_y);
+                    load_window_row(lq + sb * 27 + row * 3, rbase, g.pitch_y, wY, hY, x0, y0 + row, 9, in_y);
                 for (int row = 0; row < 3; ++row)
-                    load_window_row(sm.chroma[q] + sb * 48 + half * 24 + row * 8, rbase + (half ? g.off_cr : g.off_cb), g.pitch_c, wC, hC,
+                    load_window_row(cq + sb * 12 + half * 6 + row * 2, rbase + (half ? g.off_cr : g.off_cb), g.pitch_c, wC, hC,
                                     cx0, cy0 + row, 3, in_c);
-                wl = sm.luma[q] + sb * 108 + (half * 2 + 2) * 12 + 2 + (in_y ? x0 & 3 : 0);
-                wc = sm.chroma[q] + sb * 48 + half * 24 + (in_c ? cx0 & 3 : 0);
-                wpitch = 12;
+                wl = lq + sb * 27 + half * 2 * 3;
+                lpitch = 3;
+                loff = 2 + (in_y ? x0 & 3 : 0);
+                wc = cq + sb * 12 + half * 6;
+                coff = in_c ? cx0 & 3 : 0;
             }
         }
         __syncwarp();
         if (active) {
             prevY0 = curY0; prevY1 = curY1; prevC = curC; ref_prev = ref_cur; ref_cur = refidx;
-            luma_patch_4x2(wl, wpitch, vx & 3, vy & 3, curY0, curY1);
-            const int xf = vx & 7, yf = vy & 7;
-            curC = 0;
-#pragma unroll
-            for (int y = 0; y < 2; ++y)
-#pragma unroll
-                for (int x = 0; x < 2; ++x) {
-                    const int v = ((8 - xf) * (8 - yf) * wc[y * 8 + x] + xf * (8 - yf) * wc[y * 8 + x + 1] +
-                                   (8 - xf) * yf * wc[(y + 1) * 8 + x] + xf * yf * wc[(y + 1) * 8 + x + 1] + 32) >> 6;
-                    curC |= (uint32_t)v << ((y * 2 + x) * 8);
-                }
+            mc_luma_patch_4x2(wl, lpitch, loff, vx & 3, vy & 3, curY0, curY1);
+            curC = mc_chroma_patch_2x2(wc, coff, vx & 7, vy & 7);
         }
         __syncwarp();
     }
@@ -515,55 +429,42 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
     // weighted sample prediction (mc_prediction / bi_prediction, inter_prediction.cc:53-156), residual, store
     const bool uni_weighted = (wp_flag && !is_b) || (bipred_idc == 1 && is_b);
     const int ref0 = pd == 2 ? ref_prev : ref_cur, ref1 = ref_cur;
-    uint32_t outw[3] = { 0, 0, 0 };                            // 4x2 luma + 2x2 chroma bytes
+    const int mode = pd != 2 ? (uni_weighted ? 1 : 0) : (bipred_idc == 0 ? 2 : 3);
+    const uint32_t p0Y0 = pd == 2 ? prevY0 : curY0, p0Y1 = pd == 2 ? prevY1 : curY1, p0C = pd == 2 ? prevC : curC;
+    uint32_t outY0, outY1, outC;
+    {
+        int wgt[2][2] = { { 0, 0 }, { 0, 0 } }, off[2] = { 0, 0 };                 // [luma, chroma plane `half`][list]
+        if (mode == 1) {
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        const int pl = part ? 1 + half : 0;
-        const int denom = part ? denom_c : denom_y;
-        int w0 = 0, w1 = 0, o0 = 0, o1 = 0, mode;              // mode 0 copy, 1 uni weighted, 2 bi average, 3 bi weighted
-        if (pd != 2) {
-            mode = uni_weighted ? 1 : 0;
-            if (uni_weighted) {
-                w0 = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][ref0 & 31]);
-                o0 = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][ref0 & 31]);
+            for (int part = 0; part < 2; ++part) {
+                const int pl = part ? 1 + half : 0;
+                wgt[part][0] = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][ref0 & 31]);
+                off[part] = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][ref0 & 31]);
             }
-        } else if (bipred_idc == 0) mode = 2;
-        else {
-            mode = 3;
-            if (bipred_idc == 1) {
-                w0 = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][ref0 & 31]); w1 = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][ref1 & 31]);
-                o0 = (int)(int8_t)__ldg(&sl->wp_offset[0][pl][ref0 & 31]); o1 = (int)(int8_t)__ldg(&sl->wp_offset[1][pl][ref1 & 31]);
-            } else {
-                w1 = (int)__ldg(&sl->implicit_w1[ref0 & 31][ref1 & 31]); w0 = 64 - w1;
+        } else if (mode == 3) {
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const int pl = part ? 1 + half : 0;
+                if (bipred_idc == 1) {
+                    wgt[part][0] = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][ref0 & 31]);
+                    wgt[part][1] = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][ref1 & 31]);
+                    off[part] = ((int)(int8_t)__ldg(&sl->wp_offset[0][pl][ref0 & 31]) + (int)(int8_t)__ldg(&sl->wp_offset[1][pl][ref1 & 31]) + 1) >> 1;
+                } else {
+                    wgt[part][1] = (int)__ldg(&sl->implicit_w1[ref0 & 31][ref1 & 31]);
+                    wgt[part][0] = 64 - wgt[part][1];
+                }
             }
         }
-        const int n = part ? 4 : 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (i >= n) break;
-            // sample i of list 0 / list 1 and its residual
-            const uint32_t a0 = part ? (pd == 2 ? prevC : curC) : (i < 4 ? (pd == 2 ? prevY0 : curY0) : (pd == 2 ? prevY1 : curY1));
-            const uint32_t a1 = part ? curC : (i < 4 ? curY0 : curY1);
-            const int s0v = (a0 >> ((i & 3) * 8)) & 0xFF, s1v = (a1 >> ((i & 3) * 8)) & 0xFF;
-            uint32_t rw;
-            if (part) rw = (i < 2 ? resC0 : resC1) >> ((i & 1) * 16);
-            else rw = (i < 4 ? (i < 2 ? resY0.x : resY0.y) : (i < 6 ? resY1.x : resY1.y)) >> ((i & 1) * 16);
-            int v;
-            if (mode == 0) v = s0v;
-            else if (mode == 1) v = clip255(rshift_rnd(w0 * s0v, denom) + o0);
-            else if (mode == 2) v = (s0v + s1v + 1) >> 1;
-            else v = clip255(rshift_rnd(w0 * s0v + w1 * s1v, denom + 1) + ((o0 + o1 + 1) >> 1));
-            v = clip255(v + (int)(int16_t)(rw & 0xFFFF));
-            if (part == 0) outw[i >> 2] |= (uint32_t)v << ((i & 3) * 8);
-            else outw[2] |= (uint32_t)v << (i * 8);
-        }
+        outY0 = mc_weight_recon4(mode, p0Y0, curY0, wgt[0][0], wgt[0][1], denom_y, off[0], resY0.x, resY0.y);
+        outY1 = mc_weight_recon4(mode, p0Y1, curY1, wgt[0][0], wgt[0][1], denom_y, off[0], resY1.x, resY1.y);
+        outC  = mc_weight_recon4(mode, p0C,  curC,  wgt[1][0], wgt[1][1], denom_c, off[1], resC0, resC1);
     }
     uint8_t* dY = pic.dst + (size_t)(mby * 16 + ly) * g.pitch_y + mbx * 16 + lx;
     uint8_t* dC = pic.dst + (half ? g.off_cr : g.off_cb) + (size_t)(mby * 8 + cyy) * g.pitch_c + mbx * 8 + cxx;
-    *reinterpret_cast<uint32_t*>(dY) = outw[0];
-    *reinterpret_cast<uint32_t*>(dY + g.pitch_y) = outw[1];
-    *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(outw[2] & 0xFFFF);
-    *reinterpret_cast<uint16_t*>(dC + g.pitch_c) = (uint16_t)(outw[2] >> 16);
+    *reinterpret_cast<uint32_t*>(dY) = outY0;
+    *reinterpret_cast<uint32_t*>(dY + g.pitch_y) = outY1;
+    *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(outC & 0xFFFF);
+    *reinterpret_cast<uint16_t*>(dC + g.pitch_c) = (uint16_t)(outC >> 16);
 }
 
 // ---------------------------------------------------------------------------------------------------

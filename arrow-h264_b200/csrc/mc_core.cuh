@@ -1,0 +1,245 @@
+// Arithmetic core of the motion-compensation kernel: quarter-pel luma (get_block_luma, reference
+// decoder/inter_prediction.cc:158-340), eighth-pel chroma (get_block_chroma, :342-406) and weighted sample
+// prediction + reconstruction (mc_prediction / bi_prediction :53-156, Transform::construction transform.cc:913-984)
+// for the 4x2 luma / 2x2 chroma patch one lane owns.  Written on packed data:
+//   * horizontal 6-tap   : IDP.4A (u8 x s8 dot product) on 4-byte-aligned row words, taps as shifted constants
+//   * vertical 6-tap     : 16x2 SIMD-in-register (IADD3 / IMAD on biased, non-negative lanes; VIADDMNMX / VIMNMX clamps)
+//   * centre sample j    : int32 vertical 6-tap over the unrounded horizontal sums
+//   * clip + pack        : cvt.pack.sat.u8.s32 (I2IP), PRMT
+// Every quarter-pel sample is G, b, h, j or the rounded average of two of them (spec 8.4.2.2.1 == the reference's
+// branches), so the 16 fractional cases are stages predicated per lane instead of 16 code paths.
+//
+// The file compiles for the device (kernels.cu) and, with H264R_HOST_EMUL defined, for the host with the PTX
+// primitives emulated: tests/mc_core_host_test.cc checks it exhaustively against a plain restatement on the CPU.
+#ifndef H264R_MC_CORE_CUH_
+#define H264R_MC_CORE_CUH_
+
+#include <stdint.h>
+
+namespace h264r {
+
+#ifdef H264R_HOST_EMUL
+#define MC_FN static inline
+// ---- host emulation of the PTX primitives ----
+MC_FN uint32_t mc_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    const uint64_t src = (uint64_t)a | ((uint64_t)b << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t s = (sel >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(src >> (8 * (s & 7))) & 0xFF;
+        if (s & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+}
+MC_FN uint32_t mc_shf_r(uint32_t lo, uint32_t hi, uint32_t sh)          // funnel shift right, sh in [0, 31]
+{
+    const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32);
+    return (uint32_t)(v >> (sh & 31));
+}
+MC_FN int mc_dp4a_us(uint32_t a, uint32_t b, int c)                      // u8 x s8
+{
+    for (int i = 0; i < 4; ++i) c += (int)((a >> (8 * i)) & 0xFF) * (int)(int8_t)((b >> (8 * i)) & 0xFF);
+    return c;
+}
+MC_FN uint32_t mc_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)            // u8 x u8
+{
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
+    return c;
+}
+MC_FN uint32_t mc_pack_sat_u8(int a, int b, uint32_t c)                 // (c << 16) | sat_u8(a) << 8 | sat_u8(b)
+{
+    const uint32_t sa = (uint32_t)(a < 0 ? 0 : (a > 255 ? 255 : a)), sb = (uint32_t)(b < 0 ? 0 : (b > 255 ? 255 : b));
+    return (c << 16) | (sa << 8) | sb;
+}
+MC_FN uint32_t mc_viaddmax_s16x2_relu(uint32_t a, uint32_t b, uint32_t c)   // per halfword: max(max(a + b, c), 0)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 2; ++i) {
+        int x = (int)(int16_t)(uint16_t)((int16_t)(a >> (16 * i)) + (int16_t)(b >> (16 * i)));
+        const int cc = (int16_t)(c >> (16 * i));
+        if (x < cc) x = cc;
+        if (x < 0) x = 0;
+        r |= (uint32_t)(uint16_t)x << (16 * i);
+    }
+    return r;
+}
+MC_FN uint32_t mc_vmins2(uint32_t a, uint32_t b)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < 2; ++i) {
+        const int x = (int16_t)(a >> (16 * i)), y = (int16_t)(b >> (16 * i));
+        r |= (uint32_t)(uint16_t)(x < y ? x : y) << (16 * i);
+    }
+    return r;
+}
+#else
+#define MC_FN __device__ __forceinline__
+MC_FN uint32_t mc_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+MC_FN uint32_t mc_shf_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+MC_FN int mc_dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+MC_FN uint32_t mc_dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
+MC_FN uint32_t mc_pack_sat_u8(int a, int b, uint32_t c)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+MC_FN uint32_t mc_viaddmax_s16x2_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }
+MC_FN uint32_t mc_vmins2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+#endif
+
+// (a + b + 1) >> 1 on four packed bytes
+MC_FN uint32_t mc_avg_u8x4(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7F7F7F7Fu); }
+// four int32 -> four saturated bytes, v0 in byte 0
+MC_FN uint32_t mc_pack4_sat(int v0, int v1, int v2, int v3) { return mc_pack_sat_u8(v1, v0, mc_pack_sat_u8(v3, v2, 0u)); }
+
+// Horizontal 6-tap (1,-5,20,20,-5,1) at four consecutive positions.  a0|a1|a2 = twelve consecutive row bytes r0..r11
+// (r0 in byte 0 of a0); out[x] = r[x] - 5 r[x+1] + 20 r[x+2] + 20 r[x+3] - 5 r[x+4] + r[x+5] + 16.
+MC_FN void mc_htap4(uint32_t a0, uint32_t a1, uint32_t a2, int out[4])
+{
+    out[0] = mc_dp4a_us(a1, 0x000001FBu, mc_dp4a_us(a0, 0x1414FB01u, 16));
+    out[1] = mc_dp4a_us(a1, 0x0001FB14u, mc_dp4a_us(a0, 0x14FB0100u, 16));
+    out[2] = mc_dp4a_us(a1, 0x01FB1414u, mc_dp4a_us(a0, 0xFB010000u, 16));
+    out[3] = mc_dp4a_us(a2, 0x00000001u, mc_dp4a_us(a1, 0xFB1414FBu, mc_dp4a_us(a0, 0x01000000u, 16)));
+}
+
+// Luma 4x2 patch.  win = the lane's window (4-byte aligned, row pitch `pitch_words` words); off = byte offset, inside
+// the window, of the integer sample (0, 0) of the patch; the window holds the samples 2 to the left / above and 3 (+1
+// for the patch width/height) to the right / below.  xf, yf = quarter-sample fractions.  Returns the two rows packed.
+MC_FN void mc_luma_patch_4x2(const uint32_t* win, int pitch_words, int off, int xf, int yf, uint32_t& out0, uint32_t& out1)
+{
+    const bool hasB = xf != 0 && yf != 2;                       // clipped horizontal half sample b (row + dy)
+    const bool hasH = yf != 0 && xf != 2;                       // clipped vertical half sample h (column + dx)
+    const bool hasJ = (xf == 2 && yf != 0) || (yf == 2 && xf != 0);
+    const bool hasG = (xf == 0 && yf != 2) || (yf == 0 && xf != 2);
+    const int dx = xf == 3, dy = yf == 3;
+
+    // rows of the window are numbered 0..6 = sample rows -2..4
+    const unsigned hmask = hasJ ? 0x7Fu : (hasB ? 3u << (2 + dy) : 0u);                 // rows that get the horizontal 6-tap
+    const unsigned cmask = hasH ? 0x7Fu : ((hasG && yf == 0) ? 0x0Cu : 0u);             // rows whose raw samples are needed
+
+    int b1[7][4];                                                // unrounded horizontal sums + 16
+    uint32_t C[7];                                               // raw samples x+dx .. x+dx+3 of each row
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { C[k] = 0; b1[k][0] = b1[k][1] = b1[k][2] = b1[k][3] = 0; }
+
+    const int o2 = off - 2;
+    const uint32_t* wa = win + (o2 >> 2);
+    const uint32_t sha = (uint32_t)(o2 & 3) * 8;
+    const int oc = off + dx;
+    const uint32_t* wc = win + (oc >> 2);
+    const uint32_t shc = (uint32_t)(oc & 3) * 8;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        if ((hmask >> k) & 1) {
+            const uint32_t w0 = wa[k * pitch_words], w1 = wa[k * pitch_words + 1], w2 = wa[k * pitch_words + 2];
+            mc_htap4(mc_shf_r(w0, w1, sha), mc_shf_r(w1, w2, sha), w2 >> sha, b1[k]);
+        }
+        if ((cmask >> k) & 1) C[k] = mc_shf_r(wc[k * pitch_words], wc[k * pitch_words + 1], shc);
+    }
+
+    uint32_t G0 = 0, G1 = 0, B0 = 0, B1 = 0, H0 = 0, H1 = 0, J0 = 0, J1 = 0;
+    if (hasG) {                                                  // integer samples at (dx, 0) or (0, dy)
+        const bool down = xf == 0 && dy;
+        G0 = down ? C[3] : C[2];
+        G1 = down ? C[4] : C[3];
+    }
+    if (hasB) {
+        int r0[4], r1[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { r0[x] = dy ? b1[3][x] : b1[2][x]; r1[x] = dy ? b1[4][x] : b1[3][x]; }
+        B0 = mc_pack4_sat(r0[0] >> 5, r0[1] >> 5, r0[2] >> 5, r0[3] >> 5);
+        B1 = mc_pack4_sat(r1[0] >> 5, r1[1] >> 5, r1[2] >> 5, r1[3] >> 5);
+    }
+    if (hasH) {
+        // 16x2 lanes: E = columns 0 and 2, O = columns 1 and 3.  Lanes carry a bias of 2560 (= 80 << 5) + 16 so that
+        // they never go negative: the packed IMADs are then exact per lane.
+        uint32_t E[7], O[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { E[k] = mc_prmt(C[k], 0u, 0x4240u); O[k] = mc_prmt(C[k], 0u, 0x4341u); }
+        uint32_t rowE[2], rowO[2];
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+            uint32_t te = E[y] + E[y + 5] + 0x0A100A10u, to = O[y] + O[y + 5] + 0x0A100A10u;
+            te = (E[y + 2] + E[y + 3]) * 20u + te;          to = (O[y + 2] + O[y + 3]) * 20u + to;
+            te = (E[y + 1] + E[y + 4]) * 0xFFFFFFFBu + te;  to = (O[y + 1] + O[y + 4]) * 0xFFFFFFFBu + to;
+            te = (te >> 5) & 0x07FF07FFu;                   to = (to >> 5) & 0x07FF07FFu;
+            rowE[y] = mc_vmins2(mc_viaddmax_s16x2_relu(te, 0xFFB0FFB0u, 0u), 0x00FF00FFu);
+            rowO[y] = mc_vmins2(mc_viaddmax_s16x2_relu(to, 0xFFB0FFB0u, 0u), 0x00FF00FFu);
+        }
+        H0 = mc_prmt(rowE[0], rowO[0], 0x6240u);
+        H1 = mc_prmt(rowE[1], rowO[1], 0x6240u);
+    }
+    if (hasJ) {
+        int j[2][4];
+#pragma unroll
+        for (int y = 0; y < 2; ++y)
+#pragma unroll
+            for (int x = 0; x < 4; ++x)        // the +16 of every b1 sums to the +512 of the second pass
+                j[y][x] = (b1[y][x] + b1[y + 5][x] + 20 * (b1[y + 2][x] + b1[y + 3][x]) - 5 * (b1[y + 1][x] + b1[y + 4][x])) >> 10;
+        J0 = mc_pack4_sat(j[0][0], j[0][1], j[0][2], j[0][3]);
+        J1 = mc_pack4_sat(j[1][0], j[1][1], j[1][2], j[1][3]);
+    }
+    const uint32_t P0 = hasG ? G0 : (hasB ? B0 : (hasH ? H0 : J0)), P1 = hasG ? G1 : (hasB ? B1 : (hasH ? H1 : J1));
+    const uint32_t Q0 = hasJ ? J0 : (hasH ? H0 : (hasB ? B0 : G0)), Q1 = hasJ ? J1 : (hasH ? H1 : (hasB ? B1 : G1));
+    out0 = mc_avg_u8x4(P0, Q0);
+    out1 = mc_avg_u8x4(P1, Q1);
+}
+
+// Chroma 2x2 patch of one plane.  win: row pitch 2 words (8 bytes); off = byte offset of sample (0, 0), at most 5;
+// xf, yf = eighth-sample fractions.  Returns the four samples packed (row 0 in bytes 0-1, row 1 in bytes 2-3).
+MC_FN uint32_t mc_chroma_patch_2x2(const uint32_t* win, int off, int xf, int yf)
+{
+    const uint32_t* w = win + (off >> 2);
+    const uint32_t sh = (uint32_t)(off & 3) * 8;
+    uint32_t R[3];
+#pragma unroll
+    for (int y = 0; y < 3; ++y) R[y] = mc_shf_r(w[2 * y], w[2 * y + 1], sh);
+    const uint32_t wgt = (uint32_t)((8 - xf) * (8 - yf)) | (uint32_t)(xf * (8 - yf)) << 8 | (uint32_t)((8 - xf) * yf) << 16 | (uint32_t)(xf * yf) << 24;
+    uint32_t v[4];
+#pragma unroll
+    for (int y = 0; y < 2; ++y) {
+        v[2 * y]     = mc_dp4a_uu(mc_prmt(R[y], R[y + 1], 0x5410u), wgt, 32u) >> 6;
+        v[2 * y + 1] = mc_dp4a_uu(mc_prmt(R[y], R[y + 1], 0x6521u), wgt, 32u) >> 6;
+    }
+    return v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24;
+}
+
+// Weighted sample prediction of four packed samples (mc_prediction / bi_prediction, inter_prediction.cc:53-156),
+// then reconstruction clip1(pred + residual) (transform.cc:913-984).
+//   mode 0: p0                         mode 1: clip1(((w0 p0 + 2^(d-1)) >> d) + o)      [d == 0: no rounding shift]
+//   mode 2: (p0 + p1 + 1) >> 1         mode 3: clip1(((w0 p0 + w1 p1 + 2^d) >> (d + 1)) + o)
+// `o` is the final offset (mode 3: (o0 + o1 + 1) >> 1).  res01 / res23 = residuals as int16 pairs.
+MC_FN uint32_t mc_weight_recon4(int mode, uint32_t p0, uint32_t p1, int w0, int w1, int d, int o, uint32_t res01, uint32_t res23)
+{
+    uint32_t lo, hi;                                              // prediction as 16x2 pairs (s0, s1), (s2, s3)
+    if (mode & 1) {
+        int v[4];
+        const int sh = mode == 1 ? d : d + 1;
+        const int rnd = sh > 0 ? 1 << (sh - 1) : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int acc = (int)((p0 >> (8 * i)) & 0xFF) * w0 + rnd;
+            if (mode == 3) acc += (int)((p1 >> (8 * i)) & 0xFF) * w1;
+            v[i] = (acc >> sh) + o;
+        }
+        const uint32_t c = mc_pack4_sat(v[0], v[1], v[2], v[3]);  // clip1
+        lo = mc_prmt(c, 0u, 0x4140u); hi = mc_prmt(c, 0u, 0x4342u);
+    } else {
+        const uint32_t c = mode == 2 ? mc_avg_u8x4(p0, p1) : p0;
+        lo = mc_prmt(c, 0u, 0x4140u); hi = mc_prmt(c, 0u, 0x4342u);
+    }
+    lo = mc_vmins2(mc_viaddmax_s16x2_relu(lo, res01, 0u), 0x00FF00FFu);
+    hi = mc_vmins2(mc_viaddmax_s16x2_relu(hi, res23, 0u), 0x00FF00FFu);
+    return mc_prmt(lo, hi, 0x6420u);
+}
+
+} // namespace h264r
+#endif
