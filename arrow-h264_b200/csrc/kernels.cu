@@ -285,28 +285,20 @@ __device__ __forceinline__ void partition_of_block(const MbHdr& h, int is_b, int
     covers8x8 = sh4 >= 2 && sv4 >= 2;
 }
 
-// Reference window: rows [y0, y0+nrows) x bytes [x0, x0+ncols) of a plane go to shared memory.  Interior windows are
-// fetched as aligned 32-bit words (the sample x0 then sits at byte offset x0 & 3 of a window row); windows touching the
-// picture border are fetched sample by sample with clamped coordinates (== the reference's padded planes)
-// and start at byte offset 0.
-__device__ __forceinline__ bool window_interior(int x0, int y0, int ncols, int nrows, int W, int H)
+// Reference windows in shared memory.  Interior windows are fetched as aligned 32-bit words: the first sample x0 of
+// a window row then sits at byte offset x0 & 3.  Windows touching the picture border (rare) are fetched sample by
+// sample with clamped coordinates -- bit-identical to the reference's padded planes + block pre-clamp, SURVEY.md
+// 8a -- and start at byte offset 0; that path is kept out of line.
+__device__ __noinline__ void load_window_border(uint32_t* win, int pitch_words, const uint8_t* __restrict__ plane, int pitch,
+                                                int W, int H, int x0, int y0, int ncols, int nrows, int first_row, int row_step)
 {
-    const int xa = x0 & ~3;
-    return xa >= 0 && xa + (((x0 - xa) + ncols + 3) & ~3) <= W && y0 >= 0 && y0 + nrows <= H;
-}
-__device__ __forceinline__ void load_window_row(uint32_t* win_row, const uint8_t* __restrict__ plane, int pitch, int W, int H,
-                                                int x0, int y, int ncols, bool interior)
-{
-    if (interior) {
-        const int xa = x0 & ~3, nwords = ((x0 - xa) + ncols + 3) >> 2;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(plane + (size_t)y * pitch + xa);
-        for (int k = 0; k < nwords; ++k) win_row[k] = __ldg(src + k);
-    } else {
-        const uint8_t* src = plane + (size_t)clip3i(0, H - 1, y) * pitch;
-        uint8_t* dst = reinterpret_cast<uint8_t*>(win_row);
+    for (int row = first_row; row < nrows; row += row_step) {
+        const uint8_t* src = plane + (uint32_t)(clip3i(0, H - 1, y0 + row) * pitch);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(win + row * pitch_words);
         for (int c = 0; c < ncols; ++c) dst[c] = __ldg(src + clip3i(0, W - 1, x0 + c));
     }
 }
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
 
 // per-warp scratch, in 32-bit words.  Per 8x8 quadrant: luma 114 words = uniform quadrant 13 rows x 4 words | split
 // quadrant 4 blocks x (9 rows x 3 words); chroma 50 words = uniform 2 planes x (5 rows x 2 words) | split 4 blocks x
@@ -320,22 +312,21 @@ struct __align__(16) InterSmem {
 };
 static_assert(sizeof(InterSmem) % 16 == 0 && offsetof(InterSmem, motion) % 16 == 0, "InterSmem alignment");
 
+// grid = (ceil(width_mbs / 4), height_mbs, pictures of the wave): one warp per macroblock, no index divisions
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 5)
-recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g, int direct8x8)
+recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8x8)
 {
     __shared__ __align__(16) InterSmem smem_all[kWarpsPerCta];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nmb = g.width_mbs * g.height_mbs;
-    const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (gw >= (long long)num_pics * nmb) return;
-    const int pic_i = (int)(gw / nmb), addr = (int)(gw - (long long)pic_i * nmb);
-    const DevPicture& pic = pics[pic_i];
+    const int mbx = blockIdx.x * kWarpsPerCta + warp, mby = blockIdx.y;
+    if (mbx >= g.width_mbs) return;
+    const DevPicture& pic = pics[blockIdx.z];
     if (!pic.has_inter) return;
+    const int addr = mby * g.width_mbs + mbx;
     const MbHdr h = load_hdr(pic.mbs, addr);
     if (h.intra()) return;
     InterSmem& sm = smem_all[warp];
     const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
-    const int mbx = addr % g.width_mbs, mby = addr / g.width_mbs;
     const int wY = g.width_mbs * 16, hY = g.height_mbs * 16, wC = wY >> 1, hC = hY >> 1;
 
     if (lane < 12) reinterpret_cast<uint4*>(&sm.motion)[lane] = __ldg(reinterpret_cast<const uint4*>(pic.motion + addr) + lane);
@@ -370,6 +361,7 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
 
     uint32_t* const lq = sm.luma + q * kLumaQ;
     uint32_t* const cq = sm.chroma + q * kChromaQ;
+    const int pitch_y = g.pitch_y, pitch_c = g.pitch_c;
 
     // samples of the (up to) two lists, packed bytes: cur = last list done, prev = the one before
     uint32_t curY0 = 0, curY1 = 0, curC = 0, prevY0 = 0, prevY1 = 0, prevC = 0;
@@ -377,6 +369,7 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
 #pragma unroll 1
     for (int k = 0; k < 2; ++k) {
         const bool active = k == 0 || pd == 2;
+        if (k == 1 && !__any_sync(0xFFFFFFFFu, active)) break;
         const int list = pd == 2 ? k : pd;
         int vx = 0, vy = 0, refidx = 0;
         const uint32_t* wl = lq; const uint32_t* wc = cq;
@@ -390,13 +383,31 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
             if (uni) {
                 const int qvx = (mbx * 16 + qx * 8) * 4 + mvx, qvy = (mby * 16 + qy * 8) * 4 + mvy;
                 const int x0 = (qvx >> 2) - 2, y0 = (qvy >> 2) - 2, cx0 = qvx >> 3, cy0 = qvy >> 3;
-                const bool in_y = window_interior(x0, y0, 13, 13, wY, hY), in_c = window_interior(cx0, cy0, 5, 5, wC, hC);
-                for (int row = r; row < 13; row += 8)
-                    load_window_row(lq + row * 4, rbase, g.pitch_y, wY, hY, x0, y0 + row, 13, in_y);
-                for (int i = r; i < 10; i += 8) {               // chroma: 2 planes x 5 rows over 8 lanes
-                    const int pl = i >= 5, row = i - pl * 5;
-                    load_window_row(cq + pl * 10 + row * 2, rbase + (pl ? g.off_cr : g.off_cb), g.pitch_c, wC, hC,
-                                    cx0, cy0 + row, 5, in_c);
+                const int xa = x0 & ~3, cxa = cx0 & ~3;
+                const bool in_y = xa >= 0 && xa + 16 <= wY && y0 >= 0 && y0 + 13 <= hY;
+                const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 5 <= hC;
+                if (in_y) {                                     // 13 rows x 4 words: lane = (row parity, word)
+                    const int col = r & 3, rsel = r >> 2;
+                    const uint8_t* src = rbase + (uint32_t)((y0 + rsel) * pitch_y + xa + col * 4);
+                    uint32_t* dst = lq + rsel * 4 + col;
+                    uint32_t v[7];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) if (i < 6 || rsel == 0) v[i] = ldg_u32(src + (uint32_t)(i * 2 * pitch_y));
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) if (i < 6 || rsel == 0) dst[i * 8] = v[i];
+                } else load_window_border(lq, 4, rbase, pitch_y, wY, hY, x0, y0, 13, 13, r, 8);
+                if (in_c) {                                     // 2 planes x 5 rows x 2 words: lane = (row parity, plane, word)
+                    const int col = r & 1, pl = (r >> 1) & 1, rsel = r >> 2;
+                    const uint8_t* src = rbase + (pl ? g.off_cr : g.off_cb) + (uint32_t)((cy0 + rsel) * pitch_c + cxa + col * 4);
+                    uint32_t* dst = cq + pl * 10 + rsel * 2 + col;
+                    uint32_t v[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) if (i < 2 || rsel == 0) v[i] = ldg_u32(src + (uint32_t)(i * 2 * pitch_c));
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) if (i < 2 || rsel == 0) dst[i * 4] = v[i];
+                } else {
+                    const int pl = r & 1;
+                    load_window_border(cq + pl * 10, 2, rbase + (pl ? g.off_cr : g.off_cb), pitch_c, wC, hC, cx0, cy0, 5, 5, r >> 1, 4);
                 }
                 wl = lq + ((sb >> 1) * 4 + half * 2) * 4;
                 loff = 2 + (sb & 1) * 4 + (in_y ? x0 & 3 : 0);
@@ -404,16 +415,37 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
                 coff = (sb & 1) * 2 + (in_c ? cx0 & 3 : 0);
             } else {
                 const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2, cx0 = vx >> 3, cy0 = vy >> 3;
-                const bool in_y = window_interior(x0, y0, 9, 9, wY, hY), in_c = window_interior(cx0, cy0, 3, 3, wC, hC);
-                for (int row = half; row < 9; row += 2)
-                    load_window_row(lq + sb * 27 + row * 3, rbase, g.pitch_y, wY, hY, x0, y0 + row, 9, in_y);
-                for (int row = 0; row < 3; ++row)
-                    load_window_row(cq + sb * 12 + half * 6 + row * 2, rbase + (half ? g.off_cr : g.off_cb), g.pitch_c, wC, hC,
-                                    cx0, cy0 + row, 3, in_c);
-                wl = lq + sb * 27 + half * 2 * 3;
+                const int xa = x0 & ~3, cxa = cx0 & ~3;
+                const bool in_y = xa >= 0 && xa + 12 <= wY && y0 >= 0 && y0 + 9 <= hY;
+                const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 3 <= hC;
+                uint32_t* const lb = lq + sb * 27;
+                uint32_t* const cb = cq + sb * 12 + half * 6;
+                const uint8_t* const cplane = rbase + (half ? g.off_cr : g.off_cb);
+                if (in_y) {                                     // 9 rows x 3 words: the two lanes of the block take alternate rows
+                    const uint8_t* src = rbase + (uint32_t)((y0 + half) * pitch_y + xa);
+                    uint32_t* dst = lb + half * 3;
+                    uint32_t v[5][3];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) if (i < 4 || half == 0)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) v[i][c] = ldg_u32(src + (uint32_t)(i * 2 * pitch_y) + c * 4);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) if (i < 4 || half == 0)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) dst[i * 6 + c] = v[i][c];
+                } else load_window_border(lb, 3, rbase, pitch_y, wY, hY, x0, y0, 9, 9, half, 2);
+                if (in_c) {                                     // 3 rows x 2 words of this lane's plane
+                    const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa);
+                    uint32_t v[3][2];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) { v[i][0] = ldg_u32(src + (uint32_t)(i * pitch_c)); v[i][1] = ldg_u32(src + (uint32_t)(i * pitch_c) + 4); }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) { cb[i * 2] = v[i][0]; cb[i * 2 + 1] = v[i][1]; }
+                } else load_window_border(cb, 2, cplane, pitch_c, wC, hC, cx0, cy0, 3, 3, 0, 1);
+                wl = lb + half * 2 * 3;
                 lpitch = 3;
                 loff = 2 + (in_y ? x0 & 3 : 0);
-                wc = cq + sb * 12 + half * 6;
+                wc = cb;
                 coff = in_c ? cx0 & 3 : 0;
             }
         }
@@ -459,12 +491,12 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom 
         outY1 = mc_weight_recon4(mode, p0Y1, curY1, wgt[0][0], wgt[0][1], denom_y, off[0], resY1.x, resY1.y);
         outC  = mc_weight_recon4(mode, p0C,  curC,  wgt[1][0], wgt[1][1], denom_c, off[1], resC0, resC1);
     }
-    uint8_t* dY = pic.dst + (size_t)(mby * 16 + ly) * g.pitch_y + mbx * 16 + lx;
-    uint8_t* dC = pic.dst + (half ? g.off_cr : g.off_cb) + (size_t)(mby * 8 + cyy) * g.pitch_c + mbx * 8 + cxx;
+    uint8_t* dY = pic.dst + (uint32_t)((mby * 16 + ly) * pitch_y + mbx * 16 + lx);
+    uint8_t* dC = pic.dst + (half ? g.off_cr : g.off_cb) + (uint32_t)((mby * 8 + cyy) * pitch_c + mbx * 8 + cxx);
     *reinterpret_cast<uint32_t*>(dY) = outY0;
-    *reinterpret_cast<uint32_t*>(dY + g.pitch_y) = outY1;
+    *reinterpret_cast<uint32_t*>(dY + pitch_y) = outY1;
     *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(outC & 0xFFFF);
-    *reinterpret_cast<uint16_t*>(dC + g.pitch_c) = (uint16_t)(outC >> 16);
+    *reinterpret_cast<uint16_t*>(dC + pitch_c) = (uint16_t)(outC >> 16);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1156,9 +1188,8 @@ bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     }
     if (which == KERNEL_INTER) {
         if (!w.any_inter) return false;
-        const long long warps = (long long)w.num_pics * nmb;
-        const int blocks = (int)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
-        recon_inter_kernel<<<blocks, threads, 0, stream>>>(w.pics, w.num_pics, w.geom, w.direct8x8);
+        const dim3 grid((w.geom.width_mbs + kWarpsPerCta - 1) / kWarpsPerCta, w.geom.height_mbs, w.num_pics);
+        recon_inter_kernel<<<grid, threads, 0, stream>>>(w.pics, w.geom, w.direct8x8);
         return true;
     }
     if (which == KERNEL_INTRA) {
