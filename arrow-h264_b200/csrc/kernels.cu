@@ -18,6 +18,16 @@
 namespace h264r {
 
 constexpr int kWarpsPerCta = 4;
+// resident CTAs per SM the register allocation aims at (tuned on B200, scripts/tune.sh)
+#ifndef H264R_INTER_CTAS
+#define H264R_INTER_CTAS 8
+#endif
+#ifndef H264R_INTRA_CTAS
+#define H264R_INTRA_CTAS 4
+#endif
+#ifndef H264R_DEBLOCK_CTAS
+#define H264R_DEBLOCK_CTAS 8
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // small helpers
@@ -300,11 +310,11 @@ __device__ __noinline__ void load_window_border(uint32_t* win, int pitch_words, 
 }
 __device__ __forceinline__ uint32_t ldg_u32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
 
-// per-warp scratch, in 32-bit words.  Per 8x8 quadrant: luma 114 words = uniform quadrant 13 rows x 4 words | split
-// quadrant 4 blocks x (9 rows x 3 words); chroma 50 words = uniform 2 planes x (5 rows x 2 words) | split 4 blocks x
-// 2 planes x (3 rows x 2 words), + 1 word the funnel shifts may touch.  114 = 2 (mod 8): the four quadrant groups of a
-// warp read disjoint banks.
-constexpr int kLumaQ = 114, kChromaQ = 50;
+// per-warp scratch, in 32-bit words.  Per 8x8 quadrant: luma 146 words = uniform quadrant 13 rows x 4 words | split
+// quadrant 4 blocks x (9 rows x 4 words), one row pitch for both so that row offsets are immediates; chroma 50 words =
+// uniform 2 planes x (5 rows x 2 words) | split 4 blocks x 2 planes x (3 rows x 2 words), + 1 word the funnel shifts
+// may touch.  146 = 2 (mod 8): the four quadrant groups of a warp read disjoint banks.
+constexpr int kLumaQ = 146, kChromaQ = 50;
 struct __align__(16) InterSmem {
     uint32_t luma[4 * kLumaQ + 2];
     uint32_t chroma[4 * kChromaQ + 2];
@@ -313,7 +323,7 @@ struct __align__(16) InterSmem {
 static_assert(sizeof(InterSmem) % 16 == 0 && offsetof(InterSmem, motion) % 16 == 0, "InterSmem alignment");
 
 // grid = (ceil(width_mbs / 4), height_mbs, pictures of the wave): one warp per macroblock, no index divisions
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 5)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTER_CTAS)
 recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8x8)
 {
     __shared__ __align__(16) InterSmem smem_all[kWarpsPerCta];
@@ -373,7 +383,7 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
         const int list = pd == 2 ? k : pd;
         int vx = 0, vy = 0, refidx = 0;
         const uint32_t* wl = lq; const uint32_t* wc = cq;
-        int lpitch = 4, loff = 2, coff = 0;
+        int loff = 2, coff = 0;
         if (active) {
             refidx = sm.motion.ref_idx[list][origin];
             const int slot = (int)(int8_t)__ldg(&sl->ref_pic_list[list][refidx & 31]);
@@ -418,12 +428,12 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
                 const int xa = x0 & ~3, cxa = cx0 & ~3;
                 const bool in_y = xa >= 0 && xa + 12 <= wY && y0 >= 0 && y0 + 9 <= hY;
                 const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 3 <= hC;
-                uint32_t* const lb = lq + sb * 27;
+                uint32_t* const lb = lq + sb * 36;
                 uint32_t* const cb = cq + sb * 12 + half * 6;
                 const uint8_t* const cplane = rbase + (half ? g.off_cr : g.off_cb);
                 if (in_y) {                                     // 9 rows x 3 words: the two lanes of the block take alternate rows
                     const uint8_t* src = rbase + (uint32_t)((y0 + half) * pitch_y + xa);
-                    uint32_t* dst = lb + half * 3;
+                    uint32_t* dst = lb + half * 4;
                     uint32_t v[5][3];
 #pragma unroll
                     for (int i = 0; i < 5; ++i) if (i < 4 || half == 0)
@@ -432,8 +442,8 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
 #pragma unroll
                     for (int i = 0; i < 5; ++i) if (i < 4 || half == 0)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) dst[i * 6 + c] = v[i][c];
-                } else load_window_border(lb, 3, rbase, pitch_y, wY, hY, x0, y0, 9, 9, half, 2);
+                        for (int c = 0; c < 3; ++c) dst[i * 8 + c] = v[i][c];
+                } else load_window_border(lb, 4, rbase, pitch_y, wY, hY, x0, y0, 9, 9, half, 2);
                 if (in_c) {                                     // 3 rows x 2 words of this lane's plane
                     const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa);
                     uint32_t v[3][2];
@@ -442,8 +452,7 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
 #pragma unroll
                     for (int i = 0; i < 3; ++i) { cb[i * 2] = v[i][0]; cb[i * 2 + 1] = v[i][1]; }
                 } else load_window_border(cb, 2, cplane, pitch_c, wC, hC, cx0, cy0, 3, 3, 0, 1);
-                wl = lb + half * 2 * 3;
-                lpitch = 3;
+                wl = lb + half * 2 * 4;
                 loff = 2 + (in_y ? x0 & 3 : 0);
                 wc = cb;
                 coff = in_c ? cx0 & 3 : 0;
@@ -452,7 +461,9 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
         __syncwarp();
         if (active) {
             prevY0 = curY0; prevY1 = curY1; prevC = curC; ref_prev = ref_cur; ref_cur = refidx;
-            mc_luma_patch_4x2(wl, lpitch, loff, vx & 3, vy & 3, curY0, curY1);
+            const int xf = vx & 3, yf = vy & 3;
+            const bool any_j = __any_sync(__activemask(), (xf == 2 && yf != 0) || (yf == 2 && xf != 0));
+            mc_luma_patch_4x2(wl, loff, xf, yf, any_j, curY0, curY1);
             curC = mc_chroma_patch_2x2(wc, coff, vx & 7, vy & 7);
         }
         __syncwarp();
@@ -625,7 +636,7 @@ __device__ __forceinline__ int dc_value(int n, int log2n, bool a, bool b, TF T, 
     return (sum + round) >> shift;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTRA_CTAS)
 recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
 {
     __shared__ __align__(16) IntraSmem smem_all[kWarpsPerCta];
@@ -1039,7 +1050,7 @@ __device__ __forceinline__ void filter_samples(uint8_t* pix, int step, int bS, i
     if (aq) pix[step]      = (uint8_t)(q1 + clip3i(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 * 2)) >> 1));
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 8)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_DEBLOCK_CTAS)
 deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
 {
     __shared__ __align__(16) DeblockSmem smem_all[kWarpsPerCta];

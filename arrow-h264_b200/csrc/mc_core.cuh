@@ -110,25 +110,28 @@ MC_FN void mc_htap4(uint32_t a0, uint32_t a1, uint32_t a2, int out[4])
     out[3] = mc_dp4a_us(a2, 0x00000001u, mc_dp4a_us(a1, 0xFB1414FBu, mc_dp4a_us(a0, 0x01000000u, 16)));
 }
 
-// Luma 4x2 patch.  win = the lane's window (4-byte aligned, row pitch `pitch_words` words); off = byte offset, inside
+// Luma 4x2 patch.  win = the lane's window (4-byte aligned, row pitch kLumaPitchWords words); off = byte offset, inside
 // the window, of the integer sample (0, 0) of the patch; the window holds the samples 2 to the left / above and 3 (+1
 // for the patch width/height) to the right / below.  xf, yf = quarter-sample fractions.  Returns the two rows packed.
-MC_FN void mc_luma_patch_4x2(const uint32_t* win, int pitch_words, int off, int xf, int yf, uint32_t& out0, uint32_t& out1)
+//
+// One pass over the seven window rows (sample rows -2..4).  Per row, if the lane needs it:
+//   horizontal stage: four unrounded 6-tap sums (+16) -> (rows 0..2 of the patch) clipped half sample b, and the
+//                     running vertical 6-tap sums of the centre sample j (int32; the +16s add up to the +512);
+//   raw stage       : the four samples at column offset dx -> integer samples G, and the running vertical 6-tap of
+//                     the half sample h in 16x2 lanes (E = columns 0,2; O = columns 1,3).  The lanes start at
+//                     2560 + 16 (= (80 << 5) + 16) and never go negative, so packed IMADs are exact per lane.
+// `any_j` lets a warp in which no lane needs j skip those accumulations (pass true if unknown).
+constexpr int kLumaPitchWords = 4;
+MC_FN void mc_luma_patch_4x2(const uint32_t* win, int off, int xf, int yf, bool any_j, uint32_t& out0, uint32_t& out1)
 {
+    constexpr int pitch_words = kLumaPitchWords;
     const bool hasB = xf != 0 && yf != 2;                       // clipped horizontal half sample b (row + dy)
     const bool hasH = yf != 0 && xf != 2;                       // clipped vertical half sample h (column + dx)
     const bool hasJ = (xf == 2 && yf != 0) || (yf == 2 && xf != 0);
     const bool hasG = (xf == 0 && yf != 2) || (yf == 0 && xf != 2);
     const int dx = xf == 3, dy = yf == 3;
-
-    // rows of the window are numbered 0..6 = sample rows -2..4
     const unsigned hmask = hasJ ? 0x7Fu : (hasB ? 3u << (2 + dy) : 0u);                 // rows that get the horizontal 6-tap
     const unsigned cmask = hasH ? 0x7Fu : ((hasG && yf == 0) ? 0x0Cu : 0u);             // rows whose raw samples are needed
-
-    int b1[7][4];                                                // unrounded horizontal sums + 16
-    uint32_t C[7];                                               // raw samples x+dx .. x+dx+3 of each row
-#pragma unroll
-    for (int k = 0; k < 7; ++k) { C[k] = 0; b1[k][0] = b1[k][1] = b1[k][2] = b1[k][3] = 0; }
 
     const int o2 = off - 2;
     const uint32_t* wa = win + (o2 >> 2);
@@ -136,59 +139,64 @@ MC_FN void mc_luma_patch_4x2(const uint32_t* win, int pitch_words, int off, int 
     const int oc = off + dx;
     const uint32_t* wc = win + (oc >> 2);
     const uint32_t shc = (uint32_t)(oc & 3) * 8;
+
+    int jacc[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
+    uint32_t tE[2] = { 0x0A100A10u, 0x0A100A10u }, tO[2] = { 0x0A100A10u, 0x0A100A10u };
+    uint32_t Brow[3] = { 0, 0, 0 }, Grow[3] = { 0, 0, 0 };      // window rows 2, 3, 4
+    constexpr int tap[6] = { 1, -5, 20, 20, -5, 1 };
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         if ((hmask >> k) & 1) {
             const uint32_t w0 = wa[k * pitch_words], w1 = wa[k * pitch_words + 1], w2 = wa[k * pitch_words + 2];
-            mc_htap4(mc_shf_r(w0, w1, sha), mc_shf_r(w1, w2, sha), w2 >> sha, b1[k]);
+            int b1[4];
+            mc_htap4(mc_shf_r(w0, w1, sha), mc_shf_r(w1, w2, sha), w2 >> sha, b1);
+            if (k >= 2 && k <= 4) Brow[k - 2] = mc_pack4_sat(b1[0] >> 5, b1[1] >> 5, b1[2] >> 5, b1[3] >> 5);
+            if (any_j) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (k <= 5) jacc[0][x] += tap[k] * b1[x];
+                    if (k >= 1) jacc[1][x] += tap[k - 1] * b1[x];
+                }
+            }
         }
-        if ((cmask >> k) & 1) C[k] = mc_shf_r(wc[k * pitch_words], wc[k * pitch_words + 1], shc);
+        if ((cmask >> k) & 1) {
+            const uint32_t c = mc_shf_r(wc[k * pitch_words], wc[k * pitch_words + 1], shc);
+            if (k >= 2 && k <= 4) Grow[k - 2] = c;
+            const uint32_t e = mc_prmt(c, 0u, 0x4240u), o = mc_prmt(c, 0u, 0x4341u);
+            if (k <= 5) { tE[0] += (uint32_t)tap[k] * e; tO[0] += (uint32_t)tap[k] * o; }
+            if (k >= 1) { tE[1] += (uint32_t)tap[k - 1] * e; tO[1] += (uint32_t)tap[k - 1] * o; }
+        }
     }
 
-    uint32_t G0 = 0, G1 = 0, B0 = 0, B1 = 0, H0 = 0, H1 = 0, J0 = 0, J1 = 0;
+    uint32_t P0, P1, Q0, Q1;                                     // the (up to) two samples averaged per position
+    // first: G, else b, else h, else j
     if (hasG) {                                                  // integer samples at (dx, 0) or (0, dy)
         const bool down = xf == 0 && dy;
-        G0 = down ? C[3] : C[2];
-        G1 = down ? C[4] : C[3];
-    }
-    if (hasB) {
-        int r0[4], r1[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) { r0[x] = dy ? b1[3][x] : b1[2][x]; r1[x] = dy ? b1[4][x] : b1[3][x]; }
-        B0 = mc_pack4_sat(r0[0] >> 5, r0[1] >> 5, r0[2] >> 5, r0[3] >> 5);
-        B1 = mc_pack4_sat(r1[0] >> 5, r1[1] >> 5, r1[2] >> 5, r1[3] >> 5);
-    }
+        P0 = down ? Grow[1] : Grow[0];
+        P1 = down ? Grow[2] : Grow[1];
+    } else if (hasB) {
+        P0 = dy ? Brow[1] : Brow[0];
+        P1 = dy ? Brow[2] : Brow[1];
+    } else P0 = P1 = 0;
+    uint32_t H0 = 0, H1 = 0, J0 = 0, J1 = 0;
     if (hasH) {
-        // 16x2 lanes: E = columns 0 and 2, O = columns 1 and 3.  Lanes carry a bias of 2560 (= 80 << 5) + 16 so that
-        // they never go negative: the packed IMADs are then exact per lane.
-        uint32_t E[7], O[7];
+        uint32_t r[4] = { tE[0], tO[0], tE[1], tO[1] };
 #pragma unroll
-        for (int k = 0; k < 7; ++k) { E[k] = mc_prmt(C[k], 0u, 0x4240u); O[k] = mc_prmt(C[k], 0u, 0x4341u); }
-        uint32_t rowE[2], rowO[2];
-#pragma unroll
-        for (int y = 0; y < 2; ++y) {
-            uint32_t te = E[y] + E[y + 5] + 0x0A100A10u, to = O[y] + O[y + 5] + 0x0A100A10u;
-            te = (E[y + 2] + E[y + 3]) * 20u + te;          to = (O[y + 2] + O[y + 3]) * 20u + to;
-            te = (E[y + 1] + E[y + 4]) * 0xFFFFFFFBu + te;  to = (O[y + 1] + O[y + 4]) * 0xFFFFFFFBu + to;
-            te = (te >> 5) & 0x07FF07FFu;                   to = (to >> 5) & 0x07FF07FFu;
-            rowE[y] = mc_vmins2(mc_viaddmax_s16x2_relu(te, 0xFFB0FFB0u, 0u), 0x00FF00FFu);
-            rowO[y] = mc_vmins2(mc_viaddmax_s16x2_relu(to, 0xFFB0FFB0u, 0u), 0x00FF00FFu);
-        }
-        H0 = mc_prmt(rowE[0], rowO[0], 0x6240u);
-        H1 = mc_prmt(rowE[1], rowO[1], 0x6240u);
+        for (int i = 0; i < 4; ++i)
+            r[i] = mc_vmins2(mc_viaddmax_s16x2_relu((r[i] >> 5) & 0x07FF07FFu, 0xFFB0FFB0u, 0u), 0x00FF00FFu);
+        H0 = mc_prmt(r[0], r[1], 0x6240u);
+        H1 = mc_prmt(r[2], r[3], 0x6240u);
     }
     if (hasJ) {
-        int j[2][4];
-#pragma unroll
-        for (int y = 0; y < 2; ++y)
-#pragma unroll
-            for (int x = 0; x < 4; ++x)        // the +16 of every b1 sums to the +512 of the second pass
-                j[y][x] = (b1[y][x] + b1[y + 5][x] + 20 * (b1[y + 2][x] + b1[y + 3][x]) - 5 * (b1[y + 1][x] + b1[y + 4][x])) >> 10;
-        J0 = mc_pack4_sat(j[0][0], j[0][1], j[0][2], j[0][3]);
-        J1 = mc_pack4_sat(j[1][0], j[1][1], j[1][2], j[1][3]);
+        J0 = mc_pack4_sat(jacc[0][0] >> 10, jacc[0][1] >> 10, jacc[0][2] >> 10, jacc[0][3] >> 10);
+        J1 = mc_pack4_sat(jacc[1][0] >> 10, jacc[1][1] >> 10, jacc[1][2] >> 10, jacc[1][3] >> 10);
     }
-    const uint32_t P0 = hasG ? G0 : (hasB ? B0 : (hasH ? H0 : J0)), P1 = hasG ? G1 : (hasB ? B1 : (hasH ? H1 : J1));
-    const uint32_t Q0 = hasJ ? J0 : (hasH ? H0 : (hasB ? B0 : G0)), Q1 = hasJ ? J1 : (hasH ? H1 : (hasB ? B1 : G1));
+    if (!hasG && !hasB) { P0 = hasH ? H0 : J0; P1 = hasH ? H1 : J1; }
+    // second: j, else h, else b, else G (== first when only one kind is present)
+    if (hasJ) { Q0 = J0; Q1 = J1; }
+    else if (hasH) { Q0 = H0; Q1 = H1; }
+    else if (hasB) { Q0 = dy ? Brow[1] : Brow[0]; Q1 = dy ? Brow[2] : Brow[1]; }
+    else { Q0 = P0; Q1 = P1; }
     out0 = mc_avg_u8x4(P0, Q0);
     out1 = mc_avg_u8x4(P1, Q1);
 }

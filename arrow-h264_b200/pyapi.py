@@ -100,7 +100,8 @@ def recon_lib():
     """The CUDA engine.  Raises if it is not built: there is no CPU fallback."""
     global _recon
     if _recon is None:
-        path = os.path.join(HERE, "libh264recon.so")
+        # H264R_LIB: another build of the same library (kernel-tuning experiments, scripts/tune.sh)
+        path = os.environ.get("H264R_LIB") or os.path.join(HERE, "libh264recon.so")
         if not os.path.exists(path):
             raise RuntimeError("libh264recon.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                                "the engine has no CPU fallback")

@@ -242,11 +242,13 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
         eng.wait()
     barrier()
     s2 = eng.stats()
+    # steps are enqueued back to back like a streaming decoder would (the engine orders each wave's H2D after the
+    # previous use of its staging in HBM, each frame's D2H after the wave that produced it); one join at the end
     t_start = time.perf_counter()
     for _ in range(args.steps):
         eng.replay(1, E2E)
         download_all()
-        eng.wait()
+    eng.wait()
     t_e2e = time.perf_counter() - t_start
     s3 = eng.stats()
     barrier()

@@ -78,14 +78,14 @@ static void test_luma()
     for (int iter = 0; iter < 4000; ++iter) {
         const int pattern = iter % 6;
         fill(win, sizeof(win), pattern);
-        for (int pitch_words = 3; pitch_words <= 4; ++pitch_words) {
-            const int pitch = pitch_words * 4;
-            const int max_off = pitch_words == 4 ? 2 + 4 + 3 : 2 + 3;       // uniform quadrant / split block
+        {
+            const int pitch = kLumaPitchWords * 4;
+            const int max_off = 2 + 4 + 3;                                  // uniform quadrant, second block, x0 & 3 == 3
             for (int off = 2; off <= max_off; ++off)
                 for (int xf = 0; xf < 4; ++xf)
                     for (int yf = 0; yf < 4; ++yf) {
                         uint32_t o0, o1;
-                        mc_luma_patch_4x2(reinterpret_cast<const uint32_t*>(win), pitch_words, off, xf, yf, o0, o1);
+                        mc_luma_patch_4x2(reinterpret_cast<const uint32_t*>(win), off, xf, yf, true, o0, o1);
                         auto W = [&](int x, int y) { return (int)win[(y + 2) * pitch + off + x]; };
                         for (int y = 0; y < 2; ++y)
                             for (int x = 0; x < 4; ++x) {
