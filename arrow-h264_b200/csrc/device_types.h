@@ -16,11 +16,14 @@ struct FrameGeom {
     size_t off_cb, off_cr, bytes;    // plane offsets inside the allocation
 };
 
-// Output of the parallel deblock pre-pass, input of the deblock wavefront: 32 bytes per MB.
+// Output of the parallel deblock pre-pass, input of the deblock wavefront: 64 bytes per MB.
+//   bs[dir * 2 + (edge >> 1)], nibble (edge & 1) * 4 + group = boundary strength 0..4 of the 4-sample group of that edge
+//   par[plane][type], type 0 = left MB edge, 1 = internal edges, 2 = top MB edge: the filter thresholds of
+//   filter_edge (deblock.cc:469-474 + tables :294-324) packed as alpha | beta << 8 | tc0[bS=1] << 13 | tc0[2] << 18 |
+//   tc0[3] << 23, so that tc0(bS) = (par >> (8 + 5 * bS)) & 31.
 struct DeblockDesc {
-    uint32_t bs[3];                  // bit planes of bS; bit index = dir*16 + edge*4 + 4-sample group
-    uint8_t  ia[9], ib[9];           // indexA / indexB for [left MB edge, internal, top MB edge] x [Y, Cb, Cr]
-    uint8_t  pad[2];
+    uint32_t bs[4];
+    uint32_t par[3][4];              // [Y, Cb, Cr][type 0..2, pad]
 };
 
 struct DevPicture {

@@ -11,7 +11,7 @@ using namespace h264r;
 
 static_assert(sizeof(h264r_mb) == 32, "h264r_mb must be 32 bytes");
 static_assert(sizeof(h264r_mb_motion) == 192, "h264r_mb_motion must be 192 bytes");
-static_assert(sizeof(DeblockDesc) == 32, "DeblockDesc must be 32 bytes");
+static_assert(sizeof(DeblockDesc) == 64, "DeblockDesc must be 64 bytes");
 static_assert(sizeof(h264r_slice) % 16 == 0, "h264r_slice must keep 16-byte alignment in arrays");
 
 namespace {

@@ -26,7 +26,7 @@ constexpr int kWarpsPerCta = 4;
 #define H264R_INTRA_CTAS 4
 #endif
 #ifndef H264R_DEBLOCK_CTAS
-#define H264R_DEBLOCK_CTAS 8
+#define H264R_DEBLOCK_CTAS 6
 #endif
 
 // ---------------------------------------------------------------------------------------------------
@@ -904,7 +904,7 @@ __constant__ uint8_t c_tc0[52][3] = {
     {2,2,4},{2,3,4},{2,3,4},{3,3,5},{3,4,6},{3,4,6},{4,5,7},{4,5,8},{4,6,9},{5,7,10},{6,8,11},{6,8,13},{7,10,14},{8,11,16},{9,12,18},
     {10,13,20},{11,15,23},{13,17,25} };
 
-// ---- pass 1 (fully parallel): per-MB deblock descriptor = boundary strengths + alpha/beta table indexes ----
+// ---- pass 1 (fully parallel): per-MB deblock descriptor = boundary strengths + filter thresholds ----
 
 __device__ __forceinline__ int mv_differs(const h264r_mb_motion* a, int ba, int la, const h264r_mb_motion* b, int bb, int lb)
 {
@@ -926,8 +926,8 @@ __device__ __forceinline__ int bs_compare(const h264r_mb_motion* mp, int bp, con
            (mv_differs(mp, bp, 0, mq, bq, 1) | mv_differs(mp, bp, 1, mq, bq, 0));
 }
 
-// Deblock::strength (deblock.cc:78-289) + the qPav/indexA/indexB part of filter_edge (deblock.cc:469-474).
-// One THREAD per MB (the work is scalar: 32 strengths and 18 table indexes out of three MB headers).
+// Deblock::strength (deblock.cc:78-289) + the qPav/indexA/indexB/alpha/beta/tc0 part of filter_edge (deblock.cc:469-474,
+// tables :294-324).  One THREAD per MB (the work is scalar: 32 strengths and 9 threshold sets out of three MB headers).
 struct HdrLite { int mb_type, flags, slice_idx, qp_y, qp_c[2], cbp_blks; };
 __device__ __forceinline__ HdrLite load_hdr_lite(const h264r_mb* mbs, int addr)
 {
@@ -953,7 +953,7 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
     const h264r_slice* sl = pic.slices + Q.slice_idx;
     const int idc = __ldg(&sl->disable_deblocking_filter_idc);
     uint4* out = reinterpret_cast<uint4*>(pic.desc + q);
-    if (idc == 1) { out[0] = make_uint4(0, 0, 0, 0); out[1] = make_uint4(0, 0, 0, 0); return; }
+    if (idc == 1) { out[0] = make_uint4(0, 0, 0, 0); return; }           // no strengths: the thresholds are never read
 
     bool left = mbx > 0, top = mby > 0;
     HdrLite PL = Q, PT = Q;
@@ -962,7 +962,7 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
     const bool q_intra = Q.flags & H264R_MB_FLAG_INTRA, t8 = Q.flags & H264R_MB_FLAG_T8x8;
     const bool p_skip = __ldg(&sl->slice_type) == H264R_P_SLICE && Q.mb_type == 0;
 
-    uint32_t b0 = 0, b1 = 0, b2 = 0;
+    uint32_t bs[4] = { 0, 0, 0, 0 };
 #pragma unroll
     for (int dir = 0; dir < 2; ++dir) {
         const bool mbedge = dir == 0 ? left : top;
@@ -973,12 +973,9 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
             const bool on = e == 0 ? mbedge : !(t8 && (e & 1));
             if (!on) continue;
             if (e > 0 && p_skip) continue;
+            const int wi = dir * 2 + (e >> 1), sh = (e & 1) * 16;
             const bool p_intra = e ? q_intra : (PN.flags & H264R_MB_FLAG_INTRA) != 0;
-            if (p_intra || q_intra) {
-                const uint32_t m = 0xFu << (dir * 16 + e * 4);
-                if (e == 0) b2 |= m; else { b0 |= m; b1 |= m; }        // 4 = 100b, 3 = 011b
-                continue;
-            }
+            if (p_intra || q_intra) { bs[wi] |= (e == 0 ? 0x4444u : 0x3333u) << sh; continue; }
             const int pcbp = e ? Q.cbp_blks : PN.cbp_blks;
             const int pidx = e ? q : pn_idx;
             const bool same_part = e > 0 && (Q.mb_type == 1 || Q.mb_type == (dir == 0 ? 2 : 3));
@@ -986,68 +983,101 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
             for (int k4 = 0; k4 < 4; ++k4) {
                 const int blkQ = dir == 0 ? k4 * 4 + e : e * 4 + k4;
                 const int blkP = dir == 0 ? k4 * 4 + (e ? e - 1 : 3) : (e ? e - 1 : 3) * 4 + k4;
-                const int bit = dir * 16 + e * 4 + k4;
-                if (((Q.cbp_blks >> blkQ) & 1) || ((pcbp >> blkP) & 1)) b1 |= 1u << bit;          // 2
-                else if (!same_part && bs_compare(pic.motion + pidx, blkP, pic.motion + q, blkQ)) b0 |= 1u << bit;   // 1
+                uint32_t v = 0;
+                if (((Q.cbp_blks >> blkQ) & 1) || ((pcbp >> blkP) & 1)) v = 2;
+                else if (!same_part && bs_compare(pic.motion + pidx, blkP, pic.motion + q, blkQ)) v = 1;
+                bs[wi] |= v << (sh + k4 * 4);
             }
         }
     }
-    // table indexes: combo = type*3 + plane, type 0 = left MB edge, 1 = internal edge, 2 = top MB edge
+    out[0] = make_uint4(bs[0], bs[1], bs[2], bs[3]);
+    // thresholds: type 0 = left MB edge, 1 = internal edge, 2 = top MB edge
     const int foa = (int)(int8_t)__ldg(&sl->filter_offset_a), fob = (int)(int8_t)__ldg(&sl->filter_offset_b);
-    uint32_t w[5] = { 0, 0, 0, 0, 0 };
 #pragma unroll
-    for (int c = 0; c < 9; ++c) {
-        const int t = c / 3, pl = c % 3;
-        const HdrLite& P = t == 0 ? PL : (t == 2 ? PT : Q);
-        const int qp_p = pl ? P.qp_c[pl - 1] : P.qp_y, qp_q = pl ? Q.qp_c[pl - 1] : Q.qp_y;
-        const int qPav = (qp_p + qp_q + 1) >> 1;
-        const uint32_t ia = (uint32_t)clip3i(0, 51, qPav + foa), ib = (uint32_t)clip3i(0, 51, qPav + fob);
-        const int ba = c, bb = 9 + c;                       // byte positions inside words 3..7
-        w[ba >> 2] |= ia << ((ba & 3) * 8);
-        w[bb >> 2] |= ib << ((bb & 3) * 8);
+    for (int pl = 0; pl < 3; ++pl) {
+        uint32_t w[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const HdrLite& P = t == 0 ? PL : (t == 2 ? PT : Q);
+            const int qp_p = pl ? P.qp_c[pl - 1] : P.qp_y, qp_q = pl ? Q.qp_c[pl - 1] : Q.qp_y;
+            const int qPav = (qp_p + qp_q + 1) >> 1;
+            const int ia = clip3i(0, 51, qPav + foa), ib = clip3i(0, 51, qPav + fob);
+            w[t] = (uint32_t)c_alpha[ia] | (uint32_t)c_beta[ib] << 8 | (uint32_t)c_tc0[ia][0] << 13 |
+                   (uint32_t)c_tc0[ia][1] << 18 | (uint32_t)c_tc0[ia][2] << 23;
+        }
+        out[1 + pl] = make_uint4(w[0], w[1], w[2], 0);
     }
-    out[0] = make_uint4(b0, b1, b2, w[0]);
-    out[1] = make_uint4(w[1], w[2], w[3], w[4]);
 }
 
 // ---- pass 2 (row wavefront): filtering, in place ----
 //
-// Tile layout per warp (bytes): luma rows -4..15: index (y+4)*32 + (x+16), x in -4..15 (own 16 samples 16-byte aligned);
-// chroma plane pl at 640 + pl*192: rows -4..7: index (y+4)*16 + (x+8), x in -4..7.
-struct DeblockSmem {
-    __align__(16) uint8_t t[640 + 2 * 192];
+// One warp filters the SAME macroblock row of TWO pictures of the wave: lanes 0..15 picture A, lanes 16..31 picture B
+// (one instruction stream, independent data: the filter is a data-dependent scalar recipe per line, so a picture can
+// keep only 16 lanes busy).  Lane l of a half owns luma line l and chroma line l & 7 of plane l >> 3.
+//   vertical edges  : the lane's row lives in registers (left 4 samples carried from the previous MB + own 16 / 8),
+//                     the four (two) edges are filtered in sequence without touching memory;
+//   horizontal edges: the row goes through a shared-memory tile (transposition), the lane then owns a column; the
+//                     4 (2) samples above the MB come straight from global memory, prefetched one MB ahead when the row
+//                     above is known to be far enough.
+// Tile per half: luma 16 rows x 32 B (own 16 samples at byte 16, so that rows are 16-byte aligned), chroma 2 planes x
+// 8 rows x 16 B (own 8 samples at byte 8).
+struct __align__(16) DeblockSmem {
+    uint8_t y[2][16 * 32];
+    uint8_t c[2][2][8 * 16];
 };
 
-// filter_strong / filter_normal (deblock.cc:327-415) across one edge in the shared-memory tile; pix -> q0.
-// One instruction stream for luma and chroma lanes (chroma is data, not control flow).
-__device__ __forceinline__ void filter_samples(uint8_t* pix, int step, int bS, int alpha, int beta, int tc0, bool chroma)
+// filter_strong / filter_normal (deblock.cc:327-415) on the samples across one edge: p[0] = p0 ... p[3] = p3.
+template <bool kChroma>
+__device__ __forceinline__ void filter_edge(int bS, uint32_t par, int (&p)[4], int (&q)[4])
 {
-    const int p0 = pix[-step], p1 = pix[-2 * step], q0 = pix[0], q1 = pix[step];
+    if (bS == 0) return;
+    const int alpha = par & 0xFF, beta = (par >> 8) & 31;
+    const int p0 = p[0], p1 = p[1], q0 = q[0], q1 = q[1];
     if (!(abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta)) return;
-    const int p2 = pix[-3 * step], q2 = pix[2 * step];
-    const bool ap = !chroma && abs(p2 - p0) < beta, aq = !chroma && abs(q2 - q0) < beta;
+    const int tc0 = (par >> (8 + 5 * bS)) & 31;                  // bS 1..3 (unused for bS 4)
+    if (kChroma) {
+        if (bS == 4) {
+            p[0] = (2 * p1 + p0 + q1 + 2) >> 2;
+            q[0] = (2 * q1 + q0 + p1 + 2) >> 2;
+        } else {
+            const int tc = tc0 + 1;
+            const int delta = clip3i(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
+            p[0] = clip255(p0 + delta);
+            q[0] = clip255(q0 - delta);
+        }
+        return;
+    }
+    const int p2 = p[2], q2 = q[2];
+    const bool ap = abs(p2 - p0) < beta, aq = abs(q2 - q0) < beta;
     if (bS == 4) {
         const bool small = abs(p0 - q0) < (alpha >> 2) + 2;
         if (ap && small) {
-            const int p3 = pix[-4 * step];
-            pix[-step]     = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-            pix[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
-            pix[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-        } else pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+            p[0] = (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3;
+            p[1] = (p2 + p1 + p0 + q0 + 2) >> 2;
+            p[2] = (2 * p[3] + 3 * p2 + p1 + p0 + q0 + 4) >> 3;
+        } else p[0] = (2 * p1 + p0 + q1 + 2) >> 2;
         if (aq && small) {
-            const int q3 = pix[3 * step];
-            pix[0]        = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-            pix[step]     = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
-            pix[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
-        } else pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+            q[0] = (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3;
+            q[1] = (p0 + q0 + q1 + q2 + 2) >> 2;
+            q[2] = (2 * q[3] + 3 * q2 + q1 + q0 + p0 + 4) >> 3;
+        } else q[0] = (2 * q1 + q0 + p1 + 2) >> 2;
         return;
     }
-    const int tc = chroma ? tc0 + 1 : tc0 + (ap ? 1 : 0) + (aq ? 1 : 0);
+    const int tc = tc0 + (ap ? 1 : 0) + (aq ? 1 : 0);
     const int delta = clip3i(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
-    pix[-step] = (uint8_t)clip255(p0 + delta);
-    pix[0]     = (uint8_t)clip255(q0 - delta);
-    if (ap) pix[-2 * step] = (uint8_t)(p1 + clip3i(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 * 2)) >> 1));
-    if (aq) pix[step]      = (uint8_t)(q1 + clip3i(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 * 2)) >> 1));
+    p[0] = clip255(p0 + delta);
+    q[0] = clip255(q0 - delta);
+    if (ap) p[1] = p1 + clip3i(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 * 2)) >> 1);
+    if (aq) q[1] = q1 + clip3i(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 * 2)) >> 1);
+}
+
+__device__ __forceinline__ void unpack4(uint32_t w, int* v)
+{
+    v[0] = w & 0xFF; v[1] = __byte_perm(w, 0, 0x4441); v[2] = __byte_perm(w, 0, 0x4442); v[3] = w >> 24;
+}
+__device__ __forceinline__ uint32_t pack4(const int* v)
+{
+    return __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_DEBLOCK_CTAS)
@@ -1059,129 +1089,175 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
     __syncthreads();
     const int W = g.width_mbs, H = g.height_mbs;
     const int groups = (H + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int rg = s_ticket / num_pics, pic_i = s_ticket - rg * num_pics;      // row-group-major, see recon_intra_kernel
+    const int npairs = (num_pics + 1) >> 1;
+    const int rg = s_ticket / npairs, pair = s_ticket - rg * npairs;            // row-group-major, see recon_intra_kernel
     if (rg >= groups) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mby = rg * kWarpsPerCta + warp;
     if (mby >= H) return;
-    const DevPicture& pic = pics[pic_i];
-    if (!pic.run_deblock) return;
-    uint8_t* const T = smem_all[warp].t;
-    int* progress = pic.row_progress + H;                // [1][H]
+    const int half = lane >> 4, l = lane & 15, cpl = l >> 3, cl = l & 7;
+    const int pic_i = pair * 2 + half;
+    const DevPicture& pic = pics[min(pic_i, num_pics - 1)];
+    const bool enabled = pic_i < num_pics && pic.run_deblock;                   // this half has a picture to filter
+    if (!__any_sync(0xFFFFFFFFu, enabled)) return;
+    DeblockSmem& sm = smem_all[warp];
+    uint8_t* const TY = sm.y[half];
+    uint8_t* const TC = sm.c[half][cpl];
+    int* const progress = pic.row_progress + H;          // [1][H]
     uint8_t* const dY = pic.dst;
-    const size_t off_c[2] = { g.off_cb, g.off_cr };
-    const uint32_t* desc = reinterpret_cast<const uint32_t*>(pic.desc + (size_t)mby * W);
+    uint8_t* const dC = pic.dst + (cpl ? g.off_cr : g.off_cb);
+    const int pitch_y = g.pitch_y, pitch_c = g.pitch_c;
+    const uint4* const desc = reinterpret_cast<const uint4*>(pic.desc + (size_t)mby * W);
+    const int py = mby * 16, cy = mby * 8;
+    const int gshY = (l >> 2) * 4, gshC = (cl >> 1) * 4;   // nibble position of this lane's 4-sample group
 
-    // per-lane line geometry: lanes 0..15 = luma line, 16..31 = chroma line (plane, line)
-    const bool is_c = lane >= 16;
-    const int cpl = (lane >> 3) & 1, line = is_c ? (lane & 7) : lane;
-    const int tile_base = is_c ? 640 + cpl * 192 : 0;
-    const int tstride = is_c ? 16 : 32, tx0 = is_c ? 8 : 16;
-    const int nedges = is_c ? 2 : 4;
-
-    int known = mby > 0 ? 0 : 0x7FFFFFFF;                 // progress of the row above as last observed
+    int known = (mby > 0 && enabled) ? 0 : 0x7FFFFFFF;    // progress of the row above as last observed (per half)
     const int* const prog_above = progress + mby - 1;
-    bool top_pref = false;                                // top border of the coming MB already in registers
-    uint4 topY = make_uint4(0, 0, 0, 0); uint2 topC = make_uint2(0, 0);
-    // lanes 0..3: luma rows -4..-1; lanes 4..7: chroma rows -2..-1 of both planes
-    const int tpl = (lane >> 1) & 1, tr = lane & 1;
 
-    // prefetch: descriptor word (lanes 0..7) and the MB's own samples of MB 0
-    uint32_t dnext = lane < 8 ? __ldg(desc + lane) : 0;
-    uint4 ownY = make_uint4(0, 0, 0, 0); uint2 ownC = make_uint2(0, 0);
-    {
-        if (!is_c) ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (size_t)(mby * 16 + line) * g.pitch_y));
-        else ownC = __ldcg(reinterpret_cast<const uint2*>(dY + off_c[cpl] + (size_t)(mby * 8 + line) * g.pitch_c));
+    // prefetch of MB 0: descriptor (strengths, luma thresholds, thresholds of this lane's chroma plane), own samples
+    uint4 n_bs = make_uint4(0, 0, 0, 0), n_py = n_bs, n_pc = n_bs, n_ownY = n_bs; uint2 n_ownC = make_uint2(0, 0);
+    if (enabled) {
+        n_bs = __ldg(desc); 
+        if (n_bs.x | n_bs.y | n_bs.z | n_bs.w) { n_py = __ldg(desc + 1); n_pc = __ldg(desc + 2 + cpl); }
+        n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y)));
+        n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c)));
     }
+    bool top_pref = false;                                // top samples of the coming MB already in registers
+    uint32_t n_topY = 0, n_topC = 0;                      // rows -4..-1 of luma column l / rows -2..-1 of chroma column cl
 
     for (int mbx = 0; mbx < W; ++mbx) {
-        const uint32_t dcur = dnext;
-        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, dcur, 0), b1 = __shfl_sync(0xFFFFFFFFu, dcur, 1), b2 = __shfl_sync(0xFFFFFFFFu, dcur, 2);
-        const uint32_t any = b0 | b1 | b2;
-        const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
+        const uint4 bs = n_bs, parY = n_py, parC = n_pc, ownY = n_ownY; const uint2 ownC = n_ownC;
+        const bool have_top = top_pref; const uint32_t pTopY = n_topY, pTopC = n_topC;
+        const int px = mbx * 16, cx = mbx * 8;
+        const bool any = (bs.x | bs.y | bs.z | bs.w) != 0;
+        const bool top_on = enabled && bs.z != 0 && (bs.z & 0xFFFF) != 0;        // dir 1, edge 0 has a non-zero strength
 
-        // carry: the previous MB's last 4 columns become this MB's left border; then drop in this MB's own samples
-        if (mbx > 0) {
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(T + tile_base + (line + 4) * tstride + tx0 + (is_c ? 4 : 12));
-            __syncwarp();
-            *reinterpret_cast<uint32_t*>(T + tile_base + (line + 4) * tstride + tx0 - 4) = v;
-        }
-        if (!is_c) *reinterpret_cast<uint4*>(T + (line + 4) * 32 + 16) = ownY;
-        else *reinterpret_cast<uint2*>(T + tile_base + (line + 4) * 16 + 8) = ownC;
+        // previous MB's last four samples of this lane's rows (final values), before the tile rows are overwritten
+        const uint32_t carryY = *reinterpret_cast<const uint32_t*>(TY + l * 32 + 16 + 12);
+        const uint32_t carryC = *reinterpret_cast<const uint32_t*>(TC + cl * 16 + 8 + 4);
 
-        // prefetch the next MB (descriptor + own samples): independent of every other MB of this kernel
-        if (mbx + 1 < W) {
-            if (lane < 8) dnext = __ldg(desc + (mbx + 1) * 8 + lane);
-            if (!is_c) ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (size_t)(py + line) * g.pitch_y + px + 16));
-            else ownC = __ldcg(reinterpret_cast<const uint2*>(dY + off_c[cpl] + (size_t)(cy + line) * g.pitch_c + cx + 8));
+        // prefetch the next MB: independent of every other MB of this kernel
+        if (mbx + 1 < W && enabled) {
+            n_bs = __ldg(desc + (mbx + 1) * 4);
+            if (n_bs.x | n_bs.y | n_bs.z | n_bs.w) { n_py = __ldg(desc + (mbx + 1) * 4 + 1); n_pc = __ldg(desc + (mbx + 1) * 4 + 2 + cpl); }
+            n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y + px + 16)));
+            n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx + 8)));
         }
-        const bool top = (any >> 16) & 0xF, left = any & 0xF;
-        const bool have_top = top_pref;
-        const uint4 curTopY = topY; const uint2 curTopC = topC;
-        // top border of the next MB, if the row above is already known to be far enough
+        // top samples of the next MB, if the row above is already known to be far enough
         top_pref = false;
-        if (mby > 0 && mbx + 1 < W && known >= min(mbx + 3, W)) {
+        if (mby > 0 && mbx + 1 < W && enabled && known >= min(mbx + 3, W)) {
             top_pref = true;
-            if (lane < 4) topY = __ldcg(reinterpret_cast<const uint4*>(dY + (size_t)(py - 4 + lane) * g.pitch_y + px + 16));
-            else if (lane < 8) topC = __ldcg(reinterpret_cast<const uint2*>(dY + off_c[tpl] + (size_t)(cy - 2 + tr) * g.pitch_c + cx + 8));
+            const uint8_t* ty = dY + (uint32_t)((py - 4) * pitch_y + px + 16 + l);
+            n_topY = (uint32_t)__ldcg(ty) | (uint32_t)__ldcg(ty + pitch_y) << 8 | (uint32_t)__ldcg(ty + 2 * pitch_y) << 16 | (uint32_t)__ldcg(ty + 3 * pitch_y) << 24;
+            const uint8_t* tc = dC + (uint32_t)((cy - 2) * pitch_c + cx + 8 + cl);
+            n_topC = (uint32_t)__ldcg(tc) | (uint32_t)__ldcg(tc + pitch_c) << 8;
         }
-        if (!any) { publish_row(progress + mby, mbx + 1, lane, false); continue; }
 
-        if (top) {
-            if (have_top) {
-                if (lane < 4) *reinterpret_cast<uint4*>(T + lane * 32 + 16) = curTopY;
-                else if (lane < 8) *reinterpret_cast<uint2*>(T + 640 + tpl * 192 + (2 + tr) * 16 + 8) = curTopC;
-            } else {
-                wait_row_cached(prog_above, min(mbx + 2, W), known);
-                if (lane < 4)
-                    *reinterpret_cast<uint4*>(T + lane * 32 + 16) = __ldcg(reinterpret_cast<const uint4*>(dY + (size_t)(py - 4 + lane) * g.pitch_y + px));
-                else if (lane < 8)
-                    *reinterpret_cast<uint2*>(T + 640 + tpl * 192 + (2 + tr) * 16 + 8) =
-                        __ldcg(reinterpret_cast<const uint2*>(dY + off_c[tpl] + (size_t)(cy - 2 + tr) * g.pitch_c + cx));
+        if (!__any_sync(0xFFFFFFFFu, any && enabled)) {
+            // nothing to filter in either picture: the tile still has to carry this MB's samples to the next one
+            *reinterpret_cast<uint4*>(TY + l * 32 + 16) = ownY;
+            *reinterpret_cast<uint2*>(TC + cl * 16 + 8) = ownC;
+            publish_row(progress + mby, mbx + 1, lane & 15, false);      // both halves publish through their own lane 0
+            continue;
+        }
+
+        // ---- vertical edges, in registers ----
+        {
+            int v[20];
+            unpack4(carryY, v); unpack4(ownY.x, v + 4); unpack4(ownY.y, v + 8); unpack4(ownY.z, v + 12); unpack4(ownY.w, v + 16);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = enabled ? ((e < 2 ? bs.x : bs.y) >> ((e & 1) * 16 + gshY)) & 7 : 0;
+                int p[4] = { v[4 * e + 3], v[4 * e + 2], v[4 * e + 1], v[4 * e] }, q[4] = { v[4 * e + 4], v[4 * e + 5], v[4 * e + 6], v[4 * e + 7] };
+                filter_edge<false>(s, e ? parY.y : parY.x, p, q);
+                v[4 * e + 2] = p[1]; v[4 * e + 1] = p[2]; v[4 * e + 3] = p[0];
+                v[4 * e + 4] = q[0]; v[4 * e + 5] = q[1]; v[4 * e + 6] = q[2];
             }
+            *reinterpret_cast<uint4*>(TY + l * 32 + 16) = make_uint4(pack4(v + 4), pack4(v + 8), pack4(v + 12), pack4(v + 16));
+            if (enabled && (bs.x & 0xFFFF) && mbx > 0)         // columns 13..15 of the left MB
+                *reinterpret_cast<uint32_t*>(dY + (uint32_t)((py + l) * pitch_y + px - 4)) = pack4(v);
         }
-        __syncwarp();
+        {
+            int v[12];
+            unpack4(carryC, v); unpack4(ownC.x, v + 4); unpack4(ownC.y, v + 8);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int s = enabled ? ((e ? bs.y : bs.x) >> gshC) & 7 : 0;          // chroma edge e <- luma edge 2e
+                int p[4] = { v[4 * e + 3], v[4 * e + 2], 0, 0 }, q[4] = { v[4 * e + 4], v[4 * e + 5], 0, 0 };
+                filter_edge<true>(s, e ? parC.y : parC.x, p, q);
+                v[4 * e + 3] = p[0]; v[4 * e + 4] = q[0];
+            }
+            *reinterpret_cast<uint2*>(TC + cl * 16 + 8) = make_uint2(pack4(v + 4), pack4(v + 8));
+            if (enabled && (bs.x & 0xFFFF) && mbx > 0)
+                *reinterpret_cast<uint32_t*>(dC + (uint32_t)((cy + cl) * pitch_c + cx - 4)) = pack4(v);
+        }
 
-        // index tables = bytes 12..29 of the descriptor (words 3..7, held by lanes 3..7)
-        uint32_t dw[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) dw[k] = __shfl_sync(0xFFFFFFFFu, dcur, 3 + k);
-        // ---- dir 0: vertical edges; dir 1: horizontal edges ----
-#pragma unroll
-        for (int dir = 0; dir < 2; ++dir) {
-            const int step = dir == 0 ? 1 : tstride;
-            uint8_t* linep = T + tile_base + (dir == 0 ? (line + 4) * tstride + tx0 : 4 * tstride + tx0 + line);
-            for (int e = 0; e < nedges; ++e) {
-                const int E = is_c ? 2 * e : e;
-                const int bit = dir * 16 + E * 4 + (is_c ? line >> 1 : line >> 2);
-                const int s = ((b0 >> bit) & 1) | (((b1 >> bit) & 1) << 1) | (((b2 >> bit) & 1) << 2);
-                if (s) {
-                    const int combo = (e == 0 ? (dir == 0 ? 0 : 2) : 1) * 3 + (is_c ? 1 + cpl : 0);
-                    const int ba = 12 + combo, bb = 21 + combo;
-                    const int ia = (dw[(ba >> 2) - 3] >> ((ba & 3) * 8)) & 0xFF;
-                    const int ib = (dw[(bb >> 2) - 3] >> ((bb & 3) * 8)) & 0xFF;
-                    filter_samples(linep + e * 4 * step, step, s, c_alpha[ia], c_beta[ib], s < 4 ? c_tc0[ia][s - 1] : 0, is_c);
+        // ---- samples above the MB (the row above must be two MBs ahead) ----
+        uint32_t topY = pTopY, topC = pTopC;
+        if (__any_sync(0xFFFFFFFFu, top_on && !have_top)) {
+            const int need = min(mbx + 2, W);
+            if (top_on && known < need) {
+                if (l == 0) {
+                    unsigned ns = 32;
+                    while (ld_relaxed(prog_above) < need) { __nanosleep(ns); if (ns < 512) ns *= 2; }
+                    known = ld_acquire(prog_above);
                 }
             }
             __syncwarp();
-        }
-
-        // ---- write back: own samples, left 4 columns (if that edge was filtered), top rows (ditto) ----
-        if (!is_c) *reinterpret_cast<uint4*>(dY + (size_t)(py + line) * g.pitch_y + px) = *reinterpret_cast<const uint4*>(T + (line + 4) * 32 + 16);
-        else *reinterpret_cast<uint2*>(dY + off_c[cpl] + (size_t)(cy + line) * g.pitch_c + cx) = *reinterpret_cast<const uint2*>(T + tile_base + (line + 4) * 16 + 8);
-        if (left) {
-            if (!is_c) *reinterpret_cast<uint32_t*>(dY + (size_t)(py + line) * g.pitch_y + px - 4) = *reinterpret_cast<const uint32_t*>(T + (line + 4) * 32 + 12);
-            else *reinterpret_cast<uint32_t*>(dY + off_c[cpl] + (size_t)(cy + line) * g.pitch_c + cx - 4) = *reinterpret_cast<const uint32_t*>(T + tile_base + (line + 4) * 16 + 4);
-        }
-        if (top) {
-            if (lane >= 1 && lane < 4)
-                *reinterpret_cast<uint4*>(dY + (size_t)(py - 4 + lane) * g.pitch_y + px) = *reinterpret_cast<const uint4*>(T + lane * 32 + 16);
-            else if (lane == 4 || lane == 5) {
-                const int pl = lane & 1;
-                *reinterpret_cast<uint2*>(dY + off_c[pl] + (size_t)(cy - 1) * g.pitch_c + cx) = *reinterpret_cast<const uint2*>(T + 640 + pl * 192 + 3 * 16 + 8);
+            known = __shfl_sync(0xFFFFFFFFu, known, lane & 16);
+            if (top_on && !have_top) {
+                const uint8_t* ty = dY + (uint32_t)((py - 4) * pitch_y + px + l);
+                topY = (uint32_t)__ldcg(ty) | (uint32_t)__ldcg(ty + pitch_y) << 8 | (uint32_t)__ldcg(ty + 2 * pitch_y) << 16 | (uint32_t)__ldcg(ty + 3 * pitch_y) << 24;
+                const uint8_t* tc = dC + (uint32_t)((cy - 2) * pitch_c + cx + cl);
+                topC = (uint32_t)__ldcg(tc) | (uint32_t)__ldcg(tc + pitch_c) << 8;
             }
         }
-        publish_row(progress + mby, mbx + 1, lane, true);
+        __syncwarp();                                      // tile rows (vertical pass) visible to the column owners
+
+        // ---- horizontal edges: lane l = luma column l, chroma column cl of plane cpl ----
+        {
+            int v[20];
+            unpack4(topY, v);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[4 + r] = TY[r * 32 + 16 + l];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = enabled ? ((e < 2 ? bs.z : bs.w) >> ((e & 1) * 16 + gshY)) & 7 : 0;
+                int p[4] = { v[4 * e + 3], v[4 * e + 2], v[4 * e + 1], v[4 * e] }, q[4] = { v[4 * e + 4], v[4 * e + 5], v[4 * e + 6], v[4 * e + 7] };
+                filter_edge<false>(s, e ? parY.y : parY.z, p, q);
+                v[4 * e + 2] = p[1]; v[4 * e + 1] = p[2]; v[4 * e + 3] = p[0];
+                v[4 * e + 4] = q[0]; v[4 * e + 5] = q[1]; v[4 * e + 6] = q[2];
+            }
+#pragma unroll
+            for (int r = 0; r < 15; ++r) TY[r * 32 + 16 + l] = (uint8_t)v[4 + r];
+            if (top_on) {                                  // rows 13..15 of the MB above
+                uint8_t* ty = dY + (uint32_t)((py - 3) * pitch_y + px + l);
+                ty[0] = (uint8_t)v[1]; ty[pitch_y] = (uint8_t)v[2]; ty[2 * pitch_y] = (uint8_t)v[3];
+            }
+        }
+        {
+            int v[10];                                     // rows -2, -1, 0..7
+            v[0] = topC & 0xFF; v[1] = (topC >> 8) & 0xFF;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) v[2 + r] = TC[r * 16 + 8 + cl];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int s = enabled ? ((e ? bs.w : bs.z) >> gshC) & 7 : 0;
+                int p[4] = { v[4 * e + 1], v[4 * e], 0, 0 }, q[4] = { v[4 * e + 2], v[4 * e + 3], 0, 0 };
+                filter_edge<true>(s, e ? parC.y : parC.z, p, q);
+                v[4 * e + 1] = p[0]; v[4 * e + 2] = q[0];
+            }
+            TC[0 * 16 + 8 + cl] = (uint8_t)v[2]; TC[3 * 16 + 8 + cl] = (uint8_t)v[5]; TC[4 * 16 + 8 + cl] = (uint8_t)v[6];
+            if (top_on) dC[(uint32_t)((cy - 1) * pitch_c + cx + cl)] = (uint8_t)v[1];
+        }
+        __syncwarp();
+
+        // ---- write back the MB's own samples ----
+        if (enabled) {
+            *reinterpret_cast<uint4*>(dY + (uint32_t)((py + l) * pitch_y + px)) = *reinterpret_cast<const uint4*>(TY + l * 32 + 16);
+            *reinterpret_cast<uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx)) = *reinterpret_cast<const uint2*>(TC + cl * 16 + 8);
+        }
+        publish_row(progress + mby, mbx + 1, lane & 15, true);
     }
 }
 
@@ -1214,7 +1290,7 @@ bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
         deblock_prep_kernel<<<(int)((total + 127) / 128), 128, 0, stream>>>(w.pics, w.num_pics, w.geom);
         return true;
     }
-    deblock_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
+    deblock_kernel<<<((w.num_pics + 1) / 2) * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
     return true;
 }
 
