@@ -1111,14 +1111,18 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
     const int py = mby * 16, cy = mby * 8;
     const int gshY = (l >> 2) * 4, gshC = (cl >> 1) * 4;   // nibble position of this lane's 4-sample group
 
+    // Progress protocol: a row publishes v after the vertical pass and the horizontal pass of MB v (its store of the
+    // left MB's columns 13..15 has long been issued) and before MB v's own write-back; v == W after the last MB.
+    // progress >= v therefore says: MBs < v are complete, and MB v no longer touches MB v-1.  MB x of the row below
+    // reads and writes rows 12..15 of MB x above, so it needs progress >= min(x + 1, W)  (after
+    // (x+1, y-1)'s left edge, before (x-1, y+1)).
     int known = (mby > 0 && enabled) ? 0 : 0x7FFFFFFF;    // progress of the row above as last observed (per half)
     const int* const prog_above = progress + mby - 1;
 
     // prefetch of MB 0: descriptor (strengths, luma thresholds, thresholds of this lane's chroma plane), own samples
     uint4 n_bs = make_uint4(0, 0, 0, 0), n_py = n_bs, n_pc = n_bs, n_ownY = n_bs; uint2 n_ownC = make_uint2(0, 0);
     if (enabled) {
-        n_bs = __ldg(desc); 
-        if (n_bs.x | n_bs.y | n_bs.z | n_bs.w) { n_py = __ldg(desc + 1); n_pc = __ldg(desc + 2 + cpl); }
+        n_bs = __ldg(desc); n_py = __ldg(desc + 1); n_pc = __ldg(desc + 2 + cpl);
         n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y)));
         n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c)));
     }
@@ -1127,10 +1131,11 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
 
     for (int mbx = 0; mbx < W; ++mbx) {
         const uint4 bs = n_bs, parY = n_py, parC = n_pc, ownY = n_ownY; const uint2 ownC = n_ownC;
-        const bool have_top = top_pref; const uint32_t pTopY = n_topY, pTopC = n_topC;
+        const bool have_top = top_pref;
+        uint32_t topY = n_topY, topC = n_topC;
         const int px = mbx * 16, cx = mbx * 8;
         const bool any = (bs.x | bs.y | bs.z | bs.w) != 0;
-        const bool top_on = enabled && bs.z != 0 && (bs.z & 0xFFFF) != 0;        // dir 1, edge 0 has a non-zero strength
+        const bool top_on = enabled && (bs.z & 0xFFFF) != 0;                     // dir 1, edge 0 has a non-zero strength
 
         // previous MB's last four samples of this lane's rows (final values), before the tile rows are overwritten
         const uint32_t carryY = *reinterpret_cast<const uint32_t*>(TY + l * 32 + 16 + 12);
@@ -1138,27 +1143,44 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
 
         // prefetch the next MB: independent of every other MB of this kernel
         if (mbx + 1 < W && enabled) {
-            n_bs = __ldg(desc + (mbx + 1) * 4);
-            if (n_bs.x | n_bs.y | n_bs.z | n_bs.w) { n_py = __ldg(desc + (mbx + 1) * 4 + 1); n_pc = __ldg(desc + (mbx + 1) * 4 + 2 + cpl); }
+            n_bs = __ldg(desc + (mbx + 1) * 4); n_py = __ldg(desc + (mbx + 1) * 4 + 1); n_pc = __ldg(desc + (mbx + 1) * 4 + 2 + cpl);
             n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y + px + 16)));
             n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx + 8)));
-        }
-        // top samples of the next MB, if the row above is already known to be far enough
-        top_pref = false;
-        if (mby > 0 && mbx + 1 < W && enabled && known >= min(mbx + 3, W)) {
-            top_pref = true;
-            const uint8_t* ty = dY + (uint32_t)((py - 4) * pitch_y + px + 16 + l);
-            n_topY = (uint32_t)__ldcg(ty) | (uint32_t)__ldcg(ty + pitch_y) << 8 | (uint32_t)__ldcg(ty + 2 * pitch_y) << 16 | (uint32_t)__ldcg(ty + 3 * pitch_y) << 24;
-            const uint8_t* tc = dC + (uint32_t)((cy - 2) * pitch_c + cx + 8 + cl);
-            n_topC = (uint32_t)__ldcg(tc) | (uint32_t)__ldcg(tc + pitch_c) << 8;
         }
 
         if (!__any_sync(0xFFFFFFFFu, any && enabled)) {
             // nothing to filter in either picture: the tile still has to carry this MB's samples to the next one
             *reinterpret_cast<uint4*>(TY + l * 32 + 16) = ownY;
             *reinterpret_cast<uint2*>(TC + cl * 16 + 8) = ownC;
-            publish_row(progress + mby, mbx + 1, lane & 15, false);      // both halves publish through their own lane 0
+            top_pref = false;
+            publish_row(progress + mby, mbx, lane & 15, false);          // both halves publish through their own lane 0
             continue;
+        }
+
+        // ---- samples above the MB: wait for the row above, issue the loads; they land during the vertical pass ----
+        if (__any_sync(0xFFFFFFFFu, top_on && !have_top)) {
+            const int need = min(mbx + 1, W);
+            if (top_on && known < need && l == 0) {
+                unsigned ns = 16;
+                while ((known = ld_acquire(prog_above)) < need) { __nanosleep(ns); if (ns < 128) ns *= 2; }
+            }
+            __syncwarp();
+            known = __shfl_sync(0xFFFFFFFFu, known, lane & 16);
+            if (top_on && !have_top) {
+                const uint8_t* ty = dY + (uint32_t)((py - 4) * pitch_y + px + l);
+                topY = (uint32_t)__ldcg(ty) | (uint32_t)__ldcg(ty + pitch_y) << 8 | (uint32_t)__ldcg(ty + 2 * pitch_y) << 16 | (uint32_t)__ldcg(ty + 3 * pitch_y) << 24;
+                const uint8_t* tc = dC + (uint32_t)((cy - 2) * pitch_c + cx + cl);
+                topC = (uint32_t)__ldcg(tc) | (uint32_t)__ldcg(tc + pitch_c) << 8;
+            }
+        }
+        // top samples of the next MB, if the row above is already known to be far enough
+        top_pref = false;
+        if (mby > 0 && mbx + 1 < W && enabled && known >= min(mbx + 2, W)) {
+            top_pref = true;
+            const uint8_t* ty = dY + (uint32_t)((py - 4) * pitch_y + px + 16 + l);
+            n_topY = (uint32_t)__ldcg(ty) | (uint32_t)__ldcg(ty + pitch_y) << 8 | (uint32_t)__ldcg(ty + 2 * pitch_y) << 16 | (uint32_t)__ldcg(ty + 3 * pitch_y) << 24;
+            const uint8_t* tc = dC + (uint32_t)((cy - 2) * pitch_c + cx + 8 + cl);
+            n_topC = (uint32_t)__ldcg(tc) | (uint32_t)__ldcg(tc + pitch_c) << 8;
         }
 
         // ---- vertical edges, in registers ----
@@ -1190,27 +1212,6 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
             *reinterpret_cast<uint2*>(TC + cl * 16 + 8) = make_uint2(pack4(v + 4), pack4(v + 8));
             if (enabled && (bs.x & 0xFFFF) && mbx > 0)
                 *reinterpret_cast<uint32_t*>(dC + (uint32_t)((cy + cl) * pitch_c + cx - 4)) = pack4(v);
-        }
-
-        // ---- samples above the MB (the row above must be two MBs ahead) ----
-        uint32_t topY = pTopY, topC = pTopC;
-        if (__any_sync(0xFFFFFFFFu, top_on && !have_top)) {
-            const int need = min(mbx + 2, W);
-            if (top_on && known < need) {
-                if (l == 0) {
-                    unsigned ns = 32;
-                    while (ld_relaxed(prog_above) < need) { __nanosleep(ns); if (ns < 512) ns *= 2; }
-                    known = ld_acquire(prog_above);
-                }
-            }
-            __syncwarp();
-            known = __shfl_sync(0xFFFFFFFFu, known, lane & 16);
-            if (top_on && !have_top) {
-                const uint8_t* ty = dY + (uint32_t)((py - 4) * pitch_y + px + l);
-                topY = (uint32_t)__ldcg(ty) | (uint32_t)__ldcg(ty + pitch_y) << 8 | (uint32_t)__ldcg(ty + 2 * pitch_y) << 16 | (uint32_t)__ldcg(ty + 3 * pitch_y) << 24;
-                const uint8_t* tc = dC + (uint32_t)((cy - 2) * pitch_c + cx + cl);
-                topC = (uint32_t)__ldcg(tc) | (uint32_t)__ldcg(tc + pitch_c) << 8;
-            }
         }
         __syncwarp();                                      // tile rows (vertical pass) visible to the column owners
 
@@ -1250,15 +1251,16 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
             TC[0 * 16 + 8 + cl] = (uint8_t)v[2]; TC[3 * 16 + 8 + cl] = (uint8_t)v[5]; TC[4 * 16 + 8 + cl] = (uint8_t)v[6];
             if (top_on) dC[(uint32_t)((cy - 1) * pitch_c + cx + cl)] = (uint8_t)v[1];
         }
-        __syncwarp();
+        // MBs < mbx are complete and this MB is done with its left neighbour (stores issued a pass ago: cheap release)
+        publish_row(progress + mby, mbx, lane & 15, true);             // includes the __syncwarp the tile needs
 
         // ---- write back the MB's own samples ----
         if (enabled) {
             *reinterpret_cast<uint4*>(dY + (uint32_t)((py + l) * pitch_y + px)) = *reinterpret_cast<const uint4*>(TY + l * 32 + 16);
             *reinterpret_cast<uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx)) = *reinterpret_cast<const uint2*>(TC + cl * 16 + 8);
         }
-        publish_row(progress + mby, mbx + 1, lane & 15, true);
     }
+    publish_row(progress + mby, W, lane & 15, true);
 }
 
 // ---------------------------------------------------------------------------------------------------
