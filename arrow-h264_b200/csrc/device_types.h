@@ -28,7 +28,8 @@ struct DeblockDesc {
 
 struct DevPicture {
     const h264r_mb*        mbs;
-    const h264r_mb_motion* motion;
+    h264r_mb_motion*       motion;                    // [nmb], device only: expanded by motion_expand_kernel
+    const uint8_t*         packed_motion;             // 12-byte entries (engine.cu pack_motion), indexed by h264r_mb::reserved2
     const h264r_slice*     slices;
     const h264r_level*     levels;
     int16_t*               resid;                     // [nmb][384] residual plane, device only (residual_kernel)
@@ -51,10 +52,10 @@ struct WaveLaunch {
     int   any_inter, any_intra, any_deblock;
 };
 
-// Kernel launchers of one wave (kernels.cu).  which: 0 residual (parallel), 1 inter (parallel), 2 intra wavefront, 3 deblock descriptors (parallel), 4 deblock wavefront.
-// Returns true if a kernel was launched (false when the wave has no work of that kind).
+// Kernel launchers of one wave (kernels.cu).  which: 0 motion expansion + residual (parallel), 1 inter (parallel), 2 intra wavefront,
+// 3 deblock descriptors (parallel), 4 deblock wavefront.  Returns the number of kernels launched (0 when the wave has no work of that kind).
 enum { KERNEL_RESID = 0, KERNEL_INTER = 1, KERNEL_INTRA = 2, KERNEL_DBPREP = 3, KERNEL_DEBLOCK = 4, KERNEL_KINDS = 5 };
-bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);
+int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);
 
 } // namespace h264r
 #endif

@@ -23,6 +23,8 @@ struct Frame {
     bool used = false;
     int write_wave = -1, read_wave = -1;      // bookkeeping inside one flush
     cudaEvent_t ready = nullptr;              // ev_done of the wave that last wrote this frame (owned by the pool)
+    cudaEvent_t read_done = nullptr;          // recorded on the D2H stream after the last asynchronous download
+    bool pending_read = false;                // a download was enqueued since the frame was last (re)written
 };
 
 enum SlotState { SLOT_FREE = 0, SLOT_FILLING, SLOT_QUEUED, SLOT_INFLIGHT };
@@ -32,6 +34,9 @@ struct Slot {
     uint8_t* dev = nullptr;
     DeblockDesc* dev_desc = nullptr;          // device only: output of the deblock pre-pass
     int16_t* dev_resid = nullptr;             // device only: residual plane [nmb][384]
+    h264r_mb_motion* dev_motion = nullptr;    // device only: motion expanded from the packed form (motion_expand_kernel)
+    uint8_t* host_motion = nullptr;           // pinned, host only: the full per-MB motion array the parser side fills
+    uint32_t motion_entries = 0;              // packed 12-byte motion entries behind the level list
     SlotState state = SLOT_FREE;
     h264r_pic_params pp;
     h264r_frame dst = -1;
@@ -46,6 +51,7 @@ struct WaveRecord {
     WaveLaunch launch;
     size_t progress_bytes;
     std::vector<WaveCopy> copies;             // H2D copies of the picture descriptions of this wave
+    std::vector<int> dst_frames;              // frames written by this wave
     cudaEvent_t ev_h2d = nullptr;             // recorded on the H2D stream after the wave's copies
     cudaEvent_t ev_done = nullptr;            // recorded on the compute stream after the wave's kernels
 };
@@ -62,7 +68,7 @@ struct h264r_ctx {
     h264r_seq_params seq;
     FrameGeom geom;
     int nmb = 0;
-    size_t off_mbs = 0, off_motion = 0, off_slices = 0, off_levels = 0, slot_bytes = 0;
+    size_t off_mbs = 0, off_slices = 0, off_levels = 0, slot_bytes = 0;   // levels are followed by the packed motion
     uint32_t level_capacity = 0;
     std::vector<Frame> frames;
     std::vector<Slot> slots;
@@ -88,6 +94,34 @@ int cuda_fail(h264r_ctx* c, cudaError_t e, const char* what)
     return H264R_ERR_CUDA;
 }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); } while (0)
+
+// Packed motion.  Entry = mv[0], mv[1] (int16 x, y each), ref_idx[0], ref_idx[1], ref_pic[0], ref_pic[1]: 12 bytes.
+// code 0 none | 1 one entry for the MB | 2 rows 0-1 / rows 2-3 | 3 columns 0-1 / columns 2-3 | 4 quadrants | 5 all 16.
+const uint32_t kPackedEntries[6] = { 0, 1, 2, 2, 4, 16 };
+inline void motion_entry(const h264r_mb_motion& m, int blk, uint8_t* e)
+{
+    memcpy(e, m.mv[0][blk], 4); memcpy(e + 4, m.mv[1][blk], 4);
+    e[8] = (uint8_t)m.ref_idx[0][blk]; e[9] = (uint8_t)m.ref_idx[1][blk];
+    e[10] = (uint8_t)m.ref_pic[0][blk]; e[11] = (uint8_t)m.ref_pic[1][blk];
+}
+int pack_motion(const h264r_mb_motion& m, uint8_t* out)
+{
+    uint8_t e[16][12];
+    for (int b = 0; b < 16; ++b) motion_entry(m, b, e[b]);
+    auto same = [&](int a, int b) { return memcmp(e[a], e[b], 12) == 0; };
+    bool quad = true;
+    for (int q = 0; q < 4 && quad; ++q) {
+        const int b0 = (q >> 1) * 8 + (q & 1) * 2;
+        quad = same(b0, b0 + 1) && same(b0, b0 + 4) && same(b0, b0 + 5);
+    }
+    if (!quad) { memcpy(out, e, sizeof(e)); return 5; }
+    const bool top = same(0, 2), bottom = same(8, 10), left = same(0, 8), right = same(2, 10);
+    if (top && bottom && left) { memcpy(out, e[0], 12); return 1; }
+    if (top && bottom) { memcpy(out, e[0], 12); memcpy(out + 12, e[8], 12); return 2; }
+    if (left && right) { memcpy(out, e[0], 12); memcpy(out + 12, e[2], 12); return 3; }
+    memcpy(out, e[0], 12); memcpy(out + 12, e[2], 12); memcpy(out + 24, e[8], 12); memcpy(out + 36, e[10], 12);
+    return 4;
+}
 
 bool frame_ok(const h264r_ctx* c, h264r_frame f) { return f >= 0 && f < (int)c->frames.size() && c->frames[f].used; }
 
@@ -138,6 +172,11 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
             CU(cudaEventRecord(rec.ev_h2d, ctx->s_h2d));
             CU(cudaStreamWaitEvent(ctx->stream, rec.ev_h2d, 0));
         }
+        // write-after-read: a frame still being downloaded (asynchronously, on the D2H stream) is not overwritten
+        for (int f : rec.dst_frames) {
+            Frame& fr = ctx->frames[f];
+            if (fr.pending_read) { CU(cudaStreamWaitEvent(ctx->stream, fr.read_done, 0)); fr.pending_read = false; }
+        }
         CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
         for (int kind = 0; kind < KERNEL_KINDS; ++kind) {
             if (time_kernels) {
@@ -148,10 +187,10 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
                 }
                 CU(cudaEventRecord(ctx->timer_events[timer_used], ctx->stream));
             }
-            const bool launched = launch_wave_kernel(rec.launch, kind, ctx->stream);
+            const int launched = launch_wave_kernel(rec.launch, kind, ctx->stream);
             if (launched) {
-                ctx->stats.kernel_launches += 1;
-                if (launches) launches[kind + 1] += 1;
+                ctx->stats.kernel_launches += (uint64_t)launched;
+                if (launches) launches[kind + 1] += launched;
                 if (time_kernels) {
                     CU(cudaEventRecord(ctx->timer_events[timer_used + 1], ctx->stream));
                     pend.push_back({ kind, timer_used });
@@ -232,22 +271,26 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     ctx->nmb = sp->width_mbs * sp->height_mbs;
 
     ctx->off_mbs = 0;
-    ctx->off_motion = align_up(ctx->off_mbs + sizeof(h264r_mb) * ctx->nmb, 256);
-    ctx->off_slices = align_up(ctx->off_motion + sizeof(h264r_mb_motion) * ctx->nmb, 256);
+    ctx->off_slices = align_up(ctx->off_mbs + sizeof(h264r_mb) * ctx->nmb, 256);
     ctx->off_levels = align_up(ctx->off_slices + sizeof(h264r_slice) * sp->max_slices_per_picture, 256);
     ctx->level_capacity = sp->max_levels_per_picture > 0 ? (uint32_t)sp->max_levels_per_picture
                                                           : (uint32_t)H264R_COEFFS_PER_MB * (uint32_t)ctx->nmb;
-    ctx->slot_bytes = align_up(ctx->off_levels + sizeof(h264r_level) * (size_t)ctx->level_capacity, 256);
+    // worst case of the packed motion: 16 entries of 12 bytes per MB
+    ctx->slot_bytes = align_up(ctx->off_levels + sizeof(h264r_level) * (size_t)ctx->level_capacity + sizeof(h264r_mb_motion) * ctx->nmb, 256);
 
     ctx->frames.resize(sp->max_frames);
     ctx->slots.resize(sp->max_pictures_in_flight);
     // one pinned and one device arena for all staging slots
     uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr; int16_t* d_resid = nullptr;
+    uint8_t* h_motion = nullptr; h264r_mb_motion* d_motion = nullptr;
+    const size_t motion_bytes = sizeof(h264r_mb_motion) * (size_t)ctx->nmb;
     const size_t arena = ctx->slot_bytes * sp->max_pictures_in_flight;
     e = cudaHostAlloc((void**)&h_arena, arena, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_arena, arena);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_desc, sizeof(DeblockDesc) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_resid, sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)ctx->nmb * sp->max_pictures_in_flight);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&h_motion, motion_bytes * sp->max_pictures_in_flight, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_motion, motion_bytes * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
@@ -259,6 +302,8 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         if (d_arena) cudaFree(d_arena);
         if (d_desc) cudaFree(d_desc);
         if (d_resid) cudaFree(d_resid);
+        if (h_motion) cudaFreeHost(h_motion);
+        if (d_motion) cudaFree(d_motion);
         if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
         if (ctx->d_pics) cudaFree(ctx->d_pics);
         if (ctx->d_sync) cudaFree(ctx->d_sync);
@@ -271,6 +316,8 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         ctx->slots[i].dev = d_arena + ctx->slot_bytes * i;
         ctx->slots[i].dev_desc = d_desc + (size_t)ctx->nmb * i;
         ctx->slots[i].dev_resid = d_resid + (size_t)H264R_COEFFS_PER_MB * ctx->nmb * i;
+        ctx->slots[i].host_motion = h_motion + motion_bytes * i;
+        ctx->slots[i].dev_motion = d_motion + (size_t)ctx->nmb * i;
     }
     *out = ctx;
     return H264R_OK;
@@ -281,8 +328,9 @@ void h264r_destroy(h264r_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
-    for (Frame& f : ctx->frames) if (f.dev) cudaFree(f.dev);
-    if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); cudaFree(ctx->slots[0].dev_resid); }
+    for (Frame& f : ctx->frames) { if (f.dev) cudaFree(f.dev); if (f.read_done) cudaEventDestroy(f.read_done); }
+    if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); cudaFree(ctx->slots[0].dev_resid);
+                                cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_motion); }
     cudaFreeHost(ctx->h_pics); cudaFree(ctx->d_pics); cudaFree(ctx->d_sync);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) if (ctx->table_ev[i]) cudaEventDestroy(ctx->table_ev[i]);
@@ -337,7 +385,7 @@ int h264r_picture_begin(h264r_ctx* ctx, h264r_frame dst, const h264r_pic_params*
     sl.state = SLOT_FILLING; sl.pp = *pp; sl.dst = dst; sl.used_levels = 0;
     ctx->filling = s;
     out->mbs = reinterpret_cast<h264r_mb*>(sl.host + ctx->off_mbs);
-    out->motion = reinterpret_cast<h264r_mb_motion*>(sl.host + ctx->off_motion);
+    out->motion = reinterpret_cast<h264r_mb_motion*>(sl.host_motion);
     out->slices = reinterpret_cast<h264r_slice*>(sl.host + ctx->off_slices);
     out->levels = reinterpret_cast<h264r_level*>(sl.host + ctx->off_levels);
     out->level_capacity = ctx->level_capacity;
@@ -352,11 +400,24 @@ int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels)
     Slot& sl = ctx->slots[ctx->filling];
     sl.used_levels = num_levels;
     // validate what would otherwise become an out-of-bounds access on the device
-    const h264r_mb* mbs = reinterpret_cast<const h264r_mb*>(sl.host + ctx->off_mbs);
+    h264r_mb* mbs = reinterpret_cast<h264r_mb*>(sl.host + ctx->off_mbs);
+    // The per-MB motion (192 bytes, the 16 pic_motion_params the parser side filled) crosses PCIe in packed form: only
+    // the distinct entries of an MB (1 when all 16 blocks agree, 2 for halves, 4 for quadrants, else 16), 12 bytes each,
+    // right behind the level list.  reserved2 of the header = first entry << 4 | code; motion_expand_kernel restores
+    // the full array in HBM.  Intra MBs send nothing (their motion is never read).
+    const h264r_mb_motion* motion = reinterpret_cast<const h264r_mb_motion*>(sl.host_motion);
+    uint8_t* const packed = sl.host + ctx->off_levels + sizeof(h264r_level) * (size_t)num_levels;
+    uint32_t entries = 0;
     int has_intra = 0, has_inter = 0, bad = 0, unsupported = 0;
     for (int i = 0; i < ctx->nmb; ++i) {
-        const h264r_mb& m = mbs[i];
-        if (m.flags & H264R_MB_FLAG_INTRA) has_intra = 1; else has_inter = 1;
+        h264r_mb& m = mbs[i];
+        if (m.flags & H264R_MB_FLAG_INTRA) { has_intra = 1; m.reserved2 = 0; }
+        else {
+            has_inter = 1;
+            const int code = pack_motion(motion[i], packed + (size_t)12 * entries);
+            m.reserved2 = entries << 4 | (uint32_t)code;
+            entries += kPackedEntries[code];
+        }
         if (m.slice_idx >= sl.pp.num_slices) bad = 1;
         if (m.coeff_count && ((uint64_t)m.coeff_offset + m.coeff_count > num_levels)) bad = 1;   // positions are checked on the device
         if (m.mb_type > H264R_MB_IPCM || m.mb_type == 11) unsupported = 1;        // SI and friends
@@ -374,7 +435,7 @@ int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels)
         sl.state = SLOT_FREE; ctx->filling = -1;
         return unsupported ? H264R_ERR_UNSUPPORTED : H264R_ERR_INVALID;
     }
-    sl.has_intra = has_intra; sl.has_inter = has_inter;
+    sl.has_intra = has_intra; sl.has_inter = has_inter; sl.motion_entries = entries;
     sl.state = SLOT_QUEUED;
     ctx->queue.push_back(ctx->filling);
     ctx->filling = -1;
@@ -427,7 +488,8 @@ int h264r_flush(h264r_ctx* ctx)
         DevPicture& p = h_table[k];
         memset(&p, 0, sizeof(p));
         p.mbs = reinterpret_cast<const h264r_mb*>(s.dev + ctx->off_mbs);
-        p.motion = reinterpret_cast<const h264r_mb_motion*>(s.dev + ctx->off_motion);
+        p.motion = s.dev_motion;
+        p.packed_motion = s.dev + ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels;
         p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
         p.levels = reinterpret_cast<const h264r_level*>(s.dev + ctx->off_levels);
         p.resid = s.dev_resid;
@@ -454,13 +516,13 @@ int h264r_flush(h264r_ctx* ctx)
         L.any_inter = L.any_intra = L.any_deblock = 0;
         for (int k = b; k < e; ++k) {
             Slot& s = ctx->slots[order[k]];
-            rec.copies.push_back({ order[k], ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels });
+            rec.copies.push_back({ order[k], ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels + (size_t)12 * s.motion_entries });
             L.any_inter |= s.has_inter; L.any_intra |= s.has_intra; L.any_deblock |= s.pp.run_deblock;
         }
         rec.progress_bytes = sizeof(int) * (64 + ctx->sync_ints_per_pic * (size_t)L.num_pics);
         rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx);
         if (!rec.ev_h2d || !rec.ev_done) return H264R_ERR_CUDA;
-        for (int k = b; k < e; ++k) ctx->frames[ctx->slots[order[k]].dst].ready = rec.ev_done;
+        for (int k = b; k < e; ++k) { ctx->frames[ctx->slots[order[k]].dst].ready = rec.ev_done; rec.dst_frames.push_back(ctx->slots[order[k]].dst); }
         ctx->last_waves.push_back(rec);
     }
     for (int qi : ctx->queue) ctx->slots[qi].state = SLOT_INFLIGHT;   // reusable once the streams have drained (h264r_wait)
@@ -531,6 +593,10 @@ int h264r_frame_download_async(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_
     const uint8_t* d = ctx->frames[f].dev;
     if (ctx->frames[f].ready) CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->frames[f].ready, 0));
     { const int rc = copy_frame_d2h(ctx, ctx->s_d2h, d, y, cb, cr, pitch_y, pitch_c); if (rc != H264R_OK) return rc; }
+    Frame& fr = ctx->frames[f];
+    if (!fr.read_done) CU(cudaEventCreateWithFlags(&fr.read_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(fr.read_done, ctx->s_d2h));
+    fr.pending_read = true;
     ctx->stats.d2h_bytes += (uint64_t)w * h * 3 / 2;
     return H264R_OK;
 }

@@ -1265,35 +1265,84 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
 
 // ---------------------------------------------------------------------------------------------------
 
-bool launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
+// Restores the full per-MB motion array (h264r_mb_motion, what the parser side filled) from the packed entries that
+// crossed PCIe (engine.cu pack_motion).  One thread per 16-byte chunk of an MB's 192 bytes.
+__global__ void __launch_bounds__(256)
+motion_expand_kernel(const DevPicture* __restrict__ pics, int num_pics, int nmb)
+{
+    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_pic = (long long)nmb * 12;
+    if (gi >= (long long)num_pics * per_pic) return;
+    const int pic_i = (int)(gi / per_pic);
+    const int rem = (int)(gi - (long long)pic_i * per_pic), mb = rem / 12, chunk = rem - mb * 12;
+    const DevPicture& pic = pics[pic_i];
+    if (!pic.has_inter) return;
+    const uint32_t r2 = __ldg(reinterpret_cast<const uint32_t*>(pic.mbs + mb) + 7);
+    const int code = r2 & 15;
+    if (code == 0) return;
+    const uint8_t* __restrict__ base = pic.packed_motion + (size_t)(r2 >> 4) * 12;
+    auto entry_of = [&](int b) {
+        switch (code) {
+        case 1: return 0;
+        case 2: return b >> 3;
+        case 3: return (b >> 1) & 1;
+        case 4: return ((b >> 3) << 1) | ((b >> 1) & 1);
+        default: return b;
+        }
+    };
+    uint32_t w[4];
+    if (chunk < 8) {                                       // mv[list][4 blocks]
+        const int list = chunk >> 2, b0 = (chunk & 3) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t*>(base + entry_of(b0 + k) * 12 + list * 4));
+    } else {                                               // ref_idx[list][16] (chunks 8, 9) / ref_pic[list][16] (10, 11)
+        const int off = 8 + (chunk - 8);                   // byte inside the entry: 8, 9 ref_idx; 10, 11 ref_pic
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v |= (uint32_t)__ldg(base + entry_of(k * 4 + j) * 12 + off) << (8 * j);
+            w[k] = v;
+        }
+    }
+    reinterpret_cast<uint4*>(pic.motion + mb)[chunk] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
 {
     const int nmb = w.geom.width_mbs * w.geom.height_mbs;
     const int threads = kWarpsPerCta * 32;
     const int groups = (w.geom.height_mbs + kWarpsPerCta - 1) / kWarpsPerCta;
     if (which == KERNEL_RESID) {
+        int n = 1;
+        if (w.any_inter) {
+            const long long total = (long long)w.num_pics * nmb * 12;
+            motion_expand_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(w.pics, w.num_pics, nmb);
+            n = 2;
+        }
         const long long warps = (long long)w.num_pics * nmb;
         residual_kernel<<<(int)((warps + kWarpsPerCta - 1) / kWarpsPerCta), threads, 0, stream>>>(w.pics, w.num_pics, w.geom);
-        return true;
+        return n;
     }
     if (which == KERNEL_INTER) {
-        if (!w.any_inter) return false;
+        if (!w.any_inter) return 0;
         const dim3 grid((w.geom.width_mbs + kWarpsPerCta - 1) / kWarpsPerCta, w.geom.height_mbs, w.num_pics);
         recon_inter_kernel<<<grid, threads, 0, stream>>>(w.pics, w.geom, w.direct8x8);
-        return true;
+        return 1;
     }
     if (which == KERNEL_INTRA) {
-        if (!w.any_intra) return false;
+        if (!w.any_intra) return 0;
         recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
-        return true;
+        return 1;
     }
-    if (!w.any_deblock) return false;
+    if (!w.any_deblock) return 0;
     if (which == KERNEL_DBPREP) {
         const long long total = (long long)w.num_pics * nmb;
         deblock_prep_kernel<<<(int)((total + 127) / 128), 128, 0, stream>>>(w.pics, w.num_pics, w.geom);
-        return true;
+        return 1;
     }
     deblock_kernel<<<((w.num_pics + 1) / 2) * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
-    return true;
+    return 1;
 }
 
 } // namespace h264r

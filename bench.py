@@ -262,8 +262,11 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
         def f_k_d2h(): eng.replay(1, 0); download_all()
         def f_d2h_only(): download_all()
         def f_all(): eng.replay(1, E2E); download_all()
+        def f_k_d2h_async(): eng.replay(1, pyapi.Engine.REPLAY_ASYNC); download_all()
+        def f_h2d_k_async(): eng.replay(1, E2E)
         print(f"[diag] kernels {timed(lambda: eng.replay(1, 0)):.1f} ms | h2d+kernels {timed(f_h2d_only):.1f} | "
-              f"kernels+d2h {timed(f_k_d2h):.1f} | d2h only {timed(f_d2h_only):.1f} | all {timed(f_all):.1f}", file=sys.stderr)
+              f"kernels+d2h {timed(f_k_d2h):.1f} | d2h only {timed(f_d2h_only):.1f} | all {timed(f_all):.1f} | "
+              f"pipelined: kernels+d2h {timed(f_k_d2h_async, 4):.1f}, h2d+kernels {timed(f_h2d_k_async, 4):.1f}, all {timed(f_all, 4):.1f}", file=sys.stderr)
         t0 = time.perf_counter(); download_all(); t_issue = (time.perf_counter() - t0) * 1e3; eng.wait()
         print(f"[diag] host time to issue {npics} async downloads: {t_issue:.1f} ms", file=sys.stderr)
 

@@ -93,11 +93,14 @@ typedef struct h264r_mb {
             uint8_t sub_mb_pred_mode[4]; /* SubMbPredMode[mbPartIdx] after direct-mode resolution     */
         } inter;
     } u;
-    uint32_t reserved2;
+    uint32_t reserved2;              /* engine-internal (index of the MB's packed motion), overwritten by
+                                        h264r_picture_submit; callers leave it alone                    */
 } h264r_mb;
 
 /* per-macroblock motion: 192 bytes.  The 16 pic_motion_params (framebuf/picture.h:66-71) of the MB,   */
-/* 4x4 blocks in raster order (by*4+bx).  Only read for non-intra MBs.                                */
+/* 4x4 blocks in raster order (by*4+bx).  Only read for non-intra MBs.  This array stays in host       */
+/* memory: h264r_picture_submit packs it (one entry per distinct partition of an MB, 12 bytes each)    */
+/* for the host->device copy and the GPU restores the full array in HBM.                               */
 typedef struct h264r_mb_motion {
     int16_t mv[2][16][2];            /* [list][blk][x,y] quarter-pel                                   */
     int8_t  ref_idx[2][16];          /* pic_motion_params::ref_idx (may be 0 for an unused list, quirk 2) */
