@@ -37,19 +37,24 @@ struct DevPicture {
     const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]
     int*                   row_progress;              // [2][height_mbs]: intra wavefront, deblock wavefront
     DeblockDesc*           desc;                      // [nmb], device only
+    const uint32_t*        intra_list;                // raster-ordered addresses of the intra MBs (pictures that also have inter MBs)
+    uint32_t*              mb_done;                   // [nmb], device only: epoch stamp of the launch that reconstructed the intra MB
     int                    run_deblock;
     int                    has_intra;                 // any intra MB in the picture (host-side hint)
     int                    has_inter;
-    int                    pad;
+    int                    intra_count;               // entries of intra_list; 0 for all-intra pictures (row wavefront instead)
 };
 
 struct WaveLaunch {
     const DevPicture* pics;          // device array
     int   num_pics;
-    int*  tickets;                   // device: [2] work-ticket counters (intra, deblock), zeroed per wave
+    int*  tickets;                   // device: work-ticket counters ([0] intra rows, [1] deblock, [2] sparse intra), zeroed per wave
     FrameGeom geom;
     int   direct8x8;
     int   any_inter, any_intra, any_deblock;
+    int   any_intra_rows;            // some picture of the wave is all-intra: row wavefront kernel
+    int   max_intra_sparse;          // largest intra_count of the wave (0: no sparse-intra kernel)
+    uint32_t epoch;                  // stamp of this launch sequence for DevPicture::mb_done
 };
 
 // Kernel launchers of one wave (kernels.cu).  which: 0 motion expansion + residual (parallel), 1 inter (parallel), 2 intra wavefront,

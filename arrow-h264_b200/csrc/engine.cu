@@ -37,6 +37,8 @@ struct Slot {
     h264r_mb_motion* dev_motion = nullptr;    // device only: motion expanded from the packed form (motion_expand_kernel)
     uint8_t* host_motion = nullptr;           // pinned, host only: the full per-MB motion array the parser side fills
     uint32_t motion_entries = 0;              // packed 12-byte motion entries behind the level list
+    uint32_t intra_count = 0;                 // intra-MB address list behind the packed motion (mixed pictures only)
+    uint32_t* dev_mb_done = nullptr;          // device only: per-MB epoch stamps of the sparse intra kernel
     SlotState state = SLOT_FREE;
     h264r_pic_params pp;
     h264r_frame dst = -1;
@@ -73,6 +75,8 @@ struct h264r_ctx {
     std::vector<Frame> frames;
     std::vector<Slot> slots;
     std::vector<int> queue;                   // slot indexes in submission order
+    std::vector<uint32_t> scratch_list;       // intra-MB addresses of the picture being submitted
+    uint32_t epoch = 0;                       // launch-sequence counter (DevPicture::mb_done stamps)
     int filling = -1;
     DevPicture* h_pics = nullptr;             // pinned, [2][max_pictures_in_flight]: alternating halves per flush
     DevPicture* d_pics = nullptr;
@@ -178,6 +182,7 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
             if (fr.pending_read) { CU(cudaStreamWaitEvent(ctx->stream, fr.read_done, 0)); fr.pending_read = false; }
         }
         CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
+        rec.launch.epoch = ++ctx->epoch;
         for (int kind = 0; kind < KERNEL_KINDS; ++kind) {
             if (time_kernels) {
                 while (ctx->timer_events.size() < timer_used + 2) {
@@ -276,13 +281,14 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     ctx->level_capacity = sp->max_levels_per_picture > 0 ? (uint32_t)sp->max_levels_per_picture
                                                           : (uint32_t)H264R_COEFFS_PER_MB * (uint32_t)ctx->nmb;
     // worst case of the packed motion: 16 entries of 12 bytes per MB
-    ctx->slot_bytes = align_up(ctx->off_levels + sizeof(h264r_level) * (size_t)ctx->level_capacity + sizeof(h264r_mb_motion) * ctx->nmb, 256);
+    // and of the intra-MB address list: 4 bytes per MB
+    ctx->slot_bytes = align_up(ctx->off_levels + sizeof(h264r_level) * (size_t)ctx->level_capacity + (sizeof(h264r_mb_motion) + 4) * ctx->nmb, 256);
 
     ctx->frames.resize(sp->max_frames);
     ctx->slots.resize(sp->max_pictures_in_flight);
     // one pinned and one device arena for all staging slots
     uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr; int16_t* d_resid = nullptr;
-    uint8_t* h_motion = nullptr; h264r_mb_motion* d_motion = nullptr;
+    uint8_t* h_motion = nullptr; h264r_mb_motion* d_motion = nullptr; uint32_t* d_done = nullptr;
     const size_t motion_bytes = sizeof(h264r_mb_motion) * (size_t)ctx->nmb;
     const size_t arena = ctx->slot_bytes * sp->max_pictures_in_flight;
     e = cudaHostAlloc((void**)&h_arena, arena, cudaHostAllocDefault);
@@ -291,6 +297,8 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_resid, sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&h_motion, motion_bytes * sp->max_pictures_in_flight, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_motion, motion_bytes * sp->max_pictures_in_flight);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_done, sizeof(uint32_t) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
+    if (e == cudaSuccess) e = cudaMemset(d_done, 0, sizeof(uint32_t) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
@@ -304,6 +312,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         if (d_resid) cudaFree(d_resid);
         if (h_motion) cudaFreeHost(h_motion);
         if (d_motion) cudaFree(d_motion);
+        if (d_done) cudaFree(d_done);
         if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
         if (ctx->d_pics) cudaFree(ctx->d_pics);
         if (ctx->d_sync) cudaFree(ctx->d_sync);
@@ -318,6 +327,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         ctx->slots[i].dev_resid = d_resid + (size_t)H264R_COEFFS_PER_MB * ctx->nmb * i;
         ctx->slots[i].host_motion = h_motion + motion_bytes * i;
         ctx->slots[i].dev_motion = d_motion + (size_t)ctx->nmb * i;
+        ctx->slots[i].dev_mb_done = d_done + (size_t)ctx->nmb * i;
     }
     *out = ctx;
     return H264R_OK;
@@ -330,7 +340,7 @@ void h264r_destroy(h264r_ctx* ctx)
     cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
     for (Frame& f : ctx->frames) { if (f.dev) cudaFree(f.dev); if (f.read_done) cudaEventDestroy(f.read_done); }
     if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); cudaFree(ctx->slots[0].dev_resid);
-                                cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_motion); }
+                                cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_motion); cudaFree(ctx->slots[0].dev_mb_done); }
     cudaFreeHost(ctx->h_pics); cudaFree(ctx->d_pics); cudaFree(ctx->d_sync);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) if (ctx->table_ev[i]) cudaEventDestroy(ctx->table_ev[i]);
@@ -409,9 +419,10 @@ int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels)
     uint8_t* const packed = sl.host + ctx->off_levels + sizeof(h264r_level) * (size_t)num_levels;
     uint32_t entries = 0;
     int has_intra = 0, has_inter = 0, bad = 0, unsupported = 0;
+    ctx->scratch_list.clear();
     for (int i = 0; i < ctx->nmb; ++i) {
         h264r_mb& m = mbs[i];
-        if (m.flags & H264R_MB_FLAG_INTRA) { has_intra = 1; m.reserved2 = 0; }
+        if (m.flags & H264R_MB_FLAG_INTRA) { has_intra = 1; m.reserved2 = 0; ctx->scratch_list.push_back((uint32_t)i); }
         else {
             has_inter = 1;
             const int code = pack_motion(motion[i], packed + (size_t)12 * entries);
@@ -436,6 +447,13 @@ int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels)
         return unsupported ? H264R_ERR_UNSUPPORTED : H264R_ERR_INVALID;
     }
     sl.has_intra = has_intra; sl.has_inter = has_inter; sl.motion_entries = entries;
+    // Mixed pictures reconstruct their (few) intra MBs one warp each, ordered by per-MB dependencies: the raster-ordered
+    // address list follows the packed motion.  All-intra pictures run the row wavefront and need no list.
+    sl.intra_count = 0;
+    if (has_intra && has_inter) {
+        sl.intra_count = (uint32_t)ctx->scratch_list.size();
+        memcpy(packed + (size_t)12 * entries, ctx->scratch_list.data(), sizeof(uint32_t) * ctx->scratch_list.size());
+    }
     sl.state = SLOT_QUEUED;
     ctx->queue.push_back(ctx->filling);
     ctx->filling = -1;
@@ -490,6 +508,9 @@ int h264r_flush(h264r_ctx* ctx)
         p.mbs = reinterpret_cast<const h264r_mb*>(s.dev + ctx->off_mbs);
         p.motion = s.dev_motion;
         p.packed_motion = s.dev + ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels;
+        p.intra_list = reinterpret_cast<const uint32_t*>(p.packed_motion + (size_t)12 * s.motion_entries);
+        p.intra_count = (int)s.intra_count;
+        p.mb_done = s.dev_mb_done;
         p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
         p.levels = reinterpret_cast<const h264r_level*>(s.dev + ctx->off_levels);
         p.resid = s.dev_resid;
@@ -513,11 +534,13 @@ int h264r_flush(h264r_ctx* ctx)
         WaveLaunch& L = rec.launch;
         L.pics = d_table + b; L.num_pics = e - b; L.tickets = ctx->d_sync; L.geom = ctx->geom;
         L.direct8x8 = ctx->seq.direct_8x8_inference_flag;
-        L.any_inter = L.any_intra = L.any_deblock = 0;
+        L.any_inter = L.any_intra = L.any_deblock = L.any_intra_rows = L.max_intra_sparse = 0; L.epoch = 0;
         for (int k = b; k < e; ++k) {
             Slot& s = ctx->slots[order[k]];
-            rec.copies.push_back({ order[k], ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels + (size_t)12 * s.motion_entries });
+            rec.copies.push_back({ order[k], ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels + (size_t)12 * s.motion_entries + sizeof(uint32_t) * s.intra_count });
             L.any_inter |= s.has_inter; L.any_intra |= s.has_intra; L.any_deblock |= s.pp.run_deblock;
+            L.any_intra_rows |= (s.has_intra && !s.has_inter);
+            L.max_intra_sparse = std::max(L.max_intra_sparse, (int)s.intra_count);
         }
         rec.progress_bytes = sizeof(int) * (64 + ctx->sync_ints_per_pic * (size_t)L.num_pics);
         rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx);

@@ -636,6 +636,213 @@ __device__ __forceinline__ int dc_value(int n, int log2n, bool a, bool b, TF T, 
     return (sum + round) >> shift;
 }
 
+// Reconstruction of one intra macroblock by one warp (mb_pred_intra / mb_pred_ipcm, decoder.cc:149-215): neighbour
+// availability, neighbour samples of the current unfiltered picture, prediction + residual block by block through a
+// shared-memory tile, store.  The caller has made sure that the neighbouring MBs are reconstructed and visible.
+__device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, const FrameGeom& g, IntraSmem& sm, const MbHdr& h,
+                                                     int mbx, int mby, int lane)
+{
+    const int W = g.width_mbs, H = g.height_mbs;
+    const int addr = mby * W + mbx;
+    uint8_t* const dY = pic.dst;
+    uint8_t* const dC[2] = { pic.dst + g.off_cb, pic.dst + g.off_cr };
+    const h264r_slice* sl = pic.slices + h.slice_idx;
+    const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
+
+    if (h.mb_type == H264R_MB_IPCM) {                 // mb_pred_ipcm, decoder.cc:149-168
+        const h264r_level* __restrict__ lv = pic.levels + h.coeff_offset;
+        for (int i = lane; i < h.coeff_count; i += 32) {
+            const uint32_t e = __ldg(lv + i);
+            const int p = (int)(e & 0xFFFFu), v = (int)(e >> 16) & 0xFF;
+            if (p < 256) dY[(size_t)(py + (p >> 4)) * g.pitch_y + px + (p & 15)] = (uint8_t)v;
+            else if (p < 384) {
+                const int pl = (p - 256) >> 6, q = (p - 256) & 63;
+                dC[pl][(size_t)(cy + (q >> 3)) * g.pitch_c + cx + (q & 7)] = (uint8_t)v;
+            }
+        }
+        return;
+    }
+
+    // availability of the four neighbouring MBs (neighbour.cc:123-175 + slice_nr + constrained intra)
+    const uint32_t w0 = (uint32_t)h.mb_type | (uint32_t)h.flags << 8 | (uint32_t)h.slice_idx << 16;
+    const bool ci = __ldg(&sl->constrained_intra_pred_flag) != 0;
+    const bool aL  = nb_avail(pic.mbs, W, H, addr, w0, mbx - 1, mby, ci);
+    const bool aT  = nb_avail(pic.mbs, W, H, addr, w0, mbx, mby - 1, ci);
+    const bool aTL = nb_avail(pic.mbs, W, H, addr, w0, mbx - 1, mby - 1, ci);
+    const bool aTR = nb_avail(pic.mbs, W, H, addr, w0, mbx + 1, mby - 1, ci);
+
+    // neighbour samples of the current, unfiltered picture -> tiles (L1-bypassing loads: other SMs wrote them)
+    if (mby > 0) {
+        if (lane < 8) {                                // luma top row, cols -4..27
+            const int x = px - 4 + lane * 4;
+            uint32_t v = 0;
+            if (x >= 0 && x < W * 16) v = ldcg_u32(dY + (size_t)(py - 1) * g.pitch_y + x);
+            reinterpret_cast<uint32_t*>(sm.ty)[lane] = v;
+        } else if (lane < 16) {                        // chroma top rows, cols -4..11
+            const int c = lane - 8, pl = c >> 2, x = cx - 4 + (c & 3) * 4;
+            uint32_t v = 0;
+            if (x >= 0 && x < W * 8) v = ldcg_u32(dC[pl] + (size_t)(cy - 1) * g.pitch_c + x);
+            reinterpret_cast<uint32_t*>(sm.tc[pl])[c & 3] = v;
+        }
+    }
+    if (mbx > 0) {
+        if (lane < 16) TY(-1, lane) = ldcg_u8(dY + (size_t)(py + lane) * g.pitch_y + px - 1);
+        else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = ldcg_u8(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx - 1); }
+    }
+    {   // residual plane written by residual_kernel (48 x 16 B), or zeros
+        const uint4* rsrc = reinterpret_cast<const uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
+        const bool has = h.has_resid();
+        for (int v = lane; v < 48; v += 32)
+            reinterpret_cast<uint4*>(sm.res)[v] = has ? __ldg(rsrc + v) : make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();                                      // tiles and residual visible
+
+    // ---- luma ----
+    if (h.mb_type == H264R_MB_I16x16) {
+        auto T = [&](int i) { return (int)TY(i, -1); };
+        auto L = [&](int i) { return (int)TY(-1, i); };
+        const int y = lane >> 1, x0 = (lane & 1) * 8;
+        int pa = 0, pb = 0, pc = 0, dcv = 0;
+        if (h.i16mode == 3) plane_params(16, false, T, L, pa, pb, pc);
+        else if (h.i16mode == 2) dcv = dc_value(16, 4, aL, aT, T, L);
+        int v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int x = x0 + i;
+            int p;
+            if (h.i16mode == 0) p = T(x);
+            else if (h.i16mode == 1) p = L(y);
+            else if (h.i16mode == 2) p = dcv;
+            else p = clip255((pa + pb * (x - 7) + pc * (y - 7) + 16) >> 5);
+            v[i] = clip255(p + sm.res[y * 16 + x]);
+        }
+        __syncwarp();                                  // all lanes have read the border before the tile is written
+#pragma unroll
+        for (int i = 0; i < 8; ++i) TY(x0 + i, y) = (uint8_t)v[i];
+    } else {
+        const bool is8 = h.mb_type == H264R_MB_I8x8;
+        const int n = is8 ? 8 : 4, nblk = is8 ? 4 : 16;
+        for (int k = 0; k < nblk; ++k) {
+            int xO, yO;
+            if (is8) { xO = (k & 1) * 8; yO = (k >> 1) * 8; }
+            else { xO = ((k >> 2) & 1) * 8 + (k & 1) * 4; yO = (k >> 3) * 8 + ((k >> 1) & 1) * 4; }
+            const int mode = ((k < 8 ? h.u0 >> (4 * k) : h.u1 >> (4 * (k - 8)))) & 15;
+            const bool avA = xO > 0 ? true : aL;
+            const bool avB = yO > 0 ? true : aT;
+            const bool avD = (xO > 0 && yO > 0) ? true : (xO > 0 ? aT : (yO > 0 ? aL : aTL));
+            bool avC;
+            if (yO == 0) avC = (xO + n < 16) ? aT : aTR;
+            else avC = xO + n < 16;
+            if (!is8 && xO == 4 && (yO == 4 || yO == 12)) avC = false;
+            if (is8 && xO == 8 && yO == 8) avC = false;
+            const int tmax = avC ? 2 * n - 1 : n - 1;  // C substitution: p(x,-1) = p(n-1,-1) for x >= n
+
+            if (!is8) {
+                auto T = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
+                auto L = [&](int i) { return (int)TY(xO - 1, yO + i); };
+                int v = 0;
+                const int x = lane & 3, y = (lane >> 2) & 3;
+                if (lane < 16) {
+                    const int dcv = mode == 2 ? dc_value(4, 2, avA, avB, T, L) : 0;
+                    v = clip255(pred_dir_sample(mode, 4, x, y, dcv, T, L) + sm.res[(yO + y) * 16 + xO + x]);
+                }
+                __syncwarp();
+                if (lane < 16) TY(xO + x, yO + y) = (uint8_t)v;
+                __syncwarp();
+            } else {
+                // reference sample filtering (Intra8x8::filtering, intra_prediction.cc:413-447)
+                auto To = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
+                auto Lo = [&](int i) { return (int)TY(xO - 1, yO + i); };
+                if (lane < 16) {                       // p'(lane, -1)
+                    int f = 0;
+                    if (avB) {
+                        if (lane == 0) f = avD ? (To(-1) + 2 * To(0) + To(1) + 2) >> 2 : (3 * To(0) + To(1) + 2) >> 2;
+                        else if (lane == 15) f = (To(14) + 3 * To(15) + 2) >> 2;
+                        else f = (To(lane - 1) + 2 * To(lane) + To(lane + 1) + 2) >> 2;
+                    }
+                    sm.ft[lane + 1] = (uint8_t)f;
+                } else if (lane < 24) {                // p'(-1, i)
+                    const int i = lane - 16;
+                    int f = 0;
+                    if (avA) {
+                        if (i == 0) f = avD ? (Lo(-1) + 2 * Lo(0) + Lo(1) + 2) >> 2 : (3 * Lo(0) + Lo(1) + 2) >> 2;
+                        else if (i == 7) f = (Lo(6) + 3 * Lo(7) + 2) >> 2;
+                        else f = (Lo(i - 1) + 2 * Lo(i) + Lo(i + 1) + 2) >> 2;
+                    }
+                    sm.fl[i + 1] = (uint8_t)f;
+                } else if (lane == 24) {               // p'(-1, -1)
+                    int f = 0;
+                    if (avD) {
+                        const int c = To(-1);
+                        if (avA && avB) f = (To(0) + 2 * c + Lo(0) + 2) >> 2;
+                        else if (avB) f = (3 * c + To(0) + 2) >> 2;
+                        else if (avA) f = (3 * c + Lo(0) + 2) >> 2;
+                        else f = c;
+                    }
+                    sm.ft[0] = sm.fl[0] = (uint8_t)f;
+                }
+                __syncwarp();
+                auto T = [&](int i) { return (int)sm.ft[i + 1]; };
+                auto L = [&](int i) { return (int)sm.fl[i + 1]; };
+                const int dcv = mode == 2 ? dc_value(8, 3, avA, avB, T, L) : 0;
+                const int y = lane >> 2, x0 = (lane & 3) * 2;
+                int v[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    v[i] = clip255(pred_dir_sample(mode, 8, x0 + i, y, dcv, T, L) + sm.res[(yO + y) * 16 + xO + x0 + i]);
+                __syncwarp();
+                TY(xO + x0, yO + y) = (uint8_t)v[0]; TY(xO + x0 + 1, yO + y) = (uint8_t)v[1];
+                __syncwarp();
+            }
+        }
+    }
+
+    // ---- chroma: lanes 0..15 Cb, 16..31 Cr; 4 samples per lane ----
+    {
+        const int pl = lane >> 4, l16 = lane & 15, y = l16 >> 1, x0 = (l16 & 1) * 4;
+        auto T = [&](int i) { return (int)TC(pl, i, -1); };
+        auto L = [&](int i) { return (int)TC(pl, -1, i); };
+        const int m = h.cmode;                         // 0 DC, 1 H, 2 V, 3 plane
+        int pa = 0, pb = 0, pc = 0, dcv = 0;
+        if (m == 3) plane_params(8, true, T, L, pa, pb, pc);
+        else if (m == 0) {                             // DC of this lane's 4x4 block (intra_prediction.cc:825-849)
+            const int xO = x0, yO = y & 4;
+            bool a, b;
+            if ((xO == 0 && yO == 0) || (xO > 0 && yO > 0)) { a = aL; b = aT; }
+            else if (xO > 0) { a = aT ? false : aL; b = aT; }
+            else { a = aL; b = aL ? false : aT; }
+            auto T4 = [&](int i) { return T(xO + i); };
+            auto L4 = [&](int i) { return L(yO + i); };
+            dcv = dc_value(4, 2, a, b, T4, L4);
+        }
+        int v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int x = x0 + i;
+            int p;
+            if (m == 0) p = dcv;
+            else if (m == 1) p = L(y);
+            else if (m == 2) p = T(x);
+            else p = clip255((pa + pb * (x - 3) + pc * (y - 3) + 16) >> 5);
+            v[i] = clip255(p + sm.res[256 + pl * 64 + y * 8 + x]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) TC(pl, x0 + i, y) = (uint8_t)v[i];
+    }
+    __syncwarp();
+
+    // ---- store the reconstructed MB ----
+    if (lane < 16) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(&TY(0, lane));
+        *reinterpret_cast<uint4*>(dY + (size_t)(py + lane) * g.pitch_y + px) = make_uint4(r[0], r[1], r[2], r[3]);
+    } else {
+        const int c = lane - 16, pl = c >> 3, y = c & 7;
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(&TC(pl, 0, y));
+        *reinterpret_cast<uint2*>(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx) = make_uint2(r[0], r[1]);
+    }
+}
+
 __global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTRA_CTAS)
 recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
 {
@@ -653,7 +860,7 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
     const int mby = rg * kWarpsPerCta + warp;
     if (mby >= H) return;
     const DevPicture& pic = pics[pic_i];
-    if (!pic.has_intra) return;
+    if (!pic.has_intra || pic.has_inter) return;         // mixed pictures: recon_intra_sparse_kernel
     IntraSmem& sm = smem_all[warp];
     int* progress = pic.row_progress;                    // [0][H]
     uint8_t* const dY = pic.dst;
@@ -689,206 +896,51 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
         const MbHdr h = load_hdr(pic.mbs, addr);
         if (mby > 0) wait_row_cached(progress + mby - 1, min(mbx + 2, W), known);
 
-        const h264r_slice* sl = pic.slices + h.slice_idx;
-        const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
-
-        if (h.mb_type == H264R_MB_IPCM) {                 // mb_pred_ipcm, decoder.cc:149-168
-            const h264r_level* __restrict__ lv = pic.levels + h.coeff_offset;
-            for (int i = lane; i < h.coeff_count; i += 32) {
-                const uint32_t e = __ldg(lv + i);
-                const int p = (int)(e & 0xFFFFu), v = (int)(e >> 16) & 0xFF;
-                if (p < 256) dY[(size_t)(py + (p >> 4)) * g.pitch_y + px + (p & 15)] = (uint8_t)v;
-                else if (p < 384) {
-                    const int pl = (p - 256) >> 6, q = (p - 256) & 63;
-                    dC[pl][(size_t)(cy + (q >> 3)) * g.pitch_c + cx + (q & 7)] = (uint8_t)v;
-                }
-            }
-            publish_row(progress + mby, done_to, lane, true);
-            continue;                                      // next intra MB of the chunk
-        }
-
-        // availability of the four neighbouring MBs (neighbour.cc:123-175 + slice_nr + constrained intra)
-        const uint32_t w0 = (uint32_t)h.mb_type | (uint32_t)h.flags << 8 | (uint32_t)h.slice_idx << 16;
-        const bool ci = __ldg(&sl->constrained_intra_pred_flag) != 0;
-        const bool aL  = nb_avail(pic.mbs, W, H, addr, w0, mbx - 1, mby, ci);
-        const bool aT  = nb_avail(pic.mbs, W, H, addr, w0, mbx, mby - 1, ci);
-        const bool aTL = nb_avail(pic.mbs, W, H, addr, w0, mbx - 1, mby - 1, ci);
-        const bool aTR = nb_avail(pic.mbs, W, H, addr, w0, mbx + 1, mby - 1, ci);
-
-        // neighbour samples of the current, unfiltered picture -> tiles (L1-bypassing loads: other SMs wrote them)
-        if (mby > 0) {
-            if (lane < 8) {                                // luma top row, cols -4..27
-                const int x = px - 4 + lane * 4;
-                uint32_t v = 0;
-                if (x >= 0 && x < W * 16) v = ldcg_u32(dY + (size_t)(py - 1) * g.pitch_y + x);
-                reinterpret_cast<uint32_t*>(sm.ty)[lane] = v;
-            } else if (lane < 16) {                        // chroma top rows, cols -4..11
-                const int c = lane - 8, pl = c >> 2, x = cx - 4 + (c & 3) * 4;
-                uint32_t v = 0;
-                if (x >= 0 && x < W * 8) v = ldcg_u32(dC[pl] + (size_t)(cy - 1) * g.pitch_c + x);
-                reinterpret_cast<uint32_t*>(sm.tc[pl])[c & 3] = v;
-            }
-        }
-        if (mbx > 0) {
-            if (lane < 16) TY(-1, lane) = ldcg_u8(dY + (size_t)(py + lane) * g.pitch_y + px - 1);
-            else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = ldcg_u8(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx - 1); }
-        }
-        {   // residual plane written by residual_kernel (48 x 16 B), or zeros
-            const uint4* rsrc = reinterpret_cast<const uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
-            const bool has = h.has_resid();
-            for (int v = lane; v < 48; v += 32)
-                reinterpret_cast<uint4*>(sm.res)[v] = has ? __ldg(rsrc + v) : make_uint4(0, 0, 0, 0);
-        }
-        __syncwarp();                                      // tiles and residual visible
-
-        // ---- luma ----
-        if (h.mb_type == H264R_MB_I16x16) {
-            auto T = [&](int i) { return (int)TY(i, -1); };
-            auto L = [&](int i) { return (int)TY(-1, i); };
-            const int y = lane >> 1, x0 = (lane & 1) * 8;
-            int pa = 0, pb = 0, pc = 0, dcv = 0;
-            if (h.i16mode == 3) plane_params(16, false, T, L, pa, pb, pc);
-            else if (h.i16mode == 2) dcv = dc_value(16, 4, aL, aT, T, L);
-            int v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int x = x0 + i;
-                int p;
-                if (h.i16mode == 0) p = T(x);
-                else if (h.i16mode == 1) p = L(y);
-                else if (h.i16mode == 2) p = dcv;
-                else p = clip255((pa + pb * (x - 7) + pc * (y - 7) + 16) >> 5);
-                v[i] = clip255(p + sm.res[y * 16 + x]);
-            }
-            __syncwarp();                                  // all lanes have read the border before the tile is written
-#pragma unroll
-            for (int i = 0; i < 8; ++i) TY(x0 + i, y) = (uint8_t)v[i];
-        } else {
-            const bool is8 = h.mb_type == H264R_MB_I8x8;
-            const int n = is8 ? 8 : 4, nblk = is8 ? 4 : 16;
-            for (int k = 0; k < nblk; ++k) {
-                int xO, yO;
-                if (is8) { xO = (k & 1) * 8; yO = (k >> 1) * 8; }
-                else { xO = ((k >> 2) & 1) * 8 + (k & 1) * 4; yO = (k >> 3) * 8 + ((k >> 1) & 1) * 4; }
-                const int mode = ((k < 8 ? h.u0 >> (4 * k) : h.u1 >> (4 * (k - 8)))) & 15;
-                const bool avA = xO > 0 ? true : aL;
-                const bool avB = yO > 0 ? true : aT;
-                const bool avD = (xO > 0 && yO > 0) ? true : (xO > 0 ? aT : (yO > 0 ? aL : aTL));
-                bool avC;
-                if (yO == 0) avC = (xO + n < 16) ? aT : aTR;
-                else avC = xO + n < 16;
-                if (!is8 && xO == 4 && (yO == 4 || yO == 12)) avC = false;
-                if (is8 && xO == 8 && yO == 8) avC = false;
-                const int tmax = avC ? 2 * n - 1 : n - 1;  // C substitution: p(x,-1) = p(n-1,-1) for x >= n
-
-                if (!is8) {
-                    auto T = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
-                    auto L = [&](int i) { return (int)TY(xO - 1, yO + i); };
-                    int v = 0;
-                    const int x = lane & 3, y = (lane >> 2) & 3;
-                    if (lane < 16) {
-                        const int dcv = mode == 2 ? dc_value(4, 2, avA, avB, T, L) : 0;
-                        v = clip255(pred_dir_sample(mode, 4, x, y, dcv, T, L) + sm.res[(yO + y) * 16 + xO + x]);
-                    }
-                    __syncwarp();
-                    if (lane < 16) TY(xO + x, yO + y) = (uint8_t)v;
-                    __syncwarp();
-                } else {
-                    // reference sample filtering (Intra8x8::filtering, intra_prediction.cc:413-447)
-                    auto To = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
-                    auto Lo = [&](int i) { return (int)TY(xO - 1, yO + i); };
-                    if (lane < 16) {                       // p'(lane, -1)
-                        int f = 0;
-                        if (avB) {
-                            if (lane == 0) f = avD ? (To(-1) + 2 * To(0) + To(1) + 2) >> 2 : (3 * To(0) + To(1) + 2) >> 2;
-                            else if (lane == 15) f = (To(14) + 3 * To(15) + 2) >> 2;
-                            else f = (To(lane - 1) + 2 * To(lane) + To(lane + 1) + 2) >> 2;
-                        }
-                        sm.ft[lane + 1] = (uint8_t)f;
-                    } else if (lane < 24) {                // p'(-1, i)
-                        const int i = lane - 16;
-                        int f = 0;
-                        if (avA) {
-                            if (i == 0) f = avD ? (Lo(-1) + 2 * Lo(0) + Lo(1) + 2) >> 2 : (3 * Lo(0) + Lo(1) + 2) >> 2;
-                            else if (i == 7) f = (Lo(6) + 3 * Lo(7) + 2) >> 2;
-                            else f = (Lo(i - 1) + 2 * Lo(i) + Lo(i + 1) + 2) >> 2;
-                        }
-                        sm.fl[i + 1] = (uint8_t)f;
-                    } else if (lane == 24) {               // p'(-1, -1)
-                        int f = 0;
-                        if (avD) {
-                            const int c = To(-1);
-                            if (avA && avB) f = (To(0) + 2 * c + Lo(0) + 2) >> 2;
-                            else if (avB) f = (3 * c + To(0) + 2) >> 2;
-                            else if (avA) f = (3 * c + Lo(0) + 2) >> 2;
-                            else f = c;
-                        }
-                        sm.ft[0] = sm.fl[0] = (uint8_t)f;
-                    }
-                    __syncwarp();
-                    auto T = [&](int i) { return (int)sm.ft[i + 1]; };
-                    auto L = [&](int i) { return (int)sm.fl[i + 1]; };
-                    const int dcv = mode == 2 ? dc_value(8, 3, avA, avB, T, L) : 0;
-                    const int y = lane >> 2, x0 = (lane & 3) * 2;
-                    int v[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        v[i] = clip255(pred_dir_sample(mode, 8, x0 + i, y, dcv, T, L) + sm.res[(yO + y) * 16 + xO + x0 + i]);
-                    __syncwarp();
-                    TY(xO + x0, yO + y) = (uint8_t)v[0]; TY(xO + x0 + 1, yO + y) = (uint8_t)v[1];
-                    __syncwarp();
-                }
-            }
-        }
-
-        // ---- chroma: lanes 0..15 Cb, 16..31 Cr; 4 samples per lane ----
-        {
-            const int pl = lane >> 4, l16 = lane & 15, y = l16 >> 1, x0 = (l16 & 1) * 4;
-            auto T = [&](int i) { return (int)TC(pl, i, -1); };
-            auto L = [&](int i) { return (int)TC(pl, -1, i); };
-            const int m = h.cmode;                         // 0 DC, 1 H, 2 V, 3 plane
-            int pa = 0, pb = 0, pc = 0, dcv = 0;
-            if (m == 3) plane_params(8, true, T, L, pa, pb, pc);
-            else if (m == 0) {                             // DC of this lane's 4x4 block (intra_prediction.cc:825-849)
-                const int xO = x0, yO = y & 4;
-                bool a, b;
-                if ((xO == 0 && yO == 0) || (xO > 0 && yO > 0)) { a = aL; b = aT; }
-                else if (xO > 0) { a = aT ? false : aL; b = aT; }
-                else { a = aL; b = aL ? false : aT; }
-                auto T4 = [&](int i) { return T(xO + i); };
-                auto L4 = [&](int i) { return L(yO + i); };
-                dcv = dc_value(4, 2, a, b, T4, L4);
-            }
-            int v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int x = x0 + i;
-                int p;
-                if (m == 0) p = dcv;
-                else if (m == 1) p = L(y);
-                else if (m == 2) p = T(x);
-                else p = clip255((pa + pb * (x - 3) + pc * (y - 3) + 16) >> 5);
-                v[i] = clip255(p + sm.res[256 + pl * 64 + y * 8 + x]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) TC(pl, x0 + i, y) = (uint8_t)v[i];
-        }
-        __syncwarp();
-
-        // ---- store the reconstructed MB ----
-        if (lane < 16) {
-            const uint32_t* r = reinterpret_cast<const uint32_t*>(&TY(0, lane));
-            *reinterpret_cast<uint4*>(dY + (size_t)(py + lane) * g.pitch_y + px) = make_uint4(r[0], r[1], r[2], r[3]);
-        } else {
-            const int c = lane - 16, pl = c >> 3, y = c & 7;
-            const uint32_t* r = reinterpret_cast<const uint32_t*>(&TC(pl, 0, y));
-            *reinterpret_cast<uint2*>(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx) = make_uint2(r[0], r[1]);
-        }
+        intra_reconstruct_mb(pic, g, sm, h, mbx, mby, lane);
         publish_row(progress + mby, done_to, lane, true);
        }
       }
     }
+}
+
+// Intra MBs of pictures that also have inter MBs (P/B pictures: a few percent of the MBs, mostly isolated).  One warp
+// per intra MB, taken in raster order from the picture's address list; the warp waits only for those of its four
+// neighbours (left, top-left, top, top-right) that are intra MBs themselves -- inter neighbours were reconstructed by
+// recon_inter_kernel.  Completion is an epoch stamp per MB (no clearing between launches).  Tickets interleave the
+// pictures of the wave and run in raster order inside a picture, so a warp only ever waits for warps that already
+// hold a ticket.
+__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTRA_CTAS)
+recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g, uint32_t epoch)
+{
+    __shared__ __align__(16) IntraSmem smem_all[kWarpsPerCta];
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[2], 1);
+    __syncthreads();
+    const int grp = s_ticket / num_pics, pic_i = s_ticket - grp * num_pics;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const DevPicture& pic = pics[pic_i];
+    const int idx = grp * kWarpsPerCta + warp;
+    if (idx >= pic.intra_count) return;
+    const int W = g.width_mbs, H = g.height_mbs;
+    const int addr = (int)__ldg(pic.intra_list + idx);
+    const int mby = addr / W, mbx = addr - mby * W;
+    const MbHdr h = load_hdr(pic.mbs, addr);
+    if (lane < 4) {
+        const int nx = mbx + (lane == 3 ? 1 : (lane == 2 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // A, D, B, C
+        if (nx >= 0 && nx < W && ny >= 0) {
+            const int nb = ny * W + nx;
+            if ((load_hdr_word0(pic.mbs, nb) >> 8) & H264R_MB_FLAG_INTRA) {
+                const int* flag = reinterpret_cast<const int*>(pic.mb_done + nb);
+                unsigned ns = 16;
+                while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
+            }
+        }
+    }
+    __syncwarp();
+    intra_reconstruct_mb(pic, g, smem_all[warp], h, mbx, mby, lane);
+    (void)H;
+    __syncwarp();
+    if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + addr), (int)epoch);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1331,9 +1383,17 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
         return 1;
     }
     if (which == KERNEL_INTRA) {
-        if (!w.any_intra) return 0;
-        recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
-        return 1;
+        int n = 0;
+        if (w.any_intra_rows) {
+            recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
+            ++n;
+        }
+        if (w.max_intra_sparse > 0) {
+            const int grps = (w.max_intra_sparse + kWarpsPerCta - 1) / kWarpsPerCta;
+            recon_intra_sparse_kernel<<<w.num_pics * grps, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
+            ++n;
+        }
+        return n;
     }
     if (!w.any_deblock) return 0;
     if (which == KERNEL_DBPREP) {
