@@ -636,17 +636,57 @@ __device__ __forceinline__ int dc_value(int n, int log2n, bool a, bool b, TF T, 
     return (sum + round) >> shift;
 }
 
+// Intra4x4 directional predictors as data: for mode m and sample position pos = y * 4 + x,
+//     pred = (S[a] + 2 * S[b] + S[c] + 2) >> 2,
+// S[o] = the tile sample at byte offset o from the block origin (row pitch 32: p(i,-1) = -32 + i, p(-1,j) = 32 j - 1,
+// the corner = -33); a | b << 8 | c << 16 as signed bytes.  Two-tap averages are (a, b, a), copies (a, a, a), the
+// "(x + 3y + 2) >> 2" end cases (a, b, b): the nine-way switch of intra_prediction.cc:187-356 becomes one table read.
+// Generated from pred_dir_sample() (the I8x8 path still evaluates it directly); mode 2 (DC) is computed, not tabulated.
+__device__ const uint32_t c_i4_pred[9 * 16] = {
+    0xE0E0E0, 0xE1E1E1, 0xE2E2E2, 0xE3E3E3, 0xE0E0E0, 0xE1E1E1, 0xE2E2E2, 0xE3E3E3, 0xE0E0E0, 0xE1E1E1, 0xE2E2E2, 0xE3E3E3, 0xE0E0E0, 0xE1E1E1, 0xE2E2E2, 0xE3E3E3,
+    0xFFFFFF, 0xFFFFFF, 0xFFFFFF, 0xFFFFFF, 0x1F1F1F, 0x1F1F1F, 0x1F1F1F, 0x1F1F1F, 0x3F3F3F, 0x3F3F3F, 0x3F3F3F, 0x3F3F3F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F,
+    0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000,
+    0xE2E1E0, 0xE3E2E1, 0xE4E3E2, 0xE5E4E3, 0xE3E2E1, 0xE4E3E2, 0xE5E4E3, 0xE6E5E4, 0xE4E3E2, 0xE5E4E3, 0xE6E5E4, 0xE7E6E5, 0xE5E4E3, 0xE6E5E4, 0xE7E6E5, 0xE7E7E6,
+    0xFFDFE0, 0xE1E0DF, 0xE2E1E0, 0xE3E2E1, 0x1FFFDF, 0xFFDFE0, 0xE1E0DF, 0xE2E1E0, 0x3F1FFF, 0x1FFFDF, 0xFFDFE0, 0xE1E0DF, 0x5F3F1F, 0x3F1FFF, 0x1FFFDF, 0xFFDFE0,
+    0xDFE0DF, 0xE0E1E0, 0xE1E2E1, 0xE2E3E2, 0xE0DFFF, 0xE1E0DF, 0xE2E1E0, 0xE3E2E1, 0xDFFF1F, 0xDFE0DF, 0xE0E1E0, 0xE1E2E1, 0xFF1F3F, 0xE0DFFF, 0xE1E0DF, 0xE2E1E0,
+    0xDFFFDF, 0xE0DFFF, 0xDFE0E1, 0xE0E1E2, 0xFF1FFF, 0x1FFFDF, 0xDFFFDF, 0xE0DFFF, 0x1F3F1F, 0x3F1FFF, 0xFF1FFF, 0x1FFFDF, 0x3F5F3F, 0x5F3F1F, 0x1F3F1F, 0x3F1FFF,
+    0xE0E1E0, 0xE1E2E1, 0xE2E3E2, 0xE3E4E3, 0xE2E1E0, 0xE3E2E1, 0xE4E3E2, 0xE5E4E3, 0xE1E2E1, 0xE2E3E2, 0xE3E4E3, 0xE4E5E4, 0xE3E2E1, 0xE4E3E2, 0xE5E4E3, 0xE6E5E4,
+    0xFF1FFF, 0x3F1FFF, 0x1F3F1F, 0x5F3F1F, 0x1F3F1F, 0x5F3F1F, 0x3F5F3F, 0x5F5F3F, 0x3F5F3F, 0x5F5F3F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F,
+};
+
+// Everything about an intra MB that does not depend on its neighbours being reconstructed: header, the header words
+// of the four neighbouring MBs (lane & 3 = 0 left, 1 top, 2 top-left, 3 top-right), the residual, the slice's
+// constrained_intra_pred_flag.  Loaded ahead of time (next MB of the row / before the dependency wait).
+struct IntraPre {
+    MbHdr h;
+    uint32_t nbw;                   // header word 0 of neighbour (lane & 3), 0xFFFFFFFF outside the picture
+    uint4 r0, r1;                   // residual chunks lane and 32 + lane (lanes 0..15) of the MB's 48 x 16 bytes
+    int ci;
+};
+__device__ __forceinline__ void intra_prefetch(const DevPicture& pic, const FrameGeom& g, int mbx, int mby, int lane, IntraPre& p)
+{
+    const int W = g.width_mbs, addr = mby * W + mbx;
+    p.h = load_hdr(pic.mbs, addr);
+    const int k = lane & 3;
+    const int nx = mbx + (k == 3 ? 1 : (k == 1 ? 0 : -1)), ny = mby - (k == 0 ? 0 : 1);
+    p.nbw = 0xFFFFFFFFu;
+    if (nx >= 0 && nx < W && ny >= 0) p.nbw = load_hdr_word0(pic.mbs, ny * W + nx);
+    const uint4* rsrc = reinterpret_cast<const uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
+    p.r0 = __ldg(rsrc + lane);
+    p.r1 = lane < 16 ? __ldg(rsrc + 32 + lane) : make_uint4(0, 0, 0, 0);
+    p.ci = (int)__ldg(&(pic.slices + p.h.slice_idx)->constrained_intra_pred_flag);
+}
+
 // Reconstruction of one intra macroblock by one warp (mb_pred_intra / mb_pred_ipcm, decoder.cc:149-215): neighbour
 // availability, neighbour samples of the current unfiltered picture, prediction + residual block by block through a
 // shared-memory tile, store.  The caller has made sure that the neighbouring MBs are reconstructed and visible.
-__device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, const FrameGeom& g, IntraSmem& sm, const MbHdr& h,
+__device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, const FrameGeom& g, IntraSmem& sm, const IntraPre& pre,
                                                      int mbx, int mby, int lane)
 {
-    const int W = g.width_mbs, H = g.height_mbs;
-    const int addr = mby * W + mbx;
+    const MbHdr& h = pre.h;
+    const int W = g.width_mbs;
     uint8_t* const dY = pic.dst;
     uint8_t* const dC[2] = { pic.dst + g.off_cb, pic.dst + g.off_cr };
-    const h264r_slice* sl = pic.slices + h.slice_idx;
     const int px = mbx * 16, py = mby * 16, cx = mbx * 8, cy = mby * 8;
 
     if (h.mb_type == H264R_MB_IPCM) {                 // mb_pred_ipcm, decoder.cc:149-168
@@ -663,13 +703,17 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
         return;
     }
 
-    // availability of the four neighbouring MBs (neighbour.cc:123-175 + slice_nr + constrained intra)
+    // availability of the four neighbouring MBs (neighbour.cc:123-175 + slice_nr + constrained intra): the neighbour
+    // exists, belongs to the same slice and -- with constrained_intra_pred -- is an intra MB.  All four precede the MB
+    // in raster order.
     const uint32_t w0 = (uint32_t)h.mb_type | (uint32_t)h.flags << 8 | (uint32_t)h.slice_idx << 16;
-    const bool ci = __ldg(&sl->constrained_intra_pred_flag) != 0;
-    const bool aL  = nb_avail(pic.mbs, W, H, addr, w0, mbx - 1, mby, ci);
-    const bool aT  = nb_avail(pic.mbs, W, H, addr, w0, mbx, mby - 1, ci);
-    const bool aTL = nb_avail(pic.mbs, W, H, addr, w0, mbx - 1, mby - 1, ci);
-    const bool aTR = nb_avail(pic.mbs, W, H, addr, w0, mbx + 1, mby - 1, ci);
+    bool av[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t nw = __shfl_sync(0xFFFFFFFFu, pre.nbw, k);
+        av[k] = nw != 0xFFFFFFFFu && (nw >> 16) == (w0 >> 16) && (!pre.ci || ((nw >> 8) & H264R_MB_FLAG_INTRA));
+    }
+    const bool aL = av[0], aT = av[1], aTL = av[2], aTR = av[3];
 
     // neighbour samples of the current, unfiltered picture -> tiles (L1-bypassing loads: other SMs wrote them)
     if (mby > 0) {
@@ -690,10 +734,9 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
         else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = ldcg_u8(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx - 1); }
     }
     {   // residual plane written by residual_kernel (48 x 16 B), or zeros
-        const uint4* rsrc = reinterpret_cast<const uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
         const bool has = h.has_resid();
-        for (int v = lane; v < 48; v += 32)
-            reinterpret_cast<uint4*>(sm.res)[v] = has ? __ldg(rsrc + v) : make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(sm.res)[lane] = has ? pre.r0 : make_uint4(0, 0, 0, 0);
+        if (lane < 16) reinterpret_cast<uint4*>(sm.res)[32 + lane] = has ? pre.r1 : make_uint4(0, 0, 0, 0);
     }
     __syncwarp();                                      // tiles and residual visible
 
@@ -719,9 +762,43 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
         __syncwarp();                                  // all lanes have read the border before the tile is written
 #pragma unroll
         for (int i = 0; i < 8; ++i) TY(x0 + i, y) = (uint8_t)v[i];
+    } else if (h.mb_type != H264R_MB_I8x8) {
+        // I_4x4: sixteen blocks in coding order, each waiting for the previous one through the tile; lane = sample
+        const int x = lane & 3, y = (lane >> 2) & 3;
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            const int xO = ((k >> 2) & 1) * 8 + (k & 1) * 4, yO = (k >> 3) * 8 + ((k >> 1) & 1) * 4;
+            const int mode = ((k < 8 ? h.u0 >> (4 * k) : h.u1 >> (4 * (k - 8)))) & 15;
+            const bool avA = xO > 0 ? true : aL;
+            const bool avB = yO > 0 ? true : aT;
+            bool avC;
+            if (yO == 0) avC = (xO + 4 < 16) ? aT : aTR;
+            else avC = xO + 4 < 16;
+            if (xO == 4 && (yO == 4 || yO == 12)) avC = false;
+            const uint8_t* const blk = &TY(xO, yO);
+            const int r = sm.res[(yO + y) * 16 + xO + x];
+            int pv;
+            if (mode == 2) {                           // DC (intra_prediction.cc:206-232)
+                const int top = __dp4a(*reinterpret_cast<const uint32_t*>(blk - 32), 0x01010101u, 0u);
+                const int left = (int)blk[-1] + blk[31] + blk[63] + blk[95];
+                pv = avA && avB ? (top + left + 4) >> 3 : (avA ? (left + 2) >> 2 : (avB ? (top + 2) >> 2 : 128));
+            } else {
+                const uint32_t e = __ldg(&c_i4_pred[min(mode, 8) * 16 + (lane & 15)]);
+                int oa = (int)(int8_t)(e & 0xFF), ob = (int)(int8_t)((e >> 8) & 0xFF), oc = (int)(int8_t)((e >> 16) & 0xFF);
+                if (!avC) {                            // p(x,-1), x = 4..7 -> p(3,-1) (intra_prediction.cc:182-185)
+                    if (oa > -29 && oa < -1) oa = -29;
+                    if (ob > -29 && ob < -1) ob = -29;
+                    if (oc > -29 && oc < -1) oc = -29;
+                }
+                pv = ((int)blk[oa] + 2 * (int)blk[ob] + (int)blk[oc] + 2) >> 2;
+            }
+            const int v = clip255(pv + r);
+            if (lane < 16) TY(xO + x, yO + y) = (uint8_t)v;      // the block never reads its own samples: no barrier before
+            __syncwarp();
+        }
     } else {
-        const bool is8 = h.mb_type == H264R_MB_I8x8;
-        const int n = is8 ? 8 : 4, nblk = is8 ? 4 : 16;
+        const bool is8 = true;
+        const int n = 8, nblk = 4;
         for (int k = 0; k < nblk; ++k) {
             int xO, yO;
             if (is8) { xO = (k & 1) * 8; yO = (k >> 1) * 8; }
@@ -885,18 +962,26 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
           for (int c = 7; c >= 0; --c) if (c >= c0 && masks[c]) nx = x0 + c * 32 + __ffs(masks[c]) - 1;
           return nx;
       };
-      { const int first = next_intra(0); if (first > x0) publish_row(progress + mby, first, lane, false); }
+      IntraPre nxt;
+      { const int first = next_intra(0);
+        if (first > x0) publish_row(progress + mby, first, lane, false);
+        if (first < xend) intra_prefetch(pic, g, first, mby, lane, nxt); }
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
        while (masks[c]) {
         const int mbx = x0 + c * 32 + __ffs(masks[c]) - 1;
         masks[c] &= masks[c] - 1;
         const int done_to = next_intra(c);                 // published after this MB: the next intra MB of the row
-        const int addr = mby * W + mbx;
-        const MbHdr h = load_hdr(pic.mbs, addr);
-        if (mby > 0) wait_row_cached(progress + mby - 1, min(mbx + 2, W), known);
-
-        intra_reconstruct_mb(pic, g, sm, h, mbx, mby, lane);
+        const IntraPre cur = nxt;
+        if (done_to < xend) intra_prefetch(pic, g, done_to, mby, lane, nxt);    // lands while this MB is reconstructed
+        if (mby > 0) {
+            const int need = min(mbx + 2, W);
+            if (known < need) {
+                if (lane == 0) { unsigned ns = 16; while ((known = ld_acquire(progress + mby - 1)) < need) { __nanosleep(ns); if (ns < 128) ns *= 2; } }
+                known = __shfl_sync(0xFFFFFFFFu, known, 0);
+            }
+        }
+        intra_reconstruct_mb(pic, g, sm, cur, mbx, mby, lane);
         publish_row(progress + mby, done_to, lane, true);
        }
       }
@@ -924,20 +1009,16 @@ recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int
     const int W = g.width_mbs, H = g.height_mbs;
     const int addr = (int)__ldg(pic.intra_list + idx);
     const int mby = addr / W, mbx = addr - mby * W;
-    const MbHdr h = load_hdr(pic.mbs, addr);
-    if (lane < 4) {
-        const int nx = mbx + (lane == 3 ? 1 : (lane == 2 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // A, D, B, C
-        if (nx >= 0 && nx < W && ny >= 0) {
-            const int nb = ny * W + nx;
-            if ((load_hdr_word0(pic.mbs, nb) >> 8) & H264R_MB_FLAG_INTRA) {
-                const int* flag = reinterpret_cast<const int*>(pic.mb_done + nb);
-                unsigned ns = 16;
-                while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
-            }
-        }
+    IntraPre pre;
+    intra_prefetch(pic, g, mbx, mby, lane, pre);          // header, neighbour headers, residual: all in flight at once
+    if (lane < 4 && pre.nbw != 0xFFFFFFFFu && ((pre.nbw >> 8) & H264R_MB_FLAG_INTRA)) {
+        const int nx = mbx + (lane == 3 ? 1 : (lane == 1 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // left, top, top-left, top-right
+        const int* flag = reinterpret_cast<const int*>(pic.mb_done + ny * W + nx);
+        unsigned ns = 16;
+        while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
     }
     __syncwarp();
-    intra_reconstruct_mb(pic, g, smem_all[warp], h, mbx, mby, lane);
+    intra_reconstruct_mb(pic, g, smem_all[warp], pre, mbx, mby, lane);
     (void)H;
     __syncwarp();
     if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + addr), (int)epoch);

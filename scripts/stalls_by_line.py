@@ -21,7 +21,10 @@ for l in dis.splitlines():
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: line = (os.path.basename(m.group(1)), int(m.group(2))); continue
     if cur and re.match(r'\s+/\*[0-9a-f]{4,}\*/', l): per[cur].append(line)
-fn = [f for f in per if kname in f][0]
+kn = rows[secs[launch]][1]
+print('section kernel:', kn[:60])
+base = kn.split('(')[0].split('::')[-1]
+fn = [f for f in per if ('%d%sE' % (len(base), base)) in f][0]
 lines = per[fn]
 if len(lines) != len(data): print('warning: cubin has %d instructions, report %d (different build)' % (len(lines), len(data)))
 agg = {}; tot = 0; tote = 0
