@@ -1349,6 +1349,7 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
         __syncwarp();                                      // tile rows (vertical pass) visible to the column owners
 
         // ---- horizontal edges: lane l = luma column l, chroma column cl of plane cpl ----
+        uint32_t upY = 0, upC = 0;                         // filtered samples of the MB above, stored after the publish
         {
             int v[20];
             unpack4(topY, v);
@@ -1364,10 +1365,7 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
             }
 #pragma unroll
             for (int r = 0; r < 15; ++r) TY[r * 32 + 16 + l] = (uint8_t)v[4 + r];
-            if (top_on) {                                  // rows 13..15 of the MB above
-                uint8_t* ty = dY + (uint32_t)((py - 3) * pitch_y + px + l);
-                ty[0] = (uint8_t)v[1]; ty[pitch_y] = (uint8_t)v[2]; ty[2 * pitch_y] = (uint8_t)v[3];
-            }
+            upY = (uint32_t)v[1] | (uint32_t)v[2] << 8 | (uint32_t)v[3] << 16;     // rows 13..15 of the MB above
         }
         {
             int v[10];                                     // rows -2, -1, 0..7
@@ -1382,12 +1380,17 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
                 v[4 * e + 1] = p[0]; v[4 * e + 2] = q[0];
             }
             TC[0 * 16 + 8 + cl] = (uint8_t)v[2]; TC[3 * 16 + 8 + cl] = (uint8_t)v[5]; TC[4 * 16 + 8 + cl] = (uint8_t)v[6];
-            if (top_on) dC[(uint32_t)((cy - 1) * pitch_c + cx + cl)] = (uint8_t)v[1];
+            upC = (uint32_t)v[1];
         }
         // MBs < mbx are complete and this MB is done with its left neighbour (stores issued a pass ago: cheap release)
         publish_row(progress + mby, mbx, lane & 15, true);             // includes the __syncwarp the tile needs
 
-        // ---- write back the MB's own samples ----
+        // ---- write back: rows 13..15 of the MB above (nobody in this launch reads them again), then the MB's own samples ----
+        if (top_on) {
+            uint8_t* ty = dY + (uint32_t)((py - 3) * pitch_y + px + l);
+            ty[0] = (uint8_t)upY; ty[pitch_y] = (uint8_t)(upY >> 8); ty[2 * pitch_y] = (uint8_t)(upY >> 16);
+            dC[(uint32_t)((cy - 1) * pitch_c + cx + cl)] = (uint8_t)upC;
+        }
         if (enabled) {
             *reinterpret_cast<uint4*>(dY + (uint32_t)((py + l) * pitch_y + px)) = *reinterpret_cast<const uint4*>(TY + l * 32 + 16);
             *reinterpret_cast<uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx)) = *reinterpret_cast<const uint2*>(TC + cl * 16 + 8);
