@@ -56,6 +56,7 @@ struct WaveRecord {
     std::vector<int> dst_frames;              // frames written by this wave
     cudaEvent_t ev_h2d = nullptr;             // recorded on the H2D stream after the wave's copies
     cudaEvent_t ev_done = nullptr;            // recorded on the compute stream after the wave's kernels
+    cudaEvent_t ev_side = nullptr;            // recorded on the side stream after the wave's neighbour-independent kernels
 };
 
 } // namespace
@@ -64,6 +65,10 @@ struct h264r_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;            // compute
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_side = nullptr;            // kernels that depend on nothing but the picture description (motion
+                                              // expansion, residual, deblock descriptors): they run ahead of, and
+                                              // underneath, the latency-bound wavefront kernels of earlier waves
+    cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> event_pool;      // reused across flushes
     size_t events_used = 0;
     std::vector<cudaEvent_t> timer_events;    // H264R_REPLAY_TIME_KERNELS
@@ -158,13 +163,44 @@ cudaEvent_t take_event(h264r_ctx* c)
     return c->event_pool[c->events_used++];
 }
 
-// Runs the recorded waves of the last flush.  H2D copies go to their own stream and are joined per wave; a wave's
-// copies also wait for the previous run of the same wave (its staging in HBM is being overwritten).
+// Runs the recorded waves of the last flush on three streams:
+//   H2D stream   : the picture descriptions of a wave (they wait for the previous run of the same wave, whose staging
+//                  in HBM they overwrite);
+//   side stream  : the kernels that need nothing but the description -- motion expansion, residual, deblock
+//                  descriptors.  They run ahead, underneath the latency-bound wavefront kernels of earlier waves;
+//   compute      : inter, intra, deblock of the wave, after the side kernels of the wave and the waves before it.
+// With time_kernels everything runs on the compute stream, one kernel at a time, bracketed by events.
 int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int* launches)
 {
     size_t timer_used = 0;
     struct Pending { int kind; size_t ev; };
     std::vector<Pending> pend;
+    cudaStream_t side = time_kernels ? ctx->stream : ctx->s_side;
+    if (!time_kernels) {                                   // the side stream sees everything enqueued so far (picture table)
+        CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CU(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+    }
+    auto launch = [&](WaveRecord& rec, int kind, cudaStream_t st) -> int {
+        if (time_kernels) {
+            while (ctx->timer_events.size() < timer_used + 2) {
+                cudaEvent_t ev = nullptr;
+                if (cudaEventCreate(&ev) != cudaSuccess) return H264R_ERR_CUDA;
+                ctx->timer_events.push_back(ev);
+            }
+            if (cudaEventRecord(ctx->timer_events[timer_used], st) != cudaSuccess) return H264R_ERR_CUDA;
+        }
+        const int launched = launch_wave_kernel(rec.launch, kind, st);
+        if (launched) {
+            ctx->stats.kernel_launches += (uint64_t)launched;
+            if (launches) launches[kind + 1] += launched;
+            if (time_kernels) {
+                if (cudaEventRecord(ctx->timer_events[timer_used + 1], st) != cudaSuccess) return H264R_ERR_CUDA;
+                pend.push_back({ kind, timer_used });
+                timer_used += 2;
+            }
+        }
+        return H264R_OK;
+    };
     for (WaveRecord& rec : ctx->last_waves) {
         if (h2d) {
             CU(cudaStreamWaitEvent(ctx->s_h2d, rec.ev_done, 0));          // no-op before the first record
@@ -174,7 +210,17 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
                 ctx->stats.h2d_bytes += c.bytes;
             }
             CU(cudaEventRecord(rec.ev_h2d, ctx->s_h2d));
-            CU(cudaStreamWaitEvent(ctx->stream, rec.ev_h2d, 0));
+            CU(cudaStreamWaitEvent(side, rec.ev_h2d, 0));
+        }
+        rec.launch.epoch = ++ctx->epoch;
+        // side kernels: their outputs (expanded motion, residual plane, deblock descriptors) are per picture slot; the
+        // previous run of this wave must have consumed them
+        if (!time_kernels) CU(cudaStreamWaitEvent(side, rec.ev_done, 0));
+        { const int rc = launch(rec, KERNEL_RESID, side); if (rc != H264R_OK) return rc; }
+        { const int rc = launch(rec, KERNEL_DBPREP, side); if (rc != H264R_OK) return rc; }
+        if (!time_kernels) {
+            CU(cudaEventRecord(rec.ev_side, side));
+            CU(cudaStreamWaitEvent(ctx->stream, rec.ev_side, 0));
         }
         // write-after-read: a frame still being downloaded (asynchronously, on the D2H stream) is not overwritten
         for (int f : rec.dst_frames) {
@@ -182,27 +228,9 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
             if (fr.pending_read) { CU(cudaStreamWaitEvent(ctx->stream, fr.read_done, 0)); fr.pending_read = false; }
         }
         CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
-        rec.launch.epoch = ++ctx->epoch;
-        for (int kind = 0; kind < KERNEL_KINDS; ++kind) {
-            if (time_kernels) {
-                while (ctx->timer_events.size() < timer_used + 2) {
-                    cudaEvent_t ev = nullptr;
-                    CU(cudaEventCreate(&ev));
-                    ctx->timer_events.push_back(ev);
-                }
-                CU(cudaEventRecord(ctx->timer_events[timer_used], ctx->stream));
-            }
-            const int launched = launch_wave_kernel(rec.launch, kind, ctx->stream);
-            if (launched) {
-                ctx->stats.kernel_launches += (uint64_t)launched;
-                if (launches) launches[kind + 1] += launched;
-                if (time_kernels) {
-                    CU(cudaEventRecord(ctx->timer_events[timer_used + 1], ctx->stream));
-                    pend.push_back({ kind, timer_used });
-                    timer_used += 2;
-                }
-            }
-        }
+        { const int rc = launch(rec, KERNEL_INTER, ctx->stream); if (rc != H264R_OK) return rc; }
+        { const int rc = launch(rec, KERNEL_INTRA, ctx->stream); if (rc != H264R_OK) return rc; }
+        { const int rc = launch(rec, KERNEL_DEBLOCK, ctx->stream); if (rc != H264R_OK) return rc; }
         CU(cudaGetLastError());
         CU(cudaEventRecord(rec.ev_done, ctx->stream));
         ctx->stats.waves += 1;
@@ -262,6 +290,8 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
     if (e != cudaSuccess) { delete ctx; return H264R_ERR_CUDA; }
@@ -337,7 +367,7 @@ void h264r_destroy(h264r_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
+    cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_side); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
     for (Frame& f : ctx->frames) { if (f.dev) cudaFree(f.dev); if (f.read_done) cudaEventDestroy(f.read_done); }
     if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); cudaFree(ctx->slots[0].dev_resid);
                                 cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_motion); cudaFree(ctx->slots[0].dev_mb_done); }
@@ -346,7 +376,8 @@ void h264r_destroy(h264r_ctx* ctx)
     for (int i = 0; i < 2; ++i) if (ctx->table_ev[i]) cudaEventDestroy(ctx->table_ev[i]);
     for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->timer_events) cudaEventDestroy(ev);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h); cudaStreamDestroy(ctx->s_side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 
@@ -543,8 +574,8 @@ int h264r_flush(h264r_ctx* ctx)
             L.max_intra_sparse = std::max(L.max_intra_sparse, (int)s.intra_count);
         }
         rec.progress_bytes = sizeof(int) * (64 + ctx->sync_ints_per_pic * (size_t)L.num_pics);
-        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx);
-        if (!rec.ev_h2d || !rec.ev_done) return H264R_ERR_CUDA;
+        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx); rec.ev_side = take_event(ctx);
+        if (!rec.ev_h2d || !rec.ev_done || !rec.ev_side) return H264R_ERR_CUDA;
         for (int k = b; k < e; ++k) { ctx->frames[ctx->slots[order[k]].dst].ready = rec.ev_done; rec.dst_frames.push_back(ctx->slots[order[k]].dst); }
         ctx->last_waves.push_back(rec);
     }
@@ -561,6 +592,7 @@ int h264r_wait(h264r_ctx* ctx, h264r_frame f)
     (void)f;                                                      // in-order streams: waiting for one waits for all
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->s_h2d));
+    CU(cudaStreamSynchronize(ctx->s_side));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->s_d2h));
     for (Slot& t : ctx->slots) if (t.state == SLOT_INFLIGHT) t.state = SLOT_FREE;
