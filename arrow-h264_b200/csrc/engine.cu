@@ -3,8 +3,10 @@
 #include "device_types.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <utility>
 #include <algorithm>
 
 using namespace h264r;
@@ -25,6 +27,10 @@ struct Frame {
     cudaEvent_t ready = nullptr;              // ev_done of the wave that last wrote this frame (owned by the pool)
     cudaEvent_t read_done = nullptr;          // recorded on the D2H stream after the last asynchronous download
     bool pending_read = false;                // a download was enqueued since the frame was last (re)written
+    int group = -1;                           // stream group of the picture that last wrote the frame (affinity of its successors)
+    int ready_group = -1;                     // group whose record `ready` belongs to
+    uint64_t ready_flush = 0;                 // flush in which `ready` was assigned (events are recycled per flush)
+    std::vector<std::pair<cudaEvent_t, int> > readers;   // (ev_done, group) of the records of this flush that read the frame
 };
 
 enum SlotState { SLOT_FREE = 0, SLOT_FILLING, SLOT_QUEUED, SLOT_INFLIGHT };
@@ -45,6 +51,7 @@ struct Slot {
     uint32_t used_levels = 0;
     int has_intra = 0, has_inter = 0;
     int wave = 0;
+    int group = 0;
 };
 
 struct WaveCopy { int slot; size_t bytes; };
@@ -54,12 +61,16 @@ struct WaveRecord {
     size_t progress_bytes;
     std::vector<WaveCopy> copies;             // H2D copies of the picture descriptions of this wave
     std::vector<int> dst_frames;              // frames written by this wave
+    int group = 0;                            // stream group that runs the record
+    std::vector<cudaEvent_t> deps;            // ev_done of records of OTHER groups this one must follow (cross-group references)
     cudaEvent_t ev_h2d = nullptr;             // recorded on the H2D stream after the wave's copies
     cudaEvent_t ev_done = nullptr;            // recorded on the compute stream after the wave's kernels
     cudaEvent_t ev_side = nullptr;            // recorded on the side stream after the wave's neighbour-independent kernels
 };
 
 } // namespace
+
+enum { kMaxGroups = 4 };
 
 struct h264r_ctx {
     int device = 0;
@@ -69,6 +80,17 @@ struct h264r_ctx {
                                               // expansion, residual, deblock descriptors): they run ahead of, and
                                               // underneath, the latency-bound wavefront kernels of earlier waves
     cudaEvent_t ev_fork = nullptr;
+    // Independent streams (closed GOPs) are spread over `num_groups` groups, each with its own compute + side stream,
+    // tickets and progress counters: the latency-bound wavefront kernels of one group run underneath the
+    // throughput-bound kernels of the others.  g_main[0] == stream, g_side[0] == s_side.
+    int num_groups = 1;
+    int rr_group = 0;                         // round-robin cursor for pictures without a queued predecessor
+    cudaStream_t g_main[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
+    cudaStream_t g_side[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t g_tail[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
+    size_t sync_ints_per_group = 0;
+    uint64_t flush_serial = 0;
+    bool cross_group = false;                 // the last flush has references across groups
     std::vector<cudaEvent_t> event_pool;      // reused across flushes
     size_t events_used = 0;
     std::vector<cudaEvent_t> timer_events;    // H264R_REPLAY_TIME_KERNELS
@@ -170,15 +192,21 @@ cudaEvent_t take_event(h264r_ctx* c)
 //                  descriptors.  They run ahead, underneath the latency-bound wavefront kernels of earlier waves;
 //   compute      : inter, intra, deblock of the wave, after the side kernels of the wave and the waves before it.
 // With time_kernels everything runs on the compute stream, one kernel at a time, bracketed by events.
-int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int* launches)
+int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int* launches, bool fork_join)
 {
     size_t timer_used = 0;
     struct Pending { int kind; size_t ev; };
     std::vector<Pending> pend;
-    cudaStream_t side = time_kernels ? ctx->stream : ctx->s_side;
-    if (!time_kernels) {                                   // the side stream sees everything enqueued so far (picture table)
+    const int G = ctx->num_groups;
+    if (!time_kernels && (fork_join || ctx->cross_group)) {
+        // every stream of every group starts behind everything enqueued so far on every compute stream (picture table
+        // upload on `stream`; with cross-group references also the previous run of the other groups)
+        for (int gi = 1; gi < G; ++gi) { CU(cudaEventRecord(ctx->g_tail[gi], ctx->g_main[gi])); CU(cudaStreamWaitEvent(ctx->stream, ctx->g_tail[gi], 0)); }
         CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        CU(cudaStreamWaitEvent(side, ctx->ev_fork, 0));
+        for (int gi = 0; gi < G; ++gi) {
+            if (gi > 0) CU(cudaStreamWaitEvent(ctx->g_main[gi], ctx->ev_fork, 0));
+            CU(cudaStreamWaitEvent(ctx->g_side[gi], ctx->ev_fork, 0));
+        }
     }
     auto launch = [&](WaveRecord& rec, int kind, cudaStream_t st) -> int {
         if (time_kernels) {
@@ -202,6 +230,8 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         return H264R_OK;
     };
     for (WaveRecord& rec : ctx->last_waves) {
+        cudaStream_t main = time_kernels ? ctx->stream : ctx->g_main[rec.group];
+        cudaStream_t side = time_kernels ? ctx->stream : ctx->g_side[rec.group];
         if (h2d) {
             CU(cudaStreamWaitEvent(ctx->s_h2d, rec.ev_done, 0));          // no-op before the first record
             for (const WaveCopy& c : rec.copies) {
@@ -214,29 +244,32 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         }
         rec.launch.epoch = ++ctx->epoch;
         // side kernels: their outputs (expanded motion, residual plane, deblock descriptors) are per picture slot; the
-        // previous run of this wave must have consumed them
+        // previous run of this record must have consumed them
         if (!time_kernels) CU(cudaStreamWaitEvent(side, rec.ev_done, 0));
         { const int rc = launch(rec, KERNEL_RESID, side); if (rc != H264R_OK) return rc; }
         { const int rc = launch(rec, KERNEL_DBPREP, side); if (rc != H264R_OK) return rc; }
         if (!time_kernels) {
             CU(cudaEventRecord(rec.ev_side, side));
-            CU(cudaStreamWaitEvent(ctx->stream, rec.ev_side, 0));
+            CU(cudaStreamWaitEvent(main, rec.ev_side, 0));
+            for (cudaEvent_t dep : rec.deps) CU(cudaStreamWaitEvent(main, dep, 0));
         }
         // write-after-read: a frame still being downloaded (asynchronously, on the D2H stream) is not overwritten
         for (int f : rec.dst_frames) {
             Frame& fr = ctx->frames[f];
-            if (fr.pending_read) { CU(cudaStreamWaitEvent(ctx->stream, fr.read_done, 0)); fr.pending_read = false; }
+            if (fr.pending_read) { CU(cudaStreamWaitEvent(main, fr.read_done, 0)); fr.pending_read = false; }
         }
-        CU(cudaMemsetAsync(ctx->d_sync, 0, rec.progress_bytes, ctx->stream));
-        { const int rc = launch(rec, KERNEL_INTER, ctx->stream); if (rc != H264R_OK) return rc; }
-        { const int rc = launch(rec, KERNEL_INTRA, ctx->stream); if (rc != H264R_OK) return rc; }
-        { const int rc = launch(rec, KERNEL_DEBLOCK, ctx->stream); if (rc != H264R_OK) return rc; }
+        CU(cudaMemsetAsync(rec.launch.tickets, 0, rec.progress_bytes, main));
+        { const int rc = launch(rec, KERNEL_INTER, main); if (rc != H264R_OK) return rc; }
+        { const int rc = launch(rec, KERNEL_INTRA, main); if (rc != H264R_OK) return rc; }
+        { const int rc = launch(rec, KERNEL_DEBLOCK, main); if (rc != H264R_OK) return rc; }
         CU(cudaGetLastError());
-        CU(cudaEventRecord(rec.ev_done, ctx->stream));
+        CU(cudaEventRecord(rec.ev_done, main));
         ctx->stats.waves += 1;
         ctx->stats.pictures += (uint64_t)rec.launch.num_pics;
         ctx->stats.macroblocks += (uint64_t)rec.launch.num_pics * ctx->nmb;
     }
+    if (!time_kernels && fork_join)                        // `stream` ends behind every group
+        for (int gi = 1; gi < G; ++gi) { CU(cudaEventRecord(ctx->g_tail[gi], ctx->g_main[gi])); CU(cudaStreamWaitEvent(ctx->stream, ctx->g_tail[gi], 0)); }
     if (time_kernels && ms_kernel) {
         CU(cudaStreamSynchronize(ctx->stream));
         for (const Pending& p : pend) {
@@ -333,7 +366,24 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
     ctx->sync_ints_per_pic = align_up((size_t)2 * sp->height_mbs, 32);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_sync, sizeof(int) * (64 + ctx->sync_ints_per_pic * sp->max_pictures_in_flight));
+    {   // H264R_STREAM_GROUPS: number of stream groups (1..4).  Default 1: on B200 with 64 x 1080p streams the kernels
+        // are throughput-bound, and 2..4 groups measured 6-10 % slower; more groups only pay
+        // when a flush holds few pictures per wave.
+        const char* env = getenv("H264R_STREAM_GROUPS");
+        ctx->num_groups = env ? atoi(env) : 1;
+        if (ctx->num_groups < 1) ctx->num_groups = 1;
+        if (ctx->num_groups > kMaxGroups) ctx->num_groups = kMaxGroups;
+    }
+    ctx->g_main[0] = ctx->stream; ctx->g_side[0] = ctx->s_side;
+    for (int gi = 0; gi < ctx->num_groups && e == cudaSuccess; ++gi) {
+        if (gi > 0) {
+            e = cudaStreamCreateWithFlags(&ctx->g_main[gi], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->g_side[gi], cudaStreamNonBlocking);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->g_tail[gi], cudaEventDisableTiming);
+    }
+    ctx->sync_ints_per_group = 64 + ctx->sync_ints_per_pic * sp->max_pictures_in_flight;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_sync, sizeof(int) * ctx->sync_ints_per_group * ctx->num_groups);
     if (e != cudaSuccess) {
         snprintf(ctx->cuda_err, sizeof(ctx->cuda_err), "allocation: %s", cudaGetErrorString(e));
         if (h_arena) cudaFreeHost(h_arena);
@@ -367,7 +417,12 @@ void h264r_destroy(h264r_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->s_side); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->s_d2h);
+    cudaDeviceSynchronize();
+    for (int gi = 0; gi < kMaxGroups; ++gi) {
+        if (gi > 0 && ctx->g_main[gi]) cudaStreamDestroy(ctx->g_main[gi]);
+        if (gi > 0 && ctx->g_side[gi]) cudaStreamDestroy(ctx->g_side[gi]);
+        if (ctx->g_tail[gi]) cudaEventDestroy(ctx->g_tail[gi]);
+    }
     for (Frame& f : ctx->frames) { if (f.dev) cudaFree(f.dev); if (f.read_done) cudaEventDestroy(f.read_done); }
     if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); cudaFree(ctx->slots[0].dev_resid);
                                 cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_motion); cudaFree(ctx->slots[0].dev_mb_done); }
@@ -516,15 +571,34 @@ int h264r_flush(h264r_ctx* ctx)
         }
         num_waves = std::max(num_waves, w + 1);
     }
+    // ---- stream groups: a picture joins the group of the picture that produced its first known reference ----
+    const int G = ctx->num_groups;
+    ctx->flush_serial += 1;
+    for (Frame& f : ctx->frames) f.readers.clear();
+    for (int qi : ctx->queue) {
+        Slot& s = ctx->slots[qi];
+        int grp = -1;
+        for (int i = 0; i < s.pp.num_ref_frames && grp < 0; ++i) grp = ctx->frames[s.pp.ref_frames[i]].group;
+        if (grp < 0 || grp >= G) { grp = ctx->rr_group; ctx->rr_group = (ctx->rr_group + 1) % G; }
+        s.group = grp;
+        ctx->frames[s.dst].group = grp;
+    }
     std::vector<int> order(ctx->queue);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->slots[a].wave < ctx->slots[b].wave; });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const Slot& x = ctx->slots[a]; const Slot& y = ctx->slots[b];
+        return x.wave != y.wave ? x.wave < y.wave : x.group < y.group;
+    });
 
-    // ---- device picture table (one upload for all waves) ----
-    const int H = ctx->geom.height_mbs;
+    // ---- records = runs of equal (wave, group) in that order ----
+    std::vector<int> rec_begin;
+    for (size_t k = 0; k < order.size(); ++k) {
+        const Slot& c = ctx->slots[order[k]];
+        if (k == 0 || c.wave != ctx->slots[order[k - 1]].wave || c.group != ctx->slots[order[k - 1]].group) rec_begin.push_back((int)k);
+    }
+    rec_begin.push_back((int)order.size());
+
+    // ---- device picture table (one upload for all records) ----
     ctx->last_waves.clear();
-    std::vector<int> wave_begin(num_waves + 1, 0);
-    for (size_t k = 0; k < order.size(); ++k) wave_begin[ctx->slots[order[k]].wave + 1] = (int)k + 1;
-    for (int w = 1; w <= num_waves; ++w) wave_begin[w] = std::max(wave_begin[w], wave_begin[w - 1]);
     // the picture table alternates between two halves so that this flush never overwrites what the previous
     // (possibly still running) flush reads
     ctx->table_idx ^= 1;
@@ -532,56 +606,80 @@ int h264r_flush(h264r_ctx* ctx)
     CU(cudaEventSynchronize(ctx->table_ev[ctx->table_idx]));
     DevPicture* const h_table = ctx->h_pics + table_off;
     DevPicture* const d_table = ctx->d_pics + table_off;
-    for (size_t k = 0; k < order.size(); ++k) {
-        Slot& s = ctx->slots[order[k]];
-        DevPicture& p = h_table[k];
-        memset(&p, 0, sizeof(p));
-        p.mbs = reinterpret_cast<const h264r_mb*>(s.dev + ctx->off_mbs);
-        p.motion = s.dev_motion;
-        p.packed_motion = s.dev + ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels;
-        p.intra_list = reinterpret_cast<const uint32_t*>(p.packed_motion + (size_t)12 * s.motion_entries);
-        p.intra_count = (int)s.intra_count;
-        p.mb_done = s.dev_mb_done;
-        p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
-        p.levels = reinterpret_cast<const h264r_level*>(s.dev + ctx->off_levels);
-        p.resid = s.dev_resid;
-        p.dst = ctx->frames[s.dst].dev;
-        p.desc = s.dev_desc;
-        for (int i = 0; i < H264R_MAX_REFS; ++i)
-            p.ref[i] = i < s.pp.num_ref_frames ? ctx->frames[s.pp.ref_frames[i]].dev : ctx->frames[s.dst].dev;
-        const int pos_in_wave = (int)k - wave_begin[s.wave];
-        p.row_progress = ctx->d_sync + 64 + ctx->sync_ints_per_pic * pos_in_wave;
-        p.run_deblock = s.pp.run_deblock; p.has_intra = s.has_intra; p.has_inter = s.has_inter;
-    }
+    for (size_t r = 0; r + 1 < rec_begin.size(); ++r)
+        for (int k = rec_begin[r]; k < rec_begin[r + 1]; ++k) {
+            Slot& s = ctx->slots[order[k]];
+            DevPicture& p = h_table[k];
+            memset(&p, 0, sizeof(p));
+            p.mbs = reinterpret_cast<const h264r_mb*>(s.dev + ctx->off_mbs);
+            p.motion = s.dev_motion;
+            p.packed_motion = s.dev + ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels;
+            p.intra_list = reinterpret_cast<const uint32_t*>(p.packed_motion + (size_t)12 * s.motion_entries);
+            p.intra_count = (int)s.intra_count;
+            p.mb_done = s.dev_mb_done;
+            p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
+            p.levels = reinterpret_cast<const h264r_level*>(s.dev + ctx->off_levels);
+            p.resid = s.dev_resid;
+            p.dst = ctx->frames[s.dst].dev;
+            p.desc = s.dev_desc;
+            for (int i = 0; i < H264R_MAX_REFS; ++i)
+                p.ref[i] = i < s.pp.num_ref_frames ? ctx->frames[s.pp.ref_frames[i]].dev : ctx->frames[s.dst].dev;
+            p.row_progress = ctx->d_sync + ctx->sync_ints_per_group * s.group + 64 + ctx->sync_ints_per_pic * (size_t)(k - rec_begin[r]);
+            p.run_deblock = s.pp.run_deblock; p.has_intra = s.has_intra; p.has_inter = s.has_inter;
+        }
     CU(cudaMemcpyAsync(d_table, h_table, sizeof(DevPicture) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += sizeof(DevPicture) * order.size();
 
-    // ---- per wave: record what to copy and what to launch, then run it (H2D stream || compute stream) ----
+    // ---- per record: what to copy, what to launch, which records of other groups to follow ----
     ctx->events_used = 0;
-    for (int w = 0; w < num_waves; ++w) {
-        const int b = wave_begin[w], e = wave_begin[w + 1];
-        if (e <= b) continue;
+    ctx->cross_group = false;
+    for (size_t r = 0; r + 1 < rec_begin.size(); ++r) {
+        const int b = rec_begin[r], e = rec_begin[r + 1];
         WaveRecord rec;
+        rec.group = ctx->slots[order[b]].group;
         WaveLaunch& L = rec.launch;
-        L.pics = d_table + b; L.num_pics = e - b; L.tickets = ctx->d_sync; L.geom = ctx->geom;
+        L.pics = d_table + b; L.num_pics = e - b; L.tickets = ctx->d_sync + ctx->sync_ints_per_group * rec.group; L.geom = ctx->geom;
         L.direct8x8 = ctx->seq.direct_8x8_inference_flag;
         L.any_inter = L.any_intra = L.any_deblock = L.any_intra_rows = L.max_intra_sparse = 0; L.epoch = 0;
+        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx); rec.ev_side = take_event(ctx);
+        if (!rec.ev_h2d || !rec.ev_done || !rec.ev_side) return H264R_ERR_CUDA;
+        auto follow = [&](cudaEvent_t ev, int grp) {
+            if (!ev || grp == rec.group) return;
+            if (std::find(rec.deps.begin(), rec.deps.end(), ev) == rec.deps.end()) rec.deps.push_back(ev);
+            ctx->cross_group = true;
+        };
         for (int k = b; k < e; ++k) {
             Slot& s = ctx->slots[order[k]];
             rec.copies.push_back({ order[k], ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels + (size_t)12 * s.motion_entries + sizeof(uint32_t) * s.intra_count });
             L.any_inter |= s.has_inter; L.any_intra |= s.has_intra; L.any_deblock |= s.pp.run_deblock;
             L.any_intra_rows |= (s.has_intra && !s.has_inter);
             L.max_intra_sparse = std::max(L.max_intra_sparse, (int)s.intra_count);
+            // read-after-write on the references, write-after-read / write-after-write on the destination, as far as
+            // the other side belongs to this flush and to another group (same group: stream order; earlier flushes:
+            // the fork at the start of the run)
+            for (int i = 0; i < s.pp.num_ref_frames; ++i) {
+                Frame& f = ctx->frames[s.pp.ref_frames[i]];
+                if (f.ready_flush == ctx->flush_serial) follow(f.ready, f.ready_group);
+            }
+            Frame& d = ctx->frames[s.dst];
+            if (d.ready_flush == ctx->flush_serial) follow(d.ready, d.ready_group);
+            for (const std::pair<cudaEvent_t, int>& rd : d.readers) follow(rd.first, rd.second);
+        }
+        for (int k = b; k < e; ++k) {
+            Slot& s = ctx->slots[order[k]];
+            for (int i = 0; i < s.pp.num_ref_frames; ++i) ctx->frames[s.pp.ref_frames[i]].readers.push_back(std::make_pair(rec.ev_done, rec.group));
+        }
+        for (int k = b; k < e; ++k) {
+            Frame& d = ctx->frames[ctx->slots[order[k]].dst];
+            d.ready = rec.ev_done; d.ready_group = rec.group; d.ready_flush = ctx->flush_serial; d.readers.clear();
+            rec.dst_frames.push_back(ctx->slots[order[k]].dst);
         }
         rec.progress_bytes = sizeof(int) * (64 + ctx->sync_ints_per_pic * (size_t)L.num_pics);
-        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx); rec.ev_side = take_event(ctx);
-        if (!rec.ev_h2d || !rec.ev_done || !rec.ev_side) return H264R_ERR_CUDA;
-        for (int k = b; k < e; ++k) { ctx->frames[ctx->slots[order[k]].dst].ready = rec.ev_done; rec.dst_frames.push_back(ctx->slots[order[k]].dst); }
         ctx->last_waves.push_back(rec);
     }
     for (int qi : ctx->queue) ctx->slots[qi].state = SLOT_INFLIGHT;   // reusable once the streams have drained (h264r_wait)
     ctx->queue.clear();
-    const int rc = run_waves(ctx, true, false, nullptr, nullptr);
+    const int rc = run_waves(ctx, true, false, nullptr, nullptr, true);
     if (rc == H264R_OK) CU(cudaEventRecord(ctx->table_ev[ctx->table_idx], ctx->stream));
     return rc;
 }
@@ -592,8 +690,7 @@ int h264r_wait(h264r_ctx* ctx, h264r_frame f)
     (void)f;                                                      // in-order streams: waiting for one waits for all
     cudaSetDevice(ctx->device);
     CU(cudaStreamSynchronize(ctx->s_h2d));
-    CU(cudaStreamSynchronize(ctx->s_side));
-    CU(cudaStreamSynchronize(ctx->stream));
+    for (int gi = 0; gi < ctx->num_groups; ++gi) { CU(cudaStreamSynchronize(ctx->g_side[gi])); CU(cudaStreamSynchronize(ctx->g_main[gi])); }
     CU(cudaStreamSynchronize(ctx->s_d2h));
     for (Slot& t : ctx->slots) if (t.state == SLOT_INFLIGHT) t.state = SLOT_FREE;
     return H264R_OK;
@@ -607,7 +704,7 @@ int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_
     int rc;
     if (flags & H264R_REPLAY_ASYNC) {
         for (int it = 0; it < iterations; ++it) {
-            rc = run_waves(ctx, (flags & H264R_REPLAY_H2D) != 0, false, nullptr, nullptr);
+            rc = run_waves(ctx, (flags & H264R_REPLAY_H2D) != 0, false, nullptr, nullptr, false);
             if (rc != H264R_OK) return rc;
         }
         return H264R_OK;
@@ -618,7 +715,7 @@ int h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_
     int launches[6] = { 0, 0, 0, 0, 0, 0 };
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int it = 0; it < iterations; ++it) {
-        rc = run_waves(ctx, (flags & H264R_REPLAY_H2D) != 0, (flags & H264R_REPLAY_TIME_KERNELS) != 0, ms, launches);
+        rc = run_waves(ctx, (flags & H264R_REPLAY_H2D) != 0, (flags & H264R_REPLAY_TIME_KERNELS) != 0, ms, launches, true);
         if (rc != H264R_OK) return rc;
     }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
