@@ -488,6 +488,19 @@ int h264r_picture_begin(h264r_ctx* ctx, h264r_frame dst, const h264r_pic_params*
     return H264R_OK;
 }
 
+int h264r_picture_update(h264r_ctx* ctx, const h264r_pic_params* pp)
+{
+    if (!ctx || !pp) return H264R_ERR_INVALID;
+    if (ctx->filling < 0) return H264R_ERR_STATE;
+    if (pp->num_slices <= 0 || pp->num_slices > ctx->seq.max_slices_per_picture) return H264R_ERR_INVALID;
+    if (pp->num_ref_frames < 0 || pp->num_ref_frames > H264R_MAX_REFS) return H264R_ERR_INVALID;
+    for (int i = 0; i < pp->num_ref_frames; ++i)
+        if (pp->ref_frames[i] < 0 || pp->ref_frames[i] >= (int)ctx->frames.size() || !ctx->frames[pp->ref_frames[i]].dev)
+            return H264R_ERR_INVALID;
+    ctx->slots[ctx->filling].pp = *pp;
+    return H264R_OK;
+}
+
 int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels)
 {
     if (!ctx) return H264R_ERR_INVALID;

@@ -184,6 +184,10 @@ int  h264r_frame_release(h264r_ctx* ctx, h264r_frame f);
 
 /* replaces: init_picture + Decoder::init (core/slice_data.cc:149-313, 618).  Reserves a staging slot. */
 int  h264r_picture_begin(h264r_ctx* ctx, h264r_frame dst, const h264r_pic_params* pp, h264r_pic_buffers* out);
+/* Replaces the picture parameters given to h264r_picture_begin while the picture is still being filled: a parser
+ * learns the number of slices, further reference pictures (slices of one picture may list different references)
+ * and whether any slice enables the deblocking filter only as it goes along (core/slice_data.cc:618 runs per slice). */
+int  h264r_picture_update(h264r_ctx* ctx, const h264r_pic_params* pp);
 /* replaces: Decoder::deblock_filter at exit_picture (framebuf/picture.cc:253): the picture is complete
  * on the host side; it is queued.  `num_levels` = entries of the level list actually used.           */
 int  h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels);

@@ -1,0 +1,58 @@
+"""SURVEY.md 8f items 1 + 3: the reference's OWN decoder (NAL/slice parsing, CAVLC, motion-vector prediction, DPB, YUV
+writer -- compiled unmodified from /root/reference by integration/Makefile) with its reconstruction classes replaced by
+the binding integration/decoder_gpu.cc + libh264recon.so, against the unmodified reference decoder, on bitstreams
+written by tests/h264_writer.py.  The outputs must be byte-identical.
+
+The binaries are built where /root/reference exists (`__graft_entry__.build()`), stay out of git and travel to the
+GPU box; where they are missing the tests skip (they never read /root/reference at run time)."""
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+import h264_writer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "integration", "_build", "ldecod_ref")
+GPU = os.path.join(ROOT, "integration", "_build", "ldecod_gpu")
+
+CASES = [(11, 9, 8, 7), (5, 4, 10, 3), (20, 15, 6, 11), (1, 1, 4, 5), (3, 7, 7, 9)]
+
+
+def decode(binary, stream, workdir, name):
+    src = os.path.join(workdir, name + ".264")
+    out = os.path.join(workdir, name + ".yuv")
+    with open(src, "wb") as f:
+        f.write(stream)
+    r = subprocess.run([binary, "-i", src, "-o", out], cwd=workdir, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    with open(out, "rb") as f:
+        return f.read(), r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="integration/_build/ldecod_ref not built")
+@pytest.mark.parametrize("w,h,frames,seed", CASES)
+def test_writer_streams_are_decodable_by_the_reference(tmp_path, w, h, frames, seed):
+    stream = h264_writer.make_stream(w, h, frames, seed)
+    yuv, log = decode(REF, stream, str(tmp_path), "ref")
+    assert len(yuv) == frames * w * h * 384, log[-1500:]
+    assert "Error" not in log and "error" not in log, log[-1500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU)), reason="integration/_build binaries not built")
+@pytest.mark.parametrize("w,h,frames,seed", CASES)
+def test_reference_decoder_on_the_gpu_engine_is_bit_exact(tmp_path, w, h, frames, seed):
+    stream = h264_writer.make_stream(w, h, frames, seed)
+    want, _ = decode(REF, stream, str(tmp_path), "ref")
+    got, log = decode(GPU, stream, str(tmp_path), "gpu")
+    assert len(got) == len(want), log[-1500:]
+    fsz = w * h * 384
+    for i in range(frames):
+        a, b = want[i * fsz:(i + 1) * fsz], got[i * fsz:(i + 1) * fsz]
+        if a != b:
+            k = next(j for j in range(fsz) if a[j] != b[j])
+            plane = "Y" if k < w * h * 256 else ("Cb" if k < w * h * 320 else "Cr")
+            pytest.fail(f"output frame {i}: first difference in plane {plane} at byte {k} (reference {a[k]}, gpu {b[k]})")
+    assert hashlib.md5(got).hexdigest() == hashlib.md5(want).hexdigest()
