@@ -84,6 +84,7 @@ struct h264r_ctx {
     // tickets and progress counters: the latency-bound wavefront kernels of one group run underneath the
     // throughput-bound kernels of the others.  g_main[0] == stream, g_side[0] == s_side.
     int num_groups = 1;
+    int group_policy = 0;                     // 0: by stream (reference affinity, round robin); 1: by role (see h264r_create)
     int rr_group = 0;                         // round-robin cursor for pictures without a queued predecessor
     cudaStream_t g_main[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t g_side[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };
@@ -366,19 +367,36 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
     ctx->sync_ints_per_pic = align_up((size_t)2 * sp->height_mbs, 32);
-    {   // H264R_STREAM_GROUPS: number of stream groups (1..4).  Default 1: on B200 with 64 x 1080p streams the kernels
-        // are throughput-bound, and 2..4 groups measured 6-10 % slower; more groups only pay
-        // when a flush holds few pictures per wave.
+    {   // H264R_STREAM_GROUPS = number of stream groups (1..4, default 1), each with its own compute + side stream,
+        // tickets and progress counters; H264R_GROUP_POLICY says how pictures are dealt to them:
+        //   stream (default): whole streams (GOP chains), round robin;
+        //   role: group 0 = the reference CHAIN (pictures that later pictures of the same flush predict from: I/P) on
+        //         high-priority streams, groups 1.. = LEAVES (pictures nobody in the flush references: B).
+        // Measured on B200, 64 x 1080p x 16 pictures (profiles/r1_groups_experiment.txt): 1 group 37.2 ms/step,
+        // 2 groups by role 39.3, 3 by role 40.6, 2 by stream 39.8.  The wavefront kernels are bound by their critical
+        // path; co-scheduled throughput kernels lengthen every step of that path (there is no intra-SM priority), so
+        // concurrency between groups loses more than it fills.  Groups only pay when a flush holds few pictures per wave.
         const char* env = getenv("H264R_STREAM_GROUPS");
+        const char* pol = getenv("H264R_GROUP_POLICY");
         ctx->num_groups = env ? atoi(env) : 1;
         if (ctx->num_groups < 1) ctx->num_groups = 1;
         if (ctx->num_groups > kMaxGroups) ctx->num_groups = kMaxGroups;
+        ctx->group_policy = (pol && strcmp(pol, "role") == 0 && ctx->num_groups > 1) ? 1 : 0;
+    }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // numerically lower = higher priority
+    const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_lo;
+    if (ctx->group_policy == 1 && e == cudaSuccess) {
+        // the chain's compute stream was created with default priority above: replace it
+        cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->s_side);
+        e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->s_side, cudaStreamNonBlocking, prio_mid);
     }
     ctx->g_main[0] = ctx->stream; ctx->g_side[0] = ctx->s_side;
     for (int gi = 0; gi < ctx->num_groups && e == cudaSuccess; ++gi) {
         if (gi > 0) {
-            e = cudaStreamCreateWithFlags(&ctx->g_main[gi], cudaStreamNonBlocking);
-            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->g_side[gi], cudaStreamNonBlocking);
+            e = cudaStreamCreateWithPriority(&ctx->g_main[gi], cudaStreamNonBlocking, prio_lo);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->g_side[gi], cudaStreamNonBlocking, prio_lo);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->g_tail[gi], cudaEventDisableTiming);
     }
@@ -588,6 +606,19 @@ int h264r_flush(h264r_ctx* ctx)
     const int G = ctx->num_groups;
     ctx->flush_serial += 1;
     for (Frame& f : ctx->frames) f.readers.clear();
+    if (ctx->group_policy == 1) {
+        // by role: a picture some later picture of this flush predicts from belongs to the chain (group 0), the others
+        // are leaves, dealt round robin to groups 1..G-1
+        std::vector<char> referenced(ctx->frames.size(), 0);
+        int rr = 0;
+        for (size_t k = ctx->queue.size(); k-- > 0; ) {
+            Slot& s = ctx->slots[ctx->queue[k]];
+            s.group = referenced[s.dst] ? 0 : 1 + (rr++ % (G - 1));
+            referenced[s.dst] = 0;                                      // an earlier picture in the same frame is another picture
+            for (int i = 0; i < s.pp.num_ref_frames; ++i) referenced[s.pp.ref_frames[i]] = 1;
+            ctx->frames[s.dst].group = s.group;
+        }
+    } else
     for (int qi : ctx->queue) {
         Slot& s = ctx->slots[qi];
         int grp = -1;

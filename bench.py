@@ -34,6 +34,17 @@ UNIT = "MB/s"          # MB = macroblocks; output bytes/s = val
 CONFIG_ID = 5
 
 
+def measured_traffic():
+    """DRAM bytes per picture by kernel and picture type, from the newest ncu --set full capture committed under
+    profiles/ (scripts/gpu_profile.sh; bench.py never runs under a profiler itself)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), key=os.path.getmtime)
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        return json.load(f)["bytes_per_picture"], os.path.relpath(files[-1], ROOT)
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -179,12 +190,14 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex:
         all_pics = list(ex.map(generate_stream, [(sid, frames) for sid in my_streams]))
     acct = [0] * 10
+    pics_by_type = {"P": 0, "B": 0, "I": 0}
     frames_of = [dict() for _ in range(streams)]
     out_frames = []
     for i in range(frames):                       # picture i of every stream, decode order
         for s in range(streams):
             pic = all_pics[s][i]
             dst = eng.frame_alloc()
+            pics_by_type["PBI"[pic.info.pic_type]] += 1
             frames_of[s][pic.info.pic_index] = dst
             eng.submit(pic, dst, [frames_of[s][pic.info.ref_pic_index[k]] for k in range(pic.info.num_refs)])
             out_frames.append(dst)
@@ -295,6 +308,13 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     dom_bytes_per_launch = k_bytes[dom] / max(1, kn[dom + 1])
     achieved = dom_bytes_per_launch / (dom_ms_per_launch * 1e-3) / 1e9 if dom_ms_per_launch > 0 else 0.0
     step_gbs = acct[0] / (t_dev / args.steps) / 1e9
+    # measured DRAM traffic of the dominant kernel per launch: bytes per picture of each type (ncu capture of the same
+    # wave shapes, committed under profiles/) x this workload's pictures / its launches; scaled with the picture size
+    traffic, traffic_src = None, None
+    tb, traffic_src = measured_traffic()
+    tkey = {"residual": "residual", "inter": "inter", "intra": "intra", "deblock_prep": "deblock_prep", "deblock": "deblock"}[names[dom]]
+    if tb and tkey in tb:
+        traffic = sum(tb[tkey].get(t, 0.0) * n for t, n in pics_by_type.items()) * (nmb / 8160.0) / max(1, kn[dom + 1])
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -309,7 +329,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
                 "d2h_bytes_per_step": int((s3.d2h_bytes - s2.d2h_bytes) // args.steps)},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": names[dom] + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
                      "whole_step": {"algorithmic_bytes": acct[0], "achieved": step_gbs, "frac": step_gbs / peak,
                                     "bytes_per_mb": acct[0] / total_mb},

@@ -13,6 +13,7 @@ so = os.path.join(root, 'arrow-h264_b200', 'libh264recon.so')
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 secs = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name'] + [len(rows)]
+if len(secs) > 2 and all(rows[secs[k]][1] == rows[secs[k + 1]][1] for k in range(0, len(secs) - 1, 2)): launch *= 2   # this ncu prints every launch twice
 hdr = rows[secs[launch] + 1]
 ix = {h: i for i, h in enumerate(hdr)}
 counts = [(r[ix['Source']], int(r[ix['Instructions Executed']] or 0)) for r in rows[secs[launch] + 2:secs[launch + 1]] if len(r) >= len(hdr)]

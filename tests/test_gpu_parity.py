@@ -133,3 +133,70 @@ def test_engine_rejects_bad_input():
         eng.frame_release(99)
     eng.close()
     st.close()
+
+
+def test_gpu_full_size_multi_stream_workload():
+    """The bench workload at full size (BASELINE configs[4]: 64 independent 1080p High-profile streams, here 7 pictures
+    each = waves of 64, 64, 192 and 128 pictures, flushed at once like bench.py does).  Four sampled streams are
+    compared picture by picture with the oracle; a checksum of checksums over all 448 frames must not change when
+    the same descriptions are replayed from HBM (kernel-only path) and re-uploaded (end-to-end path)."""
+    cfg, n, nstreams, sampled = 5, 7, 64, (0, 9, 31, 63)
+    st = pyapi.SynthStream(cfg, 0, 0, 0, n)
+    seq = st.seq
+    st.close()
+    assert (seq.width_mbs, seq.height_mbs) == (120, 68)
+    want = {}
+    for s in sampled:
+        port = O.CpuDecoder("port", seq)
+        want[s] = O.run_stream(port, cfg, s, 0, 0, n)
+        port.close()
+    eng = pyapi.Engine(seq, max_frames=nstreams * n, max_pictures=nstreams * n, max_slices=4, max_levels=8160 * 96)
+    streams = [pyapi.SynthStream(cfg, s, 0, 0, n) for s in range(nstreams)]
+    frames = [dict() for _ in range(nstreams)]
+    order = []
+    for _ in range(n):
+        for s, st in enumerate(streams):
+            pic = st.next()
+            dst = eng.frame_alloc()
+            frames[s][pic.info.pic_index] = dst
+            eng.submit(pic, dst, [frames[s][pic.info.ref_pic_index[i]] for i in range(pic.info.num_refs)])
+            order.append((s, pic.info.pic_index, dst))
+    for st in streams:
+        st.close()
+    eng.flush()
+    eng.wait()
+
+    def digest_all():
+        per = {}
+        for s, idx, dst in order:
+            per[(s, idx)] = hashlib.md5(b"".join(eng.download(dst))).hexdigest()
+        total = hashlib.md5("".join(per[k] for k in sorted(per)).encode()).hexdigest()
+        return per, total
+
+    per, total = digest_all()
+    for s in sampled:
+        for idx in range(n):
+            assert per[(s, idx)] == want[s][idx], f"stream {s} picture {idx} differs from the oracle"
+    eng.replay(1, 0)
+    assert digest_all()[1] == total, "kernel-only replay changed the output"
+    eng.replay(1, pyapi.Engine.REPLAY_H2D | pyapi.Engine.REPLAY_ASYNC)
+    eng.wait()
+    assert digest_all()[1] == total, "end-to-end replay changed the output"
+    eng.close()
+
+
+def test_gpu_4k_wavefront_stress():
+    """BASELINE configs[3] at its full size (3840x2160 = 240x135 MB): all-intra + P + B pictures with low QP and
+    deblock offsets of +-6 -- the longest wavefronts (508 steps) -- against the oracle, every picture."""
+    cfg, sidx, n = 4, 2, 4
+    st = pyapi.SynthStream(cfg, sidx, 0, 0, n)
+    seq, nfr = st.seq, st.num_frames
+    st.close()
+    assert (seq.width_mbs, seq.height_mbs) == (240, 135)
+    port = O.CpuDecoder("port", seq)
+    want = O.run_stream(port, cfg, sidx, 0, 0, n)
+    port.close()
+    eng = pyapi.Engine(seq, max_frames=nfr + 1, max_pictures=nfr, max_slices=4)
+    got = run_stream_gpu(eng, cfg, sidx, 0, 0, n, flush_every=nfr)
+    eng.close()
+    assert got == want
