@@ -37,6 +37,7 @@ struct DevPicture {
     const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]
     int*                   row_progress;              // [2][height_mbs]: intra wavefront, deblock wavefront
     DeblockDesc*           desc;                      // [nmb], device only
+    uint64_t*              mbox;                      // [nmb][24], device only: deblock row-to-row mailboxes { 4 samples, epoch }
     const uint32_t*        intra_list;                // raster-ordered addresses of the intra MBs (pictures that also have inter MBs)
     uint32_t*              mb_done;                   // [nmb], device only: epoch stamp of the launch that reconstructed the intra MB
     int                    run_deblock;

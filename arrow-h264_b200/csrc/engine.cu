@@ -45,6 +45,7 @@ struct Slot {
     uint32_t motion_entries = 0;              // packed 12-byte motion entries behind the level list
     uint32_t intra_count = 0;                 // intra-MB address list behind the packed motion (mixed pictures only)
     uint32_t* dev_mb_done = nullptr;          // device only: per-MB epoch stamps of the sparse intra kernel
+    uint64_t* dev_mbox = nullptr;             // device only: deblock mailboxes [nmb][24]
     SlotState state = SLOT_FREE;
     h264r_pic_params pp;
     h264r_frame dst = -1;
@@ -352,7 +353,8 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     ctx->slots.resize(sp->max_pictures_in_flight);
     // one pinned and one device arena for all staging slots
     uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr; int16_t* d_resid = nullptr;
-    uint8_t* h_motion = nullptr; h264r_mb_motion* d_motion = nullptr; uint32_t* d_done = nullptr;
+    uint8_t* h_motion = nullptr; h264r_mb_motion* d_motion = nullptr; uint32_t* d_done = nullptr; uint64_t* d_mbox = nullptr;
+    const size_t mbox_words = (size_t)24 * ctx->nmb;
     const size_t motion_bytes = sizeof(h264r_mb_motion) * (size_t)ctx->nmb;
     const size_t arena = ctx->slot_bytes * sp->max_pictures_in_flight;
     e = cudaHostAlloc((void**)&h_arena, arena, cudaHostAllocDefault);
@@ -363,6 +365,8 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_motion, motion_bytes * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_done, sizeof(uint32_t) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaMemset(d_done, 0, sizeof(uint32_t) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_mbox, sizeof(uint64_t) * mbox_words * sp->max_pictures_in_flight);
+    if (e == cudaSuccess) e = cudaMemset(d_mbox, 0, sizeof(uint64_t) * mbox_words * sp->max_pictures_in_flight);   // epoch 0 is never used
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
@@ -411,6 +415,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         if (h_motion) cudaFreeHost(h_motion);
         if (d_motion) cudaFree(d_motion);
         if (d_done) cudaFree(d_done);
+        if (d_mbox) cudaFree(d_mbox);
         if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
         if (ctx->d_pics) cudaFree(ctx->d_pics);
         if (ctx->d_sync) cudaFree(ctx->d_sync);
@@ -426,6 +431,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         ctx->slots[i].host_motion = h_motion + motion_bytes * i;
         ctx->slots[i].dev_motion = d_motion + (size_t)ctx->nmb * i;
         ctx->slots[i].dev_mb_done = d_done + (size_t)ctx->nmb * i;
+        ctx->slots[i].dev_mbox = d_mbox + mbox_words * i;
     }
     *out = ctx;
     return H264R_OK;
@@ -443,7 +449,7 @@ void h264r_destroy(h264r_ctx* ctx)
     }
     for (Frame& f : ctx->frames) { if (f.dev) cudaFree(f.dev); if (f.read_done) cudaEventDestroy(f.read_done); }
     if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); cudaFree(ctx->slots[0].dev_resid);
-                                cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_motion); cudaFree(ctx->slots[0].dev_mb_done); }
+                                cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_motion); cudaFree(ctx->slots[0].dev_mb_done); cudaFree(ctx->slots[0].dev_mbox); }
     cudaFreeHost(ctx->h_pics); cudaFree(ctx->d_pics); cudaFree(ctx->d_sync);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) if (ctx->table_ev[i]) cudaEventDestroy(ctx->table_ev[i]);
@@ -661,6 +667,7 @@ int h264r_flush(h264r_ctx* ctx)
             p.intra_list = reinterpret_cast<const uint32_t*>(p.packed_motion + (size_t)12 * s.motion_entries);
             p.intra_count = (int)s.intra_count;
             p.mb_done = s.dev_mb_done;
+            p.mbox = s.dev_mbox;
             p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
             p.levels = reinterpret_cast<const h264r_level*>(s.dev + ctx->off_levels);
             p.resid = s.dev_resid;

@@ -1149,15 +1149,44 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
 // keep only 16 lanes busy).  Lane l of a half owns luma line l and chroma line l & 7 of plane l >> 3.
 //   vertical edges  : the lane's row lives in registers (left 4 samples carried from the previous MB + own 16 / 8),
 //                     the four (two) edges are filtered in sequence without touching memory;
-//   horizontal edges: the row goes through a shared-memory tile (transposition), the lane then owns a column; the
-//                     4 (2) samples above the MB come straight from global memory, prefetched one MB ahead when the row
-//                     above is known to be far enough.
-// Tile per half: luma 16 rows x 32 B (own 16 samples at byte 16, so that rows are 16-byte aligned), chroma 2 planes x
-// 8 rows x 16 B (own 8 samples at byte 8).
+//   horizontal edges: the row goes through a shared-memory tile (transposition), the lane then owns a column.
+//
+// Rows talk through MAILBOXES, not through the frame (the low-latency protocol of collective libraries: data and
+// flag travel in the same 64-bit word, so neither side needs a fence).  The last four luma rows and the last two
+// rows of each chroma plane of MB (x, y) -- the only samples MB (x, y+1) reads or changes -- are final once the row's
+// warp has filtered the left edge of MB (x+1, y).  At that point the warp posts them as 24 words of
+// { 4 samples, launch epoch } (st.relaxed.gpu.u64, single-copy atomic); the warp of row y+1 polls the 24 words of
+// mailbox (x, y), filters its top edge on them, and is the ONLY writer of luma rows 13..15 / chroma row 7 of row y in
+// the frame (row y's own warp stores rows 0..12 / 0..6 unless it is the last row).  Every frame byte therefore has
+// one writer per launch, there is no release/acquire pair in the kernel, and the samples above an MB arrive with the
+// notification instead of one more round trip after it.  Epoch stamps make clearing unnecessary.
+//
+// Shared-memory tile per half: luma 16 rows x 48 B (own 16 samples at byte 16; 48 keeps the 128-bit row accesses of a
+// quarter warp on distinct banks), chroma 2 planes x 8 rows x 16 B (own 8 samples at byte 8), plus the mailbox words
+// of the MB above (4 luma rows x 16 B, 2 x 2 chroma rows x 8 B).  The halves are skewed so that the byte accesses of
+// the column pass (all 32 lanes in one wavefront) fall on disjoint banks.
+constexpr int kTileP = 48;                                   // luma tile row pitch
+constexpr int kTileHalfY = 16 * kTileP + 16;                 // half B starts 4 banks further
+constexpr int kTilePlaneC = 8 * 16 + 8;                      // chroma plane stride (2 banks further)
+constexpr int kTileHalfC = 2 * kTilePlaneC + 16;             // = 288 = 32 (mod 128)
 struct __align__(16) DeblockSmem {
-    uint8_t y[2][16 * 32];
-    uint8_t c[2][2][8 * 16];
+    uint8_t y[2 * kTileHalfY];
+    uint8_t c[2 * kTileHalfC];
+    uint8_t top_y[2][4 * 16];
+    uint8_t top_c[2][2][2 * 8];
 };
+constexpr int kMboxWords = 24;                               // per MB: 16 luma words (rows 12..15) + 8 chroma words (rows 6, 7 of Cb, Cr)
+
+__device__ __forceinline__ void st_mbox(uint64_t* p, uint32_t data, uint32_t epoch)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"((uint64_t)data | ((uint64_t)epoch << 32)) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_mbox(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // filter_strong / filter_normal (deblock.cc:327-415) on the samples across one edge: p[0] = p0 ... p[3] = p3.
 template <bool kChroma>
@@ -1214,7 +1243,7 @@ __device__ __forceinline__ uint32_t pack4(const int* v)
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_DEBLOCK_CTAS)
-deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
+deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g, uint32_t epoch)
 {
     __shared__ __align__(16) DeblockSmem smem_all[kWarpsPerCta];
     __shared__ int s_ticket;
@@ -1234,23 +1263,28 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
     const bool enabled = pic_i < num_pics && pic.run_deblock;                   // this half has a picture to filter
     if (!__any_sync(0xFFFFFFFFu, enabled)) return;
     DeblockSmem& sm = smem_all[warp];
-    uint8_t* const TY = sm.y[half];
-    uint8_t* const TC = sm.c[half][cpl];
-    int* const progress = pic.row_progress + H;          // [1][H]
+    uint8_t* const TY = sm.y + half * kTileHalfY;
+    uint8_t* const TCh = sm.c + half * kTileHalfC;         // both planes of this half
+    uint8_t* const TC = TCh + cpl * kTilePlaneC;           // this lane's plane
+    uint8_t* const TOPY = sm.top_y[half];
+    uint8_t* const TOPC = sm.top_c[half][0];
     uint8_t* const dY = pic.dst;
     uint8_t* const dC = pic.dst + (cpl ? g.off_cr : g.off_cb);
     const int pitch_y = g.pitch_y, pitch_c = g.pitch_c;
     const uint4* const desc = reinterpret_cast<const uint4*>(pic.desc + (size_t)mby * W);
     const int py = mby * 16, cy = mby * 8;
     const int gshY = (l >> 2) * 4, gshC = (cl >> 1) * 4;   // nibble position of this lane's 4-sample group
-
-    // Progress protocol: a row publishes v after the vertical pass and the horizontal pass of MB v (its store of the
-    // left MB's columns 13..15 has long been issued) and before MB v's own write-back; v == W after the last MB.
-    // progress >= v therefore says: MBs < v are complete, and MB v no longer touches MB v-1.  MB x of the row below
-    // reads and writes rows 12..15 of MB x above, so it needs progress >= min(x + 1, W)  (after
-    // (x+1, y-1)'s left edge, before (x-1, y+1)).
-    int known = (mby > 0 && enabled) ? 0 : 0x7FFFFFFF;    // progress of the row above as last observed (per half)
-    const int* const prog_above = progress + mby - 1;
+    const bool has_above = mby > 0, has_below = mby + 1 < H;                    // warp-uniform
+    const bool own_y = enabled && (l <= 12 || !has_below);                      // frame rows this warp stores itself
+    const bool own_c = enabled && (cl <= 6 || !has_below);
+    uint64_t* const box_out = pic.mbox + (size_t)mby * W * kMboxWords;          // posted by this row
+    const uint64_t* const box_in = pic.mbox + (size_t)(has_above ? mby - 1 : 0) * W * kMboxWords;
+    // mailbox word this lane posts: luma word l = row 12 + (l >> 2), samples 4 (l & 3)..; chroma word l (l < 8) = plane
+    // l >> 2, row 6 + ((l >> 1) & 1), samples 4 (l & 1)..  The last word of a row is final only after the next MB's
+    // left edge: it comes from the lane that owns that row in the vertical pass.
+    const uint8_t* const boxsrc_y = TY + (12 + (l >> 2)) * kTileP + 16 + 4 * (l & 3);
+    const uint8_t* const boxsrc_c = TCh + ((l >> 2) & 1) * kTilePlaneC + (6 + ((l >> 1) & 1)) * 16 + 8 + 4 * (l & 1);
+    const int boxlane_y = (lane & 16) + 12 + (l >> 2), boxlane_c = (lane & 16) + ((l >> 2) & 1) * 8 + 6 + ((l >> 1) & 1);
 
     // prefetch of MB 0: descriptor (strengths, luma thresholds, thresholds of this lane's chroma plane), own samples
     uint4 n_bs = make_uint4(0, 0, 0, 0), n_py = n_bs, n_pc = n_bs, n_ownY = n_bs; uint2 n_ownC = make_uint2(0, 0);
@@ -1259,19 +1293,20 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
         n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y)));
         n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c)));
     }
-    bool top_pref = false;                                // top samples of the coming MB already in registers
-    uint32_t n_topY = 0, n_topC = 0;                      // rows -4..-1 of luma column l / rows -2..-1 of chroma column cl
+    uint32_t boxY = 0, boxC = 0;                          // this lane's mailbox words of the previous MB (after its horizontal pass)
 
     for (int mbx = 0; mbx < W; ++mbx) {
         const uint4 bs = n_bs, parY = n_py, parC = n_pc, ownY = n_ownY; const uint2 ownC = n_ownC;
-        const bool have_top = top_pref;
-        uint32_t topY = n_topY, topC = n_topC;
         const int px = mbx * 16, cx = mbx * 8;
-        const bool any = (bs.x | bs.y | bs.z | bs.w) != 0;
-        const bool top_on = enabled && (bs.z & 0xFFFF) != 0;                     // dir 1, edge 0 has a non-zero strength
 
-        // previous MB's last four samples of this lane's rows (final values), before the tile rows are overwritten
-        const uint32_t carryY = *reinterpret_cast<const uint32_t*>(TY + l * 32 + 16 + 12);
+        // mailbox of the MB above: issued now, looked at after the vertical pass
+        uint64_t t0 = 0, t1 = 0;
+        if (has_above && enabled) {
+            t0 = ld_mbox(box_in + mbx * kMboxWords + l);
+            if (l < 8) t1 = ld_mbox(box_in + mbx * kMboxWords + 16 + l);
+        }
+        // previous MB's last four samples of this lane's rows (final but for this MB's left edge)
+        const uint32_t carryY = *reinterpret_cast<const uint32_t*>(TY + l * kTileP + 16 + 12);
         const uint32_t carryC = *reinterpret_cast<const uint32_t*>(TC + cl * 16 + 8 + 4);
 
         // prefetch the next MB: independent of every other MB of this kernel
@@ -1281,42 +1316,8 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
             n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx + 8)));
         }
 
-        if (!__any_sync(0xFFFFFFFFu, any && enabled)) {
-            // nothing to filter in either picture: the tile still has to carry this MB's samples to the next one
-            *reinterpret_cast<uint4*>(TY + l * 32 + 16) = ownY;
-            *reinterpret_cast<uint2*>(TC + cl * 16 + 8) = ownC;
-            top_pref = false;
-            publish_row(progress + mby, mbx, lane & 15, false);          // both halves publish through their own lane 0
-            continue;
-        }
-
-        // ---- samples above the MB: wait for the row above, issue the loads; they land during the vertical pass ----
-        if (__any_sync(0xFFFFFFFFu, top_on && !have_top)) {
-            const int need = min(mbx + 1, W);
-            if (top_on && known < need && l == 0) {
-                unsigned ns = 16;
-                while ((known = ld_acquire(prog_above)) < need) { __nanosleep(ns); if (ns < 128) ns *= 2; }
-            }
-            __syncwarp();
-            known = __shfl_sync(0xFFFFFFFFu, known, lane & 16);
-            if (top_on && !have_top) {
-                const uint8_t* ty = dY + (uint32_t)((py - 4) * pitch_y + px + l);
-                topY = (uint32_t)__ldcg(ty) | (uint32_t)__ldcg(ty + pitch_y) << 8 | (uint32_t)__ldcg(ty + 2 * pitch_y) << 16 | (uint32_t)__ldcg(ty + 3 * pitch_y) << 24;
-                const uint8_t* tc = dC + (uint32_t)((cy - 2) * pitch_c + cx + cl);
-                topC = (uint32_t)__ldcg(tc) | (uint32_t)__ldcg(tc + pitch_c) << 8;
-            }
-        }
-        // top samples of the next MB, if the row above is already known to be far enough
-        top_pref = false;
-        if (mby > 0 && mbx + 1 < W && enabled && known >= min(mbx + 2, W)) {
-            top_pref = true;
-            const uint8_t* ty = dY + (uint32_t)((py - 4) * pitch_y + px + 16 + l);
-            n_topY = (uint32_t)__ldcg(ty) | (uint32_t)__ldcg(ty + pitch_y) << 8 | (uint32_t)__ldcg(ty + 2 * pitch_y) << 16 | (uint32_t)__ldcg(ty + 3 * pitch_y) << 24;
-            const uint8_t* tc = dC + (uint32_t)((cy - 2) * pitch_c + cx + 8 + cl);
-            n_topC = (uint32_t)__ldcg(tc) | (uint32_t)__ldcg(tc + pitch_c) << 8;
-        }
-
         // ---- vertical edges, in registers ----
+        uint32_t leftY, leftC;                             // the previous MB's last four samples after this MB's left edge
         {
             int v[20];
             unpack4(carryY, v); unpack4(ownY.x, v + 4); unpack4(ownY.y, v + 8); unpack4(ownY.z, v + 12); unpack4(ownY.w, v + 16);
@@ -1328,9 +1329,10 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
                 v[4 * e + 2] = p[1]; v[4 * e + 1] = p[2]; v[4 * e + 3] = p[0];
                 v[4 * e + 4] = q[0]; v[4 * e + 5] = q[1]; v[4 * e + 6] = q[2];
             }
-            *reinterpret_cast<uint4*>(TY + l * 32 + 16) = make_uint4(pack4(v + 4), pack4(v + 8), pack4(v + 12), pack4(v + 16));
-            if (enabled && (bs.x & 0xFFFF) && mbx > 0)         // columns 13..15 of the left MB
-                *reinterpret_cast<uint32_t*>(dY + (uint32_t)((py + l) * pitch_y + px - 4)) = pack4(v);
+            *reinterpret_cast<uint4*>(TY + l * kTileP + 16) = make_uint4(pack4(v + 4), pack4(v + 8), pack4(v + 12), pack4(v + 16));
+            leftY = pack4(v);
+            if (own_y && (bs.x & 0xFFFF) && mbx > 0)          // columns 13..15 of the left MB
+                *reinterpret_cast<uint32_t*>(dY + (uint32_t)((py + l) * pitch_y + px - 4)) = leftY;
         }
         {
             int v[12];
@@ -1343,18 +1345,45 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
                 v[4 * e + 3] = p[0]; v[4 * e + 4] = q[0];
             }
             *reinterpret_cast<uint2*>(TC + cl * 16 + 8) = make_uint2(pack4(v + 4), pack4(v + 8));
-            if (enabled && (bs.x & 0xFFFF) && mbx > 0)
-                *reinterpret_cast<uint32_t*>(dC + (uint32_t)((cy + cl) * pitch_c + cx - 4)) = pack4(v);
+            leftC = pack4(v);
+            if (own_c && (bs.x & 0xFFFF) && mbx > 0)
+                *reinterpret_cast<uint32_t*>(dC + (uint32_t)((cy + cl) * pitch_c + cx - 4)) = leftC;
         }
-        __syncwarp();                                      // tile rows (vertical pass) visible to the column owners
+
+        // ---- post the mailbox of the previous MB: its bottom rows are final now ----
+        {
+            const uint32_t fy = __shfl_sync(0xFFFFFFFFu, leftY, boxlane_y), fc = __shfl_sync(0xFFFFFFFFu, leftC, boxlane_c);
+            if (has_below && enabled && mbx > 0) {
+                st_mbox(box_out + (mbx - 1) * kMboxWords + l, (l & 3) == 3 ? fy : boxY, epoch);
+                if (l < 8) st_mbox(box_out + (mbx - 1) * kMboxWords + 16 + l, (l & 1) ? fc : boxC, epoch);
+            }
+        }
+
+        // ---- mailbox of the MB above: normally there already ----
+        if (has_above) {
+            bool waiting = enabled && ((uint32_t)(t0 >> 32) != epoch || (l < 8 && (uint32_t)(t1 >> 32) != epoch));
+            unsigned ns = 16;
+            while (__any_sync(0xFFFFFFFFu, waiting)) {
+                if (waiting) {
+                    __nanosleep(ns); if (ns < 128) ns *= 2;
+                    t0 = ld_mbox(box_in + mbx * kMboxWords + l);
+                    if (l < 8) t1 = ld_mbox(box_in + mbx * kMboxWords + 16 + l);
+                    waiting = (uint32_t)(t0 >> 32) != epoch || (l < 8 && (uint32_t)(t1 >> 32) != epoch);
+                }
+            }
+            reinterpret_cast<uint32_t*>(TOPY)[l] = (uint32_t)t0;           // row 12 + (l >> 2), samples 4 (l & 3)..
+            if (l < 8) reinterpret_cast<uint32_t*>(TOPC)[l] = (uint32_t)t1;
+        }
+        __syncwarp();                                      // tile rows (vertical pass) and the rows above visible to the column owners
 
         // ---- horizontal edges: lane l = luma column l, chroma column cl of plane cpl ----
-        uint32_t upY = 0, upC = 0;                         // filtered samples of the MB above, stored after the publish
+        uint32_t upY = 0, upC = 0;                         // samples of the MB above after the top edge
         {
             int v[20];
-            unpack4(topY, v);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) v[4 + r] = TY[r * 32 + 16 + l];
+            for (int r = 0; r < 4; ++r) v[r] = has_above ? TOPY[r * 16 + l] : 0;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[4 + r] = TY[r * kTileP + 16 + l];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int s = enabled ? ((e < 2 ? bs.z : bs.w) >> ((e & 1) * 16 + gshY)) & 7 : 0;
@@ -1364,12 +1393,12 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
                 v[4 * e + 4] = q[0]; v[4 * e + 5] = q[1]; v[4 * e + 6] = q[2];
             }
 #pragma unroll
-            for (int r = 0; r < 15; ++r) TY[r * 32 + 16 + l] = (uint8_t)v[4 + r];
+            for (int r = 0; r < 15; ++r) TY[r * kTileP + 16 + l] = (uint8_t)v[4 + r];
             upY = (uint32_t)v[1] | (uint32_t)v[2] << 8 | (uint32_t)v[3] << 16;     // rows 13..15 of the MB above
         }
         {
             int v[10];                                     // rows -2, -1, 0..7
-            v[0] = topC & 0xFF; v[1] = (topC >> 8) & 0xFF;
+            v[0] = has_above ? TOPC[cpl * 16 + cl] : 0; v[1] = has_above ? TOPC[cpl * 16 + 8 + cl] : 0;
 #pragma unroll
             for (int r = 0; r < 8; ++r) v[2 + r] = TC[r * 16 + 8 + cl];
 #pragma unroll
@@ -1382,21 +1411,26 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
             TC[0 * 16 + 8 + cl] = (uint8_t)v[2]; TC[3 * 16 + 8 + cl] = (uint8_t)v[5]; TC[4 * 16 + 8 + cl] = (uint8_t)v[6];
             upC = (uint32_t)v[1];
         }
-        // MBs < mbx are complete and this MB is done with its left neighbour (stores issued a pass ago: cheap release)
-        publish_row(progress + mby, mbx, lane & 15, true);             // includes the __syncwarp the tile needs
+        __syncwarp();                                      // the tile holds the MB after both passes
 
-        // ---- write back: rows 13..15 of the MB above (nobody in this launch reads them again), then the MB's own samples ----
-        if (top_on) {
+        // ---- write back: rows 13..15 / row 7 of the MB above (this warp is their only writer), then the MB's own rows ----
+        if (has_above && enabled) {
             uint8_t* ty = dY + (uint32_t)((py - 3) * pitch_y + px + l);
             ty[0] = (uint8_t)upY; ty[pitch_y] = (uint8_t)(upY >> 8); ty[2 * pitch_y] = (uint8_t)(upY >> 16);
             dC[(uint32_t)((cy - 1) * pitch_c + cx + cl)] = (uint8_t)upC;
         }
-        if (enabled) {
-            *reinterpret_cast<uint4*>(dY + (uint32_t)((py + l) * pitch_y + px)) = *reinterpret_cast<const uint4*>(TY + l * 32 + 16);
-            *reinterpret_cast<uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx)) = *reinterpret_cast<const uint2*>(TC + cl * 16 + 8);
-        }
+        if (own_y) *reinterpret_cast<uint4*>(dY + (uint32_t)((py + l) * pitch_y + px)) = *reinterpret_cast<const uint4*>(TY + l * kTileP + 16);
+        if (own_c) *reinterpret_cast<uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx)) = *reinterpret_cast<const uint2*>(TC + cl * 16 + 8);
+        // this lane's mailbox words of the MB (their last samples are replaced after the next MB's left edge)
+        boxY = *reinterpret_cast<const uint32_t*>(boxsrc_y);
+        boxC = *reinterpret_cast<const uint32_t*>(boxsrc_c);
+        __syncwarp();                                      // before the next vertical pass overwrites the tile rows
     }
-    publish_row(progress + mby, W, lane & 15, true);
+    // the last MB of the row has no right neighbour: its bottom rows are final as they stand
+    if (has_below && enabled) {
+        st_mbox(box_out + (W - 1) * kMboxWords + l, boxY, epoch);
+        if (l < 8) st_mbox(box_out + (W - 1) * kMboxWords + 16 + l, boxC, epoch);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1485,7 +1519,7 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
         deblock_prep_kernel<<<(int)((total + 127) / 128), 128, 0, stream>>>(w.pics, w.num_pics, w.geom);
         return 1;
     }
-    deblock_kernel<<<((w.num_pics + 1) / 2) * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
+    deblock_kernel<<<((w.num_pics + 1) / 2) * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
     return 1;
 }
 
