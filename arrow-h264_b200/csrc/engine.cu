@@ -67,6 +67,7 @@ struct WaveRecord {
     cudaEvent_t ev_h2d = nullptr;             // recorded on the H2D stream after the wave's copies
     cudaEvent_t ev_done = nullptr;            // recorded on the compute stream after the wave's kernels
     cudaEvent_t ev_side = nullptr;            // recorded on the side stream after the wave's neighbour-independent kernels
+    cudaEvent_t ev_inter = nullptr;           // recorded on the compute stream after the wave's inter kernel
 };
 
 } // namespace
@@ -93,6 +94,9 @@ struct h264r_ctx {
     size_t sync_ints_per_group = 0;
     uint64_t flush_serial = 0;
     bool cross_group = false;                 // the last flush has references across groups
+    bool side_gate = false;                   // H264R_SIDE_GATE=1: side kernels of wave k+1 start when the inter kernel of wave k has
+                                              // finished, i.e. underneath its wavefront kernels (measured: no gain, 34.7 vs 34.6 ms/step)
+    cudaEvent_t gate[kMaxGroups] = { nullptr, nullptr, nullptr, nullptr };   // ev_inter of the group's latest record
     std::vector<cudaEvent_t> event_pool;      // reused across flushes
     size_t events_used = 0;
     std::vector<cudaEvent_t> timer_events;    // H264R_REPLAY_TIME_KERNELS
@@ -248,6 +252,9 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         // side kernels: their outputs (expanded motion, residual plane, deblock descriptors) are per picture slot; the
         // previous run of this record must have consumed them
         if (!time_kernels) CU(cudaStreamWaitEvent(side, rec.ev_done, 0));
+        // Throughput-bound side kernels are scheduled underneath the latency-bound wavefront kernels (intra, deblock) of
+        // the wave before, not against its inter kernel: they start when that inter kernel has finished.
+        if (!time_kernels && ctx->side_gate && ctx->gate[rec.group]) CU(cudaStreamWaitEvent(side, ctx->gate[rec.group], 0));
         { const int rc = launch(rec, KERNEL_RESID, side); if (rc != H264R_OK) return rc; }
         { const int rc = launch(rec, KERNEL_DBPREP, side); if (rc != H264R_OK) return rc; }
         if (!time_kernels) {
@@ -262,6 +269,7 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         }
         CU(cudaMemsetAsync(rec.launch.tickets, 0, rec.progress_bytes, main));
         { const int rc = launch(rec, KERNEL_INTER, main); if (rc != H264R_OK) return rc; }
+        if (!time_kernels && ctx->side_gate) { CU(cudaEventRecord(rec.ev_inter, main)); ctx->gate[rec.group] = rec.ev_inter; }
         { const int rc = launch(rec, KERNEL_INTRA, main); if (rc != H264R_OK) return rc; }
         { const int rc = launch(rec, KERNEL_DEBLOCK, main); if (rc != H264R_OK) return rc; }
         CU(cudaGetLastError());
@@ -387,20 +395,29 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         if (ctx->num_groups > kMaxGroups) ctx->num_groups = kMaxGroups;
         ctx->group_policy = (pol && strcmp(pol, "role") == 0 && ctx->num_groups > 1) ? 1 : 0;
     }
+    // Priorities: the compute streams (inter, intra, deblock: the dependency chain of the pictures) above the side
+    // streams (motion expansion, residual, deblock descriptors: work that only has to be ready a wave ahead), so that
+    // side CTAs fill the SMs the wavefront kernels leave idle instead of competing with the inter kernel.
+    // Measured (profiles/r1_groups_experiment.txt): 35.9 ms/step against 34.6 with equal priorities -- the compute
+    // stream then waits for late side kernels at every wave start -- so equal is the default; H264R_SIDE_PRIORITY=low
+    // selects the lower side priority.  With the role policy the chain group sits above the leaf groups.
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // numerically lower = higher priority
-    const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_lo;
-    if (ctx->group_policy == 1 && e == cudaSuccess) {
-        // the chain's compute stream was created with default priority above: replace it
+    const char* sp_env = getenv("H264R_SIDE_PRIORITY");
+    { const char* ge = getenv("H264R_SIDE_GATE"); ctx->side_gate = ge && atoi(ge) != 0; }
+    const bool side_low = sp_env && strcmp(sp_env, "low") == 0;
+    if (e == cudaSuccess) {
+        // the streams created above have the default priority: replace them
         cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->s_side);
         e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->s_side, cudaStreamNonBlocking, prio_mid);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->s_side, cudaStreamNonBlocking, side_low ? prio_lo : prio_hi);
     }
     ctx->g_main[0] = ctx->stream; ctx->g_side[0] = ctx->s_side;
     for (int gi = 0; gi < ctx->num_groups && e == cudaSuccess; ++gi) {
         if (gi > 0) {
-            e = cudaStreamCreateWithPriority(&ctx->g_main[gi], cudaStreamNonBlocking, prio_lo);
-            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->g_side[gi], cudaStreamNonBlocking, prio_lo);
+            const int main_prio = ctx->group_policy == 1 ? (prio_hi < prio_lo ? prio_hi + 1 : prio_lo) : prio_hi;
+            e = cudaStreamCreateWithPriority(&ctx->g_main[gi], cudaStreamNonBlocking, main_prio);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->g_side[gi], cudaStreamNonBlocking, side_low ? prio_lo : main_prio);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->g_tail[gi], cudaEventDisableTiming);
     }
@@ -683,6 +700,7 @@ int h264r_flush(h264r_ctx* ctx)
 
     // ---- per record: what to copy, what to launch, which records of other groups to follow ----
     ctx->events_used = 0;
+    for (int gi = 0; gi < kMaxGroups; ++gi) ctx->gate[gi] = nullptr;   // the pool's events get new roles
     ctx->cross_group = false;
     for (size_t r = 0; r + 1 < rec_begin.size(); ++r) {
         const int b = rec_begin[r], e = rec_begin[r + 1];
@@ -692,8 +710,8 @@ int h264r_flush(h264r_ctx* ctx)
         L.pics = d_table + b; L.num_pics = e - b; L.tickets = ctx->d_sync + ctx->sync_ints_per_group * rec.group; L.geom = ctx->geom;
         L.direct8x8 = ctx->seq.direct_8x8_inference_flag;
         L.any_inter = L.any_intra = L.any_deblock = L.any_intra_rows = L.max_intra_sparse = 0; L.epoch = 0;
-        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx); rec.ev_side = take_event(ctx);
-        if (!rec.ev_h2d || !rec.ev_done || !rec.ev_side) return H264R_ERR_CUDA;
+        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx); rec.ev_side = take_event(ctx); rec.ev_inter = take_event(ctx);
+        if (!rec.ev_h2d || !rec.ev_done || !rec.ev_side || !rec.ev_inter) return H264R_ERR_CUDA;
         auto follow = [&](cudaEvent_t ev, int grp) {
             if (!ev || grp == rec.group) return;
             if (std::find(rec.deps.begin(), rec.deps.end(), ev) == rec.deps.end()) rec.deps.push_back(ev);

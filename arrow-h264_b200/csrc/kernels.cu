@@ -26,7 +26,7 @@ constexpr int kWarpsPerCta = 4;
 #define H264R_INTRA_CTAS 4
 #endif
 #ifndef H264R_DEBLOCK_CTAS
-#define H264R_DEBLOCK_CTAS 6
+#define H264R_DEBLOCK_CTAS 4
 #endif
 
 // ---------------------------------------------------------------------------------------------------
