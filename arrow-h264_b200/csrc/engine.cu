@@ -822,6 +822,32 @@ int h264r_frame_download_async(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_
     return H264R_OK;
 }
 
+int h264r_frame_download_cropped(h264r_ctx* ctx, h264r_frame f, int crop_left, int crop_right, int crop_top, int crop_bottom,
+                                 uint8_t* y, uint8_t* cb, uint8_t* cr, int pitch_y, int pitch_c)
+{
+    if (!ctx || f < 0 || f >= (int)ctx->frames.size() || !ctx->frames[f].dev || !y || !cb || !cr) return H264R_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    const FrameGeom& g = ctx->geom;
+    const int W = g.width_mbs * 16, H = g.height_mbs * 16;
+    if (crop_left < 0 || crop_right < 0 || crop_top < 0 || crop_bottom < 0 || ((crop_left | crop_right | crop_top | crop_bottom) & 1) ||
+        crop_left + crop_right >= W || crop_top + crop_bottom >= H) return H264R_ERR_INVALID;
+    const int w = W - crop_left - crop_right, h = H - crop_top - crop_bottom;
+    if (pitch_y < w || pitch_c < w / 2) return H264R_ERR_INVALID;
+    Frame& fr = ctx->frames[f];
+    const uint8_t* d = fr.dev;
+    if (fr.ready) CU(cudaStreamWaitEvent(ctx->s_d2h, fr.ready, 0));
+    CU(cudaMemcpy2DAsync(y, pitch_y, d + (size_t)crop_top * g.pitch_y + crop_left, g.pitch_y, w, h, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    const size_t coff = (size_t)(crop_top / 2) * g.pitch_c + crop_left / 2;
+    CU(cudaMemcpy2DAsync(cb, pitch_c, d + g.off_cb + coff, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU(cudaMemcpy2DAsync(cr, pitch_c, d + g.off_cr + coff, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    if (!fr.read_done) CU(cudaEventCreateWithFlags(&fr.read_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(fr.read_done, ctx->s_d2h));
+    fr.pending_read = true;
+    CU(cudaStreamSynchronize(ctx->s_d2h));
+    ctx->stats.d2h_bytes += (uint64_t)w * h * 3 / 2;
+    return H264R_OK;
+}
+
 int h264r_frame_download(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb, uint8_t* cr, int pitch_y, int pitch_c)
 {
     if (!ctx || f < 0 || f >= (int)ctx->frames.size() || !ctx->frames[f].dev || !y || !cb || !cr) return H264R_ERR_INVALID;

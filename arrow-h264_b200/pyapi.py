@@ -120,6 +120,8 @@ def recon_lib():
         L.h264r_frame_upload.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.h264r_replay_last_flush.argtypes = [P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.h264r_frame_download_async.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.h264r_frame_download_cropped.argtypes = [P, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_int, C.c_int]
         L.h264r_host_alloc.restype = C.c_void_p
         L.h264r_host_alloc.argtypes = [C.c_size_t]
         L.h264r_host_free.argtypes = [C.c_void_p]
@@ -248,6 +250,16 @@ class Engine:
         cb = (C.c_uint8 * (self.w * self.h // 4))()
         cr = (C.c_uint8 * (self.w * self.h // 4))()
         self._check(self.L.h264r_frame_download(self.ctx, f, y, cb, cr, self.w, self.w // 2), "h264r_frame_download")
+        return bytes(y), bytes(cb), bytes(cr)
+
+    def download_cropped(self, f, left, right, top, bottom):
+        """The display rectangle (frame cropping offsets in luma samples); does not wait for pictures queued behind `f`."""
+        w, h = self.w - left - right, self.h - top - bottom
+        y = (C.c_uint8 * (w * h))()
+        cb = (C.c_uint8 * (w * h // 4))()
+        cr = (C.c_uint8 * (w * h // 4))()
+        self._check(self.L.h264r_frame_download_cropped(self.ctx, f, left, right, top, bottom, y, cb, cr, w, w // 2),
+                    "h264r_frame_download_cropped")
         return bytes(y), bytes(cb), bytes(cr)
 
     def upload(self, f, y, cb, cr):

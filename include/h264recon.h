@@ -208,6 +208,11 @@ int  h264r_frame_upload(h264r_ctx* ctx, h264r_frame f, const uint8_t* y, const u
  * stream, overlapping later waves; destination should be pinned (h264r_host_alloc).  h264r_wait(ctx, -1) joins. */
 int  h264r_frame_download_async(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb, uint8_t* cr,
                                 int pitch_y, int pitch_c);
+/* The display rectangle of a frame (frame_cropping of the SPS; offsets in luma samples, even for 4:2:0), ordered
+ * after the wave that produces `f` only -- pictures queued behind it keep running.  Blocks until the copy is done.
+ * replaces: img2buf with crop_left/right/top/bottom in write_out_picture (framebuf/output.cc:30-104, 147-187)   */
+int  h264r_frame_download_cropped(h264r_ctx* ctx, h264r_frame f, int crop_left, int crop_right, int crop_top,
+                                  int crop_bottom, uint8_t* y, uint8_t* cb, uint8_t* cr, int pitch_y, int pitch_c);
 /* pinned host memory for download destinations */
 void* h264r_host_alloc(size_t bytes);
 void  h264r_host_free(void* p);

@@ -8,10 +8,12 @@
 // sample is produced by the CUDA engine.  tests/test_integration_gpu.py decodes a bitstream with it and with the
 // unmodified reference decoder and requires byte-identical output.
 //
-// Stage 1 of SURVEY.md 8f: every picture is downloaded into storable_picture::imgY/imgUV right after its
-// reconstruction (synchronously), so the reference's DPB and output code keep working unmodified.  Reference pictures
-// additionally stay on the GPU (one engine frame per storable_picture) -- motion compensation never reads the host
-// copies.  A device-resident DPB with deferred downloads is stage 2.
+// Stage 2 of SURVEY.md 8f: the DPB is device resident.  Every storable_picture owns one engine frame; nothing is
+// copied into storable_picture::imgY/imgUV (the reference still allocates and pads them, nobody reads them: motion
+// compensation runs on the GPU, output goes through output_gpu.cc, which replaces framebuf/output.cc and downloads the
+// cropped display rectangle when the DPB releases a picture).  deblock_filter() returns as soon as the picture is
+// queued, so parsing picture N+1 overlaps the reconstruction of picture N.  Host-side readers of imgY that remain in
+// the reference (error concealment, PSNR against a reference YUV) are outside the supported subset.
 #include "global.h"
 #include "dpb.h"
 #include "slice.h"
@@ -57,7 +59,6 @@ struct GpuState {
     h264r_pic_buffers bufs;
     h264r::Decoder facade;
     bool any_deblock = false;
-    std::vector<uint8_t> y, cb, cr;                                       // download staging (uint8 -> px_t)
 } g;
 
 const int kMaxGpuFrames = 40;        // > 16 DPB frames + the current picture + headroom; table limit is H264R_MAX_REFS live entries
@@ -73,11 +74,10 @@ void open_engine(const sps_t& sps)
     memset(&sp, 0, sizeof(sp));
     sp.width_mbs = W; sp.height_mbs = H;
     sp.direct_8x8_inference_flag = sps.direct_8x8_inference_flag;
-    sp.max_frames = kMaxGpuFrames; sp.max_pictures_in_flight = 2; sp.max_slices_per_picture = 64;
+    sp.max_frames = kMaxGpuFrames; sp.max_pictures_in_flight = 4; sp.max_slices_per_picture = 64;   // 4 staging slots: up to three pictures reconstruct while the next is parsed
     sp.max_levels_per_picture = 0;
     check(h264r_create(&g.ctx, 0, &sp), "h264r_create");
     g.width_mbs = W; g.height_mbs = H;
-    g.y.resize((size_t)W * H * 256); g.cb.resize((size_t)W * H * 64); g.cr.resize((size_t)W * H * 64);
 }
 
 // engine frame of a decoded picture; every use refreshes its age
@@ -348,17 +348,15 @@ void Decoder::deblock_filter(slice_t& slice)
     check(h264r_picture_update(g.ctx, &g.pp), "h264r_picture_update");
     check(h264r_picture_submit(g.ctx, g.facade.num_levels()), "h264r_picture_submit");
     check(h264r_flush(g.ctx), "h264r_flush");
-    const h264r_frame f = frame_of(pic);
-    const int w = g.width_mbs * 16, h = g.height_mbs * 16;
-    check(h264r_frame_download(g.ctx, f, g.y.data(), g.cb.data(), g.cr.data(), w, w / 2), "h264r_frame_download");
-    for (int j = 0; j < h; ++j) for (int i = 0; i < w; ++i) pic->imgY[j][i] = g.y[(size_t)j * w + i];
-    for (int j = 0; j < h / 2; ++j)
-        for (int i = 0; i < w / 2; ++i) {
-            pic->imgUV[0][j][i] = g.cb[(size_t)j * (w / 2) + i];
-            pic->imgUV[1][j][i] = g.cr[(size_t)j * (w / 2) + i];
-        }
+    // Nothing is copied back here: the picture stays in HBM (motion compensation of later pictures reads it there) and
+    // reaches the host when the DPB outputs it (output_gpu.cc).  The call returns while the kernels run, so the parsing
+    // of the next picture overlaps this one's reconstruction.
     g.cur = nullptr;
 }
+
+// for output_gpu.cc
+h264r_ctx* gpu_engine() { return g.ctx; }
+h264r_frame gpu_frame_of_picture(const storable_picture* p) { return frame_of(p); }
 
 void Decoder::get_block_luma(storable_picture*, int, int, int, int, px_t[16][16], int, mb_t&)
 {

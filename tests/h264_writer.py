@@ -89,8 +89,9 @@ class Stream:
     LOG2_MAX_FRAME_NUM = 4
     LOG2_MAX_POC_LSB = 6
 
-    def __init__(self, width_mbs, height_mbs, seed=1, num_refs=2):
+    def __init__(self, width_mbs, height_mbs, seed=1, num_refs=2, crop=None):
         self.W, self.H = width_mbs, height_mbs
+        self.crop = crop                 # (left, right, top, bottom) in frame_crop_*_offset units (2 luma samples), or None
         self.rng = random.Random(seed)
         self.num_refs = num_refs
         self.out = bytearray()
@@ -116,7 +117,12 @@ class Stream:
         w.ue(self.H - 1)
         w.u(1, 1)                        # frame_mbs_only_flag
         w.u(1, 1)                        # direct_8x8_inference_flag
-        w.u(1, 0)                        # frame_cropping_flag
+        if self.crop:
+            w.u(1, 1)                    # frame_cropping_flag
+            for v in self.crop:
+                w.ue(v)                  # frame_crop_left/right/top/bottom_offset
+        else:
+            w.u(1, 0)                    # frame_cropping_flag
         w.u(1, 0)                        # vui_parameters_present_flag
         w.trailing()
         self.out += nal(3, 7, w.payload())
@@ -349,9 +355,9 @@ class Stream:
         return bytes(self.out)
 
 
-def make_stream(width_mbs=11, height_mbs=9, frames=8, seed=7):
-    """IDR + P pictures with every deblocking mode and a second IDR in the middle."""
-    s = Stream(width_mbs, height_mbs, seed)
+def make_stream(width_mbs=11, height_mbs=9, frames=8, seed=7, crop=None):
+    """IDR + P pictures with every deblocking mode and a second IDR in the middle; `crop` = SPS frame cropping offsets."""
+    s = Stream(width_mbs, height_mbs, seed, crop=crop)
     for i in range(frames):
         idr = i == 0 or i == frames // 2 + 1
         idc = (0, 0, 2, 1)[i % 4]

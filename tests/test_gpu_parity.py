@@ -200,3 +200,33 @@ def test_gpu_4k_wavefront_stress():
     got = run_stream_gpu(eng, cfg, sidx, 0, 0, n, flush_every=nfr)
     eng.close()
     assert got == want
+
+
+def test_cropped_download_is_the_display_rectangle():
+    """h264r_frame_download_cropped (the write_out_picture replacement, output.cc:147-187) against slices of the full
+    planes, without an intervening h264r_wait: the copy must order itself behind the picture's own wave."""
+    cfg, sidx, w, h, n = 3, 1, 24, 14, 4
+    st = pyapi.SynthStream(cfg, sidx, w, h, n)
+    eng = pyapi.Engine(st.seq, max_frames=n + 1, max_pictures=n)
+    frames, order = {}, []
+    for pic in st:
+        dst = eng.frame_alloc()
+        frames[pic.info.pic_index] = dst
+        eng.submit(pic, dst, [frames[pic.info.ref_pic_index[i]] for i in range(pic.info.num_refs)])
+        order.append(dst)
+    st.close()
+    eng.flush()
+    W, H = w * 16, h * 16
+    crops = [(0, 0, 0, 8), (2, 6, 4, 10), (16, 0, 0, 2), (0, 0, 0, 0)]
+    got = [eng.download_cropped(f, *crops[i % len(crops)]) for i, f in enumerate(order)]     # no wait before
+    eng.wait()
+    for i, f in enumerate(order):
+        l, r, t, b = crops[i % len(crops)]
+        y, cb, cr = eng.download(f)
+        want_y = b"".join(y[j * W + l:j * W + W - r] for j in range(t, H - b))
+        want_cb = b"".join(cb[j * (W // 2) + l // 2:j * (W // 2) + (W - r) // 2] for j in range(t // 2, (H - b) // 2))
+        want_cr = b"".join(cr[j * (W // 2) + l // 2:j * (W // 2) + (W - r) // 2] for j in range(t // 2, (H - b) // 2))
+        assert got[i] == (want_y, want_cb, want_cr), f"picture {i} crop {crops[i % len(crops)]}"
+    with pytest.raises(pyapi.EngineError):
+        eng.download_cropped(order[0], 1, 0, 0, 0)          # odd offsets do not exist in 4:2:0
+    eng.close()

@@ -18,6 +18,8 @@ REF = os.path.join(ROOT, "integration", "_build", "ldecod_ref")
 GPU = os.path.join(ROOT, "integration", "_build", "ldecod_gpu")
 
 CASES = [(11, 9, 8, 7), (5, 4, 10, 3), (20, 15, 6, 11), (1, 1, 4, 5), (3, 7, 7, 9)]
+# (width_mbs, height_mbs, frames, seed, frame cropping offsets left/right/top/bottom in units of two luma samples)
+CROP_CASES = [(8, 5, 6, 21, (0, 0, 0, 4)), (6, 6, 5, 22, (1, 3, 2, 5)), (120, 68, 3, 23, (0, 0, 0, 4))]
 
 
 def decode(binary, stream, workdir, name):
@@ -56,3 +58,19 @@ def test_reference_decoder_on_the_gpu_engine_is_bit_exact(tmp_path, w, h, frames
             plane = "Y" if k < w * h * 256 else ("Cb" if k < w * h * 320 else "Cr")
             pytest.fail(f"output frame {i}: first difference in plane {plane} at byte {k} (reference {a[k]}, gpu {b[k]})")
     assert hashlib.md5(got).hexdigest() == hashlib.md5(want).hexdigest()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU)), reason="integration/_build binaries not built")
+@pytest.mark.parametrize("w,h,frames,seed,crop", CROP_CASES)
+def test_cropped_output_comes_straight_from_the_device_frames(tmp_path, w, h, frames, seed, crop):
+    """with the device-resident DPB the only device->host copy is the display rectangle taken when the
+    DPB outputs a picture (integration/output_gpu.cc in place of framebuf/output.cc).  Streams with SPS frame cropping
+    (the last one is 1920x1088 coded, 1920x1080 displayed) must come out byte-identical to the reference decoder's."""
+    stream = h264_writer.make_stream(w, h, frames, seed, crop=crop)
+    want, log = decode(REF, stream, str(tmp_path), "ref")
+    cw, ch = w * 16 - 2 * (crop[0] + crop[1]), h * 16 - 2 * (crop[2] + crop[3])
+    assert len(want) == frames * cw * ch * 3 // 2, log[-1500:]
+    got, log = decode(GPU, stream, str(tmp_path), "gpu")
+    assert len(got) == len(want), log[-1500:]
+    assert got == want
