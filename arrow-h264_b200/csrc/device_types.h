@@ -28,7 +28,6 @@ struct DeblockDesc {
 
 struct DevPicture {
     const h264r_mb*        mbs;
-    h264r_mb_motion*       motion;                    // [nmb], device only: expanded by motion_expand_kernel
     const uint8_t*         packed_motion;             // 12-byte entries (engine.cu pack_motion), indexed by h264r_mb::reserved2
     const h264r_slice*     slices;
     const h264r_level*     levels;
@@ -58,7 +57,7 @@ struct WaveLaunch {
     uint32_t epoch;                  // stamp of this launch sequence for DevPicture::mb_done
 };
 
-// Kernel launchers of one wave (kernels.cu).  which: 0 motion expansion + residual (parallel), 1 inter (parallel), 2 intra wavefront,
+// Kernel launchers of one wave (kernels.cu).  which: 0 residual (parallel), 1 inter (parallel), 2 intra wavefront,
 // 3 deblock descriptors (parallel), 4 deblock wavefront.  Returns the number of kernels launched (0 when the wave has no work of that kind).
 enum { KERNEL_RESID = 0, KERNEL_INTER = 1, KERNEL_INTRA = 2, KERNEL_DBPREP = 3, KERNEL_DEBLOCK = 4, KERNEL_KINDS = 5 };
 int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);

@@ -40,7 +40,6 @@ struct Slot {
     uint8_t* dev = nullptr;
     DeblockDesc* dev_desc = nullptr;          // device only: output of the deblock pre-pass
     int16_t* dev_resid = nullptr;             // device only: residual plane [nmb][384]
-    h264r_mb_motion* dev_motion = nullptr;    // device only: motion expanded from the packed form (motion_expand_kernel)
     uint8_t* host_motion = nullptr;           // pinned, host only: the full per-MB motion array the parser side fills
     uint32_t motion_entries = 0;              // packed 12-byte motion entries behind the level list
     uint32_t intra_count = 0;                 // intra-MB address list behind the packed motion (mixed pictures only)
@@ -255,8 +254,11 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         // Throughput-bound side kernels are scheduled underneath the latency-bound wavefront kernels (intra, deblock) of
         // the wave before, not against its inter kernel: they start when that inter kernel has finished.
         if (!time_kernels && ctx->side_gate && ctx->gate[rec.group]) CU(cudaStreamWaitEvent(side, ctx->gate[rec.group], 0));
+        static const bool skip_side = getenv("H264R_EXPERIMENT_SKIP_SIDE") != nullptr;   // timing experiment only: wrong output
+        if (!skip_side || time_kernels || h2d) {
         { const int rc = launch(rec, KERNEL_RESID, side); if (rc != H264R_OK) return rc; }
         { const int rc = launch(rec, KERNEL_DBPREP, side); if (rc != H264R_OK) return rc; }
+        }
         if (!time_kernels) {
             CU(cudaEventRecord(rec.ev_side, side));
             CU(cudaStreamWaitEvent(main, rec.ev_side, 0));
@@ -361,7 +363,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     ctx->slots.resize(sp->max_pictures_in_flight);
     // one pinned and one device arena for all staging slots
     uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr; int16_t* d_resid = nullptr;
-    uint8_t* h_motion = nullptr; h264r_mb_motion* d_motion = nullptr; uint32_t* d_done = nullptr; uint64_t* d_mbox = nullptr;
+    uint8_t* h_motion = nullptr; uint32_t* d_done = nullptr; uint64_t* d_mbox = nullptr;
     const size_t mbox_words = (size_t)24 * ctx->nmb;
     const size_t motion_bytes = sizeof(h264r_mb_motion) * (size_t)ctx->nmb;
     const size_t arena = ctx->slot_bytes * sp->max_pictures_in_flight;
@@ -370,7 +372,6 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_desc, sizeof(DeblockDesc) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_resid, sizeof(int16_t) * H264R_COEFFS_PER_MB * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&h_motion, motion_bytes * sp->max_pictures_in_flight, cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_motion, motion_bytes * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_done, sizeof(uint32_t) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaMemset(d_done, 0, sizeof(uint32_t) * (size_t)ctx->nmb * sp->max_pictures_in_flight);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_mbox, sizeof(uint64_t) * mbox_words * sp->max_pictures_in_flight);
@@ -430,7 +431,6 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         if (d_desc) cudaFree(d_desc);
         if (d_resid) cudaFree(d_resid);
         if (h_motion) cudaFreeHost(h_motion);
-        if (d_motion) cudaFree(d_motion);
         if (d_done) cudaFree(d_done);
         if (d_mbox) cudaFree(d_mbox);
         if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
@@ -446,7 +446,6 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         ctx->slots[i].dev_desc = d_desc + (size_t)ctx->nmb * i;
         ctx->slots[i].dev_resid = d_resid + (size_t)H264R_COEFFS_PER_MB * ctx->nmb * i;
         ctx->slots[i].host_motion = h_motion + motion_bytes * i;
-        ctx->slots[i].dev_motion = d_motion + (size_t)ctx->nmb * i;
         ctx->slots[i].dev_mb_done = d_done + (size_t)ctx->nmb * i;
         ctx->slots[i].dev_mbox = d_mbox + mbox_words * i;
     }
@@ -466,7 +465,7 @@ void h264r_destroy(h264r_ctx* ctx)
     }
     for (Frame& f : ctx->frames) { if (f.dev) cudaFree(f.dev); if (f.read_done) cudaEventDestroy(f.read_done); }
     if (!ctx->slots.empty()) { cudaFreeHost(ctx->slots[0].host); cudaFree(ctx->slots[0].dev); cudaFree(ctx->slots[0].dev_desc); cudaFree(ctx->slots[0].dev_resid);
-                                cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_motion); cudaFree(ctx->slots[0].dev_mb_done); cudaFree(ctx->slots[0].dev_mbox); }
+                                cudaFreeHost(ctx->slots[0].host_motion); cudaFree(ctx->slots[0].dev_mb_done); cudaFree(ctx->slots[0].dev_mbox); }
     cudaFreeHost(ctx->h_pics); cudaFree(ctx->d_pics); cudaFree(ctx->d_sync);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 2; ++i) if (ctx->table_ev[i]) cudaEventDestroy(ctx->table_ev[i]);
@@ -553,8 +552,8 @@ int h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels)
     h264r_mb* mbs = reinterpret_cast<h264r_mb*>(sl.host + ctx->off_mbs);
     // The per-MB motion (192 bytes, the 16 pic_motion_params the parser side filled) crosses PCIe in packed form: only
     // the distinct entries of an MB (1 when all 16 blocks agree, 2 for halves, 4 for quadrants, else 16), 12 bytes each,
-    // right behind the level list.  reserved2 of the header = first entry << 4 | code; motion_expand_kernel restores
-    // the full array in HBM.  Intra MBs send nothing (their motion is never read).
+    // right behind the level list.  reserved2 of the header = first entry << 4 | code; the kernels read the packed
+    // entries directly (kernels.cu packed_entry).  Intra MBs send nothing (their motion is never read).
     const h264r_mb_motion* motion = reinterpret_cast<const h264r_mb_motion*>(sl.host_motion);
     uint8_t* const packed = sl.host + ctx->off_levels + sizeof(h264r_level) * (size_t)num_levels;
     uint32_t entries = 0;
@@ -679,7 +678,6 @@ int h264r_flush(h264r_ctx* ctx)
             DevPicture& p = h_table[k];
             memset(&p, 0, sizeof(p));
             p.mbs = reinterpret_cast<const h264r_mb*>(s.dev + ctx->off_mbs);
-            p.motion = s.dev_motion;
             p.packed_motion = s.dev + ctx->off_levels + sizeof(h264r_level) * (size_t)s.used_levels;
             p.intra_list = reinterpret_cast<const uint32_t*>(p.packed_motion + (size_t)12 * s.motion_entries);
             p.intra_count = (int)s.intra_count;

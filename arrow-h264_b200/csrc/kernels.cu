@@ -59,6 +59,7 @@ __device__ __forceinline__ void st_release(int* p, int v)
 struct MbHdr {
     int mb_type, flags, slice_idx, cbp_luma, cbp_chroma, qp_y, qp_c[2], i16mode, cmode, cbp_blks;
     uint32_t coeff_offset, u0, u1;        // u0/u1: the 8-byte union (intra modes | sub_mb_type, sub_mb_pred_mode)
+    uint32_t packed;                      // inter MBs: first packed motion entry << 4 | layout code (engine.cu pack_motion)
     int coeff_count;
     __device__ __forceinline__ bool intra() const { return flags & H264R_MB_FLAG_INTRA; }
     __device__ __forceinline__ bool t8() const { return flags & H264R_MB_FLAG_T8x8; }
@@ -76,13 +77,27 @@ __device__ __forceinline__ MbHdr load_hdr(const h264r_mb* mbs, int addr)
     h.qp_y = (int)(int8_t)(a.y >> 16); h.qp_c[0] = (int)(int8_t)(a.y >> 24);
     h.qp_c[1] = (int)(int8_t)(a.z & 0xFF); h.i16mode = (a.z >> 8) & 0xFF; h.cmode = (a.z >> 16) & 0xFF;
     h.cbp_blks = a.w & 0xFFFF; h.coeff_count = a.w >> 16;
-    h.coeff_offset = b.x; h.u0 = b.y; h.u1 = b.z;
+    h.coeff_offset = b.x; h.u0 = b.y; h.u1 = b.z; h.packed = b.w;
     return h;
 }
 // first word only: mb_type | flags << 8 | slice_idx << 16
 __device__ __forceinline__ uint32_t load_hdr_word0(const h264r_mb* mbs, int addr)
 {
     return __ldg(reinterpret_cast<const unsigned int*>(mbs + addr));
+}
+
+// Packed motion (engine.cu pack_motion): the distinct motion entries of an MB, 12 bytes each = mv[0], mv[1] (int16 x, y),
+// ref_idx[0], ref_idx[1], ref_pic[0], ref_pic[1].  Layout code 1: one entry | 2: rows 0-1 / rows 2-3 | 3: columns 0-1 /
+// columns 2-3 | 4: quadrants | 5: all sixteen 4x4 blocks.  Returns the three words of the entry that covers block b.
+__device__ __forceinline__ int packed_entry_index(uint32_t packed, int b)
+{
+    const int code = packed & 15, row2 = b >> 3, col2 = (b >> 1) & 1;
+    const int within = code == 5 ? b : ((code == 2 || code == 4) ? row2 << (code == 4) : 0) + ((code == 3 || code == 4) ? col2 : 0);
+    return (int)(packed >> 4) + within;
+}
+__device__ __forceinline__ const uint32_t* packed_entry(const uint8_t* packed_motion, uint32_t packed, int b)
+{
+    return reinterpret_cast<const uint32_t*>(packed_motion) + (size_t)packed_entry_index(packed, b) * 3;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -139,15 +154,14 @@ __device__ __forceinline__ void idct8_1d(int* p, int stride, bool final_pass)
 struct __align__(16) ResidSmem { int cof[384]; unsigned nz; };
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-residual_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g)
+residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 {
     __shared__ __align__(16) ResidSmem smem_all[kWarpsPerCta];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nmb = g.width_mbs * g.height_mbs;
-    const long long gw = (long long)blockIdx.x * kWarpsPerCta + warp;
-    if (gw >= (long long)num_pics * nmb) return;
-    const int pic_i = (int)(gw / nmb), addr = (int)(gw - (long long)pic_i * nmb);
-    const DevPicture& pic = pics[pic_i];
+    const int addr = blockIdx.x * kWarpsPerCta + warp;     // grid = (ceil(nmb / 4), 1, pictures): no index divisions
+    if (addr >= nmb) return;
+    const DevPicture& pic = pics[blockIdx.z];
     const MbHdr h = load_hdr(pic.mbs, addr);
     if (!h.has_resid()) return;
     ResidSmem& sm = smem_all[warp];
@@ -254,14 +268,17 @@ residual_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g)
     }
     __syncwarp();
 
-    // 384 x int16 = 48 x 16 B
+    // 384 x int16 = 48 x 16 B; saturating pack to int16 pairs, then the [-255, 255] clamp on both halves at once
     uint4* out = reinterpret_cast<uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
     for (int v = lane; v < 48; v += 32) {
         const int* r = res + v * 8;
         uint32_t w[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            w[k] = (uint32_t)(uint16_t)(int16_t)clip3i(-255, 255, r[2 * k]) | (uint32_t)(uint16_t)(int16_t)clip3i(-255, 255, r[2 * k + 1]) << 16;
+        for (int k = 0; k < 4; ++k) {
+            uint32_t pr;
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(pr) : "r"(r[2 * k + 1]), "r"(r[2 * k]));
+            w[k] = __vmaxs2(__vmins2(pr, 0x00FF00FFu), 0xFF01FF01u);
+        }
         out[v] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
@@ -339,7 +356,13 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
     const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
     const int wY = g.width_mbs * 16, hY = g.height_mbs * 16, wC = wY >> 1, hC = hY >> 1;
 
-    if (lane < 12) reinterpret_cast<uint4*>(&sm.motion)[lane] = __ldg(reinterpret_cast<const uint4*>(pic.motion + addr) + lane);
+    if (lane < 16) {                                     // the MB's sixteen motion entries, from the packed form
+        const uint32_t* e = packed_entry(pic.packed_motion, h.packed, lane);
+        const uint32_t m0 = __ldg(e), m1 = __ldg(e + 1), m2 = __ldg(e + 2);
+        *reinterpret_cast<uint32_t*>(sm.motion.mv[0][lane]) = m0;
+        *reinterpret_cast<uint32_t*>(sm.motion.mv[1][lane]) = m1;
+        sm.motion.ref_idx[0][lane] = (int8_t)(m2 & 0xFF); sm.motion.ref_idx[1][lane] = (int8_t)((m2 >> 8) & 0xFF);
+    }
     // slice-level parameters (one 12-byte read, broadcast)
     const uint32_t s0 = __ldg(reinterpret_cast<const uint32_t*>(sl)), s1 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 1),
                    s2 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 2);
@@ -1039,29 +1062,30 @@ __constant__ uint8_t c_tc0[52][3] = {
 
 // ---- pass 1 (fully parallel): per-MB deblock descriptor = boundary strengths + filter thresholds ----
 
-__device__ __forceinline__ int mv_differs(const h264r_mb_motion* a, int ba, int la, const h264r_mb_motion* b, int bb, int lb)
+// |mv_x| or |mv_y| differ by four quarter samples or more (mvlimit 4, frame pictures); a, b = packed int16 pairs
+__device__ __forceinline__ int mv_differs(uint32_t a, uint32_t b)
 {
-    const int ax = __ldg(&a->mv[la][ba][0]), ay = __ldg(&a->mv[la][ba][1]);
-    const int bx = __ldg(&b->mv[lb][bb][0]), by = __ldg(&b->mv[lb][bb][1]);
-    return (abs(ax - bx) >= 4) | (abs(ay - by) >= 4);
+    const int dx = (int)(int16_t)(a & 0xFFFF) - (int)(int16_t)(b & 0xFFFF), dy = (int)(int16_t)(a >> 16) - (int)(int16_t)(b >> 16);
+    return (abs(dx) >= 4) | (abs(dy) >= 4);
 }
-// bs_compare_mvs, deblock.cc:35-75
-__device__ __forceinline__ int bs_compare(const h264r_mb_motion* mp, int bp, const h264r_mb_motion* mq, int bq)
+// bs_compare_mvs, deblock.cc:35-75, on two packed motion entries (words: mv[0], mv[1], ref_idx[0..1] | ref_pic[0..1] << 16)
+__device__ __forceinline__ int bs_compare(const uint32_t* ep, const uint32_t* eq)
 {
-    const int p0 = (int8_t)__ldg(&mp->ref_pic[0][bp]), p1 = (int8_t)__ldg(&mp->ref_pic[1][bp]);
-    const int q0 = (int8_t)__ldg(&mq->ref_pic[0][bq]), q1 = (int8_t)__ldg(&mq->ref_pic[1][bq]);
+    if (ep == eq) return 0;                                // the same entry: same pictures, same vectors
+    const uint32_t rp = __ldg(ep + 2), rq = __ldg(eq + 2);
+    const int p0 = (int8_t)(rp >> 16), p1 = (int8_t)(rp >> 24), q0 = (int8_t)(rq >> 16), q1 = (int8_t)(rq >> 24);
     if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;
+    const uint32_t mp0 = __ldg(ep), mp1 = __ldg(ep + 1), mq0 = __ldg(eq), mq1 = __ldg(eq + 1);
     if (p0 != p1) {
-        if (p0 == q0) return mv_differs(mp, bp, 0, mq, bq, 0) | mv_differs(mp, bp, 1, mq, bq, 1);
-        return mv_differs(mp, bp, 0, mq, bq, 1) | mv_differs(mp, bp, 1, mq, bq, 0);
+        if (p0 == q0) return mv_differs(mp0, mq0) | mv_differs(mp1, mq1);
+        return mv_differs(mp0, mq1) | mv_differs(mp1, mq0);
     }
-    return (mv_differs(mp, bp, 0, mq, bq, 0) | mv_differs(mp, bp, 1, mq, bq, 1)) &
-           (mv_differs(mp, bp, 0, mq, bq, 1) | mv_differs(mp, bp, 1, mq, bq, 0));
+    return (mv_differs(mp0, mq0) | mv_differs(mp1, mq1)) & (mv_differs(mp0, mq1) | mv_differs(mp1, mq0));
 }
 
 // Deblock::strength (deblock.cc:78-289) + the qPav/indexA/indexB/alpha/beta/tc0 part of filter_edge (deblock.cc:469-474,
 // tables :294-324).  One THREAD per MB (the work is scalar: 32 strengths and 9 threshold sets out of three MB headers).
-struct HdrLite { int mb_type, flags, slice_idx, qp_y, qp_c[2], cbp_blks; };
+struct HdrLite { int mb_type, flags, slice_idx, qp_y, qp_c[2], cbp_blks; uint32_t packed; };
 __device__ __forceinline__ HdrLite load_hdr_lite(const h264r_mb* mbs, int addr)
 {
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(mbs + addr));
@@ -1069,6 +1093,7 @@ __device__ __forceinline__ HdrLite load_hdr_lite(const h264r_mb* mbs, int addr)
     h.mb_type = a.x & 0xFF; h.flags = (a.x >> 8) & 0xFF; h.slice_idx = a.x >> 16;
     h.qp_y = (int)(int8_t)(a.y >> 16); h.qp_c[0] = (int)(int8_t)(a.y >> 24); h.qp_c[1] = (int)(int8_t)(a.z & 0xFF);
     h.cbp_blks = a.w & 0xFFFF;
+    h.packed = (h.flags & H264R_MB_FLAG_INTRA) ? 0u : __ldg(reinterpret_cast<const unsigned int*>(mbs + addr) + 7);
     return h;
 }
 
@@ -1110,7 +1135,6 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
             const bool p_intra = e ? q_intra : (PN.flags & H264R_MB_FLAG_INTRA) != 0;
             if (p_intra || q_intra) { bs[wi] |= (e == 0 ? 0x4444u : 0x3333u) << sh; continue; }
             const int pcbp = e ? Q.cbp_blks : PN.cbp_blks;
-            const int pidx = e ? q : pn_idx;
             const bool same_part = e > 0 && (Q.mb_type == 1 || Q.mb_type == (dir == 0 ? 2 : 3));
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
@@ -1118,7 +1142,8 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
                 const int blkP = dir == 0 ? k4 * 4 + (e ? e - 1 : 3) : (e ? e - 1 : 3) * 4 + k4;
                 uint32_t v = 0;
                 if (((Q.cbp_blks >> blkQ) & 1) || ((pcbp >> blkP) & 1)) v = 2;
-                else if (!same_part && bs_compare(pic.motion + pidx, blkP, pic.motion + q, blkQ)) v = 1;
+                else if (!same_part && bs_compare(packed_entry(pic.packed_motion, e ? Q.packed : PN.packed, blkP),
+                                                   packed_entry(pic.packed_motion, Q.packed, blkQ))) v = 1;
                 bs[wi] |= v << (sh + k4 * 4);
             }
         }
@@ -1435,63 +1460,14 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
 
 // ---------------------------------------------------------------------------------------------------
 
-// Restores the full per-MB motion array (h264r_mb_motion, what the parser side filled) from the packed entries that
-// crossed PCIe (engine.cu pack_motion).  One thread per 16-byte chunk of an MB's 192 bytes.
-__global__ void __launch_bounds__(256)
-motion_expand_kernel(const DevPicture* __restrict__ pics, int num_pics, int nmb)
-{
-    const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long per_pic = (long long)nmb * 12;
-    if (gi >= (long long)num_pics * per_pic) return;
-    const int pic_i = (int)(gi / per_pic);
-    const int rem = (int)(gi - (long long)pic_i * per_pic), mb = rem / 12, chunk = rem - mb * 12;
-    const DevPicture& pic = pics[pic_i];
-    if (!pic.has_inter) return;
-    const uint32_t r2 = __ldg(reinterpret_cast<const uint32_t*>(pic.mbs + mb) + 7);
-    const int code = r2 & 15;
-    if (code == 0) return;
-    const uint8_t* __restrict__ base = pic.packed_motion + (size_t)(r2 >> 4) * 12;
-    auto entry_of = [&](int b) {
-        switch (code) {
-        case 1: return 0;
-        case 2: return b >> 3;
-        case 3: return (b >> 1) & 1;
-        case 4: return ((b >> 3) << 1) | ((b >> 1) & 1);
-        default: return b;
-        }
-    };
-    uint32_t w[4];
-    if (chunk < 8) {                                       // mv[list][4 blocks]
-        const int list = chunk >> 2, b0 = (chunk & 3) * 4;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) w[k] = __ldg(reinterpret_cast<const uint32_t*>(base + entry_of(b0 + k) * 12 + list * 4));
-    } else {                                               // ref_idx[list][16] (chunks 8, 9) / ref_pic[list][16] (10, 11)
-        const int off = 8 + (chunk - 8);                   // byte inside the entry: 8, 9 ref_idx; 10, 11 ref_pic
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v |= (uint32_t)__ldg(base + entry_of(k * 4 + j) * 12 + off) << (8 * j);
-            w[k] = v;
-        }
-    }
-    reinterpret_cast<uint4*>(pic.motion + mb)[chunk] = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
 {
     const int nmb = w.geom.width_mbs * w.geom.height_mbs;
     const int threads = kWarpsPerCta * 32;
     const int groups = (w.geom.height_mbs + kWarpsPerCta - 1) / kWarpsPerCta;
     if (which == KERNEL_RESID) {
-        int n = 1;
-        if (w.any_inter) {
-            const long long total = (long long)w.num_pics * nmb * 12;
-            motion_expand_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(w.pics, w.num_pics, nmb);
-            n = 2;
-        }
-        const long long warps = (long long)w.num_pics * nmb;
-        residual_kernel<<<(int)((warps + kWarpsPerCta - 1) / kWarpsPerCta), threads, 0, stream>>>(w.pics, w.num_pics, w.geom);
+        const int n = 1;
+        residual_kernel<<<dim3((nmb + kWarpsPerCta - 1) / kWarpsPerCta, 1, w.num_pics), threads, 0, stream>>>(w.pics, w.geom);
         return n;
     }
     if (which == KERNEL_INTER) {
