@@ -199,7 +199,7 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
             const int c = p - 256, pl = c >> 6, x = c & 7, y = (c >> 3) & 7;
             if (((x | y) & 3) == 0) val = l;
             else {
-                const int qc = h.qp_c[pl], cper = qc / 6, crem = qc - cper * 6;
+                const int qc = pl ? h.qp_c[1] : h.qp_c[0], cper = qc / 6, crem = qc - cper * 6;   // (no dynamic index: keeps h in registers)
                 val = ((l * (int)__ldg(&sl->level_scale_4x4[inter][pl + 1][crem][(y & 3) * 4 + (x & 3)])) * (1 << cper) + 8) >> 4;
             }
             nz |= 1u << (16 + pl * 4 + (y >> 2) * 2 + (x >> 2));
@@ -237,7 +237,7 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
     }
     if (h.cbp_chroma && (nz >> 16)) {
         if (lane == 1 || lane == 2) {
-            const int pl = lane - 1, qc = h.qp_c[pl], cper = qc / 6, crem = qc - cper * 6;
+            const int pl = lane - 1, qc = pl ? h.qp_c[1] : h.qp_c[0], cper = qc / 6, crem = qc - cper * 6;
             int* c = res + 256 + pl * 64;
             int c00 = c[0], c01 = c[4], c10 = c[32], c11 = c[36];
             int e00 = c00 + c01, e01 = c00 - c01, e10 = c10 + c11, e11 = c10 - c11;
@@ -260,11 +260,11 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
         __syncwarp();
         if (nz & m8) idct8_1d(blk + i, 16, true);
         if (lane < 8 && ((nz >> (16 + lane)) & 1)) idct4_inplace(res + 256 + (lane >> 2) * 64 + ((lane >> 1) & 1) * 32 + (lane & 1) * 4, 8);
-    } else if (lane < 16) {
-        if ((nz >> lane) & 1) idct4_inplace(res + (lane >> 2) * 64 + (lane & 3) * 4, 16);
     } else if (lane < 24) {
+        // one instruction stream for the sixteen luma blocks (lanes 0..15, row pitch 16) and the eight chroma blocks
         const int c = lane - 16;
-        if ((nz >> lane) & 1) idct4_inplace(res + 256 + (c >> 2) * 64 + ((c >> 1) & 1) * 32 + (c & 1) * 4, 8);
+        int* const blk = lane < 16 ? res + (lane >> 2) * 64 + (lane & 3) * 4 : res + 256 + (c >> 2) * 64 + ((c >> 1) & 1) * 32 + (c & 1) * 4;
+        if ((nz >> lane) & 1) idct4_inplace(blk, lane < 16 ? 16 : 8);
     }
     __syncwarp();
 
@@ -290,7 +290,7 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 // entry the reference reads (partition origin), the prediction direction, and whether the partition covers the
 // whole 8x8 quadrant of the block.  Partition steps in 4x4 units per type 0..7 ({0,0},{4,4},{4,2},{2,4},{2,2},{2,1},
 // {1,2},{1,1}) are nibbles of two constants.
-__device__ __forceinline__ void partition_of_block(const MbHdr& h, int is_b, int direct_spatial, const h264r_mb_motion* m,
+__device__ __forceinline__ void partition_of_block(const MbHdr& h, int is_b, int direct_spatial, const uint32_t* refs,
                                                    int direct8x8, int blk, int& origin, int& dir, bool& covers8x8)
 {
     const int bx = blk & 3, by = blk >> 2;
@@ -304,7 +304,8 @@ __device__ __forceinline__ void partition_of_block(const MbHdr& h, int is_b, int
     if (mode == 0) sh4 = sv4 = direct8x8 ? 2 : 1;
     if (is_b && h.mb_type == H264R_MB_8x8 && direct_spatial) {
         const int b = j0 * 4 + i0;
-        pd = m->ref_idx[1][b] < 0 ? 0 : (m->ref_idx[0][b] < 0 ? 1 : 2);
+        const uint32_t rw = refs[b];                       // ref_idx[0] | ref_idx[1] << 8 | ref_pic[0] << 16 | ref_pic[1] << 24
+        pd = (int8_t)(rw >> 8) < 0 ? 0 : ((int8_t)rw < 0 ? 1 : 2);
     }
     const int i = bx & ~(sh4 - 1), j = by & ~(sv4 - 1);   // partitions are aligned to their own size
     origin = j * 4 + i;
@@ -335,9 +336,10 @@ constexpr int kLumaQ = 146, kChromaQ = 50;
 struct __align__(16) InterSmem {
     uint32_t luma[4 * kLumaQ + 2];
     uint32_t chroma[4 * kChromaQ + 2];
-    h264r_mb_motion motion;
+    uint32_t mv[2][16];                   // the MB's sixteen motion entries (from the packed form): mv x | y << 16 per list
+    uint32_t refs[16];                    // ref_idx[0] | ref_idx[1] << 8 | ref_pic[0] << 16 | ref_pic[1] << 24
 };
-static_assert(sizeof(InterSmem) % 16 == 0 && offsetof(InterSmem, motion) % 16 == 0, "InterSmem alignment");
+static_assert(sizeof(InterSmem) % 16 == 0, "InterSmem alignment");
 
 // grid = (ceil(width_mbs / 4), height_mbs, pictures of the wave): one warp per macroblock, no index divisions
 __global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTER_CTAS)
@@ -359,9 +361,7 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
     if (lane < 16) {                                     // the MB's sixteen motion entries, from the packed form
         const uint32_t* e = packed_entry(pic.packed_motion, h.packed, lane);
         const uint32_t m0 = __ldg(e), m1 = __ldg(e + 1), m2 = __ldg(e + 2);
-        *reinterpret_cast<uint32_t*>(sm.motion.mv[0][lane]) = m0;
-        *reinterpret_cast<uint32_t*>(sm.motion.mv[1][lane]) = m1;
-        sm.motion.ref_idx[0][lane] = (int8_t)(m2 & 0xFF); sm.motion.ref_idx[1][lane] = (int8_t)((m2 >> 8) & 0xFF);
+        sm.mv[0][lane] = m0; sm.mv[1][lane] = m1; sm.refs[lane] = m2;
     }
     // slice-level parameters (one 12-byte read, broadcast)
     const uint32_t s0 = __ldg(reinterpret_cast<const uint32_t*>(sl)), s1 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 1),
@@ -378,7 +378,7 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
     const int sb = r >> 1, half = r & 1;
     const int blk = (qy * 2 + (sb >> 1)) * 4 + qx * 2 + (sb & 1);
     int origin, pd; bool uni;
-    partition_of_block(h, is_b, direct_spatial, &sm.motion, direct8x8, blk, origin, pd, uni);
+    partition_of_block(h, is_b, direct_spatial, sm.refs, direct8x8, blk, origin, pd, uni);
 
     // residual of this lane's samples (issued early; consumed at the end)
     const int lx = (blk & 3) * 4, ly = (blk >> 2) * 4 + half * 2;          // luma position in the MB
@@ -408,10 +408,13 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
         const uint32_t* wl = lq; const uint32_t* wc = cq;
         int loff = 2, coff = 0;
         if (active) {
-            refidx = sm.motion.ref_idx[list][origin];
-            const int slot = (int)(int8_t)__ldg(&sl->ref_pic_list[list][refidx & 31]);
+            // the entry names the reference picture itself (ref_pic = slot of pic_params.ref_frames, the identity the
+            // deblocking rule compares): RefPicList[list][ref_idx] resolved by the parser side, one load less in the chain
+            const uint32_t rw = sm.refs[origin], mvw = sm.mv[list][origin];
+            refidx = (int)(int8_t)(rw >> (8 * list));
+            const int slot = (int)(int8_t)(rw >> (16 + 8 * list));
             const uint8_t* __restrict__ rbase = pic.ref[slot & 31];
-            const int mvx = sm.motion.mv[list][origin][0], mvy = sm.motion.mv[list][origin][1];
+            const int mvx = (int)(int16_t)(mvw & 0xFFFF), mvy = (int)(int16_t)(mvw >> 16);
             vx = (mbx * 16 + (blk & 3) * 4) * 4 + mvx; vy = (mby * 16 + (blk >> 2) * 4) * 4 + mvy;   // this block's position
             if (uni) {
                 const int qvx = (mbx * 16 + qx * 8) * 4 + mvx, qvy = (mby * 16 + qy * 8) * 4 + mvy;

@@ -100,12 +100,15 @@ typedef struct h264r_mb {
 /* per-macroblock motion: 192 bytes.  The 16 pic_motion_params (framebuf/picture.h:66-71) of the MB,   */
 /* 4x4 blocks in raster order (by*4+bx).  Only read for non-intra MBs.  This array stays in host       */
 /* memory: h264r_picture_submit packs it (one entry per distinct partition of an MB, 12 bytes each)    */
-/* for the host->device copy and the GPU restores the full array in HBM.                               */
+/* for the host->device copy; the kernels read the packed entries directly.                           */
 typedef struct h264r_mb_motion {
     int16_t mv[2][16][2];            /* [list][blk][x,y] quarter-pel                                   */
     int8_t  ref_idx[2][16];          /* pic_motion_params::ref_idx (may be 0 for an unused list, quirk 2) */
     int8_t  ref_pic[2][16];          /* identity of pic_motion_params::ref_pic: index into
-                                        h264r_pic_params::ref_frames, -1 == nullptr                    */
+                                        h264r_pic_params::ref_frames, -1 == nullptr.  For a list the
+                                        block predicts from it is the picture motion compensation reads
+                                        (== ref_pic_list[list][ref_idx], as the reference's parser sets
+                                        it, parser/interpret_mv.cc) and the one the bS rule compares    */
 } h264r_mb_motion;
 
 /* per-slice table.  Fields of shr_t / pps_t read by the path plus the tables the reference builds per
