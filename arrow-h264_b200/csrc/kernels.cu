@@ -539,6 +539,21 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
 // ---------------------------------------------------------------------------------------------------
 // row wavefront plumbing
 
+// Mailbox word: 4 samples + the launch epoch in one 64-bit store / load (single-copy atomic): the data arrives with its
+// own flag, so neither side needs a fence (the low-latency protocol of collective libraries).  Epochs make clearing
+// unnecessary; the intra wavefront tags its words with bit 31 so that they never pass for deblock words of the same wave.
+__device__ __forceinline__ void st_mbox(uint64_t* p, uint32_t data, uint32_t epoch)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"((uint64_t)data | ((uint64_t)epoch << 32)) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_mbox(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+
 // Wait until the row above has completed at least `need` macroblocks.
 __device__ __forceinline__ void wait_row(const int* progress_above, int need, int lane)
 {
@@ -706,6 +721,9 @@ __device__ __forceinline__ void intra_prefetch(const DevPicture& pic, const Fram
 // Reconstruction of one intra macroblock by one warp (mb_pred_intra / mb_pred_ipcm, decoder.cc:149-215): neighbour
 // availability, neighbour samples of the current unfiltered picture, prediction + residual block by block through a
 // shared-memory tile, store.  The caller has made sure that the neighbouring MBs are reconstructed and visible.
+// kRowMode (row wavefront): the caller has put the samples above the MB (from the mailboxes of the row above) and the
+// left column (carried in the tile from the previous MB of the row) into the tiles; otherwise they are read from the frame.
+template <bool kRowMode>
 __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, const FrameGeom& g, IntraSmem& sm, const IntraPre& pre,
                                                      int mbx, int mby, int lane)
 {
@@ -720,12 +738,16 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
         for (int i = lane; i < h.coeff_count; i += 32) {
             const uint32_t e = __ldg(lv + i);
             const int p = (int)(e & 0xFFFFu), v = (int)(e >> 16) & 0xFF;
-            if (p < 256) dY[(size_t)(py + (p >> 4)) * g.pitch_y + px + (p & 15)] = (uint8_t)v;
-            else if (p < 384) {
+            if (p < 256) {
+                dY[(size_t)(py + (p >> 4)) * g.pitch_y + px + (p & 15)] = (uint8_t)v;
+                if (kRowMode) TY(p & 15, p >> 4) = (uint8_t)v;       // the row wavefront carries the MB in its tile
+            } else if (p < 384) {
                 const int pl = (p - 256) >> 6, q = (p - 256) & 63;
                 dC[pl][(size_t)(cy + (q >> 3)) * g.pitch_c + cx + (q & 7)] = (uint8_t)v;
+                if (kRowMode) TC(pl, q & 7, q >> 3) = (uint8_t)v;
             }
         }
+        if (kRowMode) __syncwarp();
         return;
     }
 
@@ -742,7 +764,7 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
     const bool aL = av[0], aT = av[1], aTL = av[2], aTR = av[3];
 
     // neighbour samples of the current, unfiltered picture -> tiles (L1-bypassing loads: other SMs wrote them)
-    if (mby > 0) {
+    if (!kRowMode && mby > 0) {
         if (lane < 8) {                                // luma top row, cols -4..27
             const int x = px - 4 + lane * 4;
             uint32_t v = 0;
@@ -755,7 +777,7 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
             reinterpret_cast<uint32_t*>(sm.tc[pl])[c & 3] = v;
         }
     }
-    if (mbx > 0) {
+    if (!kRowMode && mbx > 0) {
         if (lane < 16) TY(-1, lane) = ldcg_u8(dY + (size_t)(py + lane) * g.pitch_y + px - 1);
         else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = ldcg_u8(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx - 1); }
     }
@@ -946,8 +968,15 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
     }
 }
 
+// Mailbox of an intra MB: its bottom sample rows, 8 words = luma row 15 (4 words) | Cb row 7 (2) | Cr row 7 (2).
+constexpr int kIntraBoxWords = 8;
+constexpr uint32_t kIntraEpochTag = 0x80000000u;
+
+// All-intra pictures: one warp per MB row, rows form the 2:1 wavefront.  MB (x, y) needs, from the row above, the bottom
+// row of MB x, the first eight bottom samples of MB x+1 and the last bottom sample of MB x-1: 24 consecutive mailbox
+// words, polled by 24 lanes with one load each.  The left column never leaves the tile.  No fence, no progress counter.
 __global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTRA_CTAS)
-recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g)
+recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g, uint32_t epoch)
 {
     __shared__ __align__(16) IntraSmem smem_all[kWarpsPerCta];
     __shared__ int s_ticket;
@@ -965,52 +994,56 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
     const DevPicture& pic = pics[pic_i];
     if (!pic.has_intra || pic.has_inter) return;         // mixed pictures: recon_intra_sparse_kernel
     IntraSmem& sm = smem_all[warp];
-    int* progress = pic.row_progress;                    // [0][H]
-    uint8_t* const dY = pic.dst;
-    uint8_t* const dC[2] = { pic.dst + g.off_cb, pic.dst + g.off_cr };
+    const uint32_t tag = epoch | kIntraEpochTag;
+    uint64_t* const box_out = pic.mbox + (size_t)mby * W * kIntraBoxWords;
+    const uint64_t* const box_in = pic.mbox + (size_t)(mby > 0 ? mby - 1 : 0) * W * kIntraBoxWords;
+    const bool has_below = mby + 1 < H;
 
-    int known = mby > 0 ? 0 : 0x7FFFFFFF;                 // progress of the row above as last observed
-    // Rows are walked in super-chunks of 256 MBs: the intra MBs of the super-chunk are found up front (8 coalesced
-    // header-word loads + ballots), so that after every intra MB the row can publish the position of its NEXT
-    // intra MB -- everything before it is complete (inter MBs were reconstructed by recon_inter_kernel).
-    for (int x0 = 0; x0 < W; x0 += 256) {
-      unsigned masks[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-          const int x = x0 + c * 32 + lane;
-          masks[c] = __ballot_sync(0xFFFFFFFFu, x < W && ((load_hdr_word0(pic.mbs, mby * W + x) >> 8) & H264R_MB_FLAG_INTRA));
-      }
-      const int xend = min(x0 + 256, W);
-      // position of the first intra MB at or after chunk c0 (xend if none)
-      auto next_intra = [&](int c0) {
-          int nx = xend;
-#pragma unroll
-          for (int c = 7; c >= 0; --c) if (c >= c0 && masks[c]) nx = x0 + c * 32 + __ffs(masks[c]) - 1;
-          return nx;
-      };
-      IntraPre nxt;
-      { const int first = next_intra(0);
-        if (first > x0) publish_row(progress + mby, first, lane, false);
-        if (first < xend) intra_prefetch(pic, g, first, mby, lane, nxt); }
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
-       while (masks[c]) {
-        const int mbx = x0 + c * 32 + __ffs(masks[c]) - 1;
-        masks[c] &= masks[c] - 1;
-        const int done_to = next_intra(c);                 // published after this MB: the next intra MB of the row
+    IntraPre nxt;
+    intra_prefetch(pic, g, 0, mby, lane, nxt);
+    for (int mbx = 0; mbx < W; ++mbx) {
         const IntraPre cur = nxt;
-        if (done_to < xend) intra_prefetch(pic, g, done_to, mby, lane, nxt);    // lands while this MB is reconstructed
-        if (mby > 0) {
-            const int need = min(mbx + 2, W);
-            if (known < need) {
-                if (lane == 0) { unsigned ns = 16; while ((known = ld_acquire(progress + mby - 1)) < need) { __nanosleep(ns); if (ns < 128) ns *= 2; } }
-                known = __shfl_sync(0xFFFFFFFFu, known, 0);
-            }
+        // the 24 words around MB mbx of the row above: lane j = word j & 7 of MB mbx - 1 + (j >> 3)
+        uint64_t t = 0;
+        const int bx = mbx - 1 + (lane >> 3), bw = lane & 7;
+        // needed: the corner samples of MB mbx-1 (words 3, 5, 7), everything of MB mbx, the first two luma words of MB mbx+1
+        const bool need = mby > 0 && lane < 24 && bx >= 0 && bx < W &&
+                          (lane < 8 ? (bw == 3 || bw == 5 || bw == 7) : (lane < 16 ? true : bw < 2));
+        if (need) t = ld_mbox(box_in + (size_t)bx * kIntraBoxWords + bw);
+        if (mbx + 1 < W) intra_prefetch(pic, g, mbx + 1, mby, lane, nxt);      // lands while this MB is reconstructed
+        __syncwarp();                                      // the previous MB's tile has been stored and posted
+        if (mbx > 0) {                                     // left column = the previous MB's last column, still in the tile
+            if (lane < 16) TY(-1, lane) = TY(15, lane);
+            else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = TC(pl, 7, y); }
         }
-        intra_reconstruct_mb(pic, g, sm, cur, mbx, mby, lane);
-        publish_row(progress + mby, done_to, lane, true);
-       }
-      }
+        if (mby > 0) {
+            bool waiting = need && (uint32_t)(t >> 32) != tag;
+            unsigned ns = 16;
+            while (__any_sync(0xFFFFFFFFu, waiting)) {
+                if (waiting) {
+                    __nanosleep(ns); if (ns < 128) ns *= 2;
+                    t = ld_mbox(box_in + (size_t)bx * kIntraBoxWords + bw);
+                    waiting = (uint32_t)(t >> 32) != tag;
+                }
+            }
+            // tile row -1: luma words 0..7 = columns -4..27, chroma words 0..3 = columns -4..11 (0 outside the picture)
+            const uint32_t v = need ? (uint32_t)t : 0u;
+            if (lane < 8) {
+                if (bw == 3) reinterpret_cast<uint32_t*>(sm.ty)[0] = v;
+                else if (bw == 5) reinterpret_cast<uint32_t*>(sm.tc[0])[0] = v;
+                else if (bw == 7) reinterpret_cast<uint32_t*>(sm.tc[1])[0] = v;
+            } else if (lane < 16) {
+                if (bw < 4) reinterpret_cast<uint32_t*>(sm.ty)[1 + bw] = v;
+                else reinterpret_cast<uint32_t*>(sm.tc[(bw - 4) >> 1])[1 + (bw & 1)] = v;
+            } else if (lane < 24 && bw < 2) reinterpret_cast<uint32_t*>(sm.ty)[5 + bw] = v;
+        }
+        intra_reconstruct_mb<true>(pic, g, sm, cur, mbx, mby, lane);
+        // post the MB's bottom rows (the tile is final: the MB's own stores read it after a __syncwarp)
+        if (has_below && lane < 8) {
+            const uint32_t w = lane < 4 ? reinterpret_cast<const uint32_t*>(&TY(0, 15))[lane]
+                                        : reinterpret_cast<const uint32_t*>(&TC((lane - 4) >> 1, 0, 7))[lane & 1];
+            st_mbox(box_out + (size_t)mbx * kIntraBoxWords + lane, w, tag);
+        }
     }
 }
 
@@ -1044,7 +1077,7 @@ recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int
         while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
     }
     __syncwarp();
-    intra_reconstruct_mb(pic, g, smem_all[warp], pre, mbx, mby, lane);
+    intra_reconstruct_mb<false>(pic, g, smem_all[warp], pre, mbx, mby, lane);
     (void)H;
     __syncwarp();
     if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + addr), (int)epoch);
@@ -1204,17 +1237,6 @@ struct __align__(16) DeblockSmem {
     uint8_t top_c[2][2][2 * 8];
 };
 constexpr int kMboxWords = 24;                               // per MB: 16 luma words (rows 12..15) + 8 chroma words (rows 6, 7 of Cb, Cr)
-
-__device__ __forceinline__ void st_mbox(uint64_t* p, uint32_t data, uint32_t epoch)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"((uint64_t)data | ((uint64_t)epoch << 32)) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_mbox(const uint64_t* p)
-{
-    uint64_t v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // filter_strong / filter_normal (deblock.cc:327-415) on the samples across one edge: p[0] = p0 ... p[3] = p3.
 template <bool kChroma>
@@ -1482,7 +1504,7 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     if (which == KERNEL_INTRA) {
         int n = 0;
         if (w.any_intra_rows) {
-            recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom);
+            recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
             ++n;
         }
         if (w.max_intra_sparse > 0) {
