@@ -20,7 +20,7 @@ namespace h264r {
 constexpr int kWarpsPerCta = 4;
 // resident CTAs per SM the register allocation aims at (tuned on B200, scripts/tune.sh)
 #ifndef H264R_INTER_CTAS
-#define H264R_INTER_CTAS 8
+#define H264R_INTER_CTAS 10
 #endif
 #ifndef H264R_INTRA_CTAS
 #define H264R_INTRA_CTAS 4
@@ -592,7 +592,7 @@ struct __align__(16) IntraSmem {
     __align__(16) int16_t res[384];              // this MB's residual (zero when it has none)
     __align__(16) uint8_t ty[17 * 32];
     __align__(16) uint8_t tc[2][9 * 16];
-    uint8_t  ft[20], fl[12];                     // Intra8x8 filtered reference samples: ft[i+1] = p'(i,-1), fl[i+1] = p'(-1,i)
+    __align__(4) uint8_t f8[32];                 // Intra8x8 filtered reference samples p': [7 - i] = p'(-1, i), [8] = p'(-1, -1), [12 + i] = p'(i, -1)
 };
 
 #define TY(x, y) sm.ty[((y) + 1) * 32 + (x) + 4]
@@ -693,6 +693,49 @@ __device__ const uint32_t c_i4_pred[9 * 16] = {
     0xDFFFDF, 0xE0DFFF, 0xDFE0E1, 0xE0E1E2, 0xFF1FFF, 0x1FFFDF, 0xDFFFDF, 0xE0DFFF, 0x1F3F1F, 0x3F1FFF, 0xFF1FFF, 0x1FFFDF, 0x3F5F3F, 0x5F3F1F, 0x1F3F1F, 0x3F1FFF,
     0xE0E1E0, 0xE1E2E1, 0xE2E3E2, 0xE3E4E3, 0xE2E1E0, 0xE3E2E1, 0xE4E3E2, 0xE5E4E3, 0xE1E2E1, 0xE2E3E2, 0xE3E4E3, 0xE4E5E4, 0xE3E2E1, 0xE4E3E2, 0xE5E4E3, 0xE6E5E4,
     0xFF1FFF, 0x3F1FFF, 0x1F3F1F, 0x5F3F1F, 0x1F3F1F, 0x5F3F1F, 0x3F5F3F, 0x5F5F3F, 0x3F5F3F, 0x5F5F3F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F, 0x5F5F5F,
+};
+
+// Intra8x8 directional predictors as data (scripts/gen_intra_tables.py): for mode m and sample (x, y),
+//     pred = (F[a] + 2 * F[b] + F[c] + 2) >> 2,   F = IntraSmem::f8, entry = a | b << 8 | c << 16,
+// which replaces the nine-way switch of intra_prediction.cc:449-621 evaluated twice per lane (the switch was 20 KB of
+// code in a kernel whose warps run through it once per MB: it did not fit the 32 KB instruction cache).
+__device__ const uint32_t c_i8_pred[9 * 64] = {
+    0x0C0C0C, 0x0D0D0D, 0x0E0E0E, 0x0F0F0F, 0x101010, 0x111111, 0x121212, 0x131313, 0x0C0C0C, 0x0D0D0D, 0x0E0E0E, 0x0F0F0F, 0x101010, 0x111111, 0x121212, 0x131313,
+    0x0C0C0C, 0x0D0D0D, 0x0E0E0E, 0x0F0F0F, 0x101010, 0x111111, 0x121212, 0x131313, 0x0C0C0C, 0x0D0D0D, 0x0E0E0E, 0x0F0F0F, 0x101010, 0x111111, 0x121212, 0x131313,
+    0x0C0C0C, 0x0D0D0D, 0x0E0E0E, 0x0F0F0F, 0x101010, 0x111111, 0x121212, 0x131313, 0x0C0C0C, 0x0D0D0D, 0x0E0E0E, 0x0F0F0F, 0x101010, 0x111111, 0x121212, 0x131313,
+    0x0C0C0C, 0x0D0D0D, 0x0E0E0E, 0x0F0F0F, 0x101010, 0x111111, 0x121212, 0x131313, 0x0C0C0C, 0x0D0D0D, 0x0E0E0E, 0x0F0F0F, 0x101010, 0x111111, 0x121212, 0x131313,
+    0x070707, 0x070707, 0x070707, 0x070707, 0x070707, 0x070707, 0x070707, 0x070707, 0x060606, 0x060606, 0x060606, 0x060606, 0x060606, 0x060606, 0x060606, 0x060606,
+    0x050505, 0x050505, 0x050505, 0x050505, 0x050505, 0x050505, 0x050505, 0x050505, 0x040404, 0x040404, 0x040404, 0x040404, 0x040404, 0x040404, 0x040404, 0x040404,
+    0x030303, 0x030303, 0x030303, 0x030303, 0x030303, 0x030303, 0x030303, 0x030303, 0x020202, 0x020202, 0x020202, 0x020202, 0x020202, 0x020202, 0x020202, 0x020202,
+    0x010101, 0x010101, 0x010101, 0x010101, 0x010101, 0x010101, 0x010101, 0x010101, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000,
+    0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000,
+    0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000,
+    0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000,
+    0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000,
+    0x0E0D0C, 0x0F0E0D, 0x100F0E, 0x11100F, 0x121110, 0x131211, 0x141312, 0x151413, 0x0F0E0D, 0x100F0E, 0x11100F, 0x121110, 0x131211, 0x141312, 0x151413, 0x161514,
+    0x100F0E, 0x11100F, 0x121110, 0x131211, 0x141312, 0x151413, 0x161514, 0x171615, 0x11100F, 0x121110, 0x131211, 0x141312, 0x151413, 0x161514, 0x171615, 0x181716,
+    0x121110, 0x131211, 0x141312, 0x151413, 0x161514, 0x171615, 0x181716, 0x191817, 0x131211, 0x141312, 0x151413, 0x161514, 0x171615, 0x181716, 0x191817, 0x1A1918,
+    0x141312, 0x151413, 0x161514, 0x171615, 0x181716, 0x191817, 0x1A1918, 0x1B1A19, 0x151413, 0x161514, 0x171615, 0x181716, 0x191817, 0x1A1918, 0x1B1A19, 0x1B1B1A,
+    0x07080C, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x100F0E, 0x11100F, 0x121110, 0x131211, 0x060708, 0x07080C, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x100F0E, 0x11100F, 0x121110,
+    0x050607, 0x060708, 0x07080C, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x100F0E, 0x11100F, 0x040506, 0x050607, 0x060708, 0x07080C, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x100F0E,
+    0x030405, 0x040506, 0x050607, 0x060708, 0x07080C, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x020304, 0x030405, 0x040506, 0x050607, 0x060708, 0x07080C, 0x0D0C08, 0x0E0D0C,
+    0x010203, 0x020304, 0x030405, 0x040506, 0x050607, 0x060708, 0x07080C, 0x0D0C08, 0x000102, 0x010203, 0x020304, 0x030405, 0x040506, 0x050607, 0x060708, 0x07080C,
+    0x080C08, 0x0C0D0C, 0x0D0E0D, 0x0E0F0E, 0x0F100F, 0x101110, 0x111211, 0x121312, 0x0C0807, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x100F0E, 0x11100F, 0x121110, 0x131211,
+    0x080706, 0x080C08, 0x0C0D0C, 0x0D0E0D, 0x0E0F0E, 0x0F100F, 0x101110, 0x111211, 0x070605, 0x0C0807, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x100F0E, 0x11100F, 0x121110,
+    0x060504, 0x080706, 0x080C08, 0x0C0D0C, 0x0D0E0D, 0x0E0F0E, 0x0F100F, 0x101110, 0x050403, 0x070605, 0x0C0807, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x100F0E, 0x11100F,
+    0x040302, 0x060504, 0x080706, 0x080C08, 0x0C0D0C, 0x0D0E0D, 0x0E0F0E, 0x0F100F, 0x030201, 0x050403, 0x070605, 0x0C0807, 0x0D0C08, 0x0E0D0C, 0x0F0E0D, 0x100F0E,
+    0x080708, 0x0C0807, 0x080C0D, 0x0C0D0E, 0x0D0E0F, 0x0E0F10, 0x0F1011, 0x101112, 0x070607, 0x060708, 0x080708, 0x0C0807, 0x080C0D, 0x0C0D0E, 0x0D0E0F, 0x0E0F10,
+    0x060506, 0x050607, 0x070607, 0x060708, 0x080708, 0x0C0807, 0x080C0D, 0x0C0D0E, 0x050405, 0x040506, 0x060506, 0x050607, 0x070607, 0x060708, 0x080708, 0x0C0807,
+    0x040304, 0x030405, 0x050405, 0x040506, 0x060506, 0x050607, 0x070607, 0x060708, 0x030203, 0x020304, 0x040304, 0x030405, 0x050405, 0x040506, 0x060506, 0x050607,
+    0x020102, 0x010203, 0x030203, 0x020304, 0x040304, 0x030405, 0x050405, 0x040506, 0x010001, 0x000102, 0x020102, 0x010203, 0x030203, 0x020304, 0x040304, 0x030405,
+    0x0C0D0C, 0x0D0E0D, 0x0E0F0E, 0x0F100F, 0x101110, 0x111211, 0x121312, 0x131413, 0x0E0D0C, 0x0F0E0D, 0x100F0E, 0x11100F, 0x121110, 0x131211, 0x141312, 0x151413,
+    0x0D0E0D, 0x0E0F0E, 0x0F100F, 0x101110, 0x111211, 0x121312, 0x131413, 0x141514, 0x0F0E0D, 0x100F0E, 0x11100F, 0x121110, 0x131211, 0x141312, 0x151413, 0x161514,
+    0x0E0F0E, 0x0F100F, 0x101110, 0x111211, 0x121312, 0x131413, 0x141514, 0x151615, 0x100F0E, 0x11100F, 0x121110, 0x131211, 0x141312, 0x151413, 0x161514, 0x171615,
+    0x0F100F, 0x101110, 0x111211, 0x121312, 0x131413, 0x141514, 0x151615, 0x161716, 0x11100F, 0x121110, 0x131211, 0x141312, 0x151413, 0x161514, 0x171615, 0x181716,
+    0x070607, 0x050607, 0x060506, 0x040506, 0x050405, 0x030405, 0x040304, 0x020304, 0x060506, 0x040506, 0x050405, 0x030405, 0x040304, 0x020304, 0x030203, 0x010203,
+    0x050405, 0x030405, 0x040304, 0x020304, 0x030203, 0x010203, 0x020102, 0x000102, 0x040304, 0x020304, 0x030203, 0x010203, 0x020102, 0x000102, 0x010001, 0x000001,
+    0x030203, 0x010203, 0x020102, 0x000102, 0x010001, 0x000001, 0x000000, 0x000000, 0x020102, 0x000102, 0x010001, 0x000001, 0x000000, 0x000000, 0x000000, 0x000000,
+    0x010001, 0x000001, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000,
 };
 
 // Everything about an intra MB that does not depend on its neighbours being reconstructed: header, the header words
@@ -845,80 +888,65 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
             __syncwarp();
         }
     } else {
-        const bool is8 = true;
-        const int n = 8, nblk = 4;
-        for (int k = 0; k < nblk; ++k) {
-            int xO, yO;
-            if (is8) { xO = (k & 1) * 8; yO = (k >> 1) * 8; }
-            else { xO = ((k >> 2) & 1) * 8 + (k & 1) * 4; yO = (k >> 3) * 8 + ((k >> 1) & 1) * 4; }
-            const int mode = ((k < 8 ? h.u0 >> (4 * k) : h.u1 >> (4 * (k - 8)))) & 15;
+        // I_8x8: four blocks in coding order; lane = samples (2 (lane & 3), lane >> 2) and the one to its right
+        const int y = lane >> 2, x0 = (lane & 3) * 2;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const int xO = (k & 1) * 8, yO = (k >> 1) * 8;
+            const int mode = (h.u0 >> (4 * k)) & 15;
             const bool avA = xO > 0 ? true : aL;
             const bool avB = yO > 0 ? true : aT;
             const bool avD = (xO > 0 && yO > 0) ? true : (xO > 0 ? aT : (yO > 0 ? aL : aTL));
-            bool avC;
-            if (yO == 0) avC = (xO + n < 16) ? aT : aTR;
-            else avC = xO + n < 16;
-            if (!is8 && xO == 4 && (yO == 4 || yO == 12)) avC = false;
-            if (is8 && xO == 8 && yO == 8) avC = false;
-            const int tmax = avC ? 2 * n - 1 : n - 1;  // C substitution: p(x,-1) = p(n-1,-1) for x >= n
+            const bool avC = k == 0 ? aT : (k == 1 ? aTR : k == 2);          // block 3 never has a top-right neighbour (:376)
+            const int tmax = avC ? 15 : 7;             // C substitution: p(x,-1) = p(7,-1) for x >= 8 (:404-407)
 
-            if (!is8) {
-                auto T = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
-                auto L = [&](int i) { return (int)TY(xO - 1, yO + i); };
-                int v = 0;
-                const int x = lane & 3, y = (lane >> 2) & 3;
-                if (lane < 16) {
-                    const int dcv = mode == 2 ? dc_value(4, 2, avA, avB, T, L) : 0;
-                    v = clip255(pred_dir_sample(mode, 4, x, y, dcv, T, L) + sm.res[(yO + y) * 16 + xO + x]);
+            // reference sample filtering (Intra8x8::filtering, intra_prediction.cc:413-447)
+            auto To = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
+            auto Lo = [&](int i) { return (int)TY(xO - 1, yO + i); };
+            if (lane < 16) {                           // p'(lane, -1)
+                int f = 0;
+                if (avB) {
+                    if (lane == 0) f = avD ? (To(-1) + 2 * To(0) + To(1) + 2) >> 2 : (3 * To(0) + To(1) + 2) >> 2;
+                    else if (lane == 15) f = (To(14) + 3 * To(15) + 2) >> 2;
+                    else f = (To(lane - 1) + 2 * To(lane) + To(lane + 1) + 2) >> 2;
                 }
-                __syncwarp();
-                if (lane < 16) TY(xO + x, yO + y) = (uint8_t)v;
-                __syncwarp();
-            } else {
-                // reference sample filtering (Intra8x8::filtering, intra_prediction.cc:413-447)
-                auto To = [&](int i) { return (int)TY(xO + min(i, tmax), yO - 1); };
-                auto Lo = [&](int i) { return (int)TY(xO - 1, yO + i); };
-                if (lane < 16) {                       // p'(lane, -1)
-                    int f = 0;
-                    if (avB) {
-                        if (lane == 0) f = avD ? (To(-1) + 2 * To(0) + To(1) + 2) >> 2 : (3 * To(0) + To(1) + 2) >> 2;
-                        else if (lane == 15) f = (To(14) + 3 * To(15) + 2) >> 2;
-                        else f = (To(lane - 1) + 2 * To(lane) + To(lane + 1) + 2) >> 2;
-                    }
-                    sm.ft[lane + 1] = (uint8_t)f;
-                } else if (lane < 24) {                // p'(-1, i)
-                    const int i = lane - 16;
-                    int f = 0;
-                    if (avA) {
-                        if (i == 0) f = avD ? (Lo(-1) + 2 * Lo(0) + Lo(1) + 2) >> 2 : (3 * Lo(0) + Lo(1) + 2) >> 2;
-                        else if (i == 7) f = (Lo(6) + 3 * Lo(7) + 2) >> 2;
-                        else f = (Lo(i - 1) + 2 * Lo(i) + Lo(i + 1) + 2) >> 2;
-                    }
-                    sm.fl[i + 1] = (uint8_t)f;
-                } else if (lane == 24) {               // p'(-1, -1)
-                    int f = 0;
-                    if (avD) {
-                        const int c = To(-1);
-                        if (avA && avB) f = (To(0) + 2 * c + Lo(0) + 2) >> 2;
-                        else if (avB) f = (3 * c + To(0) + 2) >> 2;
-                        else if (avA) f = (3 * c + Lo(0) + 2) >> 2;
-                        else f = c;
-                    }
-                    sm.ft[0] = sm.fl[0] = (uint8_t)f;
+                sm.f8[12 + lane] = (uint8_t)f;
+            } else if (lane < 24) {                    // p'(-1, i)
+                const int i = lane - 16;
+                int f = 0;
+                if (avA) {
+                    if (i == 0) f = avD ? (Lo(-1) + 2 * Lo(0) + Lo(1) + 2) >> 2 : (3 * Lo(0) + Lo(1) + 2) >> 2;
+                    else if (i == 7) f = (Lo(6) + 3 * Lo(7) + 2) >> 2;
+                    else f = (Lo(i - 1) + 2 * Lo(i) + Lo(i + 1) + 2) >> 2;
                 }
-                __syncwarp();
-                auto T = [&](int i) { return (int)sm.ft[i + 1]; };
-                auto L = [&](int i) { return (int)sm.fl[i + 1]; };
-                const int dcv = mode == 2 ? dc_value(8, 3, avA, avB, T, L) : 0;
-                const int y = lane >> 2, x0 = (lane & 3) * 2;
-                int v[2];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-                    v[i] = clip255(pred_dir_sample(mode, 8, x0 + i, y, dcv, T, L) + sm.res[(yO + y) * 16 + xO + x0 + i]);
-                __syncwarp();
-                TY(xO + x0, yO + y) = (uint8_t)v[0]; TY(xO + x0 + 1, yO + y) = (uint8_t)v[1];
-                __syncwarp();
+                sm.f8[7 - i] = (uint8_t)f;
+            } else if (lane == 24) {                   // p'(-1, -1)
+                int f = 0;
+                if (avD) {
+                    const int c = To(-1);
+                    if (avA && avB) f = (To(0) + 2 * c + Lo(0) + 2) >> 2;
+                    else if (avB) f = (3 * c + To(0) + 2) >> 2;
+                    else if (avA) f = (3 * c + Lo(0) + 2) >> 2;
+                    else f = c;
+                }
+                sm.f8[8] = (uint8_t)f;
             }
+            __syncwarp();
+            int p0, p1;
+            if (mode == 2) {                           // DC (intra_prediction.cc:466-492)
+                const uint32_t* fw = reinterpret_cast<const uint32_t*>(sm.f8);
+                const int left = __dp4a(fw[0], 0x01010101u, __dp4a(fw[1], 0x01010101u, 0u));
+                const int top = __dp4a(fw[3], 0x01010101u, __dp4a(fw[4], 0x01010101u, 0u));
+                p0 = p1 = avA && avB ? (left + top + 8) >> 4 : (avA ? (left + 4) >> 3 : (avB ? (top + 4) >> 3 : 128));
+            } else {
+                const uint2 e = __ldg(reinterpret_cast<const uint2*>(&c_i8_pred[min(mode, 8) * 64 + y * 8 + x0]));
+                p0 = ((int)sm.f8[e.x & 0xFF] + 2 * (int)sm.f8[(e.x >> 8) & 0xFF] + (int)sm.f8[(e.x >> 16) & 0xFF] + 2) >> 2;
+                p1 = ((int)sm.f8[e.y & 0xFF] + 2 * (int)sm.f8[(e.y >> 8) & 0xFF] + (int)sm.f8[(e.y >> 16) & 0xFF] + 2) >> 2;
+            }
+            const uint32_t r2 = *reinterpret_cast<const uint32_t*>(&sm.res[(yO + y) * 16 + xO + x0]);
+            const int v0 = clip255(p0 + (int)(int16_t)(r2 & 0xFFFF)), v1 = clip255(p1 + (int)(int16_t)(r2 >> 16));
+            *reinterpret_cast<uint16_t*>(&TY(xO + x0, yO + y)) = (uint16_t)(v0 | v1 << 8);    // the block never reads its own samples
+            __syncwarp();
         }
     }
 
