@@ -25,6 +25,9 @@ constexpr int kWarpsPerCta = 4;
 #ifndef H264R_INTRA_CTAS
 #define H264R_INTRA_CTAS 4
 #endif
+#ifndef H264R_PREP_UNROLL
+#define H264R_PREP_UNROLL 0
+#endif
 #ifndef H264R_DEBLOCK_CTAS
 #define H264R_DEBLOCK_CTAS 4
 #endif
@@ -1184,20 +1187,29 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
     const bool q_intra = Q.flags & H264R_MB_FLAG_INTRA, t8 = Q.flags & H264R_MB_FLAG_T8x8;
     const bool p_skip = __ldg(&sl->slice_type) == H264R_P_SLICE && Q.mb_type == 0;
 
-    uint32_t bs[4] = { 0, 0, 0, 0 };
+    // (loops kept rolled: unrolled, the kernel was 77 KB of code for a 32 KB instruction cache)
+    uint32_t bs0 = 0, bs1 = 0, bs2 = 0, bs3 = 0;
+    auto bs_or = [&](int wi, uint32_t v) { if (wi == 0) bs0 |= v; else if (wi == 1) bs1 |= v; else if (wi == 2) bs2 |= v; else bs3 |= v; };
+#if H264R_PREP_UNROLL < 2
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int dir = 0; dir < 2; ++dir) {
         const bool mbedge = dir == 0 ? left : top;
         const HdrLite& PN = dir == 0 ? PL : PT;
-        const int pn_idx = dir == 0 ? q - 1 : q - W;
+#if H264R_PREP_UNROLL < 1
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int e = 0; e < 4; ++e) {
             const bool on = e == 0 ? mbedge : !(t8 && (e & 1));
             if (!on) continue;
             if (e > 0 && p_skip) continue;
             const int wi = dir * 2 + (e >> 1), sh = (e & 1) * 16;
             const bool p_intra = e ? q_intra : (PN.flags & H264R_MB_FLAG_INTRA) != 0;
-            if (p_intra || q_intra) { bs[wi] |= (e == 0 ? 0x4444u : 0x3333u) << sh; continue; }
+            if (p_intra || q_intra) { bs_or(wi, (e == 0 ? 0x4444u : 0x3333u) << sh); continue; }
             const int pcbp = e ? Q.cbp_blks : PN.cbp_blks;
             const bool same_part = e > 0 && (Q.mb_type == 1 || Q.mb_type == (dir == 0 ? 2 : 3));
 #pragma unroll
@@ -1208,11 +1220,11 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
                 if (((Q.cbp_blks >> blkQ) & 1) || ((pcbp >> blkP) & 1)) v = 2;
                 else if (!same_part && bs_compare(packed_entry(pic.packed_motion, e ? Q.packed : PN.packed, blkP),
                                                    packed_entry(pic.packed_motion, Q.packed, blkQ))) v = 1;
-                bs[wi] |= v << (sh + k4 * 4);
+                bs_or(wi, v << (sh + k4 * 4));
             }
         }
     }
-    out[0] = make_uint4(bs[0], bs[1], bs[2], bs[3]);
+    out[0] = make_uint4(bs0, bs1, bs2, bs3);
     // thresholds: type 0 = left MB edge, 1 = internal edge, 2 = top MB edge
     const int foa = (int)(int8_t)__ldg(&sl->filter_offset_a), fob = (int)(int8_t)__ldg(&sl->filter_offset_b);
 #pragma unroll
