@@ -23,7 +23,7 @@ struct FrameGeom {
 //   tc0[3] << 23, so that tc0(bS) = (par >> (8 + 5 * bS)) & 31.
 struct DeblockDesc {
     uint32_t bs[4];
-    uint32_t par[3][4];              // [Y, Cb, Cr][type 0..2, pad]
+    uint32_t par[12];                // [Y, Cb, Cr][type 0..2] contiguous (9 words), 3 words unused
 };
 
 struct DevPicture {

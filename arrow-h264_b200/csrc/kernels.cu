@@ -273,7 +273,7 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 
     // 384 x int16 = 48 x 16 B; saturating pack to int16 pairs, then the [-255, 255] clamp on both halves at once
     uint4* out = reinterpret_cast<uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
-    for (int v = lane; v < 48; v += 32) {
+    auto pack8 = [&](int v) {                            // eight consecutive samples of the raster -> one 16-byte store
         const int* r = res + v * 8;
         uint32_t w[4];
 #pragma unroll
@@ -283,7 +283,9 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
             w[k] = __vmaxs2(__vmins2(pr, 0x00FF00FFu), 0xFF01FF01u);
         }
         out[v] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    };
+    pack8(lane);
+    if (lane < 16) pack8(32 + lane);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1227,20 +1229,22 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
     out[0] = make_uint4(bs0, bs1, bs2, bs3);
     // thresholds: type 0 = left MB edge, 1 = internal edge, 2 = top MB edge
     const int foa = (int)(int8_t)__ldg(&sl->filter_offset_a), fob = (int)(int8_t)__ldg(&sl->filter_offset_b);
+    uint32_t w[12];                                       // [plane][type], contiguous: no padding words
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-        uint32_t w[3];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const HdrLite& P = t == 0 ? PL : (t == 2 ? PT : Q);
             const int qp_p = pl ? P.qp_c[pl - 1] : P.qp_y, qp_q = pl ? Q.qp_c[pl - 1] : Q.qp_y;
             const int qPav = (qp_p + qp_q + 1) >> 1;
             const int ia = clip3i(0, 51, qPav + foa), ib = clip3i(0, 51, qPav + fob);
-            w[t] = (uint32_t)c_alpha[ia] | (uint32_t)c_beta[ib] << 8 | (uint32_t)c_tc0[ia][0] << 13 |
+            w[pl * 3 + t] = (uint32_t)c_alpha[ia] | (uint32_t)c_beta[ib] << 8 | (uint32_t)c_tc0[ia][0] << 13 |
                    (uint32_t)c_tc0[ia][1] << 18 | (uint32_t)c_tc0[ia][2] << 23;
         }
-        out[1 + pl] = make_uint4(w[0], w[1], w[2], 0);
     }
+    out[1] = make_uint4(w[0], w[1], w[2], w[3]);
+    out[2] = make_uint4(w[4], w[5], w[6], w[7]);
+    reinterpret_cast<uint32_t*>(out)[12] = w[8];
 }
 
 // ---- pass 2 (row wavefront): filtering, in place ----
@@ -1377,16 +1381,21 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
     const int boxlane_y = (lane & 16) + 12 + (l >> 2), boxlane_c = (lane & 16) + ((l >> 2) & 1) * 8 + 6 + ((l >> 1) & 1);
 
     // prefetch of MB 0: descriptor (strengths, luma thresholds, thresholds of this lane's chroma plane), own samples
-    uint4 n_bs = make_uint4(0, 0, 0, 0), n_py = n_bs, n_pc = n_bs, n_ownY = n_bs; uint2 n_ownC = make_uint2(0, 0);
+    // thresholds: words 4..12 of the descriptor = [Y, Cb, Cr][left edge, internal, top edge]: two 128-bit loads and one word,
+    // every loaded word used (a padded row per plane left a dead destination register that the compiler recycled at once: its
+    // write then waited for the whole load, 24 % of the kernel's stall samples in ncu v28/v33)
+    uint4 n_bs = make_uint4(0, 0, 0, 0), n_pa = n_bs, n_pb = n_bs, n_ownY = n_bs; uint2 n_ownC = make_uint2(0, 0); uint32_t n_pz = 0;
     if (enabled) {
-        n_bs = __ldg(desc); n_py = __ldg(desc + 1); n_pc = __ldg(desc + 2 + cpl);
+        n_bs = __ldg(desc); n_pa = __ldg(desc + 1); n_pb = __ldg(desc + 2); n_pz = __ldg(reinterpret_cast<const unsigned int*>(desc) + 12);
         n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y)));
         n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c)));
     }
     uint32_t boxY = 0, boxC = 0;                          // this lane's mailbox words of the previous MB (after its horizontal pass)
 
     for (int mbx = 0; mbx < W; ++mbx) {
-        const uint4 bs = n_bs, parY = n_py, parC = n_pc, ownY = n_ownY; const uint2 ownC = n_ownC;
+        const uint4 bs = n_bs, ownY = n_ownY; const uint2 ownC = n_ownC;
+        const uint4 parY = make_uint4(n_pa.x, n_pa.y, n_pa.z, 0u);
+        const uint4 parC = cpl ? make_uint4(n_pb.z, n_pb.w, n_pz, 0u) : make_uint4(n_pa.w, n_pb.x, n_pb.y, 0u);
         const int px = mbx * 16, cx = mbx * 8;
 
         // mailbox of the MB above: issued now, looked at after the vertical pass
@@ -1401,7 +1410,8 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
 
         // prefetch the next MB: independent of every other MB of this kernel
         if (mbx + 1 < W && enabled) {
-            n_bs = __ldg(desc + (mbx + 1) * 4); n_py = __ldg(desc + (mbx + 1) * 4 + 1); n_pc = __ldg(desc + (mbx + 1) * 4 + 2 + cpl);
+            n_bs = __ldg(desc + (mbx + 1) * 4); n_pa = __ldg(desc + (mbx + 1) * 4 + 1); n_pb = __ldg(desc + (mbx + 1) * 4 + 2);
+            n_pz = __ldg(reinterpret_cast<const unsigned int*>(desc + (mbx + 1) * 4) + 12);
             n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y + px + 16)));
             n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + cx + 8)));
         }
