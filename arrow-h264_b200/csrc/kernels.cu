@@ -25,6 +25,9 @@ constexpr int kWarpsPerCta = 4;
 #ifndef H264R_INTRA_CTAS
 #define H264R_INTRA_CTAS 4
 #endif
+#ifndef H264R_RESID_CTAS
+#define H264R_RESID_CTAS 14
+#endif
 #ifndef H264R_PREP_UNROLL
 #define H264R_PREP_UNROLL 0
 #endif
@@ -156,7 +159,7 @@ __device__ __forceinline__ void idct8_1d(int* p, int stride, bool final_pass)
 // [-255, 255]: clip(pred + res) cannot tell the difference) to the picture's residual plane.
 struct __align__(16) ResidSmem { int cof[384]; unsigned nz; };
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_RESID_CTAS)
 residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 {
     __shared__ __align__(16) ResidSmem smem_all[kWarpsPerCta];
