@@ -157,7 +157,13 @@ __device__ __forceinline__ void idct8_1d(int* p, int stride, bool final_pass)
 // residual_kernel: one warp per MB that received levels.  Scatters the dequantised levels into shared memory,
 // runs the DC Hadamards and the inverse transforms, and writes the MB's 384 residual samples (int16, clamped to
 // [-255, 255]: clip(pred + res) cannot tell the difference) to the picture's residual plane.
-struct __align__(16) ResidSmem { int cof[384]; unsigned nz; };
+//
+// Shared-memory layout (ints): luma 16 rows of pitch 20, chroma 2 planes x 8 rows of pitch 12, planes 104 apart.  The
+// padded pitches put the 128-bit row accesses of a quarter warp (eight 4x4 blocks, or the eight rows of an 8x8 block)
+// on eight distinct bank groups; with the raster pitches 16 / 8 they fell two to four on one, and at 14 resident CTAs
+// per SM the kernel waits on the shared-memory pipe (ncu v36: mio_throttle 4.5 cycles per issue).
+constexpr int kResP = 20, kResCP = 12, kResCPlane = 104, kResC = 16 * kResP, kResInts = kResC + 2 * kResCPlane;
+struct __align__(16) ResidSmem { int cof[kResInts]; };
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_RESID_CTAS)
 residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
@@ -179,8 +185,8 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
     const int per = h.qp_y / 6, rem = h.qp_y - per * 6;
 
 #pragma unroll
-    for (int k = 0; k < 3; ++k) reinterpret_cast<int4*>(res)[lane + 32 * k] = make_int4(0, 0, 0, 0);
-    if (lane == 0) sm.nz = 0;
+    for (int k = 0; k < (kResInts / 4 + 31) / 32; ++k)
+        if (lane + 32 * k < kResInts / 4) reinterpret_cast<int4*>(res)[lane + 32 * k] = make_int4(0, 0, 0, 0);
     __syncwarp();
 
     // scatter: dequantise at coeff_luma_ac / coeff_chroma_ac time (transform.cc:394-456); DC levels stay raw
@@ -190,9 +196,10 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
         const uint32_t e = __ldg(lv + i);
         const int p = (int)(e & 0xFFFFu), l = (int)(int16_t)(e >> 16);
         if (p >= 384 || l == 0) continue;
-        int val = 0;
+        int val = 0, at;
         if (p < 256) {
             const int x = p & 15, y = p >> 4;
+            at = p + (y << 2);                                   // y * kResP + x
             if (i16) {
                 if (((x | y) & 3) == 0) val = l;
                 else val = ((l * (int)__ldg(&sl->level_scale_4x4[0][0][rem][(y & 3) * 4 + (x & 3)])) * (1 << per) + 8) >> 4;
@@ -201,8 +208,10 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
                 else    val = ((l * (int)__ldg(&sl->level_scale_4x4[inter][0][rem][(y & 3) * 4 + (x & 3)])) * (1 << per) + 8) >> 4;
             }
             nz |= 1u << ((y >> 2) * 4 + (x >> 2));
-        } else if (h.cbp_chroma) {
+        } else {
             const int c = p - 256, pl = c >> 6, x = c & 7, y = (c >> 3) & 7;
+            at = kResC + pl * kResCPlane + y * kResCP + x;
+            if (!h.cbp_chroma) continue;
             if (((x | y) & 3) == 0) val = l;
             else {
                 const int qc = pl ? h.qp_c[1] : h.qp_c[0], cper = qc / 6, crem = qc - cper * 6;   // (no dynamic index: keeps h in registers)
@@ -210,7 +219,7 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
             }
             nz |= 1u << (16 + pl * 4 + (y >> 2) * 2 + (x >> 2));
         }
-        res[p] = val;
+        res[at] = val;
     }
     nz = __reduce_or_sync(0xFFFFFFFFu, nz);
     __syncwarp();
@@ -222,7 +231,7 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) c[i][j] = res[i * 64 + j * 4];
+                for (int j = 0; j < 4; ++j) c[i][j] = res[i * 4 * kResP + j * 4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 int a0 = c[i][0] + c[i][2], a1 = c[i][0] - c[i][2], a2 = c[i][1] - c[i][3], a3 = c[i][1] + c[i][3];
@@ -235,7 +244,7 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
                 int f[4] = { a0 + a3, a1 + a2, a1 - a2, a0 - a3 };
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    res[i * 64 + j * 4] = h.qp_y >= 36 ? (f[i] * scale) * (1 << (per - 6))
+                    res[i * 4 * kResP + j * 4] = h.qp_y >= 36 ? (f[i] * scale) * (1 << (per - 6))
                                                        : (f[i] * scale + (1 << (5 - per))) >> (6 - per);
             }
         }
@@ -244,14 +253,14 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
     if (h.cbp_chroma && (nz >> 16)) {
         if (lane == 1 || lane == 2) {
             const int pl = lane - 1, qc = pl ? h.qp_c[1] : h.qp_c[0], cper = qc / 6, crem = qc - cper * 6;
-            int* c = res + 256 + pl * 64;
-            int c00 = c[0], c01 = c[4], c10 = c[32], c11 = c[36];
+            int* c = res + kResC + pl * kResCPlane;             // DC positions (0,0) (0,4) (4,0) (4,4)
+            int c00 = c[0], c01 = c[4], c10 = c[4 * kResCP], c11 = c[4 * kResCP + 4];
             int e00 = c00 + c01, e01 = c00 - c01, e10 = c10 + c11, e11 = c10 - c11;
             const int scale = (int)__ldg(&sl->level_scale_4x4[inter][pl + 1][crem][0]);
             c[0]  = (((e00 + e10) * scale) * (1 << cper)) >> 5;
             c[4]  = (((e01 + e11) * scale) * (1 << cper)) >> 5;
-            c[32] = (((e00 - e10) * scale) * (1 << cper)) >> 5;
-            c[36] = (((e01 - e11) * scale) * (1 << cper)) >> 5;
+            c[4 * kResCP]     = (((e00 - e10) * scale) * (1 << cper)) >> 5;
+            c[4 * kResCP + 4] = (((e01 - e11) * scale) * (1 << cper)) >> 5;
         }
         nz |= 0xFF0000u;
     }
@@ -260,24 +269,24 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
     // inverse transforms, only where something is non-zero
     if (t8) {
         const int b = lane >> 3, i = lane & 7;
-        int* blk = res + (b >> 1) * 128 + (b & 1) * 8;
+        int* blk = res + (b >> 1) * 8 * kResP + (b & 1) * 8;
         const unsigned m8 = 0x33u << ((b >> 1) * 8 + (b & 1) * 2);          // the four 4x4 blocks of 8x8 block b
-        if (nz & m8) idct8_1d(blk + i * 16, 1, false);
+        if (nz & m8) idct8_1d(blk + i * kResP, 1, false);
         __syncwarp();
-        if (nz & m8) idct8_1d(blk + i, 16, true);
-        if (lane < 8 && ((nz >> (16 + lane)) & 1)) idct4_inplace(res + 256 + (lane >> 2) * 64 + ((lane >> 1) & 1) * 32 + (lane & 1) * 4, 8);
+        if (nz & m8) idct8_1d(blk + i, kResP, true);
+        if (lane < 8 && ((nz >> (16 + lane)) & 1)) idct4_inplace(res + kResC + (lane >> 2) * kResCPlane + ((lane >> 1) & 1) * 4 * kResCP + (lane & 1) * 4, kResCP);
     } else if (lane < 24) {
         // one instruction stream for the sixteen luma blocks (lanes 0..15, row pitch 16) and the eight chroma blocks
         const int c = lane - 16;
-        int* const blk = lane < 16 ? res + (lane >> 2) * 64 + (lane & 3) * 4 : res + 256 + (c >> 2) * 64 + ((c >> 1) & 1) * 32 + (c & 1) * 4;
-        if ((nz >> lane) & 1) idct4_inplace(blk, lane < 16 ? 16 : 8);
+        int* const blk = lane < 16 ? res + (lane >> 2) * 4 * kResP + (lane & 3) * 4
+                                   : res + kResC + (c >> 2) * kResCPlane + ((c >> 1) & 1) * 4 * kResCP + (c & 1) * 4;
+        if ((nz >> lane) & 1) idct4_inplace(blk, lane < 16 ? kResP : kResCP);
     }
     __syncwarp();
 
     // 384 x int16 = 48 x 16 B; saturating pack to int16 pairs, then the [-255, 255] clamp on both halves at once
     uint4* out = reinterpret_cast<uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
-    auto pack8 = [&](int v) {                            // eight consecutive samples of the raster -> one 16-byte store
-        const int* r = res + v * 8;
+    auto pack8 = [&](const int* r, int v) {              // eight consecutive samples of a row -> one 16-byte store
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -287,8 +296,8 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
         }
         out[v] = make_uint4(w[0], w[1], w[2], w[3]);
     };
-    pack8(lane);
-    if (lane < 16) pack8(32 + lane);
+    pack8(res + (lane >> 1) * kResP + (lane & 1) * 8, lane);                                       // luma row lane >> 1, half lane & 1
+    if (lane < 16) pack8(res + kResC + (lane >> 3) * kResCPlane + (lane & 7) * kResCP, 32 + lane);   // plane lane >> 3, row lane & 7
 }
 
 // ---------------------------------------------------------------------------------------------------
