@@ -502,12 +502,20 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
             }
         }
         __syncwarp();
-        if (active) {
-            prevY0 = curY0; prevY1 = curY1; prevC = curC; ref_prev = ref_cur; ref_cur = refidx;
+        {
+            // stage masks of the warp: every lane runs the stages some lane needs (warp-uniform branches, no divergence
+            // bookkeeping); lanes without a second list contribute nothing and keep their samples
             const int xf = vx & 3, yf = vy & 3;
-            const bool any_j = __any_sync(__activemask(), (xf == 2 && yf != 0) || (yf == 2 && xf != 0));
-            mc_luma_patch_4x2(wl, loff, xf, yf, any_j, curY0, curY1);
-            curC = mc_chroma_patch_2x2(wc, coff, vx & 7, vy & 7);
+            unsigned hm, cm;
+            mc_luma_masks(xf, yf, hm, cm);
+            const unsigned whm = __reduce_or_sync(0xFFFFFFFFu, active ? hm : 0u), wcm = __reduce_or_sync(0xFFFFFFFFu, active ? cm : 0u);
+            uint32_t y0, y1;
+            mc_luma_patch_4x2(wl, loff, xf, yf, whm, wcm, y0, y1);
+            const uint32_t c = mc_chroma_patch_2x2(wc, coff, vx & 7, vy & 7);
+            if (active) {
+                prevY0 = curY0; prevY1 = curY1; prevC = curC; ref_prev = ref_cur; ref_cur = refidx;
+                curY0 = y0; curY1 = y1; curC = c;
+            }
         }
         __syncwarp();
     }

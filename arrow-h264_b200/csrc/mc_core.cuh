@@ -120,9 +120,20 @@ MC_FN void mc_htap4(uint32_t a0, uint32_t a1, uint32_t a2, int out[4])
 //   raw stage       : the four samples at column offset dx -> integer samples G, and the running vertical 6-tap of
 //                     the half sample h in 16x2 lanes (E = columns 0,2; O = columns 1,3).  The lanes start at
 //                     2560 + 16 (= (80 << 5) + 16) and never go negative, so packed IMADs are exact per lane.
-// `any_j` lets a warp in which no lane needs j skip those accumulations (pass true if unknown).
+// The stages a lane needs are row masks (mc_luma_masks); the caller ORs them over the warp and passes the WARP masks:
+// every lane then runs the same stages (lanes that do not need one compute values they never select), the branches
+// are warp-uniform and cost no divergence bookkeeping.  Bit 0 of the horizontal mask is set only by lanes that need j.
+MC_FN void mc_luma_masks(int xf, int yf, unsigned& hmask, unsigned& cmask)
+{
+    const bool hasB = xf != 0 && yf != 2, hasH = yf != 0 && xf != 2;
+    const bool hasJ = (xf == 2 && yf != 0) || (yf == 2 && xf != 0);
+    const bool hasG = (xf == 0 && yf != 2) || (yf == 0 && xf != 2);
+    const int dy = yf == 3;
+    hmask = hasJ ? 0x7Fu : (hasB ? 3u << (2 + dy) : 0u);                 // rows that get the horizontal 6-tap
+    cmask = hasH ? 0x7Fu : ((hasG && yf == 0) ? 0x0Cu : 0u);             // rows whose raw samples are needed
+}
 constexpr int kLumaPitchWords = 4;
-MC_FN void mc_luma_patch_4x2(const uint32_t* win, int off, int xf, int yf, bool any_j, uint32_t& out0, uint32_t& out1)
+MC_FN void mc_luma_patch_4x2(const uint32_t* win, int off, int xf, int yf, unsigned hmask, unsigned cmask, uint32_t& out0, uint32_t& out1)
 {
     constexpr int pitch_words = kLumaPitchWords;
     const bool hasB = xf != 0 && yf != 2;                       // clipped horizontal half sample b (row + dy)
@@ -130,8 +141,7 @@ MC_FN void mc_luma_patch_4x2(const uint32_t* win, int off, int xf, int yf, bool 
     const bool hasJ = (xf == 2 && yf != 0) || (yf == 2 && xf != 0);
     const bool hasG = (xf == 0 && yf != 2) || (yf == 0 && xf != 2);
     const int dx = xf == 3, dy = yf == 3;
-    const unsigned hmask = hasJ ? 0x7Fu : (hasB ? 3u << (2 + dy) : 0u);                 // rows that get the horizontal 6-tap
-    const unsigned cmask = hasH ? 0x7Fu : ((hasG && yf == 0) ? 0x0Cu : 0u);             // rows whose raw samples are needed
+    const bool any_j = hmask & 1u;
 
     const int o2 = off - 2;
     const uint32_t* wa = win + (o2 >> 2);

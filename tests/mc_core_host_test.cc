@@ -85,7 +85,13 @@ static void test_luma()
                 for (int xf = 0; xf < 4; ++xf)
                     for (int yf = 0; yf < 4; ++yf) {
                         uint32_t o0, o1;
-                        mc_luma_patch_4x2(reinterpret_cast<const uint32_t*>(win), off, xf, yf, true, o0, o1);
+                        unsigned hm, cm;
+                        mc_luma_masks(xf, yf, hm, cm);
+                        // own masks, then every stage on (what a warp with lanes of all sixteen positions passes)
+                        mc_luma_patch_4x2(reinterpret_cast<const uint32_t*>(win), off, xf, yf, hm, cm, o0, o1);
+                        uint32_t a0, a1;
+                        mc_luma_patch_4x2(reinterpret_cast<const uint32_t*>(win), off, xf, yf, 0x7Fu, 0x7Fu, a0, a1);
+                        if ((a0 != o0 || a1 != o1) && fails++ < 20) printf("warp masks change the result at xf=%d yf=%d off=%d\n", xf, yf, off);
                         auto W = [&](int x, int y) { return (int)win[(y + 2) * pitch + off + x]; };
                         for (int y = 0; y < 2; ++y)
                             for (int x = 0; x < 4; ++x) {
