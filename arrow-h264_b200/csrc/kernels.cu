@@ -25,6 +25,9 @@ constexpr int kWarpsPerCta = 4;
 #ifndef H264R_INTRA_CTAS
 #define H264R_INTRA_CTAS 4
 #endif
+#ifndef H264R_INTER_TWO_MB
+#define H264R_INTER_TWO_MB 1
+#endif
 #ifndef H264R_RESID_CTAS
 #define H264R_RESID_CTAS 14
 #endif
@@ -44,6 +47,8 @@ __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { 
 
 __device__ __forceinline__ uint32_t ldcg_u32(const void* p) { return __ldcg(reinterpret_cast<const unsigned int*>(p)); }
 __device__ __forceinline__ uint8_t  ldcg_u8(const uint8_t* p) { return __ldcg(p); }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 __device__ __forceinline__ int ld_acquire(const int* p)
 {
@@ -559,6 +564,241 @@ recon_inter_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8
     *reinterpret_cast<uint32_t*>(dY + pitch_y) = outY1;
     *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(outC & 0xFFFF);
     *reinterpret_cast<uint16_t*>(dC + pitch_c) = (uint16_t)(outC >> 16);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inter prediction, two macroblocks per warp
+//
+// Lanes 0..15 reconstruct MB 2j, lanes 16..31 MB 2j+1 of a row; lane b of a half owns 4x4 luma block b (raster) and the
+// 2x2 chroma patches of both planes under it.  Against one-MB-per-warp with 4x2 patches: the per-MB work that is the
+// same for every lane (header, slice, partition walk, addressing, weights, loop control: two thirds of that kernel's
+// instructions) is issued once for two MBs, and a 4x4 patch filters 9 window rows for 4 output rows where two 4x2
+// patches filter 14.  If one partition covers an 8x8 quadrant its four lanes share one 13x13 luma / 5x5 chroma window,
+// otherwise every block has its own 9x9 / 3x3 window (same window layout per quadrant as above).
+struct __align__(16) Inter2Smem {
+    uint32_t luma[2][4 * kLumaQ + 2];
+    uint32_t chroma[2][4 * kChromaQ + 2];
+};
+
+__device__ __forceinline__ void partition_of_block2(const MbHdr& h, int is_b, int direct_spatial, const uint8_t* pm, int direct8x8,
+                                                    int blk, int& origin, int& dir, bool& covers8x8)
+{
+    const int bx = blk & 3, by = blk >> 2;
+    int sh0 = (0x11222440u >> (4 * (h.mb_type & 7))) & 7, sv0 = (0x12124240u >> (4 * (h.mb_type & 7))) & 7;
+    if (h.mb_type == 0) sh0 = sv0 = is_b ? 2 : 4;
+    const int i0 = bx & ~(sh0 - 1), j0 = by & ~(sv0 - 1);
+    const int b8 = 2 * (j0 >> 1) + (i0 >> 1);
+    const int mode = (h.u0 >> (8 * b8)) & 0xFF;
+    int pd = (h.u1 >> (8 * b8)) & 0xFF;
+    int sh4 = (0x11222440u >> (4 * (mode & 7))) & 7, sv4 = (0x12124240u >> (4 * (mode & 7))) & 7;
+    if (mode == 0) sh4 = sv4 = direct8x8 ? 2 : 1;
+    if (is_b && h.mb_type == H264R_MB_8x8 && direct_spatial) {
+        const uint32_t rw = __ldg(packed_entry(pm, h.packed, j0 * 4 + i0) + 2);
+        pd = (int8_t)(rw >> 8) < 0 ? 0 : ((int8_t)rw < 0 ? 1 : 2);
+    }
+    const int i = bx & ~(sh4 - 1), j = by & ~(sv4 - 1);   // partitions are aligned to their own size
+    origin = j * 4 + i;
+    dir = pd;
+    covers8x8 = sh4 >= 2 && sv4 >= 2;
+}
+
+#ifndef H264R_INTER2_CTAS
+#define H264R_INTER2_CTAS 7
+#endif
+// grid = (ceil(width_mbs / 8), height_mbs, pictures of the wave)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTER2_CTAS)
+recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8x8)
+{
+    __shared__ __align__(16) Inter2Smem smem_all[kWarpsPerCta];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = lane >> 4, b = lane & 15, bx = b & 3, by = b >> 2;
+    const int mbx = (blockIdx.x * kWarpsPerCta + warp) * 2 + m, mby = blockIdx.y;
+    const DevPicture& pic = pics[blockIdx.z];
+    if (!pic.has_inter) return;
+    const int W = g.width_mbs;
+    if ((blockIdx.x * kWarpsPerCta + warp) * 2 >= W) return;
+    const int addr = mby * W + min(mbx, W - 1);
+    const MbHdr h = load_hdr(pic.mbs, addr);
+    const bool valid = mbx < W && !h.intra();
+    if (!__any_sync(0xFFFFFFFFu, valid)) return;
+    Inter2Smem& sm = smem_all[warp];
+    const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
+    const int wY = W * 16, hY = g.height_mbs * 16, wC = wY >> 1, hC = hY >> 1;
+    const uint32_t s0 = __ldg(reinterpret_cast<const uint32_t*>(sl)), s1 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 1),
+                   s2 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 2);
+    const bool is_b = (s0 & 0xFF) == H264R_B_SLICE;
+    const int denom_y = s1 & 0xFF, denom_c = (s1 >> 8) & 0xFF, wp_flag = (s1 >> 16) & 0xFF, bipred_idc = (s1 >> 24) & 0xFF;
+    const int direct_spatial = (s2 >> 8) & 0xFF;
+
+    // the residual is needed last: pull its six lines into the L2 now (no registers held), the loads at the end then
+    // cost an L2 hit instead of one more HBM round trip on the warp's dependent chain
+    if (valid && h.has_resid() && b < 6) prefetch_l2(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB + b * 64);
+    int origin = 0, pd = 0; bool uni = true;
+    uint32_t mvw0 = 0, mvw1 = 0, rw = 0;                 // the motion entry of this block's partition
+    if (valid) {
+        partition_of_block2(h, is_b, direct_spatial, pic.packed_motion, direct8x8, b, origin, pd, uni);
+        const uint32_t* e = packed_entry(pic.packed_motion, h.packed, origin);
+        mvw0 = __ldg(e); mvw1 = __ldg(e + 1); rw = __ldg(e + 2);
+    }
+    const int q = (by >> 1) * 2 + (bx >> 1), sb = (by & 1) * 2 + (bx & 1);        // quadrant, block inside the quadrant
+    uint32_t* const lq = sm.luma[m] + q * kLumaQ;
+    uint32_t* const cq = sm.chroma[m] + q * kChromaQ;
+    const int pitch_y = g.pitch_y, pitch_c = g.pitch_c;
+
+    // samples of the (up to) two lists, packed bytes: cur = last list done, prev = the one before
+    uint32_t curY[4] = { 0, 0, 0, 0 }, prevY[4] = { 0, 0, 0, 0 }, curC[2] = { 0, 0 }, prevC[2] = { 0, 0 };
+    int ref_cur = 0, ref_prev = 0;
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        const bool active = valid && (k == 0 || pd == 2);
+        if (k == 1 && !__any_sync(0xFFFFFFFFu, active)) break;
+        const int list = pd == 2 ? k : pd;
+        int vx = 0, vy = 0, refidx = 0;
+        const uint32_t* wl = lq; const uint32_t* wc0 = cq; const uint32_t* wc1 = cq;
+        int loff = 2, coff = 0;
+        if (active) {
+            refidx = (int)(int8_t)(rw >> (8 * list));
+            const int slot = (int)(int8_t)(rw >> (16 + 8 * list));
+            const uint8_t* __restrict__ rbase = pic.ref[slot & 31];
+            const uint32_t mvw = list ? mvw1 : mvw0;
+            const int mvx = (int)(int16_t)(mvw & 0xFFFF), mvy = (int)(int16_t)(mvw >> 16);
+            vx = (mbx * 16 + bx * 4) * 4 + mvx; vy = (mby * 16 + by * 4) * 4 + mvy;       // this block's position
+            if (uni) {
+                const int qvx = (mbx * 16 + (bx >> 1) * 8) * 4 + mvx, qvy = (mby * 16 + (by >> 1) * 8) * 4 + mvy;
+                const int x0 = (qvx >> 2) - 2, y0 = (qvy >> 2) - 2, cx0 = qvx >> 3, cy0 = qvy >> 3;
+                const int xa = x0 & ~3, cxa = cx0 & ~3;
+                const bool in_y = xa >= 0 && xa + 16 <= wY && y0 >= 0 && y0 + 13 <= hY;
+                const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 5 <= hC;
+                if (in_y) {                                     // 13 rows x 4 words: lane = word column
+                    const uint8_t* src = rbase + (uint32_t)(y0 * pitch_y + xa + sb * 4);
+                    uint32_t v[13];
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) v[i] = ldg_u32(src + (uint32_t)(i * pitch_y));
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) lq[i * 4 + sb] = v[i];
+                } else load_window_border(lq, 4, rbase, pitch_y, wY, hY, x0, y0, 13, 13, sb, 4);
+                {                                               // 2 planes x 5 rows x 2 words: lane = (plane, word column)
+                    const int pl = sb >> 1, col = sb & 1;
+                    const uint8_t* cplane = rbase + (pl ? g.off_cr : g.off_cb);
+                    if (in_c) {
+                        const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa + col * 4);
+                        uint32_t v[5];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) v[i] = ldg_u32(src + (uint32_t)(i * pitch_c));
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) cq[pl * 10 + i * 2 + col] = v[i];
+                    } else load_window_border(cq + pl * 10, 2, cplane, pitch_c, wC, hC, cx0, cy0, 5, 5, col, 2);
+                }
+                wl = lq + (sb >> 1) * 4 * 4;
+                loff = 2 + (sb & 1) * 4 + (in_y ? x0 & 3 : 0);
+                wc0 = cq + (sb >> 1) * 2 * 2; wc1 = wc0 + 10;
+                coff = (sb & 1) * 2 + (in_c ? cx0 & 3 : 0);
+            } else {
+                const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2, cx0 = vx >> 3, cy0 = vy >> 3;
+                const int xa = x0 & ~3, cxa = cx0 & ~3;
+                const bool in_y = xa >= 0 && xa + 12 <= wY && y0 >= 0 && y0 + 9 <= hY;
+                const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 3 <= hC;
+                uint32_t* const lb = lq + sb * 36;
+                uint32_t* const cb = cq + sb * 12;
+                if (in_y) {                                     // 9 rows x 3 words
+                    const uint8_t* src = rbase + (uint32_t)(y0 * pitch_y + xa);
+#pragma unroll
+                    for (int i0 = 0; i0 < 9; i0 += 3) {
+                        uint32_t v[3][3];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) v[i][c] = ldg_u32(src + (uint32_t)((i0 + i) * pitch_y) + c * 4);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) lb[(i0 + i) * 4 + c] = v[i][c];
+                    }
+                } else load_window_border(lb, 4, rbase, pitch_y, wY, hY, x0, y0, 9, 9, 0, 1);
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {                // 3 rows x 2 words per plane
+                    const uint8_t* cplane = rbase + (pl ? g.off_cr : g.off_cb);
+                    if (in_c) {
+                        const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa);
+                        uint32_t v[3][2];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) { v[i][0] = ldg_u32(src + (uint32_t)(i * pitch_c)); v[i][1] = ldg_u32(src + (uint32_t)(i * pitch_c) + 4); }
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) { cb[pl * 6 + i * 2] = v[i][0]; cb[pl * 6 + i * 2 + 1] = v[i][1]; }
+                    } else load_window_border(cb + pl * 6, 2, cplane, pitch_c, wC, hC, cx0, cy0, 3, 3, 0, 1);
+                }
+                wl = lb;
+                loff = 2 + (in_y ? x0 & 3 : 0);
+                wc0 = cb; wc1 = cb + 6;
+                coff = in_c ? cx0 & 3 : 0;
+            }
+        }
+        __syncwarp();
+        {
+            const int xf = vx & 3, yf = vy & 3;
+            unsigned hm, cm;
+            mc_luma_masks_r<4>(xf, yf, hm, cm);
+            const unsigned whm = __reduce_or_sync(0xFFFFFFFFu, active ? hm : 0u), wcm = __reduce_or_sync(0xFFFFFFFFu, active ? cm : 0u);
+            uint32_t y[4];
+            mc_luma_patch<4>(wl, loff, xf, yf, whm, wcm, y);
+            const uint32_t c0 = mc_chroma_patch_2x2(wc0, coff, vx & 7, vy & 7), c1 = mc_chroma_patch_2x2(wc1, coff, vx & 7, vy & 7);
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { prevY[r] = curY[r]; curY[r] = y[r]; }
+                prevC[0] = curC[0]; prevC[1] = curC[1]; curC[0] = c0; curC[1] = c1;
+                ref_prev = ref_cur; ref_cur = refidx;
+            }
+        }
+        __syncwarp();
+    }
+    if (!valid) return;
+
+    // weighted sample prediction (mc_prediction / bi_prediction, inter_prediction.cc:53-156), residual, store
+    const bool uni_weighted = (wp_flag && !is_b) || (bipred_idc == 1 && is_b);
+    const int ref0 = pd == 2 ? ref_prev : ref_cur, ref1 = ref_cur;
+    const int mode = pd != 2 ? (uni_weighted ? 1 : 0) : (bipred_idc == 0 ? 2 : 3);
+    int wgt[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } }, off[3] = { 0, 0, 0 };             // [Y, Cb, Cr][list]
+    if (mode == 1) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            wgt[pl][0] = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][ref0 & 31]);
+            off[pl] = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][ref0 & 31]);
+        }
+    } else if (mode == 3) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            if (bipred_idc == 1) {
+                wgt[pl][0] = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][ref0 & 31]);
+                wgt[pl][1] = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][ref1 & 31]);
+                off[pl] = ((int)(int8_t)__ldg(&sl->wp_offset[0][pl][ref0 & 31]) + (int)(int8_t)__ldg(&sl->wp_offset[1][pl][ref1 & 31]) + 1) >> 1;
+            } else {
+                wgt[pl][1] = (int)__ldg(&sl->implicit_w1[ref0 & 31][ref1 & 31]);
+                wgt[pl][0] = 64 - wgt[pl][1];
+            }
+        }
+    }
+    const bool has_res = h.has_resid();
+    const int16_t* __restrict__ rs = pic.resid + (size_t)addr * H264R_COEFFS_PER_MB;
+    uint8_t* dY = pic.dst + (uint32_t)((mby * 16 + by * 4) * pitch_y + mbx * 16 + bx * 4);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const uint2 res = has_res ? __ldg(reinterpret_cast<const uint2*>(rs + (by * 4 + r) * 16 + bx * 4)) : make_uint2(0, 0);
+        const uint32_t p0 = pd == 2 ? prevY[r] : curY[r];
+        *reinterpret_cast<uint32_t*>(dY + (uint32_t)(r * pitch_y)) = mc_weight_recon4(mode, p0, curY[r], wgt[0][0], wgt[0][1], denom_y, off[0], res.x, res.y);
+    }
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+        uint32_t r0 = 0, r1 = 0;
+        if (has_res) {
+            r0 = __ldg(reinterpret_cast<const uint32_t*>(rs + 256 + pl * 64 + (by * 2) * 8 + bx * 2));
+            r1 = __ldg(reinterpret_cast<const uint32_t*>(rs + 256 + pl * 64 + (by * 2 + 1) * 8 + bx * 2));
+        }
+        const uint32_t p0 = pd == 2 ? prevC[pl] : curC[pl];
+        const uint32_t o = mc_weight_recon4(mode, p0, curC[pl], wgt[1 + pl][0], wgt[1 + pl][1], denom_c, off[1 + pl], r0, r1);
+        uint8_t* dC = pic.dst + (pl ? g.off_cr : g.off_cb) + (uint32_t)((mby * 8 + by * 2) * pitch_c + mbx * 8 + bx * 2);
+        *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(o & 0xFFFF);
+        *reinterpret_cast<uint16_t*>(dC + pitch_c) = (uint16_t)(o >> 16);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1567,8 +1807,13 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     }
     if (which == KERNEL_INTER) {
         if (!w.any_inter) return 0;
+#if H264R_INTER_TWO_MB
+        const dim3 grid((w.geom.width_mbs + 2 * kWarpsPerCta - 1) / (2 * kWarpsPerCta), w.geom.height_mbs, w.num_pics);
+        recon_inter2_kernel<<<grid, threads, 0, stream>>>(w.pics, w.geom, w.direct8x8);
+#else
         const dim3 grid((w.geom.width_mbs + kWarpsPerCta - 1) / kWarpsPerCta, w.geom.height_mbs, w.num_pics);
         recon_inter_kernel<<<grid, threads, 0, stream>>>(w.pics, w.geom, w.direct8x8);
+#endif
         return 1;
     }
     if (which == KERNEL_INTRA) {

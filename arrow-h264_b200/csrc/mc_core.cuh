@@ -123,17 +123,23 @@ MC_FN void mc_htap4(uint32_t a0, uint32_t a1, uint32_t a2, int out[4])
 // The stages a lane needs are row masks (mc_luma_masks); the caller ORs them over the warp and passes the WARP masks:
 // every lane then runs the same stages (lanes that do not need one compute values they never select), the branches
 // are warp-uniform and cost no divergence bookkeeping.  Bit 0 of the horizontal mask is set only by lanes that need j.
-MC_FN void mc_luma_masks(int xf, int yf, unsigned& hmask, unsigned& cmask)
+template <int R>                                               // R = rows of the patch: 2 (4x2) or 4 (4x4)
+MC_FN void mc_luma_masks_r(int xf, int yf, unsigned& hmask, unsigned& cmask)
 {
     const bool hasB = xf != 0 && yf != 2, hasH = yf != 0 && xf != 2;
     const bool hasJ = (xf == 2 && yf != 0) || (yf == 2 && xf != 0);
     const bool hasG = (xf == 0 && yf != 2) || (yf == 0 && xf != 2);
     const int dy = yf == 3;
-    hmask = hasJ ? 0x7Fu : (hasB ? 3u << (2 + dy) : 0u);                 // rows that get the horizontal 6-tap
-    cmask = hasH ? 0x7Fu : ((hasG && yf == 0) ? 0x0Cu : 0u);             // rows whose raw samples are needed
+    constexpr unsigned all = (1u << (R + 5)) - 1, rows = (1u << R) - 1;
+    hmask = hasJ ? all : (hasB ? rows << (2 + dy) : 0u);                 // rows that get the horizontal 6-tap
+    cmask = hasH ? all : ((hasG && yf == 0) ? rows << 2 : 0u);           // rows whose raw samples are needed
 }
+MC_FN void mc_luma_masks(int xf, int yf, unsigned& hmask, unsigned& cmask) { mc_luma_masks_r<2>(xf, yf, hmask, cmask); }
+
 constexpr int kLumaPitchWords = 4;
-MC_FN void mc_luma_patch_4x2(const uint32_t* win, int off, int xf, int yf, unsigned hmask, unsigned cmask, uint32_t& out0, uint32_t& out1)
+// 4 x R luma patch: one pass over the R + 5 window rows (sample rows -2 .. R + 2); out[r] = row r, four packed samples.
+template <int R>
+MC_FN void mc_luma_patch(const uint32_t* win, int off, int xf, int yf, unsigned hmask, unsigned cmask, uint32_t (&out)[R])
 {
     constexpr int pitch_words = kLumaPitchWords;
     const bool hasB = xf != 0 && yf != 2;                       // clipped horizontal half sample b (row + dy)
@@ -150,65 +156,74 @@ MC_FN void mc_luma_patch_4x2(const uint32_t* win, int off, int xf, int yf, unsig
     const uint32_t* wc = win + (oc >> 2);
     const uint32_t shc = (uint32_t)(oc & 3) * 8;
 
-    int jacc[2][4] = { { 0, 0, 0, 0 }, { 0, 0, 0, 0 } };
-    uint32_t tE[2] = { 0x0A100A10u, 0x0A100A10u }, tO[2] = { 0x0A100A10u, 0x0A100A10u };
-    uint32_t Brow[3] = { 0, 0, 0 }, Grow[3] = { 0, 0, 0 };      // window rows 2, 3, 4
+    int jacc[R][4];
+    uint32_t tE[R], tO[R];
+    uint32_t Brow[R + 1], Grow[R + 1];                          // window rows 2 .. R + 2
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        tE[r] = tO[r] = 0x0A100A10u;
+#pragma unroll
+        for (int x = 0; x < 4; ++x) jacc[r][x] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r <= R; ++r) Brow[r] = Grow[r] = 0;
     constexpr int tap[6] = { 1, -5, 20, 20, -5, 1 };
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
+    for (int k = 0; k < R + 5; ++k) {
         if ((hmask >> k) & 1) {
             const uint32_t w0 = wa[k * pitch_words], w1 = wa[k * pitch_words + 1], w2 = wa[k * pitch_words + 2];
             int b1[4];
             mc_htap4(mc_shf_r(w0, w1, sha), mc_shf_r(w1, w2, sha), w2 >> sha, b1);
-            if (k >= 2 && k <= 4) Brow[k - 2] = mc_pack4_sat(b1[0] >> 5, b1[1] >> 5, b1[2] >> 5, b1[3] >> 5);
+            if (k >= 2 && k <= R + 2) Brow[k - 2] = mc_pack4_sat(b1[0] >> 5, b1[1] >> 5, b1[2] >> 5, b1[3] >> 5);
             if (any_j) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    if (k <= 5) jacc[0][x] += tap[k] * b1[x];
-                    if (k >= 1) jacc[1][x] += tap[k - 1] * b1[x];
-                }
+                for (int r = 0; r < R; ++r)                     // output row r takes window rows r .. r + 5
+                    if (k >= r && k <= r + 5) {
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) jacc[r][x] += tap[k - r] * b1[x];
+                    }
             }
         }
         if ((cmask >> k) & 1) {
             const uint32_t c = mc_shf_r(wc[k * pitch_words], wc[k * pitch_words + 1], shc);
-            if (k >= 2 && k <= 4) Grow[k - 2] = c;
+            if (k >= 2 && k <= R + 2) Grow[k - 2] = c;
             const uint32_t e = mc_prmt(c, 0u, 0x4240u), o = mc_prmt(c, 0u, 0x4341u);
-            if (k <= 5) { tE[0] += (uint32_t)tap[k] * e; tO[0] += (uint32_t)tap[k] * o; }
-            if (k >= 1) { tE[1] += (uint32_t)tap[k - 1] * e; tO[1] += (uint32_t)tap[k - 1] * o; }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (k >= r && k <= r + 5) { tE[r] += (uint32_t)tap[k - r] * e; tO[r] += (uint32_t)tap[k - r] * o; }
         }
     }
 
-    uint32_t P0, P1, Q0, Q1;                                     // the (up to) two samples averaged per position
-    // first: G, else b, else h, else j
-    if (hasG) {                                                  // integer samples at (dx, 0) or (0, dy)
-        const bool down = xf == 0 && dy;
-        P0 = down ? Grow[1] : Grow[0];
-        P1 = down ? Grow[2] : Grow[1];
-    } else if (hasB) {
-        P0 = dy ? Brow[1] : Brow[0];
-        P1 = dy ? Brow[2] : Brow[1];
-    } else P0 = P1 = 0;
-    uint32_t H0 = 0, H1 = 0, J0 = 0, J1 = 0;
-    if (hasH) {
-        uint32_t r[4] = { tE[0], tO[0], tE[1], tO[1] };
+    const bool down = xf == 0 && dy;                             // integer samples at (0, dy)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            r[i] = mc_vmins2(mc_viaddmax_s16x2_relu((r[i] >> 5) & 0x07FF07FFu, 0xFFB0FFB0u, 0u), 0x00FF00FFu);
-        H0 = mc_prmt(r[0], r[1], 0x6240u);
-        H1 = mc_prmt(r[2], r[3], 0x6240u);
+    for (int r = 0; r < R; ++r) {
+        uint32_t P, Q;                                           // the (up to) two samples averaged per position
+        const uint32_t Bv = dy ? Brow[r + 1] : Brow[r];
+        // first: G, else b, else h, else j
+        if (hasG) P = down ? Grow[r + 1] : Grow[r];
+        else if (hasB) P = Bv;
+        else P = 0;
+        uint32_t Hv = 0, Jv = 0;
+        if (hasH) {
+            const uint32_t re = mc_vmins2(mc_viaddmax_s16x2_relu((tE[r] >> 5) & 0x07FF07FFu, 0xFFB0FFB0u, 0u), 0x00FF00FFu);
+            const uint32_t ro = mc_vmins2(mc_viaddmax_s16x2_relu((tO[r] >> 5) & 0x07FF07FFu, 0xFFB0FFB0u, 0u), 0x00FF00FFu);
+            Hv = mc_prmt(re, ro, 0x6240u);
+        }
+        if (hasJ) Jv = mc_pack4_sat(jacc[r][0] >> 10, jacc[r][1] >> 10, jacc[r][2] >> 10, jacc[r][3] >> 10);
+        if (!hasG && !hasB) P = hasH ? Hv : Jv;
+        // second: j, else h, else b, else G (== first when only one kind is present)
+        if (hasJ) Q = Jv;
+        else if (hasH) Q = Hv;
+        else if (hasB) Q = Bv;
+        else Q = P;
+        out[r] = mc_avg_u8x4(P, Q);
     }
-    if (hasJ) {
-        J0 = mc_pack4_sat(jacc[0][0] >> 10, jacc[0][1] >> 10, jacc[0][2] >> 10, jacc[0][3] >> 10);
-        J1 = mc_pack4_sat(jacc[1][0] >> 10, jacc[1][1] >> 10, jacc[1][2] >> 10, jacc[1][3] >> 10);
-    }
-    if (!hasG && !hasB) { P0 = hasH ? H0 : J0; P1 = hasH ? H1 : J1; }
-    // second: j, else h, else b, else G (== first when only one kind is present)
-    if (hasJ) { Q0 = J0; Q1 = J1; }
-    else if (hasH) { Q0 = H0; Q1 = H1; }
-    else if (hasB) { Q0 = dy ? Brow[1] : Brow[0]; Q1 = dy ? Brow[2] : Brow[1]; }
-    else { Q0 = P0; Q1 = P1; }
-    out0 = mc_avg_u8x4(P0, Q0);
-    out1 = mc_avg_u8x4(P1, Q1);
+}
+MC_FN void mc_luma_patch_4x2(const uint32_t* win, int off, int xf, int yf, unsigned hmask, unsigned cmask, uint32_t& out0, uint32_t& out1)
+{
+    uint32_t o[2];
+    mc_luma_patch<2>(win, off, xf, yf, hmask, cmask, o);
+    out0 = o[0]; out1 = o[1];
 }
 
 // Chroma 2x2 patch of one plane.  win: row pitch 2 words (8 bytes); off = byte offset of sample (0, 0), at most 5;

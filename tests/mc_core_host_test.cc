@@ -93,6 +93,20 @@ static void test_luma()
                         mc_luma_patch_4x2(reinterpret_cast<const uint32_t*>(win), off, xf, yf, 0x7Fu, 0x7Fu, a0, a1);
                         if ((a0 != o0 || a1 != o1) && fails++ < 20) printf("warp masks change the result at xf=%d yf=%d off=%d\n", xf, yf, off);
                         auto W = [&](int x, int y) { return (int)win[(y + 2) * pitch + off + x]; };
+                        {   // the 4x4 patch of the same position (two MBs per warp kernel)
+                            unsigned hm4, cm4; uint32_t o4[4], b4[4];
+                            mc_luma_masks_r<4>(xf, yf, hm4, cm4);
+                            mc_luma_patch<4>(reinterpret_cast<const uint32_t*>(win), off, xf, yf, hm4, cm4, o4);
+                            mc_luma_patch<4>(reinterpret_cast<const uint32_t*>(win), off, xf, yf, 0x1FFu, 0x1FFu, b4);
+                            for (int y = 0; y < 4; ++y) {
+                                if (o4[y] != b4[y] && fails++ < 20) printf("4x4: warp masks change the result at xf=%d yf=%d off=%d\n", xf, yf, off);
+                                for (int x = 0; x < 4; ++x) {
+                                    const int want = ref_luma(W, x, y, xf, yf);
+                                    const int got = (int)((o4[y] >> (8 * x)) & 0xFF);
+                                    if (want != got && fails++ < 20) printf("4x4 luma off=%d xf=%d yf=%d (%d,%d): want %d got %d\n", off, xf, yf, x, y, want, got);
+                                }
+                            }
+                        }
                         for (int y = 0; y < 2; ++y)
                             for (int x = 0; x < 4; ++x) {
                                 const int want = ref_luma(W, x, y, xf, yf);
