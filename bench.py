@@ -30,6 +30,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import pyapi  # noqa: E402
 
 METRIC = "1080p macroblocks/s reconstructed (IDCT+MC+intra+deblock)"
+
+
+def workload_name(streams, frames):
+    return (f"{streams} independent 1080p (120x68 MB) High-profile I/P/B streams x {frames} pictures per GPU "
+            "(BASELINE configs[4]; 8x8 transform, intra 8x8, bi-pred, weighted prediction, 2 slices on odd pictures)")
 UNIT = "MB/s"          # MB = macroblocks; output bytes/s = value * 384
 CONFIG_ID = 5
 
@@ -151,11 +156,14 @@ def run_reference_arm(args, rank, world):
             times.append(sec)
     sec = sum(times) / len(times)
     value = mbs / sec
-    sample = f"{cores} streams x {frames} pictures of 1080p config 5 per step, one process per core, time inside decode+deblock only"
+    sample = (f"each step = {cores} streams x {frames} pictures of that workload (a bounded sample of its streams, fresh "
+              "streams every step), one process per host core, time inside Decoder::decode + deblock_filter only")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32/u8", "data": "synthetic",
-            "config": {"workload": "1080p High I/P/B synthetic streams (config 5), bounded CPU sample", "sample": sample},
+            "config": {"workload": workload_name(args.streams, args.frames), "streams_per_gpu": args.streams,
+                       "pictures_per_step_per_gpu": args.streams * args.frames,
+                       "macroblocks_per_step_per_gpu": args.streams * args.frames * 8160, "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if kind == "ref" else "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -319,8 +327,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32/u8", "data": "synthetic",
-        "config": {"workload": f"{streams} independent 1080p (120x68 MB) High-profile I/P/B streams x {frames} pictures per GPU "
-                               "(BASELINE configs[4]; 8x8 transform, intra 8x8, bi-pred, weighted prediction, 2 slices on odd pictures)",
+        "config": {"workload": workload_name(streams, frames),
                    "streams_per_gpu": streams, "pictures_per_step_per_gpu": npics, "macroblocks_per_step_per_gpu": total_mb,
                    "l2_policy": "inputs larger than L2 (GBs of picture descriptions + 3.2 GB of frames per step)",
                    "frames_per_s": value / nmb, "output_bytes_per_s": value * 384},
