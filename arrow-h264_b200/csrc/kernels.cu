@@ -1346,7 +1346,15 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
 // recon_inter_kernel.  Completion is an epoch stamp per MB (no clearing between launches).  Tickets interleave the
 // pictures of the wave and run in raster order inside a picture, so a warp only ever waits for warps that already
 // hold a ticket.
-__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTRA_CTAS)
+#ifndef H264R_SPARSE_PER_WARP
+#define H264R_SPARSE_PER_WARP 1
+#endif
+// A warp takes H264R_SPARSE_PER_WARP consecutive entries of the list: header, neighbour headers and residual of the
+// next MB are in flight while the current one is reconstructed (the kernel is bound by those dependent loads).
+#ifndef H264R_SPARSE_CTAS
+#define H264R_SPARSE_CTAS 12
+#endif
+__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_SPARSE_CTAS)
 recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g, uint32_t epoch)
 {
     __shared__ __align__(16) IntraSmem smem_all[kWarpsPerCta];
@@ -1356,24 +1364,34 @@ recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int
     const int grp = s_ticket / num_pics, pic_i = s_ticket - grp * num_pics;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const DevPicture& pic = pics[pic_i];
-    const int idx = grp * kWarpsPerCta + warp;
-    if (idx >= pic.intra_count) return;
-    const int W = g.width_mbs, H = g.height_mbs;
-    const int addr = (int)__ldg(pic.intra_list + idx);
-    const int mby = addr / W, mbx = addr - mby * W;
-    IntraPre pre;
-    intra_prefetch(pic, g, mbx, mby, lane, pre);          // header, neighbour headers, residual: all in flight at once
-    if (lane < 4 && pre.nbw != 0xFFFFFFFFu && ((pre.nbw >> 8) & H264R_MB_FLAG_INTRA)) {
-        const int nx = mbx + (lane == 3 ? 1 : (lane == 1 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // left, top, top-left, top-right
-        const int* flag = reinterpret_cast<const int*>(pic.mb_done + ny * W + nx);
-        unsigned ns = 16;
-        while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
+    const int first = (grp * kWarpsPerCta + warp) * H264R_SPARSE_PER_WARP;
+    const int n = min(H264R_SPARSE_PER_WARP, pic.intra_count - first);
+    if (n <= 0) return;
+    const int W = g.width_mbs;
+    // the warp's addresses: lane i holds entry i
+    const int my_addr = lane < n ? (int)__ldg(pic.intra_list + first + lane) : 0;
+    IntraPre nxt;
+    int addr = __shfl_sync(0xFFFFFFFFu, my_addr, 0);
+    intra_prefetch(pic, g, addr % W, addr / W, lane, nxt);          // header, neighbour headers, residual: all in flight at once
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const IntraPre pre = nxt;
+        const int mby = addr / W, mbx = addr - mby * W, cur_addr = addr;
+        if (i + 1 < n) {
+            addr = __shfl_sync(0xFFFFFFFFu, my_addr, i + 1);
+            intra_prefetch(pic, g, addr % W, addr / W, lane, nxt);
+        }
+        if (lane < 4 && pre.nbw != 0xFFFFFFFFu && ((pre.nbw >> 8) & H264R_MB_FLAG_INTRA)) {
+            const int nx = mbx + (lane == 3 ? 1 : (lane == 1 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // left, top, top-left, top-right
+            const int* flag = reinterpret_cast<const int*>(pic.mb_done + ny * W + nx);
+            unsigned ns = 16;
+            while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
+        }
+        __syncwarp();
+        intra_reconstruct_mb<false>(pic, g, smem_all[warp], pre, mbx, mby, lane);
+        __syncwarp();
+        if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + cur_addr), (int)epoch);
     }
-    __syncwarp();
-    intra_reconstruct_mb<false>(pic, g, smem_all[warp], pre, mbx, mby, lane);
-    (void)H;
-    __syncwarp();
-    if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + addr), (int)epoch);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1823,7 +1841,8 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
             ++n;
         }
         if (w.max_intra_sparse > 0) {
-            const int grps = (w.max_intra_sparse + kWarpsPerCta - 1) / kWarpsPerCta;
+            const int per_cta = kWarpsPerCta * H264R_SPARSE_PER_WARP;
+            const int grps = (w.max_intra_sparse + per_cta - 1) / per_cta;
             recon_intra_sparse_kernel<<<w.num_pics * grps, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
             ++n;
         }
