@@ -231,6 +231,12 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
         if dist is not None:
             dist.barrier()
 
+    # clocks and throttle reasons: sampled every 100 ms by rank 0 from here (first flush, warm-up) to the end of the
+    # end-to-end region -- the GPU is busy throughout, and a sampler started right at the timed region would miss short
+    # runs (nvidia-smi needs several hundred ms to come up, longer with eight ranks on one box)
+    clk = ClockSampler(local_rank)
+    if rank == 0:
+        clk.start()
     # first run = flush (uploads everything once; afterwards the descriptions are HBM-resident)
     eng.flush()
     eng.wait()
@@ -241,8 +247,6 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
         eng.replay(1, 0)
     barrier()
     s0 = eng.stats()
-    clk = ClockSampler(local_rank)
-    clk.start()
     t_start = time.perf_counter()
     # the K steps are enqueued back to back (one call, no host round trip between steps -- a streaming decoder does not
     # stop between GOPs either) and joined once; CUDA events on the compute stream bracket exactly these K steps
@@ -250,7 +254,6 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     ev_ms = ms[0]
     eng.wait()
     t_dev = time.perf_counter() - t_start
-    clocks = clk.stop()
     s1 = eng.stats()
     launches = int(s1.kernel_launches - s0.kernel_launches)
     barrier()
@@ -273,6 +276,15 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     t_e2e = time.perf_counter() - t_start
     s3 = eng.stats()
     barrier()
+    clocks = clk.stop()
+    if rank == 0 and clocks["sm_mhz"] is None:
+        # no sample landed in the window (very short runs): sample a dedicated untimed replay of about two seconds
+        clk = ClockSampler(local_rank)
+        clk.start()
+        t_end = time.perf_counter() + 2.0
+        while time.perf_counter() < t_end:
+            eng.replay(2, 0)
+        clocks = clk.stop()
 
     if args.diag:
         def timed(fn, n=3):
