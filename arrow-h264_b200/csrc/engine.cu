@@ -254,11 +254,8 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         // Throughput-bound side kernels are scheduled underneath the latency-bound wavefront kernels (intra, deblock) of
         // the wave before, not against its inter kernel: they start when that inter kernel has finished.
         if (!time_kernels && ctx->side_gate && ctx->gate[rec.group]) CU(cudaStreamWaitEvent(side, ctx->gate[rec.group], 0));
-        static const bool skip_side = getenv("H264R_EXPERIMENT_SKIP_SIDE") != nullptr;   // timing experiment only: wrong output
-        if (!skip_side || time_kernels || h2d) {
         { const int rc = launch(rec, KERNEL_RESID, side); if (rc != H264R_OK) return rc; }
         { const int rc = launch(rec, KERNEL_DBPREP, side); if (rc != H264R_OK) return rc; }
-        }
         if (!time_kernels) {
             CU(cudaEventRecord(rec.ev_side, side));
             CU(cudaStreamWaitEvent(main, rec.ev_side, 0));

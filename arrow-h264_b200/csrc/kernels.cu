@@ -31,6 +31,9 @@ constexpr int kWarpsPerCta = 4;
 #ifndef H264R_RESID_CTAS
 #define H264R_RESID_CTAS 14
 #endif
+#ifndef H264R_PREP_CTAS
+#define H264R_PREP_CTAS 12
+#endif
 #ifndef H264R_PREP_UNROLL
 #define H264R_PREP_UNROLL 0
 #endif
@@ -1444,7 +1447,7 @@ __device__ __forceinline__ HdrLite load_hdr_lite(const h264r_mb* mbs, int addr)
     return h;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, H264R_PREP_CTAS)
 deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g)
 {
     const int W = g.width_mbs, nmb = W * g.height_mbs;
