@@ -34,7 +34,6 @@ struct DevPicture {
     int16_t*               resid;                     // [nmb][384] residual plane, device only (residual_kernel)
     uint8_t*               dst;                       // frame base
     const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]
-    int*                   row_progress;              // [2][height_mbs]: intra wavefront, deblock wavefront
     DeblockDesc*           desc;                      // [nmb], device only
     uint64_t*              mbox;                      // [nmb][24], device only: deblock row-to-row mailboxes { 4 samples, epoch }
     const uint32_t*        intra_list;                // raster-ordered addresses of the intra MBs (pictures that also have inter MBs)
@@ -48,7 +47,7 @@ struct DevPicture {
 struct WaveLaunch {
     const DevPicture* pics;          // device array
     int   num_pics;
-    int*  tickets;                   // device: work-ticket counters ([0] intra rows, [1] deblock, [2] sparse intra), zeroed per wave
+    int*  tickets;                   // device: work-ticket counters ([0] intra rows, [1] deblock, [2] sparse intra), zeroed per wave (64 ints)
     FrameGeom geom;
     int   direct8x8;
     int   any_inter, any_intra, any_deblock;

@@ -58,7 +58,6 @@ struct WaveCopy { int slot; size_t bytes; };
 
 struct WaveRecord {
     WaveLaunch launch;
-    size_t progress_bytes;
     std::vector<WaveCopy> copies;             // H2D copies of the picture descriptions of this wave
     std::vector<int> dst_frames;              // frames written by this wave
     int group = 0;                            // stream group that runs the record
@@ -114,8 +113,7 @@ struct h264r_ctx {
     DevPicture* d_pics = nullptr;
     cudaEvent_t table_ev[2] = { nullptr, nullptr };   // end of the flush that last used each half
     int table_idx = 0;
-    int* d_sync = nullptr;                    // [2 tickets (padded to 64 ints)] + per picture [2][H] progress
-    size_t sync_ints_per_pic = 0;
+    int* d_sync = nullptr;                    // per group: ticket counters (64 ints)
     std::vector<WaveRecord> last_waves;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     h264r_stats stats;
@@ -266,7 +264,7 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
             Frame& fr = ctx->frames[f];
             if (fr.pending_read) { CU(cudaStreamWaitEvent(main, fr.read_done, 0)); fr.pending_read = false; }
         }
-        CU(cudaMemsetAsync(rec.launch.tickets, 0, rec.progress_bytes, main));
+        CU(cudaMemsetAsync(rec.launch.tickets, 0, sizeof(int) * 64, main));      // the wave's ticket counters
         { const int rc = launch(rec, KERNEL_INTER, main); if (rc != H264R_OK) return rc; }
         if (!time_kernels && ctx->side_gate) { CU(cudaEventRecord(rec.ev_inter, main)); ctx->gate[rec.group] = rec.ev_inter; }
         { const int rc = launch(rec, KERNEL_INTRA, main); if (rc != H264R_OK) return rc; }
@@ -376,7 +374,6 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
-    ctx->sync_ints_per_pic = align_up((size_t)2 * sp->height_mbs, 32);
     {   // H264R_STREAM_GROUPS = number of stream groups (1..4, default 1), each with its own compute + side stream,
         // tickets and progress counters; H264R_GROUP_POLICY says how pictures are dealt to them:
         //   stream (default): whole streams (GOP chains), round robin;
@@ -419,7 +416,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->g_tail[gi], cudaEventDisableTiming);
     }
-    ctx->sync_ints_per_group = 64 + ctx->sync_ints_per_pic * sp->max_pictures_in_flight;
+    ctx->sync_ints_per_group = 64;                     // ticket counters; the rows of the wavefront kernels talk through mailboxes
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_sync, sizeof(int) * ctx->sync_ints_per_group * ctx->num_groups);
     if (e != cudaSuccess) {
         snprintf(ctx->cuda_err, sizeof(ctx->cuda_err), "allocation: %s", cudaGetErrorString(e));
@@ -687,7 +684,6 @@ int h264r_flush(h264r_ctx* ctx)
             p.desc = s.dev_desc;
             for (int i = 0; i < H264R_MAX_REFS; ++i)
                 p.ref[i] = i < s.pp.num_ref_frames ? ctx->frames[s.pp.ref_frames[i]].dev : ctx->frames[s.dst].dev;
-            p.row_progress = ctx->d_sync + ctx->sync_ints_per_group * s.group + 64 + ctx->sync_ints_per_pic * (size_t)(k - rec_begin[r]);
             p.run_deblock = s.pp.run_deblock; p.has_intra = s.has_intra; p.has_inter = s.has_inter;
         }
     CU(cudaMemcpyAsync(d_table, h_table, sizeof(DevPicture) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -738,7 +734,6 @@ int h264r_flush(h264r_ctx* ctx)
             d.ready = rec.ev_done; d.ready_group = rec.group; d.ready_flush = ctx->flush_serial; d.readers.clear();
             rec.dst_frames.push_back(ctx->slots[order[k]].dst);
         }
-        rec.progress_bytes = sizeof(int) * (64 + ctx->sync_ints_per_pic * (size_t)L.num_pics);
         ctx->last_waves.push_back(rec);
     }
     for (int qi : ctx->queue) ctx->slots[qi].state = SLOT_INFLIGHT;   // reusable once the streams have drained (h264r_wait)

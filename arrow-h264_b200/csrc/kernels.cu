@@ -59,12 +59,6 @@ __device__ __forceinline__ int ld_acquire(const int* p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ int ld_relaxed(const int* p)
-{
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void st_release(int* p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -821,35 +815,6 @@ __device__ __forceinline__ uint64_t ld_mbox(const uint64_t* p)
     return v;
 }
 
-
-// Wait until the row above has completed at least `need` macroblocks.
-__device__ __forceinline__ void wait_row(const int* progress_above, int need, int lane)
-{
-    if (lane == 0) {
-        while (ld_acquire(progress_above) < need) __nanosleep(64);
-    }
-    __syncwarp();
-}
-// st.release.gpu orders this warp's earlier stores (cumulative over the __syncwarp) before the counter update
-__device__ __forceinline__ void publish_row(int* progress, int done, int lane, bool wrote_pixels)
-{
-    (void)wrote_pixels;
-    __syncwarp();
-    if (lane == 0) st_release(progress, done);
-}
-// Progress of the row above as last observed by this warp (monotonic): polls only when the cached value is not enough.
-__device__ __forceinline__ void wait_row_cached(const int* progress_above, int need, int& known)
-{
-    if (known >= need) return;
-    int v = 0;
-    if ((threadIdx.x & 31) == 0) {
-        // poll with relaxed loads (no L1 invalidation per poll) and exponential back-off; one acquire load at the end
-        unsigned ns = 32;
-        while (ld_relaxed(progress_above) < need) { __nanosleep(ns); if (ns < 512) ns *= 2; }
-        v = ld_acquire(progress_above);
-    }
-    known = __shfl_sync(0xFFFFFFFFu, v, 0);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // intra prediction (wavefront)
