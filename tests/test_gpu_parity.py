@@ -230,3 +230,45 @@ def test_cropped_download_is_the_display_rectangle():
     with pytest.raises(pyapi.EngineError):
         eng.download_cropped(order[0], 1, 0, 0, 0)          # odd offsets do not exist in 4:2:0
     eng.close()
+
+
+@pytest.mark.parametrize("groups,policy,extra", [(2, "stream", {}), (3, "role", {}), (2, "role", {"H264R_SIDE_PRIORITY": "low", "H264R_SIDE_GATE": "1"})])
+def test_stream_group_options_keep_the_output(monkeypatch, groups, policy, extra):
+    """The engine's scheduling options (independent stream groups on their own CUDA streams, by stream or by role;
+    side-stream priority and gating -- DESIGN.md section 3, measured and off by default) only reorder launches: every
+    picture must still equal the oracle's, also after replays with cross-group dependencies."""
+    monkeypatch.setenv("H264R_STREAM_GROUPS", str(groups))
+    monkeypatch.setenv("H264R_GROUP_POLICY", policy)
+    for k, v in extra.items():
+        monkeypatch.setenv(k, v)
+    cfg, w, h, n, nstreams = 2, 13, 9, 8, 6
+    st = pyapi.SynthStream(cfg, 0, w, h, n)
+    seq = st.seq
+    st.close()
+    want = {}
+    for s in range(nstreams):
+        port = O.CpuDecoder("port", seq)
+        want[s] = O.run_stream(port, cfg, s, w, h, n)
+        port.close()
+    eng = pyapi.Engine(seq, max_frames=nstreams * n, max_pictures=nstreams * n)
+    streams = [pyapi.SynthStream(cfg, s, w, h, n) for s in range(nstreams)]
+    frames = [dict() for _ in range(nstreams)]
+    order = []
+    for _ in range(n):
+        for s, st in enumerate(streams):
+            pic = st.next()
+            dst = eng.frame_alloc()
+            frames[s][pic.info.pic_index] = dst
+            eng.submit(pic, dst, [frames[s][pic.info.ref_pic_index[i]] for i in range(pic.info.num_refs)])
+            order.append((s, pic.info.pic_index, dst))
+    for st in streams:
+        st.close()
+    eng.flush()
+    eng.wait()
+    for rounds in range(2):
+        for s, idx, dst in order:
+            d = hashlib.md5(b"".join(eng.download(dst))).hexdigest()
+            assert d == want[s][idx], f"groups={groups} policy={policy} round {rounds}: stream {s} picture {idx} differs"
+        eng.replay(2, pyapi.Engine.REPLAY_H2D | pyapi.Engine.REPLAY_ASYNC)
+        eng.wait()
+    eng.close()
