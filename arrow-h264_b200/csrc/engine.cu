@@ -81,7 +81,7 @@ struct h264r_ctx {
                                               // underneath, the latency-bound wavefront kernels of earlier waves
     cudaEvent_t ev_fork = nullptr;
     // Independent streams (closed GOPs) are spread over `num_groups` groups, each with its own compute + side stream,
-    // tickets and progress counters: the latency-bound wavefront kernels of one group run underneath the
+    // ticket counters: the latency-bound wavefront kernels of one group run underneath the
     // throughput-bound kernels of the others.  g_main[0] == stream, g_side[0] == s_side.
     int num_groups = 1;
     int group_policy = 0;                     // 0: by stream (reference affinity, round robin); 1: by role (see h264r_create)
@@ -375,7 +375,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * 2 * sp->max_pictures_in_flight);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->table_ev[i], cudaEventDisableTiming);
     {   // H264R_STREAM_GROUPS = number of stream groups (1..4, default 1), each with its own compute + side stream,
-        // tickets and progress counters; H264R_GROUP_POLICY says how pictures are dealt to them:
+        // ticket counters; H264R_GROUP_POLICY says how pictures are dealt to them:
         //   stream (default): whole streams (GOP chains), round robin;
         //   role: group 0 = the reference CHAIN (pictures that later pictures of the same flush predict from: I/P) on
         //         high-priority streams, groups 1.. = LEAVES (pictures nobody in the flush references: B).

@@ -1,10 +1,17 @@
 // sm_100a kernels of the H.264 macroblock-reconstruction path.
 //
-//   recon_inter_kernel   : one warp per inter macroblock, all pictures of a wave in one grid
-//                          (motion compensation + weighted prediction + dequant/IDCT + reconstruction)
-//   recon_intra_kernel   : one warp per macroblock ROW; rows of a picture form a 2:1 wavefront
-//                          (MB(x,y) needs (x-1,y), (x-1,y-1), (x,y-1), (x+1,y-1)); progress counters in HBM
-//   deblock_kernel       : same row wavefront; per MB bS derivation, vertical then horizontal edges, in place
+//   residual_kernel           : one warp per MB with levels: dequantisation, DC Hadamards, 4x4 / 8x8 inverse transforms
+//                               (transform.cc:394-456, 460-554, 597-733, 825-910) -> int16 residual plane
+//   recon_inter2_kernel       : two inter MBs per warp, one 4x4 block per lane, all pictures of a wave in one grid:
+//                               motion compensation, weighted prediction, residual add (inter_prediction.cc:53-406,
+//                               448-536; decoder.cc:217-262; transform.cc:913-984)
+//                               (recon_inter_kernel: the one-MB-per-warp variant, -DH264R_INTER_TWO_MB=0)
+//   recon_intra_kernel        : all-intra pictures, one warp per MB ROW; rows form a 2:1 wavefront (MB(x,y) needs (x-1,y),
+//                               (x-1,y-1), (x,y-1), (x+1,y-1)) and talk through mailboxes (intra_prediction.cc:137-904)
+//   recon_intra_sparse_kernel : the intra MBs of P/B pictures, one warp each, per-MB epoch stamps between intra neighbours
+//   deblock_prep_kernel       : boundary strengths and alpha / beta / tc0 per MB (deblock.cc:35-289, 469-474)
+//   deblock_kernel            : row wavefront, two pictures per warp, vertical then horizontal edges in place, rows talk
+//                               through mailboxes (deblock.cc:327-552)
 //
 // Arithmetic follows the reference (src/codec/h264/decoder/{transform,inter_prediction,intra_prediction,
 // deblock}.cc); the line-by-line citations live in the CPU restatement oracle/port_recon.c, whose structure
