@@ -353,6 +353,12 @@ __device__ __noinline__ void load_window_border(uint32_t* win, int pitch_words, 
     }
 }
 __device__ __forceinline__ uint32_t ldg_u32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
+// 4-byte global -> shared copy that never touches a register (LDGSTS); completion: cp_async_wait_all()
+__device__ __forceinline__ void cp_async4(uint32_t* dst, const uint8_t* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // per-warp scratch, in 32-bit words.  Per 8x8 quadrant: luma 146 words = uniform quadrant 13 rows x 4 words | split
 // quadrant 4 blocks x (9 rows x 4 words), one row pitch for both so that row offsets are immediates; chroma 50 words =
@@ -675,22 +681,16 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct
                 const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 5 <= hC;
                 if (in_y) {                                     // 13 rows x 4 words: lane = word column
                     const uint8_t* src = rbase + (uint32_t)(y0 * pitch_y + xa + sb * 4);
-                    uint32_t v[13];
 #pragma unroll
-                    for (int i = 0; i < 13; ++i) v[i] = ldg_u32(src + (uint32_t)(i * pitch_y));
-#pragma unroll
-                    for (int i = 0; i < 13; ++i) lq[i * 4 + sb] = v[i];
+                    for (int i = 0; i < 13; ++i) cp_async4(lq + i * 4 + sb, src + (uint32_t)(i * pitch_y));
                 } else load_window_border(lq, 4, rbase, pitch_y, wY, hY, x0, y0, 13, 13, sb, 4);
                 {                                               // 2 planes x 5 rows x 2 words: lane = (plane, word column)
                     const int pl = sb >> 1, col = sb & 1;
                     const uint8_t* cplane = rbase + (pl ? g.off_cr : g.off_cb);
                     if (in_c) {
                         const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa + col * 4);
-                        uint32_t v[5];
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) v[i] = ldg_u32(src + (uint32_t)(i * pitch_c));
-#pragma unroll
-                        for (int i = 0; i < 5; ++i) cq[pl * 10 + i * 2 + col] = v[i];
+                        for (int i = 0; i < 5; ++i) cp_async4(cq + pl * 10 + i * 2 + col, src + (uint32_t)(i * pitch_c));
                     } else load_window_border(cq + pl * 10, 2, cplane, pitch_c, wC, hC, cx0, cy0, 5, 5, col, 2);
                 }
                 wl = lq + (sb >> 1) * 4 * 4;
@@ -707,28 +707,17 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct
                 if (in_y) {                                     // 9 rows x 3 words
                     const uint8_t* src = rbase + (uint32_t)(y0 * pitch_y + xa);
 #pragma unroll
-                    for (int i0 = 0; i0 < 9; i0 += 3) {
-                        uint32_t v[3][3];
+                    for (int i = 0; i < 9; ++i)
 #pragma unroll
-                        for (int i = 0; i < 3; ++i)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) v[i][c] = ldg_u32(src + (uint32_t)((i0 + i) * pitch_y) + c * 4);
-#pragma unroll
-                        for (int i = 0; i < 3; ++i)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) lb[(i0 + i) * 4 + c] = v[i][c];
-                    }
+                        for (int c = 0; c < 3; ++c) cp_async4(lb + i * 4 + c, src + (uint32_t)(i * pitch_y) + c * 4);
                 } else load_window_border(lb, 4, rbase, pitch_y, wY, hY, x0, y0, 9, 9, 0, 1);
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl) {                // 3 rows x 2 words per plane
                     const uint8_t* cplane = rbase + (pl ? g.off_cr : g.off_cb);
                     if (in_c) {
                         const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa);
-                        uint32_t v[3][2];
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) { v[i][0] = ldg_u32(src + (uint32_t)(i * pitch_c)); v[i][1] = ldg_u32(src + (uint32_t)(i * pitch_c) + 4); }
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) { cb[pl * 6 + i * 2] = v[i][0]; cb[pl * 6 + i * 2 + 1] = v[i][1]; }
+                        for (int i = 0; i < 3; ++i) { cp_async4(cb + pl * 6 + i * 2, src + (uint32_t)(i * pitch_c)); cp_async4(cb + pl * 6 + i * 2 + 1, src + (uint32_t)(i * pitch_c) + 4); }
                     } else load_window_border(cb + pl * 6, 2, cplane, pitch_c, wC, hC, cx0, cy0, 3, 3, 0, 1);
                 }
                 wl = lb;
@@ -737,6 +726,7 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct
                 coff = in_c ? cx0 & 3 : 0;
             }
         }
+        cp_async_wait_all();                               // this lane's window copies have landed
         __syncwarp();
         {
             const int xf = vx & 3, yf = vy & 3;
