@@ -746,8 +746,13 @@ int h264r_flush(h264r_ctx* ctx)
 int h264r_wait(h264r_ctx* ctx, h264r_frame f)
 {
     if (!ctx) return H264R_ERR_INVALID;
-    (void)f;                                                      // in-order streams: waiting for one waits for all
     cudaSetDevice(ctx->device);
+    if (f >= 0) {
+        // one frame: the wave that produces it (pictures queued behind it keep running; staging slots stay in flight)
+        if (f >= (int)ctx->frames.size() || !ctx->frames[f].dev) return H264R_ERR_INVALID;
+        if (ctx->frames[f].ready) CU(cudaEventSynchronize(ctx->frames[f].ready));
+        return H264R_OK;
+    }
     CU(cudaStreamSynchronize(ctx->s_h2d));
     for (int gi = 0; gi < ctx->num_groups; ++gi) { CU(cudaStreamSynchronize(ctx->g_side[gi])); CU(cudaStreamSynchronize(ctx->g_main[gi])); }
     CU(cudaStreamSynchronize(ctx->s_d2h));

@@ -197,7 +197,8 @@ int  h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels);
 /* launches everything queued: pictures are grouped into dependency waves (a picture whose references
  * are produced by a queued picture goes to a later wave); every wave is one batched launch sequence.  */
 int  h264r_flush(h264r_ctx* ctx);
-/* blocks until frame `f` (or everything, f < 0) is reconstructed                                      */
+/* blocks until frame `f` is reconstructed (the wave that writes it; later pictures keep running), or, with   */
+/* f < 0, until everything queued has finished, downloads included                                         */
 int  h264r_wait(h264r_ctx* ctx, h264r_frame f);
 
 /* replaces: write_out_picture reading imgY/imgUV (framebuf/output.cc:109-227)                          */

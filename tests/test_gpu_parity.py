@@ -219,6 +219,9 @@ def test_cropped_download_is_the_display_rectangle():
     W, H = w * 16, h * 16
     crops = [(0, 0, 0, 8), (2, 6, 4, 10), (16, 0, 0, 2), (0, 0, 0, 0)]
     got = [eng.download_cropped(f, *crops[i % len(crops)]) for i, f in enumerate(order)]     # no wait before
+    eng.wait(order[1])                                       # one frame: returns once ITS wave is done
+    with pytest.raises(pyapi.EngineError):
+        eng.wait(10_000)
     eng.wait()
     for i, f in enumerate(order):
         l, r, t, b = crops[i % len(crops)]
