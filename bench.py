@@ -320,6 +320,8 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     e2e_value = world * total_mb * args.steps / t_e2e
     peak, peak_src = peaks()
     names = ["residual", "inter", "intra", "deblock_prep", "deblock"]
+    KERNEL_NAMES = {"residual": "residual_kernel", "inter": "recon_inter2_kernel", "intra": "recon_intra_kernel + recon_intra_sparse_kernel",
+                    "deblock_prep": "deblock_prep_kernel", "deblock": "deblock_kernel"}
     # algorithmic bytes of each kernel's own pass: residual = levels in + 768 B residual plane out per coded MB;
     # inter/intra = SURVEY 8d formula restricted to their MBs; deblock_prep = headers + motion in, 32 B out
     k_bytes = [acct[9], acct[1], acct[2], acct[8], acct[3]]
@@ -347,7 +349,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((s3.h2d_bytes - s2.h2d_bytes) // args.steps),
                 "d2h_bytes_per_step": int((s3.d2h_bytes - s2.d2h_bytes) // args.steps)},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": names[dom] + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": KERNEL_NAMES[names[dom]], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes_per_launch, "ms_per_launch": dom_ms_per_launch,
                      "whole_step": {"algorithmic_bytes": acct[0], "achieved": step_gbs, "frac": step_gbs / peak,
