@@ -158,7 +158,8 @@ MC_FN void mc_luma_patch(const uint32_t* win, int off, int xf, int yf, unsigned 
 
     int jacc[R][4];
     uint32_t tE[R], tO[R];
-    uint32_t Brow[R + 1], Grow[R + 1];                          // window rows 2 .. R + 2
+    uint32_t Brow[R + 1];                                       // window rows 2 .. R + 2 (the integer samples G of those rows
+                                                                // are re-read from the window at the end: five registers less)
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         tE[r] = tO[r] = 0x0A100A10u;
@@ -166,7 +167,7 @@ MC_FN void mc_luma_patch(const uint32_t* win, int off, int xf, int yf, unsigned 
         for (int x = 0; x < 4; ++x) jacc[r][x] = 0;
     }
 #pragma unroll
-    for (int r = 0; r <= R; ++r) Brow[r] = Grow[r] = 0;
+    for (int r = 0; r <= R; ++r) Brow[r] = 0;
     constexpr int tap[6] = { 1, -5, 20, 20, -5, 1 };
 #pragma unroll
     for (int k = 0; k < R + 5; ++k) {
@@ -186,7 +187,6 @@ MC_FN void mc_luma_patch(const uint32_t* win, int off, int xf, int yf, unsigned 
         }
         if ((cmask >> k) & 1) {
             const uint32_t c = mc_shf_r(wc[k * pitch_words], wc[k * pitch_words + 1], shc);
-            if (k >= 2 && k <= R + 2) Grow[k - 2] = c;
             const uint32_t e = mc_prmt(c, 0u, 0x4240u), o = mc_prmt(c, 0u, 0x4341u);
 #pragma unroll
             for (int r = 0; r < R; ++r)
@@ -200,7 +200,7 @@ MC_FN void mc_luma_patch(const uint32_t* win, int off, int xf, int yf, unsigned 
         uint32_t P, Q;                                           // the (up to) two samples averaged per position
         const uint32_t Bv = dy ? Brow[r + 1] : Brow[r];
         // first: G, else b, else h, else j
-        if (hasG) P = down ? Grow[r + 1] : Grow[r];
+        if (hasG) { const uint32_t* g = wc + (r + 2 + (down ? 1 : 0)) * pitch_words; P = mc_shf_r(g[0], g[1], shc); }
         else if (hasB) P = Bv;
         else P = 0;
         uint32_t Hv = 0, Jv = 0;
