@@ -174,13 +174,17 @@ __device__ __forceinline__ void idct8_1d(int* p, int stride, bool final_pass)
 constexpr int kResP = 20, kResCP = 12, kResCPlane = 104, kResC = 16 * kResP, kResInts = kResC + 2 * kResCPlane;
 struct __align__(16) ResidSmem { int cof[kResInts]; };
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_RESID_CTAS)
+#ifndef H264R_RESID_WARPS
+#define H264R_RESID_WARPS 4
+#endif
+constexpr int kResidWarps = H264R_RESID_WARPS;
+__global__ void __launch_bounds__(kResidWarps * 32, H264R_RESID_CTAS * 4 / H264R_RESID_WARPS)
 residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 {
-    __shared__ __align__(16) ResidSmem smem_all[kWarpsPerCta];
+    __shared__ __align__(16) ResidSmem smem_all[kResidWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nmb = g.width_mbs * g.height_mbs;
-    const int addr = blockIdx.x * kWarpsPerCta + warp;     // grid = (ceil(nmb / 4), 1, pictures): no index divisions
+    const int addr = blockIdx.x * kResidWarps + warp;     // grid = (ceil(nmb / 4), 1, pictures): no index divisions
     if (addr >= nmb) return;
     const DevPicture& pic = pics[blockIdx.z];
     const MbHdr h = load_hdr(pic.mbs, addr);
@@ -612,21 +616,25 @@ __device__ __forceinline__ void partition_of_block2(const MbHdr& h, int is_b, in
     covers8x8 = sh4 >= 2 && sv4 >= 2;
 }
 
-#ifndef H264R_INTER2_CTAS
-#define H264R_INTER2_CTAS 7
+#ifndef H264R_INTER2_WARPS
+#define H264R_INTER2_WARPS 2
 #endif
+#ifndef H264R_INTER2_CTAS
+#define H264R_INTER2_CTAS (28 / H264R_INTER2_WARPS)
+#endif
+constexpr int kInter2Warps = H264R_INTER2_WARPS;       // warps per CTA (each warp: two MBs)
 // grid = (ceil(width_mbs / 8), height_mbs, pictures of the wave)
-__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTER2_CTAS)
+__global__ void __launch_bounds__(kInter2Warps * 32, H264R_INTER2_CTAS)
 recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, int direct8x8)
 {
-    __shared__ __align__(16) Inter2Smem smem_all[kWarpsPerCta];
+    __shared__ __align__(16) Inter2Smem smem_all[kInter2Warps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = lane >> 4, b = lane & 15, bx = b & 3, by = b >> 2;
-    const int mbx = (blockIdx.x * kWarpsPerCta + warp) * 2 + m, mby = blockIdx.y;
+    const int mbx = (blockIdx.x * kInter2Warps + warp) * 2 + m, mby = blockIdx.y;
     const DevPicture& pic = pics[blockIdx.z];
     if (!pic.has_inter) return;
     const int W = g.width_mbs;
-    if ((blockIdx.x * kWarpsPerCta + warp) * 2 >= W) return;
+    if ((blockIdx.x * kInter2Warps + warp) * 2 >= W) return;
     const int addr = mby * W + min(mbx, W - 1);
     const MbHdr h = load_hdr(pic.mbs, addr);
     const bool valid = mbx < W && !h.intra();
@@ -1785,14 +1793,14 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     const int groups = (w.geom.height_mbs + kWarpsPerCta - 1) / kWarpsPerCta;
     if (which == KERNEL_RESID) {
         const int n = 1;
-        residual_kernel<<<dim3((nmb + kWarpsPerCta - 1) / kWarpsPerCta, 1, w.num_pics), threads, 0, stream>>>(w.pics, w.geom);
+        residual_kernel<<<dim3((nmb + kResidWarps - 1) / kResidWarps, 1, w.num_pics), kResidWarps * 32, 0, stream>>>(w.pics, w.geom);
         return n;
     }
     if (which == KERNEL_INTER) {
         if (!w.any_inter) return 0;
 #if H264R_INTER_TWO_MB
-        const dim3 grid((w.geom.width_mbs + 2 * kWarpsPerCta - 1) / (2 * kWarpsPerCta), w.geom.height_mbs, w.num_pics);
-        recon_inter2_kernel<<<grid, threads, 0, stream>>>(w.pics, w.geom, w.direct8x8);
+        const dim3 grid((w.geom.width_mbs + 2 * kInter2Warps - 1) / (2 * kInter2Warps), w.geom.height_mbs, w.num_pics);
+        recon_inter2_kernel<<<grid, kInter2Warps * 32, 0, stream>>>(w.pics, w.geom, w.direct8x8);
 #else
         const dim3 grid((w.geom.width_mbs + kWarpsPerCta - 1) / kWarpsPerCta, w.geom.height_mbs, w.num_pics);
         recon_inter_kernel<<<grid, threads, 0, stream>>>(w.pics, w.geom, w.direct8x8);
