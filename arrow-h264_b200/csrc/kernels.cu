@@ -1324,20 +1324,24 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
 #endif
 // A warp takes H264R_SPARSE_PER_WARP consecutive entries of the list: header, neighbour headers and residual of the
 // next MB are in flight while the current one is reconstructed (the kernel is bound by those dependent loads).
-#ifndef H264R_SPARSE_CTAS
-#define H264R_SPARSE_CTAS 12
+#ifndef H264R_SPARSE_WARPS
+#define H264R_SPARSE_WARPS 4
 #endif
-__global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_SPARSE_CTAS)
+#ifndef H264R_SPARSE_CTAS
+#define H264R_SPARSE_CTAS (48 / H264R_SPARSE_WARPS)
+#endif
+constexpr int kSparseWarps = H264R_SPARSE_WARPS;
+__global__ void __launch_bounds__(kSparseWarps * 32, H264R_SPARSE_CTAS)
 recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g, uint32_t epoch)
 {
-    __shared__ __align__(16) IntraSmem smem_all[kWarpsPerCta];
+    __shared__ __align__(16) IntraSmem smem_all[kSparseWarps];
     __shared__ int s_ticket;
     if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[2], 1);
     __syncthreads();
     const int grp = s_ticket / num_pics, pic_i = s_ticket - grp * num_pics;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const DevPicture& pic = pics[pic_i];
-    const int first = (grp * kWarpsPerCta + warp) * H264R_SPARSE_PER_WARP;
+    const int first = (grp * kSparseWarps + warp) * H264R_SPARSE_PER_WARP;
     const int n = min(H264R_SPARSE_PER_WARP, pic.intra_count - first);
     if (n <= 0) return;
     const int W = g.width_mbs;
@@ -1814,9 +1818,9 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
             ++n;
         }
         if (w.max_intra_sparse > 0) {
-            const int per_cta = kWarpsPerCta * H264R_SPARSE_PER_WARP;
+            const int per_cta = kSparseWarps * H264R_SPARSE_PER_WARP;
             const int grps = (w.max_intra_sparse + per_cta - 1) / per_cta;
-            recon_intra_sparse_kernel<<<w.num_pics * grps, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
+            recon_intra_sparse_kernel<<<w.num_pics * grps, kSparseWarps * 32, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
             ++n;
         }
         return n;
