@@ -18,8 +18,8 @@ void Decoder::assign_quant_params(int slice_nr, const int* const q4[6], const in
 void Decoder::append(FacadeMb* mb, int pos, int level)
 {
     if (mb->mbAddrX != cur_mb_) { cur_mb_ = mb->mbAddrX; cur_first_ = n_levels_; }
-    if (n_levels_ >= bufs_.level_capacity) { overflow_ = true; return; }
-    bufs_.levels[n_levels_++] = H264R_LEVEL(pos, level);
+    if (n_levels_ >= bufs_.stream_capacity) { overflow_ = true; return; }
+    bufs_.stream[n_levels_++] = H264R_LEVEL(pos, level);
 }
 
 // Transform::coeff_luma_dc, transform.cc:425-429: cof[pos.y*4][pos.x*4] = level
@@ -78,13 +78,23 @@ void Decoder::decode(FacadeMb& mb, const FacadeMotion motion[16])
     } else {
         for (int i = 0; i < 4; ++i) { h.u.inter.sub_mb_type[i] = mb.SubMbType[i]; h.u.inter.sub_mb_pred_mode[i] = mb.SubMbPredMode[i]; }
     }
-    h264r_mb_motion& m = bufs_.motion[mb.mbAddrX];
+    if (mb.is_intra_block) return;
+    // the MB's distinct motion entries go into the stream right behind its levels (the next MB's levels follow them)
+    h264r_mb_motion m;
     for (int b = 0; b < 16; ++b)
         for (int list = 0; list < 2; ++list) {
             m.mv[list][b][0] = motion[b].mv[list][0]; m.mv[list][b][1] = motion[b].mv[list][1];
             m.ref_idx[list][b] = motion[b].ref_idx[list];
             m.ref_pic[list][b] = (int8_t)motion[b].ref_pic[list];
         }
+    h264r_motion_entry e[16];
+    const int code = h264r_pack_motion(&m, e);
+    const uint32_t n = 3u * h264r_motion_entries_of_code[code];
+    if (n_levels_ + n > bufs_.stream_capacity) { overflow_ = true; return; }
+    memcpy(bufs_.stream + n_levels_, e, sizeof(uint32_t) * n);
+    h.motion = n_levels_ << 4 | (uint32_t)code;
+    n_levels_ += n;
+    cur_mb_ = -1;                                   // levels of a later MB start a new run even if the address repeats
 }
 
 } // namespace h264r

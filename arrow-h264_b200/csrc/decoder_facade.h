@@ -2,7 +2,8 @@
 // (reference src/codec/h264/decoder/decoder.h:301-338): same entry points, same argument meaning, same call order
 // as the parser uses them (parser/interpret_residual.cc:159-170, 407-414, 427-431, 471-477; core/slice_data.cc:646;
 // framebuf/picture.cc:253).  Instead of reconstructing on the CPU it records what the GPU needs into the flat
-// per-picture buffers of include/h264recon.h.  Plain C++11, no CUDA: the buffers normally are the pinned staging
+// per-picture buffers of include/h264recon.h -- levels and packed motion entries appended to the picture's stream in
+// parse order, nothing left for submit to do.  Plain C++11, no CUDA: the buffers normally are the pinned staging
 // handed out by h264r_picture_begin, but any memory works (tests use malloc).
 #ifndef H264R_DECODER_FACADE_H_
 #define H264R_DECODER_FACADE_H_
@@ -64,20 +65,20 @@ public:
     // replaces the parser's direct pokes of Transform::cof for I_PCM (parser/interpret_mb.cc:444-470)
     void pcm_sample(FacadeMb* mb, ColorPlane pl, int x, int y, int value);
 
-    // Decoder::decode (decoder.cc:65-79): the MB is completely parsed; snapshot its header and the 16
-    // pic_motion_params of dec_picture->mv_info (raster order)
+    // Decoder::decode (decoder.cc:65-79): the MB is completely parsed; snapshot its header and, packed to their distinct
+    // entries (h264r_pack_motion), the 16 pic_motion_params of dec_picture->mv_info (raster order) into the stream
     void decode(FacadeMb& mb, const FacadeMotion motion[16]);
 
     // Decoder::deblock_filter (decoder.cc:107-110) is the flush point: the caller submits the picture
-    // (h264r_picture_submit(ctx, num_levels()) + h264r_flush).
-    uint32_t num_levels() const { return n_levels_; }
+    // (h264r_picture_submit(ctx, picture, stream_words()) + h264r_flush).
+    uint32_t stream_words() const { return n_levels_; }
     bool     overflowed() const { return overflow_; }
 
 private:
     void append(FacadeMb* mb, int pos, int level);
     h264r_pic_buffers bufs_;
     int width_mbs_ = 0, height_mbs_ = 0;
-    uint32_t n_levels_ = 0;
+    uint32_t n_levels_ = 0;          // words of the stream in use (levels and motion entries)
     int cur_mb_ = -1;
     uint32_t cur_first_ = 0;
     bool overflow_ = false;

@@ -12,11 +12,12 @@ namespace h264r {
 // bit-identical to the reference's padded planes + block pre-clamp, SURVEY.md §8a derived facts).
 struct FrameGeom {
     int width_mbs, height_mbs;
-    int pitch_y, pitch_c;            // bytes; multiples of 128
+    int pitch_y, pitch_c;            // bytes; tight: 16 * width_mbs and 8 * width_mbs
     size_t off_cb, off_cr, bytes;    // plane offsets inside the allocation
 };
 
-// Output of the parallel deblock pre-pass, input of the deblock wavefront: 64 bytes per MB.
+// Deblock descriptor of one MB, written by the kernel that reconstructs the MB (it holds header and motion), read by the
+// deblock wavefront: 64 bytes.
 //   bs[dir * 2 + (edge >> 1)], nibble (edge & 1) * 4 + group = boundary strength 0..4 of the 4-sample group of that edge
 //   par[plane][type], type 0 = left MB edge, 1 = internal edges, 2 = top MB edge: the filter thresholds of
 //   filter_edge (deblock.cc:469-474 + tables :294-324) packed as alpha | beta << 8 | tc0[bS=1] << 13 | tc0[2] << 18 |
@@ -28,38 +29,36 @@ struct DeblockDesc {
 
 struct DevPicture {
     const h264r_mb*        mbs;
-    const uint8_t*         packed_motion;             // 12-byte entries (engine.cu pack_motion), indexed by h264r_mb::reserved2
     const h264r_slice*     slices;
-    const h264r_level*     levels;
-    int16_t*               resid;                     // [nmb][384] residual plane, device only (residual_kernel)
+    const uint32_t*        stream;                    // levels and packed motion entries (h264recon.h h264r_pic_buffers)
     uint8_t*               dst;                       // frame base
-    const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]
+    const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]; unused slots: a dummy frame
     DeblockDesc*           desc;                      // [nmb], device only
-    uint64_t*              mbox;                      // [nmb][24], device only: deblock row-to-row mailboxes { 4 samples, epoch }
-    const uint32_t*        intra_list;                // raster-ordered addresses of the intra MBs (pictures that also have inter MBs)
+    uint64_t*              mbox;                      // [nmb][24], device only: row-to-row mailboxes { 4 samples, epoch }
     uint32_t*              mb_done;                   // [nmb], device only: epoch stamp of the launch that reconstructed the intra MB
+    uint32_t               stream_words;              // words of `stream` in use (bounds of coeff_offset / motion)
+    int                    num_slices;
+    int                    num_refs;
     int                    run_deblock;
-    int                    has_intra;                 // any intra MB in the picture (host-side hint)
-    int                    has_inter;
-    int                    intra_count;               // entries of intra_list; 0 for all-intra pictures (row wavefront instead)
+    int                    all_intra;                 // every slice is an I slice: row wavefront; otherwise inter + sparse intra kernels
+    int                    direct8x8;                 // direct_8x8_inference_flag of the picture's stream
 };
 
 struct WaveLaunch {
     const DevPicture* pics;          // device array
     int   num_pics;
     int*  tickets;                   // device: work-ticket counters ([0] intra rows, [1] deblock, [2] sparse intra), zeroed per wave (64 ints)
+    uint32_t* err;                   // host-mapped word: kernels OR in a bit when they meet a description outside its domain
     FrameGeom geom;
-    int   direct8x8;
-    int   any_inter, any_intra, any_deblock;
+    int   any_inter, any_deblock;
     int   any_intra_rows;            // some picture of the wave is all-intra: row wavefront kernel
-    int   max_intra_sparse;          // largest intra_count of the wave (0: no sparse-intra kernel)
-    uint32_t epoch;                  // stamp of this launch sequence for DevPicture::mb_done
+    uint32_t epoch;                  // stamp of this launch sequence (mailboxes, DevPicture::mb_done)
 };
 
-// Kernel launchers of one wave (kernels.cu).  which: 0 residual (parallel), 1 inter (parallel), 2 intra wavefront,
-// 3 deblock descriptors (parallel), 4 deblock wavefront.  Returns the number of kernels launched (0 when the wave has no work of that kind).
-enum { KERNEL_RESID = 0, KERNEL_INTER = 1, KERNEL_INTRA = 2, KERNEL_DBPREP = 3, KERNEL_DEBLOCK = 4, KERNEL_KINDS = 5 };
+// Kernel launchers of one wave (kernels.cu).  Returns the number of kernels launched (0 when the wave has no work of that kind).
+enum { KERNEL_INTER = 0, KERNEL_INTRA = 1, KERNEL_DEBLOCK = 2, KERNEL_KINDS = 3 };
 int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);
+const char* wave_kernel_name(int which);
 
 } // namespace h264r
 #endif

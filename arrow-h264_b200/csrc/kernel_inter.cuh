@@ -1,0 +1,404 @@
+// recon_inter2_kernel: the inter macroblocks of a wave of pictures, TWO macroblocks per warp, one 4x4 block per lane:
+// deblock descriptor (boundary strengths + thresholds), motion compensation, weighted prediction, dequantisation +
+// inverse transform of the MB's levels, reconstruction -- one pass, nothing but the frame and the 64-byte descriptor is
+// written (inter_prediction.cc:53-406, 448-536; decoder.cc:217-262; transform.cc:394-456, 597-733, 913-984;
+// deblock.cc:35-289, 469-474).
+#ifndef H264R_KERNEL_INTER_CUH_
+#define H264R_KERNEL_INTER_CUH_
+
+#include "kernels_common.cuh"
+
+namespace h264r {
+
+#ifndef H264R_INTER2_WARPS
+#define H264R_INTER2_WARPS 2
+#endif
+#ifndef H264R_INTER2_CTAS
+#define H264R_INTER2_CTAS (28 / H264R_INTER2_WARPS)
+#endif
+
+// Reference windows in shared memory.  Interior windows are fetched as aligned 32-bit words: the first sample x0 of
+// a window row then sits at byte offset x0 & 3.  Windows touching the picture border (rare) are fetched sample by
+// sample with clamped coordinates -- bit-identical to the reference's padded planes + block pre-clamp, SURVEY.md
+// 8a -- and start at byte offset 0; that path is kept out of line.
+__device__ __noinline__ void load_window_border(uint32_t* win, int pitch_words, const uint8_t* __restrict__ plane, int pitch,
+                                                int W, int H, int x0, int y0, int ncols, int nrows, int first_row, int row_step)
+{
+    for (int row = first_row; row < nrows; row += row_step) {
+        const uint8_t* src = plane + (uint32_t)(clip3i(0, H - 1, y0 + row) * pitch);
+        uint8_t* dst = reinterpret_cast<uint8_t*>(win + row * pitch_words);
+        for (int c = 0; c < ncols; ++c) dst[c] = __ldg(src + clip3i(0, W - 1, x0 + c));
+    }
+}
+// 4-byte global -> shared copy that never touches a register (LDGSTS); completion: cp_async_wait_all()
+__device__ __forceinline__ void cp_async4(uint32_t* dst, const uint8_t* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// per-warp scratch, in 32-bit words.  Per 8x8 quadrant: luma 146 words = uniform quadrant 13 rows x 4 words | split
+// quadrant 4 blocks x (9 rows x 4 words), one row pitch for both so that row offsets are immediates; chroma 50 words =
+// uniform 2 planes x (5 rows x 2 words) | split 4 blocks x 2 planes x (3 rows x 2 words), + 1 word the funnel shifts
+// may touch.  146 = 2 (mod 8): the four quadrant groups of a warp read disjoint banks.
+// After the last prediction list the same memory is the coefficient scratch of the two macroblocks (2 x kResInts ints).
+constexpr int kLumaQ = 146, kChromaQ = 50;
+struct __align__(16) Inter2Smem {
+    uint32_t luma[2][4 * kLumaQ + 2];
+    uint32_t chroma[2][4 * kChromaQ + 2];
+};
+static_assert(sizeof(Inter2Smem) >= 2 * kResInts * sizeof(int), "the coefficient scratch aliases the reference windows");
+
+// Decoder::mb_pred_inter partition walk (decoder.cc:217-262) for 4x4 block `blk`: returns the block whose motion
+// entry the reference reads (partition origin), the prediction direction, and whether the partition covers the
+// whole 8x8 quadrant of the block.  Partition steps in 4x4 units per type 0..7 ({0,0},{4,4},{4,2},{2,4},{2,2},{2,1},
+// {1,2},{1,1}) are nibbles of two constants.
+__device__ __forceinline__ void partition_of_block2(const MbHdr& h, int is_b, int direct_spatial, const DevPicture& pic, int direct8x8,
+                                                    int blk, int& origin, int& dir, bool& covers8x8, uint32_t* err)
+{
+    const int bx = blk & 3, by = blk >> 2;
+    int sh0 = (0x11222440u >> (4 * (h.mb_type & 7))) & 7, sv0 = (0x12124240u >> (4 * (h.mb_type & 7))) & 7;
+    if (h.mb_type == 0) sh0 = sv0 = is_b ? 2 : 4;
+    const int i0 = bx & ~(sh0 - 1), j0 = by & ~(sv0 - 1);
+    const int b8 = 2 * (j0 >> 1) + (i0 >> 1);
+    const int mode = (h.u0 >> (8 * b8)) & 0xFF;
+    int pd = (h.u1 >> (8 * b8)) & 0xFF;
+    int sh4 = (0x11222440u >> (4 * (mode & 7))) & 7, sv4 = (0x12124240u >> (4 * (mode & 7))) & 7;
+    if (mode == 0) sh4 = sv4 = direct8x8 ? 2 : 1;
+    if (is_b && h.mb_type == H264R_MB_8x8 && direct_spatial) {
+        const uint32_t rw = __ldg(pic.stream + packed_entry_word(pic, h.packed, j0 * 4 + i0, err) + 2);
+        pd = (int8_t)(rw >> 8) < 0 ? 0 : ((int8_t)rw < 0 ? 1 : 2);
+    }
+    if (pd > 2) { report_error(err, ERR_HEADER); pd = 2; }
+    const int i = bx & ~(sh4 - 1), j = by & ~(sv4 - 1);   // partitions are aligned to their own size
+    origin = j * 4 + i;
+    dir = pd;
+    covers8x8 = sh4 >= 2 && sv4 >= 2;
+}
+
+constexpr int kInter2Warps = H264R_INTER2_WARPS;       // warps per CTA (each warp: two MBs)
+
+// Lanes 0..15 reconstruct MB 2j, lanes 16..31 MB 2j+1 of a row; lane b of a half owns 4x4 luma block b (raster) and the
+// 2x2 chroma patches of both planes under it.  The per-MB work that is the same for every lane (header, slice,
+// partition walk, addressing, weights, loop control) is issued once for two MBs.  If one partition covers an 8x8
+// quadrant its four lanes share one 13x13 luma / 5x5 chroma window, otherwise every block has its own 9x9 / 3x3 window.
+// grid = (ceil(width_mbs / (2 * warps)), height_mbs, pictures of the wave)
+__global__ void __launch_bounds__(kInter2Warps * 32, H264R_INTER2_CTAS)
+recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* err)
+{
+    __shared__ __align__(16) Inter2Smem smem_all[kInter2Warps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = lane >> 4, b = lane & 15, bx = b & 3, by = b >> 2;
+    const int mbx = (blockIdx.x * kInter2Warps + warp) * 2 + m, mby = blockIdx.y;
+    const DevPicture& pic = pics[blockIdx.z];
+    if (pic.all_intra) return;
+    const int W = g.width_mbs;
+    if ((blockIdx.x * kInter2Warps + warp) * 2 >= W) return;
+    const int addr = mby * W + min(mbx, W - 1);
+    MbHdr h = load_hdr(pic.mbs, addr);
+    const bool valid = mbx < W && !h.intra();
+    if (!__any_sync(0xFFFFFFFFu, valid)) return;
+    const unsigned half_mask = 0xFFFFu << (lane & 16);
+    sanitize_hdr(h, pic, err);
+    Inter2Smem& sm = smem_all[warp];
+    const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
+    const int wY = W * 16, hY = g.height_mbs * 16, wC = wY >> 1, hC = hY >> 1;
+    const uint32_t s0 = __ldg(reinterpret_cast<const uint32_t*>(sl)), s1 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 1),
+                   s2 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 2);
+    const bool is_b = (s0 & 0xFF) == H264R_B_SLICE;
+    const int denom_y = s1 & 0xFF, denom_c = (s1 >> 8) & 0xFF, wp_flag = (s1 >> 16) & 0xFF, bipred_idc = (s1 >> 24) & 0xFF;
+    const int direct_spatial = (s2 >> 8) & 0xFF;
+    const bool has_res = valid && h.has_resid();
+
+    // the levels are needed last: pull them into the L2 now (no registers held)
+    if (has_res && b * 32 < h.coeff_count) prefetch_l2(pic.stream + h.coeff_offset + b * 32);
+
+    // ---- neighbour headers for the deblock descriptor: issued with everything else, consumed while the windows load ----
+    const bool want_desc = valid && pic.run_deblock;
+    uint4 hL = make_uint4(0, 0, 0, 0), hT = hL; uint32_t pkL = 0, pkT = 0;
+    if (want_desc) {
+        if (mbx > 0) { hL = __ldg(reinterpret_cast<const uint4*>(pic.mbs + addr - 1)); pkL = __ldg(reinterpret_cast<const unsigned int*>(pic.mbs + addr - 1) + 7); }
+        if (mby > 0) { hT = __ldg(reinterpret_cast<const uint4*>(pic.mbs + addr - W)); pkT = __ldg(reinterpret_cast<const unsigned int*>(pic.mbs + addr - W) + 7); }
+    }
+
+    int origin = 0, pd = 0; bool uni = true;
+    uint32_t mvw0 = 0, mvw1 = 0, rw = 0;                 // the motion entry of this block's partition
+    uint32_t own_word = 0;
+    if (valid) {
+        partition_of_block2(h, is_b, direct_spatial, pic, pic.direct8x8, b, origin, pd, uni, err);
+        own_word = packed_entry_word(pic, h.packed, origin, err);
+        const uint32_t* e = pic.stream + own_word;
+        mvw0 = __ldg(e); mvw1 = __ldg(e + 1); rw = __ldg(e + 2);
+    }
+    const int q = (by >> 1) * 2 + (bx >> 1), sb = (by & 1) * 2 + (bx & 1);        // quadrant, block inside the quadrant
+    uint32_t* const lq = sm.luma[m] + q * kLumaQ;
+    uint32_t* const cq = sm.chroma[m] + q * kChromaQ;
+    const int pitch_y = g.pitch_y, pitch_c = g.pitch_c;
+
+    // samples of the (up to) two lists, packed bytes: cur = last list done, prev = the one before
+    uint32_t curY[4] = { 0, 0, 0, 0 }, prevY[4] = { 0, 0, 0, 0 }, curC[2] = { 0, 0 }, prevC[2] = { 0, 0 };
+    int ref_cur = 0, ref_prev = 0;
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        const bool active = valid && (k == 0 || pd == 2);
+        if (k == 1 && !__any_sync(0xFFFFFFFFu, active)) break;
+        const int list = pd == 2 ? k : pd;
+        int vx = 0, vy = 0, refidx = 0;
+        const uint32_t* wl = lq; const uint32_t* wc0 = cq; const uint32_t* wc1 = cq;
+        int loff = 2, coff = 0;
+        if (active) {
+            refidx = (int)(int8_t)(rw >> (8 * list));
+            int slot = (int)(int8_t)(rw >> (16 + 8 * list));
+            if ((unsigned)slot >= (unsigned)pic.num_refs) { report_error(err, ERR_MOTION); slot = 0; }
+            const uint8_t* __restrict__ rbase = pic.ref[slot];
+            const uint32_t mvw = list ? mvw1 : mvw0;
+            const int mvx = (int)(int16_t)(mvw & 0xFFFF), mvy = (int)(int16_t)(mvw >> 16);
+            vx = (mbx * 16 + bx * 4) * 4 + mvx; vy = (mby * 16 + by * 4) * 4 + mvy;       // this block's position
+            if (uni) {
+                const int qvx = (mbx * 16 + (bx >> 1) * 8) * 4 + mvx, qvy = (mby * 16 + (by >> 1) * 8) * 4 + mvy;
+                const int x0 = (qvx >> 2) - 2, y0 = (qvy >> 2) - 2, cx0 = qvx >> 3, cy0 = qvy >> 3;
+                const int xa = x0 & ~3, cxa = cx0 & ~3;
+                const bool in_y = xa >= 0 && xa + 16 <= wY && y0 >= 0 && y0 + 13 <= hY;
+                const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 5 <= hC;
+                if (in_y) {                                     // 13 rows x 4 words: lane = word column
+                    const uint8_t* src = rbase + (uint32_t)(y0 * pitch_y + xa + sb * 4);
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) cp_async4(lq + i * 4 + sb, src + (uint32_t)(i * pitch_y));
+                } else load_window_border(lq, 4, rbase, pitch_y, wY, hY, x0, y0, 13, 13, sb, 4);
+                {                                               // 2 planes x 5 rows x 2 words: lane = (plane, word column)
+                    const int pl = sb >> 1, col = sb & 1;
+                    const uint8_t* cplane = rbase + (pl ? g.off_cr : g.off_cb);
+                    if (in_c) {
+                        const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa + col * 4);
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) cp_async4(cq + pl * 10 + i * 2 + col, src + (uint32_t)(i * pitch_c));
+                    } else load_window_border(cq + pl * 10, 2, cplane, pitch_c, wC, hC, cx0, cy0, 5, 5, col, 2);
+                }
+                wl = lq + (sb >> 1) * 4 * 4;
+                loff = 2 + (sb & 1) * 4 + (in_y ? x0 & 3 : 0);
+                wc0 = cq + (sb >> 1) * 2 * 2; wc1 = wc0 + 10;
+                coff = (sb & 1) * 2 + (in_c ? cx0 & 3 : 0);
+            } else {
+                const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2, cx0 = vx >> 3, cy0 = vy >> 3;
+                const int xa = x0 & ~3, cxa = cx0 & ~3;
+                const bool in_y = xa >= 0 && xa + 12 <= wY && y0 >= 0 && y0 + 9 <= hY;
+                const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 3 <= hC;
+                uint32_t* const lb = lq + sb * 36;
+                uint32_t* const cb = cq + sb * 12;
+                if (in_y) {                                     // 9 rows x 3 words
+                    const uint8_t* src = rbase + (uint32_t)(y0 * pitch_y + xa);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) cp_async4(lb + i * 4 + c, src + (uint32_t)(i * pitch_y) + c * 4);
+                } else load_window_border(lb, 4, rbase, pitch_y, wY, hY, x0, y0, 9, 9, 0, 1);
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {                // 3 rows x 2 words per plane
+                    const uint8_t* cplane = rbase + (pl ? g.off_cr : g.off_cb);
+                    if (in_c) {
+                        const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) { cp_async4(cb + pl * 6 + i * 2, src + (uint32_t)(i * pitch_c)); cp_async4(cb + pl * 6 + i * 2 + 1, src + (uint32_t)(i * pitch_c) + 4); }
+                    } else load_window_border(cb + pl * 6, 2, cplane, pitch_c, wC, hC, cx0, cy0, 3, 3, 0, 1);
+                }
+                wl = lb;
+                loff = 2 + (in_y ? x0 & 3 : 0);
+                wc0 = cb; wc1 = cb + 6;
+                coff = in_c ? cx0 & 3 : 0;
+            }
+        }
+
+        // ---- deblock descriptor of the two MBs, computed while the first list's windows are in flight ----
+        if (k == 0 && __any_sync(0xFFFFFFFFu, want_desc)) {
+            const int idc = (s0 >> 8) & 0xFF;
+            // this block's OWN motion entry (the strength rule compares mv_info per 4x4 block, deblock.cc:140-170); it is the
+            // partition's entry unless the description carries different vectors inside one partition
+            uint32_t e0 = mvw0, e1 = mvw1, e2 = rw;
+            if (want_desc) {
+                const uint32_t w_own = packed_entry_word(pic, h.packed, b, err);
+                if (w_own != own_word) { const uint32_t* e = pic.stream + w_own; e0 = __ldg(e); e1 = __ldg(e + 1); e2 = __ldg(e + 2); }
+            }
+            // neighbouring blocks inside the MB come from the neighbouring lanes
+            uint32_t l0 = __shfl_sync(0xFFFFFFFFu, e0, lane - 1), l1 = __shfl_sync(0xFFFFFFFFu, e1, lane - 1), l2 = __shfl_sync(0xFFFFFFFFu, e2, lane - 1);
+            uint32_t t0 = __shfl_sync(0xFFFFFFFFu, e0, lane - 4), t1 = __shfl_sync(0xFFFFFFFFu, e1, lane - 4), t2 = __shfl_sync(0xFFFFFFFFu, e2, lane - 4);
+            uint32_t w[4] = { 0, 0, 0, 0 };
+            if (want_desc && idc != 1) {
+                const bool left_ok = mbx > 0 && !(idc == 2 && (hL.x >> 16) != (uint32_t)h.slice_idx);
+                const bool top_ok  = mby > 0 && !(idc == 2 && (hT.x >> 16) != (uint32_t)h.slice_idx);
+                const bool t8 = h.t8();
+                const bool p_skip = !is_b && h.mb_type == 0;
+                const int coded = (h.cbp_blks >> b) & 1;
+                // dir 0: the vertical edge on the left of the block (edge bx, group by); dir 1: the horizontal edge above it
+#pragma unroll
+                for (int dir = 0; dir < 2; ++dir) {
+                    const int e = dir ? by : bx, k4 = dir ? bx : by;
+                    const uint4& hN = dir ? hT : hL;
+                    bool on = e == 0 ? (dir ? top_ok : left_ok) : !(t8 && (e & 1));
+                    if (e > 0 && p_skip) on = false;
+                    int s = 0;
+                    if (on) {
+                        if (e == 0 && ((hN.x >> 8) & H264R_MB_FLAG_INTRA)) s = 4;
+                        else {
+                            const int blkP = dir ? (e ? e - 1 : 3) * 4 + k4 : k4 * 4 + (e ? e - 1 : 3);
+                            const int pcbp = e ? h.cbp_blks : (int)(hN.w & 0xFFFF);
+                            if (coded || ((pcbp >> blkP) & 1)) s = 2;
+                            else if (e > 0 && (h.mb_type == 1 || h.mb_type == (dir ? 3 : 2))) s = 0;
+                            else {
+                                uint32_t n0 = dir ? t0 : l0, n1 = dir ? t1 : l1, n2 = dir ? t2 : l2;
+                                if (e == 0) {                    // the block on the other side belongs to the neighbouring MB
+                                    const uint32_t* ne = pic.stream + packed_entry_word(pic, dir ? pkT : pkL, blkP, err);
+                                    n0 = __ldg(ne); n1 = __ldg(ne + 1); n2 = __ldg(ne + 2);
+                                }
+                                s = (n0 == e0 && n1 == e1 && n2 == e2) ? 0 : bs_compare(n0, n1, n2, e0, e1, e2);
+                            }
+                        }
+                    }
+                    w[dir * 2 + (e >> 1)] |= (uint32_t)s << ((e & 1) * 16 + k4 * 4);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = __reduce_or_sync(half_mask, w[i]);
+            if (want_desc) {
+                uint32_t* out = reinterpret_cast<uint32_t*>(pic.desc + addr);
+                if (b == 0) *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
+                if (b < 9 && idc != 1) {                         // thresholds [Y, Cb, Cr][left MB edge, internal, top MB edge]
+                    const int pl = b / 3, t = b - pl * 3;
+                    const uint32_t q1 = (uint32_t)h.cbp_luma | (uint32_t)h.qp_y << 16 | (uint32_t)h.qp_c[0] << 24, q2 = (uint32_t)h.qp_c[1];
+                    const uint32_t p1 = t == 0 ? (mbx > 0 ? hL.y : q1) : (t == 2 ? (mby > 0 ? hT.y : q1) : q1);
+                    const uint32_t p2 = t == 0 ? (mbx > 0 ? hL.z : q2) : (t == 2 ? (mby > 0 ? hT.z : q2) : q2);
+                    out[4 + b] = deblock_threshold_word(qp_of_plane(p1, p2, pl), qp_of_plane(q1, q2, pl),
+                                                        (int)(int8_t)(s0 >> 16), (int)(int8_t)(s0 >> 24));
+                }
+            }
+        }
+
+        cp_async_wait_all();                               // this lane's window copies have landed
+        __syncwarp();
+        {
+            const int xf = vx & 3, yf = vy & 3;
+            unsigned hm, cm;
+            mc_luma_masks_r<4>(xf, yf, hm, cm);
+            const unsigned whm = __reduce_or_sync(0xFFFFFFFFu, active ? hm : 0u), wcm = __reduce_or_sync(0xFFFFFFFFu, active ? cm : 0u);
+            uint32_t y[4];
+            mc_luma_patch<4>(wl, loff, xf, yf, whm, wcm, y);
+            const uint32_t c0 = mc_chroma_patch_2x2(wc0, coff, vx & 7, vy & 7), c1 = mc_chroma_patch_2x2(wc1, coff, vx & 7, vy & 7);
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { prevY[r] = curY[r]; curY[r] = y[r]; }
+                prevC[0] = curC[0]; prevC[1] = curC[1]; curC[0] = c0; curC[1] = c1;
+                ref_prev = ref_cur; ref_cur = refidx;
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- weighted sample prediction (mc_prediction / bi_prediction, inter_prediction.cc:53-156) ----
+    uint32_t predY[4], predC[2];
+    {
+        const bool uni_weighted = (wp_flag && !is_b) || (bipred_idc == 1 && is_b);
+        const int ref0 = pd == 2 ? ref_prev : ref_cur, ref1 = ref_cur;
+        const int mode = pd != 2 ? (uni_weighted ? 1 : 0) : (bipred_idc == 0 ? 2 : 3);
+        int wgt[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } }, off[3] = { 0, 0, 0 };             // [Y, Cb, Cr][list]
+        if (mode == 1) {
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+                wgt[pl][0] = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][ref0 & 31]);
+                off[pl] = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][ref0 & 31]);
+            }
+        } else if (mode == 3) {
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl) {
+                if (bipred_idc == 1) {
+                    wgt[pl][0] = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][ref0 & 31]);
+                    wgt[pl][1] = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][ref1 & 31]);
+                    off[pl] = ((int)(int8_t)__ldg(&sl->wp_offset[0][pl][ref0 & 31]) + (int)(int8_t)__ldg(&sl->wp_offset[1][pl][ref1 & 31]) + 1) >> 1;
+                } else {
+                    wgt[pl][1] = (int)__ldg(&sl->implicit_w1[ref0 & 31][ref1 & 31]);
+                    wgt[pl][0] = 64 - wgt[pl][1];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) predY[r] = mc_weight4(mode, pd == 2 ? prevY[r] : curY[r], curY[r], wgt[0][0], wgt[0][1], denom_y, off[0]);
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) predC[pl] = mc_weight4(mode, pd == 2 ? prevC[pl] : curC[pl], curC[pl], wgt[1 + pl][0], wgt[1 + pl][1], denom_c, off[1 + pl]);
+    }
+
+    // ---- residual: the windows are dead, their memory becomes the coefficient scratch of the two MBs ----
+    if (__any_sync(0xFFFFFFFFu, has_res)) {
+        int* const scratch = reinterpret_cast<int*>(&sm);
+        int* const cof = scratch + m * kResInts;
+        constexpr int kVec = 2 * kResInts / 4;                       // 16-byte chunks of the two scratch areas
+#pragma unroll
+        for (int i = 0; i < (kVec + 31) / 32; ++i)
+            if (lane + 32 * i < kVec) reinterpret_cast<int4*>(scratch)[lane + 32 * i] = make_int4(0, 0, 0, 0);
+        __syncwarp();
+        const bool t8 = h.t8();
+        unsigned nz = 0;
+        if (has_res) {
+            const uint32_t ctl = scatter_ctl(h), mode = scatter_mode(h, 1);
+            const uint32_t* __restrict__ lv = pic.stream + h.coeff_offset;
+            for (int i = b; i < h.coeff_count; i += 16) nz |= scatter_level(__ldg(lv + i), ctl, mode, sl, cof, err);
+        }
+        nz = __reduce_or_sync(half_mask, nz);
+        __syncwarp();
+        // phase 1: the lanes sb = 0 / 1 of quadrant q take chroma block q of Cb / Cr into registers and transform it;
+        //          8x8-transform MBs run the row pass of their luma blocks in place (lane sb: rows 2 sb, 2 sb + 1)
+        const bool chroma_on = has_res && h.cbp_chroma && (nz >> 16);
+        const bool do_c = chroma_on && sb < 2;
+        int* const cblk = cof + kResC + (sb & 1) * kResCPlane + (q >> 1) * 4 * kResCP + (q & 1) * 4;
+        int cd[4][4];
+        if (do_c) {
+            const int pl = sb & 1;
+            const int* cp = cof + kResC + pl * kResCPlane;
+            const int c00 = cp[0], c01 = cp[4], c10 = cp[4 * kResCP], c11 = cp[4 * kResCP + 4];
+            const int qc = pl ? h.qp_c[1] : h.qp_c[0], cper = qc / 6, crem = qc - cper * 6;
+            load_block4(cblk, kResCP, cd);
+            cd[0][0] = chroma_dc_of_block(q, c00, c01, c10, c11, (int)__ldg(&sl->level_scale_4x4[1][pl + 1][crem][0]), cper);
+            idct4_regs(cd);
+        }
+        const unsigned m8 = 0x33u << ((q >> 1) * 8 + (q & 1) * 2);          // the four 4x4 blocks of 8x8 block q
+        const bool do_8 = has_res && t8 && (nz & m8);
+        int* const blk8 = cof + (q >> 1) * 8 * kResP + (q & 1) * 8;
+        if (do_8) { idct8_1d(blk8 + (2 * sb) * kResP, 1, false); idct8_1d(blk8 + (2 * sb + 1) * kResP, 1, false); }
+        __syncwarp();
+        // phase 2: chroma blocks back to the scratch; column pass of the 8x8 blocks (lane sb: columns 2 sb, 2 sb + 1)
+        if (do_c) store_block4(cblk, kResCP, cd);
+        if (do_8) { idct8_1d(blk8 + 2 * sb, kResP, true); idct8_1d(blk8 + 2 * sb + 1, kResP, true); }
+        __syncwarp();
+        // phase 3: every lane takes its 4x4 luma block (4x4-transform MBs: coefficients, transformed in registers) and
+        //          its 2x2 chroma patches, and reconstructs
+        if (has_res) {
+            if (t8 ? (nz & m8) != 0 : ((nz >> b) & 1) != 0) {
+                int d[4][4];
+                load_block4(cof + by * 4 * kResP + bx * 4, kResP, d);
+                if (!t8) idct4_regs(d);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) predY[r] = mc_recon4(predY[r], pack_res2(d[r][0], d[r][1]), pack_res2(d[r][2], d[r][3]));
+            }
+            if (chroma_on) {
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+                    const int* cp = cof + kResC + pl * kResCPlane + by * 2 * kResCP + bx * 2;
+                    const int2 r0 = *reinterpret_cast<const int2*>(cp), r1 = *reinterpret_cast<const int2*>(cp + kResCP);
+                    predC[pl] = mc_recon4(predC[pl], pack_res2(r0.x, r0.y), pack_res2(r1.x, r1.y));
+                }
+            }
+        }
+    }
+    if (!valid) return;
+
+    // ---- store ----
+    uint8_t* dY = pic.dst + (uint32_t)((mby * 16 + by * 4) * pitch_y + mbx * 16 + bx * 4);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t*>(dY + (uint32_t)(r * pitch_y)) = predY[r];
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+        uint8_t* dC = pic.dst + (pl ? g.off_cr : g.off_cb) + (uint32_t)((mby * 8 + by * 2) * pitch_c + mbx * 8 + bx * 2);
+        *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(predC[pl] & 0xFFFF);
+        *reinterpret_cast<uint16_t*>(dC + pitch_c) = (uint16_t)(predC[pl] >> 16);
+    }
+}
+
+} // namespace h264r
+#endif

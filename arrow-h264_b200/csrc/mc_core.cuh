@@ -1,7 +1,7 @@
 // Arithmetic core of the motion-compensation kernel: quarter-pel luma (get_block_luma, reference
 // decoder/inter_prediction.cc:158-340), eighth-pel chroma (get_block_chroma, :342-406) and weighted sample
 // prediction + reconstruction (mc_prediction / bi_prediction :53-156, Transform::construction transform.cc:913-984)
-// for the 4x2 luma / 2x2 chroma patch one lane owns.  Written on packed data:
+// for the 4x4 luma / 2x2 chroma patch one lane owns.  Written on packed data:
 //   * horizontal 6-tap   : IDP.4A (u8 x s8 dot product) on 4-byte-aligned row words, taps as shifted constants
 //   * vertical 6-tap     : 16x2 SIMD-in-register (IADD3 / IMAD on biased, non-negative lanes; VIADDMNMX / VIMNMX clamps)
 //   * centre sample j    : int32 vertical 6-tap over the unrounded horizontal sums
@@ -245,14 +245,12 @@ MC_FN uint32_t mc_chroma_patch_2x2(const uint32_t* win, int off, int xf, int yf)
     return v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24;
 }
 
-// Weighted sample prediction of four packed samples (mc_prediction / bi_prediction, inter_prediction.cc:53-156),
-// then reconstruction clip1(pred + residual) (transform.cc:913-984).
+// Weighted sample prediction of four packed samples (mc_prediction / bi_prediction, inter_prediction.cc:53-156):
 //   mode 0: p0                         mode 1: clip1(((w0 p0 + 2^(d-1)) >> d) + o)      [d == 0: no rounding shift]
 //   mode 2: (p0 + p1 + 1) >> 1         mode 3: clip1(((w0 p0 + w1 p1 + 2^d) >> (d + 1)) + o)
-// `o` is the final offset (mode 3: (o0 + o1 + 1) >> 1).  res01 / res23 = residuals as int16 pairs.
-MC_FN uint32_t mc_weight_recon4(int mode, uint32_t p0, uint32_t p1, int w0, int w1, int d, int o, uint32_t res01, uint32_t res23)
+// `o` is the final offset (mode 3: (o0 + o1 + 1) >> 1).  Returns the four prediction samples packed.
+MC_FN uint32_t mc_weight4(int mode, uint32_t p0, uint32_t p1, int w0, int w1, int d, int o)
 {
-    uint32_t lo, hi;                                              // prediction as 16x2 pairs (s0, s1), (s2, s3)
     if (mode & 1) {
         int v[4];
         const int sh = mode == 1 ? d : d + 1;
@@ -263,15 +261,22 @@ MC_FN uint32_t mc_weight_recon4(int mode, uint32_t p0, uint32_t p1, int w0, int 
             if (mode == 3) acc += (int)((p1 >> (8 * i)) & 0xFF) * w1;
             v[i] = (acc >> sh) + o;
         }
-        const uint32_t c = mc_pack4_sat(v[0], v[1], v[2], v[3]);  // clip1
-        lo = mc_prmt(c, 0u, 0x4140u); hi = mc_prmt(c, 0u, 0x4342u);
-    } else {
-        const uint32_t c = mode == 2 ? mc_avg_u8x4(p0, p1) : p0;
-        lo = mc_prmt(c, 0u, 0x4140u); hi = mc_prmt(c, 0u, 0x4342u);
+        return mc_pack4_sat(v[0], v[1], v[2], v[3]);              // clip1
     }
+    return mode == 2 ? mc_avg_u8x4(p0, p1) : p0;
+}
+// Reconstruction clip1(pred + residual) (transform.cc:913-984) of four packed samples; res01 / res23 = residuals as
+// int16 pairs, each within [-32768 + 255, 32767 - 255].
+MC_FN uint32_t mc_recon4(uint32_t pred, uint32_t res01, uint32_t res23)
+{
+    uint32_t lo = mc_prmt(pred, 0u, 0x4140u), hi = mc_prmt(pred, 0u, 0x4342u);
     lo = mc_vmins2(mc_viaddmax_s16x2_relu(lo, res01, 0u), 0x00FF00FFu);
     hi = mc_vmins2(mc_viaddmax_s16x2_relu(hi, res23, 0u), 0x00FF00FFu);
     return mc_prmt(lo, hi, 0x6420u);
+}
+MC_FN uint32_t mc_weight_recon4(int mode, uint32_t p0, uint32_t p1, int w0, int w1, int d, int o, uint32_t res01, uint32_t res23)
+{
+    return mc_recon4(mc_weight4(mode, p0, p1, w0, w1, d, o), res01, res23);
 }
 
 } // namespace h264r

@@ -59,6 +59,7 @@ struct h264s_stream {
     int chroma_qp_offset[2];
     int qp_lo, qp_hi;
     int allow_b;
+    int direct8x8;                    // sps.direct_8x8_inference_flag: 0 on every third stream of the B-picture configs
     h264r::ZigZag zz;
 };
 
@@ -417,6 +418,48 @@ void set_part(Gen& g, h264r_mb_motion& m, const h264r_slice& sl, int mbx, int mb
         }
 }
 
+// One direct-predicted 8x8 quadrant (B_Skip / B_Direct_16x16, or a direct sub-macroblock of B_8x8) after direct-mode
+// resolution (parser/interpret_mv.cc:116-434).  Spatial: the direction and (refIdxL0, refIdxL1) are the MB's; the vector of
+// a list is the predicted vector or zero (colZeroFlag), decided per 8x8 block -- per 4x4 block without
+// direct_8x8_inference_flag.  Temporal: bi-predictive; refIdxL0 and both vectors follow the co-located block, again per
+// 8x8 or per 4x4.  mv0 == nullptr: the quadrant draws its own predicted vectors.
+void gen_direct_quadrant(Gen& g, h264r_mb& mb, h264r_mb_motion& m, const h264r_slice& sl, int mbx, int mby, int q,
+                         int dir, int ref0, int ref1, const int16_t* mv0, const int16_t* mv1)
+{
+    Rng& r = *g.rng;
+    const int bx0 = (q & 1) * 2, by0 = (q >> 1) * 2;
+    const bool fine = !g.s->direct8x8;                               // motion per 4x4 block
+    if (!sl.direct_spatial_mv_pred_flag) {
+        mb.u.inter.sub_mb_pred_mode[q] = H264R_PRED_BI;
+        if (!fine) { set_part(g, m, sl, mbx, mby, bx0, by0, 2, 2, H264R_PRED_BI, r.below(sl.num_ref[0]), 0); return; }
+        for (int k = 0; k < 4; ++k)
+            set_part(g, m, sl, mbx, mby, bx0 + (k & 1), by0 + (k >> 1), 1, 1, H264R_PRED_BI, r.below(sl.num_ref[0]), 0);
+        return;
+    }
+    mb.u.inter.sub_mb_pred_mode[q] = (uint8_t)dir;
+    if (!mv0 && !fine) { set_part(g, m, sl, mbx, mby, bx0, by0, 2, 2, dir, ref0, ref1); return; }
+    int16_t own0[2] = {0, 0}, own1[2] = {0, 0};
+    if (!mv0) {
+        if (dir != H264R_PRED_L1) draw_mv(g, mbx, mby, own0);
+        if (dir != H264R_PRED_L0) draw_mv(g, mbx, mby, own1);
+        mv0 = own0; mv1 = own1;
+    }
+    bool z0 = false, z1 = false;
+    if (!fine) { z0 = r.chance(20); z1 = r.chance(20); }
+    for (int k = 0; k < 4; ++k) {
+        const int b = (by0 + (k >> 1)) * 4 + bx0 + (k & 1);
+        if (fine) { z0 = r.chance(30); z1 = r.chance(30); }
+        if (dir != H264R_PRED_L1) {
+            m.ref_idx[0][b] = (int8_t)ref0; m.ref_pic[0][b] = sl.ref_pic_list[0][ref0];
+            m.mv[0][b][0] = z0 ? 0 : mv0[0]; m.mv[0][b][1] = z0 ? 0 : mv0[1];
+        }
+        if (dir != H264R_PRED_L0) {
+            m.ref_idx[1][b] = (int8_t)ref1; m.ref_pic[1][b] = sl.ref_pic_list[1][ref1];
+            m.mv[1][b][0] = z1 ? 0 : mv1[0]; m.mv[1][b][1] = z1 ? 0 : mv1[1];
+        }
+    }
+}
+
 static const int kBlockStep[8][2] = { {0,0}, {4,4}, {4,2}, {2,4}, {2,2}, {2,1}, {1,2}, {1,1} };
 
 void gen_inter_mb(Gen& g, int addr)
@@ -457,36 +500,19 @@ void gen_inter_mb(Gen& g, int addr)
             return;
         }
         // B direct: resolved direction per MB (spatial: one (refIdxL0, refIdxL1) pair for the whole MB,
-        // mv per 8x8 may be zeroed by colZeroFlag; temporal: bi, ref/mv per 8x8)
+        // mv per 8x8 -- per 4x4 without direct_8x8_inference -- may be zeroed by colZeroFlag; temporal: bi, ref/mv per
+        // 8x8 / 4x4 block)
         memset(mb.u.inter.sub_mb_type, 0, 4);
+        int ddir = H264R_PRED_BI, dref0 = 0, dref1 = 0;
+        int16_t dmv0[2] = {0, 0}, dmv1[2] = {0, 0};
         if (sl.direct_spatial_mv_pred_flag) {
-            int dir = pick_dir();
-            int ref0 = pick_ref(0), ref1 = pick_ref(1);
-            int16_t mv0[2], mv1[2]; draw_mv(g, mbx, mby, mv0); draw_mv(g, mbx, mby, mv1);
-            for (int q = 0; q < 4; ++q) {
-                mb.u.inter.sub_mb_pred_mode[q] = (uint8_t)dir;
-                bool z0 = r.chance(20), z1 = r.chance(20);
-                for (int k = 0; k < 4; ++k) {
-                    int b = ((q >> 1) * 2 + (k >> 1)) * 4 + (q & 1) * 2 + (k & 1);
-                    if (dir != H264R_PRED_L1) {
-                        m.ref_idx[0][b] = (int8_t)ref0; m.ref_pic[0][b] = sl.ref_pic_list[0][ref0];
-                        m.mv[0][b][0] = z0 ? 0 : mv0[0]; m.mv[0][b][1] = z0 ? 0 : mv0[1];
-                    }
-                    if (dir != H264R_PRED_L0) {
-                        m.ref_idx[1][b] = (int8_t)ref1; m.ref_pic[1][b] = sl.ref_pic_list[1][ref1];
-                        m.mv[1][b][0] = z1 ? 0 : mv1[0]; m.mv[1][b][1] = z1 ? 0 : mv1[1];
-                    }
-                }
-            }
-        } else {
-            for (int q = 0; q < 4; ++q) {
-                mb.u.inter.sub_mb_pred_mode[q] = H264R_PRED_BI;
-                set_part(g, m, sl, mbx, mby, (q & 1) * 2, (q >> 1) * 2, 2, 2, H264R_PRED_BI, pick_ref(0), 0);
-            }
+            ddir = pick_dir(); dref0 = pick_ref(0); dref1 = pick_ref(1);
+            draw_mv(g, mbx, mby, dmv0); draw_mv(g, mbx, mby, dmv1);
         }
+        for (int q = 0; q < 4; ++q) gen_direct_quadrant(g, mb, m, sl, mbx, mby, q, ddir, dref0, dref1, dmv0, dmv1);
         if (r.chance(50)) { mb.cbp_luma = mb.cbp_chroma = 0; mb.cbp_blks = 0; }     // B_Skip
         else {                                                                      // B_Direct_16x16
-            if (g.s->transform8x8 && r.chance(50)) mb.flags |= H264R_MB_FLAG_T8x8;
+            if (g.s->transform8x8 && r.chance(50) && g.s->direct8x8) mb.flags |= H264R_MB_FLAG_T8x8;   // 8x8 transform on direct MBs needs the inference flag
             gen_residual(g, mb, 50);
             if (mb.cbp_luma == 0) mb.flags &= (uint8_t)~H264R_MB_FLAG_T8x8;
         }
@@ -518,19 +544,15 @@ void gen_inter_mb(Gen& g, int addr)
     } else {
         mb.mb_type = H264R_MB_8x8;
         // spatial direct sub-blocks of one MB share (refIdxL0, refIdxL1) and hence the direction
-        int sdir = pick_dir(), sref0 = pick_ref(0), sref1 = is_b ? pick_ref(1) : 0;
+        const int ddir = pick_dir(), dref0 = pick_ref(0), dref1 = is_b ? pick_ref(1) : 0;
+        const int16_t* const dmv0 = nullptr; const int16_t* const dmv1 = nullptr;
         for (int q = 0; q < 4; ++q) {
             int bx0 = (q & 1) * 2, by0 = (q >> 1) * 2;
             int st = r.range(is_b ? 3 : 4, 7);                       // 3 stands for "direct" in B slices
             if (st == 3) {
                 mb.u.inter.sub_mb_type[q] = 0;
-                if (sl.direct_spatial_mv_pred_flag) {
-                    mb.u.inter.sub_mb_pred_mode[q] = (uint8_t)sdir;
-                    set_part(g, m, sl, mbx, mby, bx0, by0, 2, 2, sdir, sref0, sref1);
-                } else {
-                    mb.u.inter.sub_mb_pred_mode[q] = H264R_PRED_BI;
-                    set_part(g, m, sl, mbx, mby, bx0, by0, 2, 2, H264R_PRED_BI, pick_ref(0), 0);
-                }
+                gen_direct_quadrant(g, mb, m, sl, mbx, mby, q, ddir, dref0, dref1, dmv0, dmv1);
+                if (!g.s->direct8x8) all_ge_8x8 = false;             // 4x4-granular direct motion excludes the 8x8 transform
                 continue;
             }
             int dir = pick_dir();
@@ -633,6 +655,8 @@ h264s_stream* h264s_open(int config, int stream_idx, int width_mbs, int height_m
     s->num_frames = num_frames > 0 ? num_frames : dims[config][2];
     s->rng.s = 0x4832363400000000ull + ((uint64_t)config << 16) + ((uint64_t)stream_idx << 8);
     s->allow_b = config != H264S_CFG_CIF_BASELINE;
+    // direct_8x8_inference_flag = 0 (direct motion per 4x4 block, decoder.cc:239-242) on every third stream with B pictures
+    s->direct8x8 = !(s->allow_b && stream_idx % 3 == 2);
     s->transform8x8 = config >= H264S_CFG_1080P_HIGH;
     s->default_matrices = (config == H264S_CFG_1080P_HIGH || config == H264S_CFG_MULTI_1080P) ? (stream_idx & 1)
                         : (config == H264S_CFG_4K_HIGH ? 1 : 0);
@@ -651,7 +675,7 @@ void h264s_get_seq(const h264s_stream* s, h264r_seq_params* sp, int* num_frames)
 {
     memset(sp, 0, sizeof(*sp));
     sp->width_mbs = s->W; sp->height_mbs = s->H;
-    sp->direct_8x8_inference_flag = 1;
+    sp->direct_8x8_inference_flag = s->direct8x8;
     sp->max_frames = 8; sp->max_pictures_in_flight = 4; sp->max_slices_per_picture = 4; sp->max_levels_per_picture = 0;
     if (num_frames) *num_frames = s->num_frames;
 }
@@ -689,6 +713,7 @@ int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264
     info->pic_index = pic_idx; info->pic_type = plan.type; info->used_for_reference = plan.is_ref;
     info->poc = plan.poc; info->num_refs = nref;
     pp->num_ref_frames = nref; pp->poc = plan.poc;
+    pp->direct_8x8_inference_flag = s->direct8x8;
 
     // slices: one, or two on odd pictures of the multi-slice configs (split not row aligned)
     g.num_slices = 1;

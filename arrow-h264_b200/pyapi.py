@@ -1,4 +1,4 @@
-"""ctypes bindings of the C ABI (include/h264recon.h, include/h264synth.h).
+"""ctypes bindings of the C ABI (include/h264recon.h, include/h264recon_bench.h, include/h264synth.h).
 
 Python is only the test/bench harness language here; the product is the C-ABI shared library
 `libh264recon.so` (CUDA engine).  Nothing in this file computes a sample, and nothing here touches oracle/.
@@ -25,7 +25,7 @@ class Mb(C.Structure):
                 ("cbp_luma", C.c_uint8), ("cbp_chroma", C.c_uint8), ("qp_y", C.c_int8), ("qp_c", C.c_int8 * 2),
                 ("intra16_mode", C.c_uint8), ("chroma_mode", C.c_uint8), ("reserved0", C.c_uint8),
                 ("cbp_blks", C.c_uint16), ("coeff_count", C.c_uint16), ("coeff_offset", C.c_uint32),
-                ("u", MbUnion), ("reserved2", C.c_uint32)]
+                ("u", MbUnion), ("motion", C.c_uint32)]
 
 
 class MbMotion(C.Structure):
@@ -49,7 +49,7 @@ class Slice(C.Structure):
 class PicParams(C.Structure):
     _fields_ = [("num_slices", C.c_int32), ("num_ref_frames", C.c_int32), ("ref_frames", C.c_int32 * MAX_REFS),
                 ("run_deblock", C.c_int32), ("poc", C.c_int32), ("ref_poc", C.c_int32 * MAX_REFS),
-                ("ref_long_term", C.c_uint8 * MAX_REFS)]
+                ("ref_long_term", C.c_uint8 * MAX_REFS), ("direct_8x8_inference_flag", C.c_int32)]
 
 
 class SeqParams(C.Structure):
@@ -59,8 +59,13 @@ class SeqParams(C.Structure):
 
 
 class PicBuffers(C.Structure):
-    _fields_ = [("mbs", C.POINTER(Mb)), ("motion", C.POINTER(MbMotion)), ("slices", C.POINTER(Slice)),
-                ("levels", C.POINTER(C.c_uint32)), ("level_capacity", C.c_uint32)]
+    _fields_ = [("mbs", C.POINTER(Mb)), ("slices", C.POINTER(Slice)), ("stream", C.POINTER(C.c_uint32)),
+                ("stream_capacity", C.c_uint32), ("picture", C.c_int32)]
+
+
+class BenchPicture(C.Structure):
+    _fields_ = [("pp", PicParams), ("dst", C.c_int32), ("stream_id", C.c_int32), ("head", C.c_void_p),
+                ("stream", C.c_void_p), ("stream_words", C.c_uint32), ("pitch_y", C.c_int32), ("out", C.c_void_p)]
 
 
 class PicInfo(C.Structure):
@@ -113,7 +118,18 @@ def recon_lib():
         L.h264r_frame_alloc.argtypes = [P, C.POINTER(C.c_int32)]
         L.h264r_frame_release.argtypes = [P, C.c_int32]
         L.h264r_picture_begin.argtypes = [P, C.c_int32, C.POINTER(PicParams), C.POINTER(PicBuffers)]
-        L.h264r_picture_submit.argtypes = [P, C.c_uint32]
+        L.h264r_picture_update.argtypes = [P, C.c_int32, C.POINTER(PicParams)]
+        L.h264r_picture_fill.restype = C.c_int64
+        L.h264r_picture_fill.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]
+        L.h264r_picture_submit.argtypes = [P, C.c_int32, C.c_uint32]
+        L.h264r_pack_picture.restype = C.c_int64
+        L.h264r_pack_picture.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.h264r_bench_kernel_name.restype = C.c_char_p
+        L.h264r_bench_kernel_name.argtypes = [C.c_int]
+        L.h264r_bench_feed.restype = C.c_double
+        L.h264r_bench_feed.argtypes = [P, C.POINTER(BenchPicture), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.h264r_bench_copy_ceiling.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
         L.h264r_flush.argtypes = [P]
         L.h264r_wait.argtypes = [P, C.c_int32]
         L.h264r_frame_download.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -224,20 +240,19 @@ class Engine:
         self._check(self.L.h264r_frame_release(self.ctx, f), "h264r_frame_release")
 
     def submit(self, pic, dst, ref_frames):
-        """picture_begin + fill the pinned staging from a generated Picture + picture_submit."""
+        """picture_begin + picture_fill (copy and pack a generated Picture into the pinned staging) + picture_submit."""
         pp = PicParams.from_buffer_copy(pic.pp)
         for i, f in enumerate(ref_frames):
             pp.ref_frames[i] = f
         bufs = PicBuffers()
         self._check(self.L.h264r_picture_begin(self.ctx, dst, C.byref(pp), C.byref(bufs)), "h264r_picture_begin")
-        n = self.nmb
-        C.memmove(bufs.mbs, pic.mbs, C.sizeof(Mb) * n)
-        C.memmove(bufs.motion, pic.motion, C.sizeof(MbMotion) * n)
-        C.memmove(bufs.slices, pic.slices, C.sizeof(Slice) * pp.num_slices)
-        if pic.info.num_levels > bufs.level_capacity:
-            raise EngineError("level list larger than the staging capacity (max_levels_per_picture)")
-        C.memmove(bufs.levels, pic.levels, 4 * pic.info.num_levels)
-        self._check(self.L.h264r_picture_submit(self.ctx, pic.info.num_levels), "h264r_picture_submit")
+        words = self.L.h264r_picture_fill(self.ctx, bufs.picture, pic.mbs, pic.motion, pic.slices, pp.num_slices,
+                                          pic.levels, pic.info.num_levels)
+        if words < 0:
+            # give the slot back (a submit that fails frees it) and report
+            self.L.h264r_picture_submit(self.ctx, bufs.picture, 0xFFFFFFFF)
+            self._check(int(words), "h264r_picture_fill")
+        self._check(self.L.h264r_picture_submit(self.ctx, bufs.picture, words), "h264r_picture_submit")
 
     def flush(self):
         self._check(self.L.h264r_flush(self.ctx), "h264r_flush")
@@ -267,12 +282,22 @@ class Engine:
 
     REPLAY_H2D, REPLAY_TIME_KERNELS, REPLAY_ASYNC = 1, 2, 4
 
+    def kernel_names(self):
+        """Names of the kernel kinds the replay hook times (include/h264recon_bench.h)."""
+        names = []
+        while True:
+            n = self.L.h264r_bench_kernel_name(len(names))
+            if not n:
+                return names
+            names.append(n.decode())
+
     def replay(self, iterations=1, flags=0):
-        """Re-runs the last flush; returns (ms[total, resid, inter, intra, dbprep, deblock], launches[_, ...same])."""
-        ms = (C.c_float * 6)()
-        n = (C.c_int * 6)()
+        """Re-runs the last flush (include/h264recon_bench.h); returns (ms[total, kind 0, kind 1, ...], launches[_, ...])."""
+        ms = (C.c_float * 9)()
+        n = (C.c_int * 9)()
         self._check(self.L.h264r_replay_last_flush(self.ctx, iterations, flags, ms, n), "h264r_replay_last_flush")
-        return list(ms), list(n)
+        k = 1 + len(self.kernel_names())
+        return list(ms)[:k], list(n)[:k]
 
     def host_alloc(self, nbytes):
         p = self.L.h264r_host_alloc(nbytes)
@@ -288,13 +313,14 @@ class Engine:
                     "h264r_frame_download_async")
 
     def begin(self, dst, pp):
-        """picture_begin only: returns the staging buffers so a producer can write into pinned memory directly."""
+        """picture_begin only: returns the staging buffers (and the picture handle) so a producer can write into pinned
+        memory directly."""
         bufs = PicBuffers()
         self._check(self.L.h264r_picture_begin(self.ctx, dst, C.byref(pp), C.byref(bufs)), "h264r_picture_begin")
         return bufs
 
-    def submit_filled(self, num_levels):
-        self._check(self.L.h264r_picture_submit(self.ctx, num_levels), "h264r_picture_submit")
+    def submit_filled(self, picture, stream_words):
+        self._check(self.L.h264r_picture_submit(self.ctx, picture, stream_words), "h264r_picture_submit")
 
     def stats(self):
         s = Stats()

@@ -7,9 +7,13 @@
  * here (coefficient levels, macroblock headers, motion, slice tables); the GPU reconstructs the whole
  * picture (dequant + IDCT, motion compensation, intra prediction, deblocking) on `h264r_picture_submit`.
  *
- * Plain C, plain pointers and sizes, `int` status codes, no exceptions, no exit().  One context per GPU;
- * calls on one context must be serialised by the caller (one host thread per GPU), exactly like the
- * reference's single-threaded decoder loop (core/slice_data.cc:636-661).
+ * Plain C, plain pointers and sizes, `int` status codes, no exceptions, no exit().  One context per GPU.
+ * Threading: any number of pictures can be in the filling state at once -- the reference embeds one Decoder in every
+ * slice_t (parser/slice.h:173), so fill state belongs to the picture, not to the process.  h264r_picture_begin /
+ * _update / _fill / _submit may be called from any thread (one parser thread per stream); the buffers of a picture
+ * are written by the thread that began it, without locks.  h264r_flush, h264r_wait, the frame pool and the download
+ * calls belong to ONE thread per context (the thread that owns the GPU), like the reference's decoder loop
+ * (core/slice_data.cc:636-661).
  *
  * Supported stream subset (anything else returns H264R_ERR_UNSUPPORTED, there is NO CPU fallback):
  * 8-bit 4:2:0 frame pictures (no PAFF/MBAFF), no transform bypass, no SP/SI slices, no FMO/ASO.
@@ -84,7 +88,7 @@ typedef struct h264r_mb {
     uint16_t cbp_blks;               /* cbp_blks[0] bits 0..15: 4x4 block (by*4+bx) has luma AC levels
                                         (transform.cc:433-436; 0xFFFF for I_PCM, interpret_mb.cc:421) */
     uint16_t coeff_count;            /* number of h264r_level entries of this MB (0 = no residual)     */
-    uint32_t coeff_offset;           /* index of the MB's first entry in the picture's level list       */
+    uint32_t coeff_offset;           /* word index of the MB's first level in the picture's stream       */
     union {
         uint8_t intra_modes[8];      /* 16 nibbles, low nibble first: Intra4x4PredMode[luma4x4BlkIdx]
                                         (I_4x4) or Intra8x8PredMode[0..3] in nibbles 0..3 (I_8x8)     */
@@ -93,23 +97,45 @@ typedef struct h264r_mb {
             uint8_t sub_mb_pred_mode[4]; /* SubMbPredMode[mbPartIdx] after direct-mode resolution     */
         } inter;
     } u;
-    uint32_t reserved2;              /* engine-internal (index of the MB's packed motion), overwritten by
-                                        h264r_picture_submit; callers leave it alone                    */
+    uint32_t motion;                 /* inter MBs: (word index of the MB's first h264r_motion_entry in the
+                                        picture's stream) << 4 | layout code, see h264r_pack_motion; 0 for
+                                        intra MBs                                                       */
 } h264r_mb;
 
-/* per-macroblock motion: 192 bytes.  The 16 pic_motion_params (framebuf/picture.h:66-71) of the MB,   */
-/* 4x4 blocks in raster order (by*4+bx).  Only read for non-intra MBs.  This array stays in host       */
-/* memory: h264r_picture_submit packs it (one entry per distinct partition of an MB, 12 bytes each)    */
-/* for the host->device copy; the kernels read the packed entries directly.                           */
-typedef struct h264r_mb_motion {
-    int16_t mv[2][16][2];            /* [list][blk][x,y] quarter-pel                                   */
-    int8_t  ref_idx[2][16];          /* pic_motion_params::ref_idx (may be 0 for an unused list, quirk 2) */
-    int8_t  ref_pic[2][16];          /* identity of pic_motion_params::ref_pic: index into
+/* Motion of one partition as the device reads it: 12 bytes = three words of the picture's stream.                */
+typedef struct h264r_motion_entry {
+    int16_t mv[2][2];                /* [list][x,y] quarter-pel                                        */
+    int8_t  ref_idx[2];              /* pic_motion_params::ref_idx (may be 0 for an unused list, quirk 2) */
+    int8_t  ref_pic[2];              /* identity of pic_motion_params::ref_pic: index into
                                         h264r_pic_params::ref_frames, -1 == nullptr.  For a list the
                                         block predicts from it is the picture motion compensation reads
                                         (== ref_pic_list[list][ref_idx], as the reference's parser sets
                                         it, parser/interpret_mv.cc) and the one the bS rule compares    */
+} h264r_motion_entry;
+
+/* The 16 pic_motion_params (framebuf/picture.h:66-71) of one MB, unpacked: 192 bytes, 4x4 blocks in raster order
+ * (by*4+bx).  Host-side convenience form only (input of h264r_pack_motion / h264r_picture_fill): an MB sends just its
+ * DISTINCT entries across PCIe.                                                                          */
+typedef struct h264r_mb_motion {
+    int16_t mv[2][16][2];            /* [list][blk][x,y]                                               */
+    int8_t  ref_idx[2][16];
+    int8_t  ref_pic[2][16];
 } h264r_mb_motion;
+
+/* Packs the motion of one MB: writes the distinct entries to out[] (at most 16) and returns the layout code:
+ * 1 = one entry for the MB | 2 = rows 0-1 / rows 2-3 | 3 = columns 0-1 / columns 2-3 | 4 = the four 8x8 quadrants |
+ * 5 = all sixteen 4x4 blocks.  Entries per code: h264r_motion_entries_of_code[].  The MB header then carries
+ * motion = (word index of out[0] in the stream) << 4 | code.                                              */
+int  h264r_pack_motion(const h264r_mb_motion* m, h264r_motion_entry out[16]);
+extern const uint8_t h264r_motion_entries_of_code[6];
+/* The inverse: the sixteen per-block entries of an MB from its packed form (`motion` = h264r_mb::motion). */
+void h264r_unpack_motion(const uint32_t* stream, uint32_t motion, h264r_mb_motion* out);
+/* The same for a whole picture held in unpacked form, into caller memory (what h264r_picture_fill does into the
+ * staging): copies the levels to stream[0 .. num_levels) -- coeff_offset stays valid --, copies the headers to out_mbs
+ * (may equal mbs), appends the packed motion of every inter MB and sets h264r_mb::motion.  Host only, no CUDA.
+ * Returns the stream words used, or a negative status (H264R_ERR_NOMEM: stream_capacity too small). */
+int64_t h264r_pack_picture(int num_mbs, const h264r_mb* mbs, const h264r_mb_motion* motion, const h264r_level* levels,
+                           uint32_t num_levels, h264r_mb* out_mbs, uint32_t* stream, uint32_t stream_capacity);
 
 /* per-slice table.  Fields of shr_t / pps_t read by the path plus the tables the reference builds per
  * slice header (Decoder::assign_quant_params -> Transform::init, transform.cc:173-302).              */
@@ -148,28 +174,36 @@ typedef struct h264r_pic_params {
     int32_t     poc;                             /* informational (implicit weights are precomputed)   */
     int32_t     ref_poc[H264R_MAX_REFS];         /* informational: POC of ref_frames[i]                */
     uint8_t     ref_long_term[H264R_MAX_REFS];   /* informational                                      */
+    int32_t     direct_8x8_inference_flag;       /* sps of THIS picture's stream (decoder.cc:239-242): streams
+                                                    that share a context may differ                     */
 } h264r_pic_params;
 
-/* sequence parameters (sps_t) */
+/* context parameters (picture size = sps_t; every stream that shares the context has this size) */
 typedef struct h264r_seq_params {
     int32_t width_mbs;                           /* PicWidthInMbs                                      */
     int32_t height_mbs;                          /* FrameHeightInMbs                                   */
-    int32_t direct_8x8_inference_flag;
+    int32_t direct_8x8_inference_flag;           /* not read by the engine (h264r_pic_params carries it per
+                                                    picture); kept for single-stream callers           */
     int32_t max_frames;                          /* frame pool capacity                                */
-    int32_t max_pictures_in_flight;              /* staging slots that can be filled before a flush    */
+    int32_t max_pictures_in_flight;              /* staging slots: pictures begun but not yet copied to HBM */
     int32_t max_slices_per_picture;
-    int32_t max_levels_per_picture;              /* staging capacity of the level list; 0 = worst case
-                                                    (384 per MB)                                       */
+    int32_t max_levels_per_picture;              /* sizes the stream of a picture: capacity in words =
+                                                    this + 48 * MBs (worst-case motion); 0 = worst case
+                                                    (384 levels per MB)                                */
 } h264r_seq_params;
 
-/* host staging pointers handed out by h264r_picture_begin (pinned memory owned by the context) */
+/* Host staging of one picture, handed out by h264r_picture_begin (pinned memory owned by the context).  The layout IS
+ * the HBM layout: submit + flush copy [mbs | slices used] and [stream used] as they are, nothing is repacked.
+ *   stream: 32-bit words.  An MB's levels are coeff_count consecutive words at coeff_offset (any order inside the MB);
+ *           an inter MB's motion entries are 3 words each at (motion >> 4).  The parser side appends both as it goes:
+ *           levels while the residual is parsed (Decoder::coeff_*), motion entries when the MB is complete
+ *           (Decoder::decode). */
 typedef struct h264r_pic_buffers {
     h264r_mb*        mbs;                        /* [width_mbs*height_mbs], raster order               */
-    h264r_mb_motion* motion;                     /* [width_mbs*height_mbs]                             */
     h264r_slice*     slices;                     /* [max_slices_per_picture]                           */
-    h264r_level*     levels;                     /* [level_capacity] level list of the picture; the
-                                                    entries of one MB are contiguous (any order)        */
-    uint32_t         level_capacity;             /* h264r_seq_params::max_levels_per_picture            */
+    uint32_t*        stream;                     /* [stream_capacity] levels and motion entries        */
+    uint32_t         stream_capacity;            /* words                                              */
+    int32_t          picture;                    /* handle for _update / _fill / _submit               */
 } h264r_pic_buffers;
 
 typedef struct h264r_ctx h264r_ctx;
@@ -185,20 +219,30 @@ void h264r_destroy(h264r_ctx* ctx);
 int  h264r_frame_alloc(h264r_ctx* ctx, h264r_frame* out);
 int  h264r_frame_release(h264r_ctx* ctx, h264r_frame f);
 
-/* replaces: init_picture + Decoder::init (core/slice_data.cc:149-313, 618).  Reserves a staging slot. */
+/* replaces: init_picture + Decoder::init (core/slice_data.cc:149-313, 618).  Reserves a staging slot; blocks while
+ * all slots wait for their host->device copy (never on kernels).  Thread-safe. */
 int  h264r_picture_begin(h264r_ctx* ctx, h264r_frame dst, const h264r_pic_params* pp, h264r_pic_buffers* out);
 /* Replaces the picture parameters given to h264r_picture_begin while the picture is still being filled: a parser
  * learns the number of slices, further reference pictures (slices of one picture may list different references)
  * and whether any slice enables the deblocking filter only as it goes along (core/slice_data.cc:618 runs per slice). */
-int  h264r_picture_update(h264r_ctx* ctx, const h264r_pic_params* pp);
-/* replaces: Decoder::deblock_filter at exit_picture (framebuf/picture.cc:253): the picture is complete
- * on the host side; it is queued.  `num_levels` = entries of the level list actually used.           */
-int  h264r_picture_submit(h264r_ctx* ctx, uint32_t num_levels);
+int  h264r_picture_update(h264r_ctx* ctx, int32_t picture, const h264r_pic_params* pp);
+/* Convenience for callers that hold a complete unpacked description (generators, tests): copies mbs / slices / levels
+ * into the staging of `picture`, packs every inter MB's motion behind the levels and sets h264r_mb::motion.  Runs on
+ * the caller's thread (O(MBs)); returns the stream words used (pass them to submit) or a negative status. */
+int64_t h264r_picture_fill(h264r_ctx* ctx, int32_t picture, const h264r_mb* mbs, const h264r_mb_motion* motion,
+                           const h264r_slice* slices, int num_slices, const h264r_level* levels, uint32_t num_levels);
+/* replaces: Decoder::deblock_filter at exit_picture (framebuf/picture.cc:253): the picture is complete on the host
+ * side; it is queued.  `stream_words` = words of the stream actually used.  O(slices): the per-MB content is checked
+ * by the kernels that read it (out-of-range values are clamped and reported by h264r_wait as H264R_ERR_INVALID).
+ * Thread-safe; pictures are launched in submission order. */
+int  h264r_picture_submit(h264r_ctx* ctx, int32_t picture, uint32_t stream_words);
 /* launches everything queued: pictures are grouped into dependency waves (a picture whose references
  * are produced by a queued picture goes to a later wave); every wave is one batched launch sequence.  */
 int  h264r_flush(h264r_ctx* ctx);
-/* blocks until frame `f` is reconstructed (the wave that writes it; later pictures keep running), or, with   */
-/* f < 0, until everything queued has finished, downloads included                                         */
+/* blocks until frame `f` is reconstructed (the wave that writes it; later pictures keep running), or, with
+ * f < 0, until everything queued has finished, downloads included.  Returns H264R_ERR_INVALID if a kernel met a
+ * macroblock description outside its domain since the last wait (slice index, level range, QP, reference slot,
+ * macroblock type ...: the value was clamped, the picture is wrong, nothing was accessed out of bounds). */
 int  h264r_wait(h264r_ctx* ctx, h264r_frame f);
 
 /* replaces: write_out_picture reading imgY/imgUV (framebuf/output.cc:109-227)                          */
@@ -220,18 +264,6 @@ int  h264r_frame_download_cropped(h264r_ctx* ctx, h264r_frame f, int crop_left, 
 /* pinned host memory for download destinations */
 void* h264r_host_alloc(size_t bytes);
 void  h264r_host_free(void* p);
-
-/* Re-runs the last flush (benchmark support; the staging slots and device copies of the last flush must not have
- * been refilled since).  flags: H264R_REPLAY_H2D re-issues the host->device copies of every picture description
- * from the pinned staging (end-to-end path); without it only the kernels run on the HBM-resident inputs.
- * H264R_REPLAY_TIME_KERNELS brackets every kernel with CUDA events (serialises nothing, costs a few us each).
- * ms_out[0] = whole replay (CUDA events on the compute stream), [1] residual, [2] inter, [3] intra wavefront,
- * [4] deblock pre-pass, [5] deblock wavefront kernel time; launches_out[1..5] = launches of each kernel. */
-#define H264R_REPLAY_H2D           1
-#define H264R_REPLAY_TIME_KERNELS  2
-#define H264R_REPLAY_ASYNC         4   /* enqueue only (like h264r_flush): no host synchronisation, no timings;
-                                          the caller joins with h264r_wait.  Lets downloads overlap the kernels. */
-int  h264r_replay_last_flush(h264r_ctx* ctx, int iterations, int flags, float ms_out[6], int launches_out[6]);
 
 /* host helper restating inter_prediction.cc:112-139 (implicit bi-prediction weights)                   */
 void h264r_implicit_weights(int cur_poc, int poc0, int poc1, int long_term0, int long_term1, int* w0, int* w1);

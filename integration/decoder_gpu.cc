@@ -45,14 +45,16 @@ void check(int rc, const char* what)
 // the twelve weightScale lists Transform::init picks (transform.cc:173-262), kept per slice until Decoder::init
 struct QuantLists { int q4[6][16]; int q8[2][64]; };
 
-struct GpuFrameEntry { h264r_frame frame; uint64_t touched; };
+// Engine frame of a decoded picture.  The map below is keyed by the storable_picture's ADDRESS, which is only an
+// identity: entries are never dereferenced (the DPB frees pictures behind our back), what the engine wants to know about a
+// reference (its POC) is cached here when the picture is decoded.
+struct GpuFrameEntry { h264r_frame frame; int poc; bool live; };
 
 struct GpuState {
     h264r_ctx* ctx = nullptr;
     int width_mbs = 0, height_mbs = 0;
     std::unordered_map<const storable_picture*, GpuFrameEntry> frames;   // engine frame of every decoded picture
     std::unordered_map<const Decoder*, QuantLists> quant;                 // assign_quant_params precedes init
-    uint64_t clock = 0;
     // picture being parsed
     const storable_picture* cur = nullptr;
     h264r_pic_params pp;
@@ -61,7 +63,7 @@ struct GpuState {
     bool any_deblock = false;
 } g;
 
-const int kMaxGpuFrames = 40;        // > 16 DPB frames + the current picture + headroom; table limit is H264R_MAX_REFS live entries
+const int kMaxGpuFrames = 40;        // > 16 DPB frames + the current picture + pictures waiting for output
 
 void open_engine(const sps_t& sps)
 {
@@ -80,29 +82,48 @@ void open_engine(const sps_t& sps)
     g.width_mbs = W; g.height_mbs = H;
 }
 
-// engine frame of a decoded picture; every use refreshes its age
+// engine frame of a decoded picture
 h264r_frame frame_of(const storable_picture* p)
 {
     auto it = g.frames.find(p);
     if (it == g.frames.end()) error(500, "h264recon: reference picture was not reconstructed by the GPU path");
-    it->second.touched = ++g.clock;
     return it->second.frame;
 }
 
-// a new picture: its storable_picture may reuse the address of a freed one; the oldest untouched entries make room
-h264r_frame new_frame(const storable_picture* p)
+// Liveness follows the DPB, not a guess about use: a picture keeps its engine frame while the decoded picture buffer holds
+// it (as a reference or waiting for output -- every frame store of every layer) and is released at the first picture start
+// after the DPB dropped it.  Pictures that never enter the DPB (direct output, framebuf/dpb.cc:383-385) are released by
+// gpu_picture_freed() right after they were written.  Only the map keys are compared, nothing is dereferenced but the
+// DPB's own live frame stores.
+void sweep_dead_frames(VideoParameters* p_Vid, const storable_picture* current)
+{
+    for (auto& kv : g.frames) kv.second.live = kv.first == current;
+    for (int layer = 0; layer < MAX_NUM_DPB_LAYERS; ++layer) {
+        const decoded_picture_buffer_t* dpb = p_Vid->p_Dpb_layer[layer];
+        if (!dpb || !dpb->fs) continue;
+        for (unsigned i = 0; i < dpb->used_size; ++i) {
+            const pic_t* fs = dpb->fs[i];
+            if (!fs) continue;
+            auto it = g.frames.find(fs->frame);
+            if (it != g.frames.end()) it->second.live = true;
+        }
+    }
+    for (auto it = g.frames.begin(); it != g.frames.end(); ) {
+        if (it->second.live) { ++it; continue; }
+        h264r_frame_release(g.ctx, it->second.frame);
+        it = g.frames.erase(it);
+    }
+}
+
+// a new picture: its storable_picture may reuse the address of a freed one
+h264r_frame new_frame(const storable_picture* p, int poc)
 {
     auto it = g.frames.find(p);
     if (it != g.frames.end()) { h264r_frame_release(g.ctx, it->second.frame); g.frames.erase(it); }
-    while ((int)g.frames.size() >= H264R_MAX_REFS - 1) {
-        auto oldest = g.frames.begin();
-        for (auto i = g.frames.begin(); i != g.frames.end(); ++i) if (i->second.touched < oldest->second.touched) oldest = i;
-        h264r_frame_release(g.ctx, oldest->second.frame);
-        g.frames.erase(oldest);
-    }
+    if ((int)g.frames.size() >= H264R_MAX_REFS) error(500, "h264recon: more than %d pictures alive in the decoded picture buffer", H264R_MAX_REFS);
     h264r_frame f;
     check(h264r_frame_alloc(g.ctx, &f), "h264r_frame_alloc");
-    g.frames[p] = GpuFrameEntry{ f, ++g.clock };
+    g.frames[p] = GpuFrameEntry{ f, poc, true };
     return f;
 }
 
@@ -118,20 +139,23 @@ void begin_picture(slice_t& slice)
 {
     open_engine(*slice.active_sps);
     const storable_picture* pic = slice.dec_picture;
-    const h264r_frame dst = new_frame(pic);
+    sweep_dead_frames(slice.p_Vid, nullptr);
+    const h264r_frame dst = new_frame(pic, slice.header.PicOrderCnt);
     memset(&g.pp, 0, sizeof(g.pp));
-    // reference table of the picture: every picture the GPU still holds (later slices may list other references than
-    // the first one); ages of the ones a slice really lists are refreshed in fill_slice
+    // reference table of the picture: every picture the DPB holds (later slices may list other references than the first
+    // one).  POC and long-term state are informational for the engine (implicit weights are precomputed in fill_slice
+    // from the pictures the slice lists, which are alive).
     for (auto& kv : g.frames) {
         if (kv.first == pic) continue;
         const int i = g.pp.num_ref_frames++;
         g.pp.ref_frames[i] = kv.second.frame;
-        g.pp.ref_poc[i] = kv.first->poc;
-        g.pp.ref_long_term[i] = (uint8_t)(kv.first->is_long_term != 0);
+        g.pp.ref_poc[i] = kv.second.poc;
+        g.pp.ref_long_term[i] = 0;
     }
     g.pp.num_slices = 1;                     // grows with every slice; final value set before submit
     g.pp.poc = slice.header.PicOrderCnt;
     g.pp.run_deblock = 1;
+    g.pp.direct_8x8_inference_flag = slice.active_sps->direct_8x8_inference_flag;
     h264r_pic_params tmp = g.pp;
     tmp.num_slices = 64;                     // staging capacity check only; see end_picture
     check(h264r_picture_begin(g.ctx, dst, &tmp, &g.bufs), "h264r_picture_begin");
@@ -345,8 +369,8 @@ void Decoder::deblock_filter(slice_t& slice)
     if (pic != g.cur) error(500, "h264recon: deblock_filter for a picture that was not begun");
     // Deblock::deblock (deblock.cc:622-656): runs unless every slice has disable_deblocking_filter_idc == 1
     g.pp.run_deblock = (g.any_deblock && (0x03 & (1 << pic->used_for_reference))) ? 1 : 0;
-    check(h264r_picture_update(g.ctx, &g.pp), "h264r_picture_update");
-    check(h264r_picture_submit(g.ctx, g.facade.num_levels()), "h264r_picture_submit");
+    check(h264r_picture_update(g.ctx, g.bufs.picture, &g.pp), "h264r_picture_update");
+    check(h264r_picture_submit(g.ctx, g.bufs.picture, g.facade.stream_words()), "h264r_picture_submit");
     check(h264r_flush(g.ctx), "h264r_flush");
     // Nothing is copied back here: the picture stays in HBM (motion compensation of later pictures reads it there) and
     // reaches the host when the DPB outputs it (output_gpu.cc).  The call returns while the kernels run, so the parsing
@@ -357,6 +381,22 @@ void Decoder::deblock_filter(slice_t& slice)
 // for output_gpu.cc
 h264r_ctx* gpu_engine() { return g.ctx; }
 h264r_frame gpu_frame_of_picture(const storable_picture* p) { return frame_of(p); }
+// a picture that never entered the DPB is about to be deleted (direct_output): its engine frame goes back to the pool
+void gpu_picture_freed(const storable_picture* p)
+{
+    auto it = g.frames.find(p);
+    if (it == g.frames.end()) return;
+    h264r_frame_release(g.ctx, it->second.frame);
+    g.frames.erase(it);
+}
+
+// test hook (tests/quant_select_test.cc): the weightScale lists assign_quant_params selected for `d`, [0..5] 4x4, [6..7] 8x8
+const int* gpu_quant_list(const Decoder* d, int i)
+{
+    auto it = g.quant.find(d);
+    if (it == g.quant.end()) return nullptr;
+    return i < 6 ? it->second.q4[i] : it->second.q8[i - 6];
+}
 
 void Decoder::get_block_luma(storable_picture*, int, int, int, int, px_t[16][16], int, mb_t&)
 {

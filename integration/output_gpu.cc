@@ -24,6 +24,7 @@ using namespace vio::h264;
 namespace vio { namespace h264 {
 h264r_ctx*  gpu_engine();
 h264r_frame gpu_frame_of_picture(const storable_picture* p);
+void        gpu_picture_freed(const storable_picture* p);
 } }
 
 namespace {
@@ -74,5 +75,6 @@ void direct_output(VideoParameters* p_Vid, storable_picture* p, int p_out)
     if (p->slice.structure != FRAME) error(500, "h264recon: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
     output_picture(p_Vid, p, p_out);
     p_Vid->calculate_frame_no(p);
+    gpu_picture_freed(p);
     delete p;
 }

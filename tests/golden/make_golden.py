@@ -22,6 +22,9 @@ CASES = [
     (4, 0, 30, 17, 8), (4, 1, 17, 11, 8),
     (5, 0, 16, 10, 7), (5, 7, 16, 10, 7), (5, 63, 16, 10, 7),
     (3, 4, 1, 1, 6), (3, 5, 2, 1, 6), (3, 6, 1, 3, 6), (2, 3, 3, 2, 9),   # degenerate picture sizes
+    # streams with stream % 3 == 2 carry direct_8x8_inference_flag = 0: direct sub-macroblocks / B_Skip / B_Direct_16x16
+    # with motion per 4x4 block (decoder/decoder.cc:239-242); (2,2), (3,2) and (3,5) above are such streams too
+    (2, 5, 20, 12, 12), (3, 8, 24, 14, 10), (4, 2, 30, 17, 8), (5, 2, 16, 10, 7), (5, 8, 16, 10, 7),
 ]
 
 if __name__ == "__main__":
