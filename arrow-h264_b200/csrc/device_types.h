@@ -16,8 +16,7 @@ struct FrameGeom {
     size_t off_cb, off_cr, bytes;    // plane offsets inside the allocation
 };
 
-// Deblock descriptor of one MB, written by the kernel that reconstructs the MB (it holds header and motion), read by the
-// deblock wavefront: 64 bytes.
+// Deblock descriptor of one MB, output of the parallel pre-pass (deblock_prep_kernel), input of the deblock wavefront: 64 bytes.
 //   bs[dir * 2 + (edge >> 1)], nibble (edge & 1) * 4 + group = boundary strength 0..4 of the 4-sample group of that edge
 //   par[plane][type], type 0 = left MB edge, 1 = internal edges, 2 = top MB edge: the filter thresholds of
 //   filter_edge (deblock.cc:469-474 + tables :294-324) packed as alpha | beta << 8 | tc0[bS=1] << 13 | tc0[2] << 18 |
@@ -31,6 +30,7 @@ struct DevPicture {
     const h264r_mb*        mbs;
     const h264r_slice*     slices;
     const uint32_t*        stream;                    // levels and packed motion entries (h264recon.h h264r_pic_buffers)
+    int16_t*               resid;                     // [nmb][384] residual plane, device only (residual_kernel)
     uint8_t*               dst;                       // frame base
     const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]; unused slots: a dummy frame
     DeblockDesc*           desc;                      // [nmb], device only
@@ -56,7 +56,8 @@ struct WaveLaunch {
 };
 
 // Kernel launchers of one wave (kernels.cu).  Returns the number of kernels launched (0 when the wave has no work of that kind).
-enum { KERNEL_INTER = 0, KERNEL_INTRA = 1, KERNEL_DEBLOCK = 2, KERNEL_KINDS = 3 };
+// KERNEL_RESID and KERNEL_DBPREP need nothing but the picture description (side stream, a wave ahead).
+enum { KERNEL_RESID = 0, KERNEL_INTER = 1, KERNEL_INTRA = 2, KERNEL_DBPREP = 3, KERNEL_DEBLOCK = 4, KERNEL_KINDS = 5 };
 int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);
 const char* wave_kernel_name(int which);
 

@@ -44,7 +44,8 @@ enum SlotState { SLOT_FREE = 0, SLOT_FILLING, SLOT_QUEUED, SLOT_INFLIGHT };
 struct Slot {
     uint8_t* host = nullptr;                  // pinned
     uint8_t* dev = nullptr;
-    DeblockDesc* dev_desc = nullptr;          // device only: deblock descriptors, written by the reconstruction kernels
+    DeblockDesc* dev_desc = nullptr;          // device only: output of the deblock pre-pass
+    int16_t* dev_resid = nullptr;             // device only: residual plane [nmb][384]
     uint32_t* dev_mb_done = nullptr;          // device only: per-MB epoch stamps of the sparse intra kernel
     uint64_t* dev_mbox = nullptr;             // device only: row-to-row mailboxes [nmb][24]
     SlotState state = SLOT_FREE;
@@ -65,6 +66,7 @@ struct WaveRecord {
     std::vector<int> dst_frames;              // frames written by this wave
     cudaEvent_t ev_h2d = nullptr;             // recorded on the H2D stream after the wave's copies
     cudaEvent_t ev_done = nullptr;            // recorded on the compute stream after the wave's kernels
+    cudaEvent_t ev_side = nullptr;            // recorded on the side stream after the wave's description-only kernels
 };
 
 struct TableRegion { size_t begin, end; cudaEvent_t done; };
@@ -73,7 +75,10 @@ struct TableRegion { size_t begin, end; cudaEvent_t done; };
 
 struct h264r_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;            // compute: the three kernels of every wave, in order
+    cudaStream_t stream = nullptr;            // compute: inter, intra, deblock of every wave, in order
+    cudaStream_t s_side = nullptr;            // kernels that depend on nothing but the picture description (residual, deblock
+                                              // descriptors): they run ahead of, and underneath, the latency-bound
+                                              // wavefront kernels of earlier waves
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     // events: a ring, taken in order; an event is reused only after kEventRing later takes, long after its work is done
     // (waiting for a re-recorded event is merely conservative)
@@ -169,31 +174,33 @@ cudaEvent_t take_event(h264r_ctx* c)
     return ev;
 }
 
-// Runs the recorded waves of the last flush:
-//   H2D stream : the picture descriptions of a wave, one wave ahead of the kernels (a copy waits for the kernels that
-//                last read the HBM twin it overwrites);
-//   compute    : inter, intra (row wavefront / sparse), deblock of the wave.
-// With time_kernels every kernel is bracketed by events.
+// Runs the recorded waves of the last flush on three streams:
+//   H2D stream  : the picture descriptions of a wave, ahead of the kernels (a copy waits for the kernels that last read
+//                 the HBM twin it overwrites);
+//   side stream : the kernels that need nothing but the description -- residual, deblock descriptors.  They run ahead,
+//                 underneath the latency-bound wavefront kernels of earlier waves;
+//   compute     : inter, intra (row wavefront / sparse), deblock of the wave, after its side kernels.
+// With time_kernels everything runs on the compute stream, one kernel at a time, bracketed by events.
 int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int* launches)
 {
     size_t timer_used = 0;
     struct Pending { int kind; size_t ev; };
     std::vector<Pending> pend;
-    auto launch = [&](WaveRecord& rec, int kind) -> int {
+    auto launch = [&](WaveRecord& rec, int kind, cudaStream_t st) -> int {
         if (time_kernels) {
             while (ctx->timer_events.size() < timer_used + 2) {
                 cudaEvent_t ev = nullptr;
                 if (cudaEventCreate(&ev) != cudaSuccess) return H264R_ERR_CUDA;
                 ctx->timer_events.push_back(ev);
             }
-            if (cudaEventRecord(ctx->timer_events[timer_used], ctx->stream) != cudaSuccess) return H264R_ERR_CUDA;
+            if (cudaEventRecord(ctx->timer_events[timer_used], st) != cudaSuccess) return H264R_ERR_CUDA;
         }
-        const int launched = launch_wave_kernel(rec.launch, kind, ctx->stream);
+        const int launched = launch_wave_kernel(rec.launch, kind, st);
         if (launched) {
             ctx->stats.kernel_launches += (uint64_t)launched;
             if (launches) launches[kind + 1] += launched;
             if (time_kernels) {
-                if (cudaEventRecord(ctx->timer_events[timer_used + 1], ctx->stream) != cudaSuccess) return H264R_ERR_CUDA;
+                if (cudaEventRecord(ctx->timer_events[timer_used + 1], st) != cudaSuccess) return H264R_ERR_CUDA;
                 pend.push_back({ kind, timer_used });
                 timer_used += 2;
             }
@@ -201,6 +208,7 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         return H264R_OK;
     };
     for (WaveRecord& rec : ctx->last_waves) {
+        cudaStream_t main = ctx->stream, side = time_kernels ? ctx->stream : ctx->s_side;
         if (h2d) {
             CU(cudaStreamWaitEvent(ctx->s_h2d, rec.ev_done, 0));          // replays: the previous run of this record; no-op the first time
             for (const WaveCopy& c : rec.copies) {
@@ -211,18 +219,32 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
                 ctx->stats.h2d_bytes += c.head_bytes + c.stream_bytes;
             }
             CU(cudaEventRecord(rec.ev_h2d, ctx->s_h2d));
-            CU(cudaStreamWaitEvent(ctx->stream, rec.ev_h2d, 0));
+            CU(cudaStreamWaitEvent(side, rec.ev_h2d, 0));
         }
         rec.launch.epoch = ++ctx->epoch;
+        // side kernels: their outputs (residual plane, deblock descriptors) are per picture slot; the previous user of the
+        // slot's device buffers -- this record's previous run, or an earlier picture in the same slot -- must be done
+        if (!time_kernels) {
+            CU(cudaStreamWaitEvent(side, rec.ev_done, 0));
+            for (const WaveCopy& c : rec.copies) if (c.prev_done) CU(cudaStreamWaitEvent(side, c.prev_done, 0));
+        }
+        { const int rc = launch(rec, KERNEL_RESID, side); if (rc != H264R_OK) return rc; }
+        { const int rc = launch(rec, KERNEL_DBPREP, side); if (rc != H264R_OK) return rc; }
+        if (!time_kernels) {
+            CU(cudaEventRecord(rec.ev_side, side));
+            CU(cudaStreamWaitEvent(main, rec.ev_side, 0));
+        }
         // write-after-read: a frame still being downloaded (asynchronously, on the D2H stream) is not overwritten
         for (int f : rec.dst_frames) {
             Frame& fr = ctx->frames[f];
-            if (fr.pending_read) { CU(cudaStreamWaitEvent(ctx->stream, fr.read_done, 0)); fr.pending_read = false; }
+            if (fr.pending_read) { CU(cudaStreamWaitEvent(main, fr.read_done, 0)); fr.pending_read = false; }
         }
-        CU(cudaMemsetAsync(rec.launch.tickets, 0, sizeof(int) * 64, ctx->stream));      // the wave's ticket counters
-        for (int kind = 0; kind < KERNEL_KINDS; ++kind) { const int rc = launch(rec, kind); if (rc != H264R_OK) return rc; }
+        CU(cudaMemsetAsync(rec.launch.tickets, 0, sizeof(int) * 64, main));      // the wave's ticket counters
+        { const int rc = launch(rec, KERNEL_INTER, main); if (rc != H264R_OK) return rc; }
+        { const int rc = launch(rec, KERNEL_INTRA, main); if (rc != H264R_OK) return rc; }
+        { const int rc = launch(rec, KERNEL_DEBLOCK, main); if (rc != H264R_OK) return rc; }
         CU(cudaGetLastError());
-        CU(cudaEventRecord(rec.ev_done, ctx->stream));
+        CU(cudaEventRecord(rec.ev_done, main));
         ctx->stats.waves += 1;
         ctx->stats.pictures += (uint64_t)rec.launch.num_pics;
         ctx->stats.macroblocks += (uint64_t)rec.launch.num_pics * ctx->nmb;
@@ -296,6 +318,7 @@ void h264r_destroy(h264r_ctx* ctx)
         if (ctx->slots[0].host) cudaFreeHost(ctx->slots[0].host);
         if (ctx->slots[0].dev) cudaFree(ctx->slots[0].dev);
         if (ctx->slots[0].dev_desc) cudaFree(ctx->slots[0].dev_desc);
+        if (ctx->slots[0].dev_resid) cudaFree(ctx->slots[0].dev_resid);
         if (ctx->slots[0].dev_mb_done) cudaFree(ctx->slots[0].dev_mb_done);
         if (ctx->slots[0].dev_mbox) cudaFree(ctx->slots[0].dev_mbox);
     }
@@ -309,6 +332,7 @@ void h264r_destroy(h264r_ctx* ctx)
     for (cudaEvent_t ev : ctx->event_ring) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->timer_events) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     delete ctx;
@@ -348,11 +372,12 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     ctx->table_entries = 4 * nslots;
 
     // every CUDA failure below takes the one cleanup path (h264r_destroy frees whatever exists)
-    uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr;
+    uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr; int16_t* d_resid = nullptr;
     uint32_t* d_done = nullptr; uint64_t* d_mbox = nullptr;
     const size_t mbox_words = (size_t)24 * nmb;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
@@ -364,6 +389,8 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (d_arena) ctx->slots[0].dev = d_arena;
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_desc, sizeof(DeblockDesc) * nmb * nslots);
     if (d_desc) ctx->slots[0].dev_desc = d_desc;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_resid, sizeof(int16_t) * H264R_COEFFS_PER_MB * nmb * nslots);
+    if (d_resid) ctx->slots[0].dev_resid = d_resid;
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_done, sizeof(uint32_t) * nmb * nslots);
     if (d_done) ctx->slots[0].dev_mb_done = d_done;
     if (e == cudaSuccess) e = cudaMemset(d_done, 0, sizeof(uint32_t) * nmb * nslots);
@@ -388,6 +415,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         s.host = h_arena + ctx->slot_bytes * i;
         s.dev = d_arena + ctx->slot_bytes * i;
         s.dev_desc = d_desc + nmb * i;
+        s.dev_resid = d_resid + (size_t)H264R_COEFFS_PER_MB * nmb * i;
         s.dev_mb_done = d_done + nmb * i;
         s.dev_mbox = d_mbox + mbox_words * i;
         ctx->free_slots.push_back((int)(nslots - 1 - i));          // slot 0 is handed out first
@@ -567,6 +595,7 @@ int h264r_flush(h264r_ctx* ctx)
         for (int i = 0; i < H264R_MAX_REFS; ++i)
             p.ref[i] = i < s.pp.num_ref_frames ? ctx->frames[s.pp.ref_frames[i]].dev : ctx->dummy_frame;
         p.desc = s.dev_desc;
+        p.resid = s.dev_resid;
         p.mbox = s.dev_mbox;
         p.mb_done = s.dev_mb_done;
         p.stream_words = s.stream_words;
@@ -574,7 +603,8 @@ int h264r_flush(h264r_ctx* ctx)
         p.run_deblock = s.pp.run_deblock; p.all_intra = s.all_intra;
         p.direct8x8 = s.pp.direct_8x8_inference_flag != 0;
     }
-    CU(cudaMemcpyAsync(d_table, h_table, sizeof(DevPicture) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
+    // on the H2D stream, ahead of the descriptions: every kernel of the flush (side and compute stream) follows its wave's ev_h2d
+    CU(cudaMemcpyAsync(d_table, h_table, sizeof(DevPicture) * order.size(), cudaMemcpyHostToDevice, ctx->s_h2d));
     ctx->stats.h2d_bytes += sizeof(DevPicture) * order.size();
 
     // ---- per record: what to copy, what to launch ----
@@ -585,8 +615,8 @@ int h264r_flush(h264r_ctx* ctx)
         WaveLaunch& L = rec.launch;
         L.pics = d_table + b; L.num_pics = e - b; L.tickets = ctx->d_tickets; L.err = ctx->d_err; L.geom = ctx->geom;
         L.any_inter = L.any_deblock = L.any_intra_rows = 0; L.epoch = 0;
-        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx);
-        if (!rec.ev_h2d || !rec.ev_done) return H264R_ERR_CUDA;
+        rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx); rec.ev_side = take_event(ctx);
+        if (!rec.ev_h2d || !rec.ev_done || !rec.ev_side) return H264R_ERR_CUDA;
         for (int k = b; k < e; ++k) {
             Slot& s = ctx->slots[order[k]];
             rec.copies.push_back({ order[k], ctx->off_slices + sizeof(h264r_slice) * (size_t)s.pp.num_slices,
@@ -634,6 +664,7 @@ int h264r_wait(h264r_ctx* ctx, h264r_frame f)
         return check_device_errors(ctx);
     }
     CU(cudaStreamSynchronize(ctx->s_h2d));
+    CU(cudaStreamSynchronize(ctx->s_side));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->s_d2h));
     {

@@ -1,8 +1,6 @@
 // recon_inter2_kernel: the inter macroblocks of a wave of pictures, TWO macroblocks per warp, one 4x4 block per lane:
-// deblock descriptor (boundary strengths + thresholds), motion compensation, weighted prediction, dequantisation +
-// inverse transform of the MB's levels, reconstruction -- one pass, nothing but the frame and the 64-byte descriptor is
-// written (inter_prediction.cc:53-406, 448-536; decoder.cc:217-262; transform.cc:394-456, 597-733, 913-984;
-// deblock.cc:35-289, 469-474).
+// motion compensation, weighted prediction, residual add (inter_prediction.cc:53-406, 448-536; decoder.cc:217-262;
+// transform.cc:913-984).
 #ifndef H264R_KERNEL_INTER_CUH_
 #define H264R_KERNEL_INTER_CUH_
 
@@ -41,13 +39,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // quadrant 4 blocks x (9 rows x 4 words), one row pitch for both so that row offsets are immediates; chroma 50 words =
 // uniform 2 planes x (5 rows x 2 words) | split 4 blocks x 2 planes x (3 rows x 2 words), + 1 word the funnel shifts
 // may touch.  146 = 2 (mod 8): the four quadrant groups of a warp read disjoint banks.
-// After the last prediction list the same memory is the coefficient scratch of the two macroblocks (2 x kResInts ints).
 constexpr int kLumaQ = 146, kChromaQ = 50;
 struct __align__(16) Inter2Smem {
     uint32_t luma[2][4 * kLumaQ + 2];
     uint32_t chroma[2][4 * kChromaQ + 2];
 };
-static_assert(sizeof(Inter2Smem) >= 2 * kResInts * sizeof(int), "the coefficient scratch aliases the reference windows");
 
 // Decoder::mb_pred_inter partition walk (decoder.cc:217-262) for 4x4 block `blk`: returns the block whose motion
 // entry the reference reads (partition origin), the prediction direction, and whether the partition covers the
@@ -98,7 +94,6 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* 
     MbHdr h = load_hdr(pic.mbs, addr);
     const bool valid = mbx < W && !h.intra();
     if (!__any_sync(0xFFFFFFFFu, valid)) return;
-    const unsigned half_mask = 0xFFFFu << (lane & 16);
     sanitize_hdr(h, pic, err);
     Inter2Smem& sm = smem_all[warp];
     const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
@@ -110,24 +105,15 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* 
     const int direct_spatial = (s2 >> 8) & 0xFF;
     const bool has_res = valid && h.has_resid();
 
-    // the levels are needed last: pull them into the L2 now (no registers held)
-    if (has_res && b * 32 < h.coeff_count) prefetch_l2(pic.stream + h.coeff_offset + b * 32);
-
-    // ---- neighbour headers for the deblock descriptor: issued with everything else, consumed while the windows load ----
-    const bool want_desc = valid && pic.run_deblock;
-    uint4 hL = make_uint4(0, 0, 0, 0), hT = hL; uint32_t pkL = 0, pkT = 0;
-    if (want_desc) {
-        if (mbx > 0) { hL = __ldg(reinterpret_cast<const uint4*>(pic.mbs + addr - 1)); pkL = __ldg(reinterpret_cast<const unsigned int*>(pic.mbs + addr - 1) + 7); }
-        if (mby > 0) { hT = __ldg(reinterpret_cast<const uint4*>(pic.mbs + addr - W)); pkT = __ldg(reinterpret_cast<const unsigned int*>(pic.mbs + addr - W) + 7); }
-    }
+    // the residual is needed last: pull its six lines into the L2 now (no registers held), the loads at the end then
+    // cost an L2 hit instead of one more HBM round trip on the warp's dependent chain
+    if (has_res && b < 6) prefetch_l2(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB + b * 64);
 
     int origin = 0, pd = 0; bool uni = true;
     uint32_t mvw0 = 0, mvw1 = 0, rw = 0;                 // the motion entry of this block's partition
-    uint32_t own_word = 0;
     if (valid) {
         partition_of_block2(h, is_b, direct_spatial, pic, pic.direct8x8, b, origin, pd, uni, err);
-        own_word = packed_entry_word(pic, h.packed, origin, err);
-        const uint32_t* e = pic.stream + own_word;
+        const uint32_t* e = pic.stream + packed_entry_word(pic, h.packed, origin, err);
         mvw0 = __ldg(e); mvw1 = __ldg(e + 1); rw = __ldg(e + 2);
     }
     const int q = (by >> 1) * 2 + (bx >> 1), sb = (by & 1) * 2 + (bx & 1);        // quadrant, block inside the quadrant
@@ -208,70 +194,6 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* 
             }
         }
 
-        // ---- deblock descriptor of the two MBs, computed while the first list's windows are in flight ----
-        if (k == 0 && __any_sync(0xFFFFFFFFu, want_desc)) {
-            const int idc = (s0 >> 8) & 0xFF;
-            // this block's OWN motion entry (the strength rule compares mv_info per 4x4 block, deblock.cc:140-170); it is the
-            // partition's entry unless the description carries different vectors inside one partition
-            uint32_t e0 = mvw0, e1 = mvw1, e2 = rw;
-            if (want_desc) {
-                const uint32_t w_own = packed_entry_word(pic, h.packed, b, err);
-                if (w_own != own_word) { const uint32_t* e = pic.stream + w_own; e0 = __ldg(e); e1 = __ldg(e + 1); e2 = __ldg(e + 2); }
-            }
-            // neighbouring blocks inside the MB come from the neighbouring lanes
-            uint32_t l0 = __shfl_sync(0xFFFFFFFFu, e0, lane - 1), l1 = __shfl_sync(0xFFFFFFFFu, e1, lane - 1), l2 = __shfl_sync(0xFFFFFFFFu, e2, lane - 1);
-            uint32_t t0 = __shfl_sync(0xFFFFFFFFu, e0, lane - 4), t1 = __shfl_sync(0xFFFFFFFFu, e1, lane - 4), t2 = __shfl_sync(0xFFFFFFFFu, e2, lane - 4);
-            uint32_t w[4] = { 0, 0, 0, 0 };
-            if (want_desc && idc != 1) {
-                const bool left_ok = mbx > 0 && !(idc == 2 && (hL.x >> 16) != (uint32_t)h.slice_idx);
-                const bool top_ok  = mby > 0 && !(idc == 2 && (hT.x >> 16) != (uint32_t)h.slice_idx);
-                const bool t8 = h.t8();
-                const bool p_skip = !is_b && h.mb_type == 0;
-                const int coded = (h.cbp_blks >> b) & 1;
-                // dir 0: the vertical edge on the left of the block (edge bx, group by); dir 1: the horizontal edge above it
-#pragma unroll
-                for (int dir = 0; dir < 2; ++dir) {
-                    const int e = dir ? by : bx, k4 = dir ? bx : by;
-                    const uint4& hN = dir ? hT : hL;
-                    bool on = e == 0 ? (dir ? top_ok : left_ok) : !(t8 && (e & 1));
-                    if (e > 0 && p_skip) on = false;
-                    int s = 0;
-                    if (on) {
-                        if (e == 0 && ((hN.x >> 8) & H264R_MB_FLAG_INTRA)) s = 4;
-                        else {
-                            const int blkP = dir ? (e ? e - 1 : 3) * 4 + k4 : k4 * 4 + (e ? e - 1 : 3);
-                            const int pcbp = e ? h.cbp_blks : (int)(hN.w & 0xFFFF);
-                            if (coded || ((pcbp >> blkP) & 1)) s = 2;
-                            else if (e > 0 && (h.mb_type == 1 || h.mb_type == (dir ? 3 : 2))) s = 0;
-                            else {
-                                uint32_t n0 = dir ? t0 : l0, n1 = dir ? t1 : l1, n2 = dir ? t2 : l2;
-                                if (e == 0) {                    // the block on the other side belongs to the neighbouring MB
-                                    const uint32_t* ne = pic.stream + packed_entry_word(pic, dir ? pkT : pkL, blkP, err);
-                                    n0 = __ldg(ne); n1 = __ldg(ne + 1); n2 = __ldg(ne + 2);
-                                }
-                                s = (n0 == e0 && n1 == e1 && n2 == e2) ? 0 : bs_compare(n0, n1, n2, e0, e1, e2);
-                            }
-                        }
-                    }
-                    w[dir * 2 + (e >> 1)] |= (uint32_t)s << ((e & 1) * 16 + k4 * 4);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) w[i] = __reduce_or_sync(half_mask, w[i]);
-            if (want_desc) {
-                uint32_t* out = reinterpret_cast<uint32_t*>(pic.desc + addr);
-                if (b == 0) *reinterpret_cast<uint4*>(out) = make_uint4(w[0], w[1], w[2], w[3]);
-                if (b < 9 && idc != 1) {                         // thresholds [Y, Cb, Cr][left MB edge, internal, top MB edge]
-                    const int pl = b / 3, t = b - pl * 3;
-                    const uint32_t q1 = (uint32_t)h.cbp_luma | (uint32_t)h.qp_y << 16 | (uint32_t)h.qp_c[0] << 24, q2 = (uint32_t)h.qp_c[1];
-                    const uint32_t p1 = t == 0 ? (mbx > 0 ? hL.y : q1) : (t == 2 ? (mby > 0 ? hT.y : q1) : q1);
-                    const uint32_t p2 = t == 0 ? (mbx > 0 ? hL.z : q2) : (t == 2 ? (mby > 0 ? hT.z : q2) : q2);
-                    out[4 + b] = deblock_threshold_word(qp_of_plane(p1, p2, pl), qp_of_plane(q1, q2, pl),
-                                                        (int)(int8_t)(s0 >> 16), (int)(int8_t)(s0 >> 24));
-                }
-            }
-        }
-
         cp_async_wait_all();                               // this lane's window copies have landed
         __syncwarp();
         {
@@ -292,111 +214,52 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* 
         __syncwarp();
     }
 
-    // ---- weighted sample prediction (mc_prediction / bi_prediction, inter_prediction.cc:53-156) ----
-    uint32_t predY[4], predC[2];
-    {
-        const bool uni_weighted = (wp_flag && !is_b) || (bipred_idc == 1 && is_b);
-        const int ref0 = pd == 2 ? ref_prev : ref_cur, ref1 = ref_cur;
-        const int mode = pd != 2 ? (uni_weighted ? 1 : 0) : (bipred_idc == 0 ? 2 : 3);
-        int wgt[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } }, off[3] = { 0, 0, 0 };             // [Y, Cb, Cr][list]
-        if (mode == 1) {
-#pragma unroll
-            for (int pl = 0; pl < 3; ++pl) {
-                wgt[pl][0] = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][ref0 & 31]);
-                off[pl] = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][ref0 & 31]);
-            }
-        } else if (mode == 3) {
-#pragma unroll
-            for (int pl = 0; pl < 3; ++pl) {
-                if (bipred_idc == 1) {
-                    wgt[pl][0] = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][ref0 & 31]);
-                    wgt[pl][1] = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][ref1 & 31]);
-                    off[pl] = ((int)(int8_t)__ldg(&sl->wp_offset[0][pl][ref0 & 31]) + (int)(int8_t)__ldg(&sl->wp_offset[1][pl][ref1 & 31]) + 1) >> 1;
-                } else {
-                    wgt[pl][1] = (int)__ldg(&sl->implicit_w1[ref0 & 31][ref1 & 31]);
-                    wgt[pl][0] = 64 - wgt[pl][1];
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) predY[r] = mc_weight4(mode, pd == 2 ? prevY[r] : curY[r], curY[r], wgt[0][0], wgt[0][1], denom_y, off[0]);
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl) predC[pl] = mc_weight4(mode, pd == 2 ? prevC[pl] : curC[pl], curC[pl], wgt[1 + pl][0], wgt[1 + pl][1], denom_c, off[1 + pl]);
-    }
-
-    // ---- residual: the windows are dead, their memory becomes the coefficient scratch of the two MBs ----
-    if (__any_sync(0xFFFFFFFFu, has_res)) {
-        int* const scratch = reinterpret_cast<int*>(&sm);
-        int* const cof = scratch + m * kResInts;
-        constexpr int kVec = 2 * kResInts / 4;                       // 16-byte chunks of the two scratch areas
-#pragma unroll
-        for (int i = 0; i < (kVec + 31) / 32; ++i)
-            if (lane + 32 * i < kVec) reinterpret_cast<int4*>(scratch)[lane + 32 * i] = make_int4(0, 0, 0, 0);
-        __syncwarp();
-        const bool t8 = h.t8();
-        unsigned nz = 0;
-        if (has_res) {
-            const uint32_t ctl = scatter_ctl(h), mode = scatter_mode(h, 1);
-            const uint32_t* __restrict__ lv = pic.stream + h.coeff_offset;
-            for (int i = b; i < h.coeff_count; i += 16) nz |= scatter_level(__ldg(lv + i), ctl, mode, sl, cof, err);
-        }
-        nz = __reduce_or_sync(half_mask, nz);
-        __syncwarp();
-        // phase 1: the lanes sb = 0 / 1 of quadrant q take chroma block q of Cb / Cr into registers and transform it;
-        //          8x8-transform MBs run the row pass of their luma blocks in place (lane sb: rows 2 sb, 2 sb + 1)
-        const bool chroma_on = has_res && h.cbp_chroma && (nz >> 16);
-        const bool do_c = chroma_on && sb < 2;
-        int* const cblk = cof + kResC + (sb & 1) * kResCPlane + (q >> 1) * 4 * kResCP + (q & 1) * 4;
-        int cd[4][4];
-        if (do_c) {
-            const int pl = sb & 1;
-            const int* cp = cof + kResC + pl * kResCPlane;
-            const int c00 = cp[0], c01 = cp[4], c10 = cp[4 * kResCP], c11 = cp[4 * kResCP + 4];
-            const int qc = pl ? h.qp_c[1] : h.qp_c[0], cper = qc / 6, crem = qc - cper * 6;
-            load_block4(cblk, kResCP, cd);
-            cd[0][0] = chroma_dc_of_block(q, c00, c01, c10, c11, (int)__ldg(&sl->level_scale_4x4[1][pl + 1][crem][0]), cper);
-            idct4_regs(cd);
-        }
-        const unsigned m8 = 0x33u << ((q >> 1) * 8 + (q & 1) * 2);          // the four 4x4 blocks of 8x8 block q
-        const bool do_8 = has_res && t8 && (nz & m8);
-        int* const blk8 = cof + (q >> 1) * 8 * kResP + (q & 1) * 8;
-        if (do_8) { idct8_1d(blk8 + (2 * sb) * kResP, 1, false); idct8_1d(blk8 + (2 * sb + 1) * kResP, 1, false); }
-        __syncwarp();
-        // phase 2: chroma blocks back to the scratch; column pass of the 8x8 blocks (lane sb: columns 2 sb, 2 sb + 1)
-        if (do_c) store_block4(cblk, kResCP, cd);
-        if (do_8) { idct8_1d(blk8 + 2 * sb, kResP, true); idct8_1d(blk8 + 2 * sb + 1, kResP, true); }
-        __syncwarp();
-        // phase 3: every lane takes its 4x4 luma block (4x4-transform MBs: coefficients, transformed in registers) and
-        //          its 2x2 chroma patches, and reconstructs
-        if (has_res) {
-            if (t8 ? (nz & m8) != 0 : ((nz >> b) & 1) != 0) {
-                int d[4][4];
-                load_block4(cof + by * 4 * kResP + bx * 4, kResP, d);
-                if (!t8) idct4_regs(d);
-#pragma unroll
-                for (int r = 0; r < 4; ++r) predY[r] = mc_recon4(predY[r], pack_res2(d[r][0], d[r][1]), pack_res2(d[r][2], d[r][3]));
-            }
-            if (chroma_on) {
-#pragma unroll
-                for (int pl = 0; pl < 2; ++pl) {
-                    const int* cp = cof + kResC + pl * kResCPlane + by * 2 * kResCP + bx * 2;
-                    const int2 r0 = *reinterpret_cast<const int2*>(cp), r1 = *reinterpret_cast<const int2*>(cp + kResCP);
-                    predC[pl] = mc_recon4(predC[pl], pack_res2(r0.x, r0.y), pack_res2(r1.x, r1.y));
-                }
-            }
-        }
-    }
     if (!valid) return;
 
-    // ---- store ----
+    // weighted sample prediction (mc_prediction / bi_prediction, inter_prediction.cc:53-156), residual, store
+    const bool uni_weighted = (wp_flag && !is_b) || (bipred_idc == 1 && is_b);
+    const int ref0 = pd == 2 ? ref_prev : ref_cur, ref1 = ref_cur;
+    const int mode = pd != 2 ? (uni_weighted ? 1 : 0) : (bipred_idc == 0 ? 2 : 3);
+    int wgt[3][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 } }, off[3] = { 0, 0, 0 };             // [Y, Cb, Cr][list]
+    if (mode == 1) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            wgt[pl][0] = (int)(int8_t)__ldg(&sl->wp_weight[pd][pl][ref0 & 31]);
+            off[pl] = (int)(int8_t)__ldg(&sl->wp_offset[pd][pl][ref0 & 31]);
+        }
+    } else if (mode == 3) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+            if (bipred_idc == 1) {
+                wgt[pl][0] = (int)(int8_t)__ldg(&sl->wp_weight[0][pl][ref0 & 31]);
+                wgt[pl][1] = (int)(int8_t)__ldg(&sl->wp_weight[1][pl][ref1 & 31]);
+                off[pl] = ((int)(int8_t)__ldg(&sl->wp_offset[0][pl][ref0 & 31]) + (int)(int8_t)__ldg(&sl->wp_offset[1][pl][ref1 & 31]) + 1) >> 1;
+            } else {
+                wgt[pl][1] = (int)__ldg(&sl->implicit_w1[ref0 & 31][ref1 & 31]);
+                wgt[pl][0] = 64 - wgt[pl][1];
+            }
+        }
+    }
+    const int16_t* __restrict__ rs = pic.resid + (size_t)addr * H264R_COEFFS_PER_MB;
     uint8_t* dY = pic.dst + (uint32_t)((mby * 16 + by * 4) * pitch_y + mbx * 16 + bx * 4);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) *reinterpret_cast<uint32_t*>(dY + (uint32_t)(r * pitch_y)) = predY[r];
+    for (int r = 0; r < 4; ++r) {
+        const uint2 res = has_res ? __ldg(reinterpret_cast<const uint2*>(rs + (by * 4 + r) * 16 + bx * 4)) : make_uint2(0, 0);
+        const uint32_t p0 = pd == 2 ? prevY[r] : curY[r];
+        *reinterpret_cast<uint32_t*>(dY + (uint32_t)(r * pitch_y)) = mc_weight_recon4(mode, p0, curY[r], wgt[0][0], wgt[0][1], denom_y, off[0], res.x, res.y);
+    }
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
+        uint32_t r0 = 0, r1 = 0;
+        if (has_res) {
+            r0 = __ldg(reinterpret_cast<const uint32_t*>(rs + 256 + pl * 64 + (by * 2) * 8 + bx * 2));
+            r1 = __ldg(reinterpret_cast<const uint32_t*>(rs + 256 + pl * 64 + (by * 2 + 1) * 8 + bx * 2));
+        }
+        const uint32_t p0 = pd == 2 ? prevC[pl] : curC[pl];
+        const uint32_t o = mc_weight_recon4(mode, p0, curC[pl], wgt[1 + pl][0], wgt[1 + pl][1], denom_c, off[1 + pl], r0, r1);
         uint8_t* dC = pic.dst + (pl ? g.off_cr : g.off_cb) + (uint32_t)((mby * 8 + by * 2) * pitch_c + mbx * 8 + bx * 2);
-        *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(predC[pl] & 0xFFFF);
-        *reinterpret_cast<uint16_t*>(dC + pitch_c) = (uint16_t)(predC[pl] >> 16);
+        *reinterpret_cast<uint16_t*>(dC) = (uint16_t)(o & 0xFFFF);
+        *reinterpret_cast<uint16_t*>(dC + pitch_c) = (uint16_t)(o >> 16);
     }
 }
 

@@ -1,5 +1,4 @@
-// Intra reconstruction (intra_prediction.cc:137-904, decoder.cc:149-215) with the residual (transform.cc:394-456, 597-733,
-// 825-1095) and the deblock descriptor of every intra MB computed in the same warp:
+// Intra reconstruction (intra_prediction.cc:137-904, decoder.cc:149-215); the residual comes from residual_kernel's plane:
 //   recon_intra_kernel        : all-intra pictures, one warp per MB ROW; rows form a 2:1 wavefront (MB(x,y) needs (x-1,y),
 //                               (x-1,y-1), (x,y-1), (x+1,y-1)) and talk through mailboxes
 //   recon_intra_sparse_kernel : the intra MBs of P/B pictures: one warp per 32 consecutive MB addresses, which finds its
@@ -40,7 +39,6 @@ __device__ __forceinline__ uint64_t ld_mbox(const uint64_t* p)
 // luma tile: rows -1..15, cols -4..27 -> index (y+1)*32 + (x+4); 17 rows x 32 B
 // chroma tile per plane: rows -1..7, cols -4..11 -> index (y+1)*16 + (x+4); 9 rows x 16 B
 struct __align__(16) IntraSmem {
-    __align__(16) int cof[kResInts];             // coefficient scratch of the residual (kernels_common.cuh)
     __align__(16) int16_t res[384];              // this MB's residual (zero when it has none)
     __align__(16) uint8_t ty[17 * 32];
     __align__(16) uint8_t tc[2][9 * 16];
@@ -190,14 +188,13 @@ __device__ const uint32_t c_i8_pred[9 * 64] = {
     0x010001, 0x000001, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000, 0x000000,
 };
 
-// Everything about an intra MB that does not depend on its neighbours being reconstructed: header, the first 16 header
-// bytes of the four neighbouring MBs (lane & 3 = 0 left, 1 top, 2 top-left, 3 top-right), the slice's first word and
-// constrained_intra_pred_flag.  Loaded ahead of time (next MB of the row / before the dependency wait); the MB's levels
-// are pulled into the L2 at the same time.
+// Everything about an intra MB that does not depend on its neighbours being reconstructed: header, the header words
+// of the four neighbouring MBs (lane & 3 = 0 left, 1 top, 2 top-left, 3 top-right), the residual, the slice's
+// constrained_intra_pred_flag.  Loaded ahead of time (next MB of the row / before the dependency wait).
 struct IntraPre {
     MbHdr h;
-    uint32_t nbw, nb1, nb2;         // header words 0..2 of neighbour (lane & 3); nbw = 0xFFFFFFFF outside the picture
-    uint32_t sl0;                   // slice_type | disable_deblocking_filter_idc << 8 | FilterOffsetA << 16 | FilterOffsetB << 24
+    uint32_t nbw;                   // header word 0 of neighbour (lane & 3), 0xFFFFFFFF outside the picture
+    uint4 r0, r1;                   // residual chunks lane and 32 + lane (lanes 0..15) of the MB's 48 x 16 bytes
     int ci;
 };
 __device__ __forceinline__ void intra_prefetch(const DevPicture& pic, const FrameGeom& g, int mbx, int mby, int lane, IntraPre& p, uint32_t* err)
@@ -207,138 +204,12 @@ __device__ __forceinline__ void intra_prefetch(const DevPicture& pic, const Fram
     sanitize_hdr(p.h, pic, err);
     const int k = lane & 3;
     const int nx = mbx + (k == 3 ? 1 : (k == 1 ? 0 : -1)), ny = mby - (k == 0 ? 0 : 1);
-    p.nbw = 0xFFFFFFFFu; p.nb1 = p.nb2 = 0;
-    if (nx >= 0 && nx < W && ny >= 0) {
-        const uint4 n = __ldg(reinterpret_cast<const uint4*>(pic.mbs + ny * W + nx));
-        p.nbw = n.x; p.nb1 = n.y; p.nb2 = n.z;
-    }
-    const h264r_slice* sl = pic.slices + p.h.slice_idx;
-    p.sl0 = __ldg(reinterpret_cast<const uint32_t*>(sl));
-    p.ci = (int)__ldg(&sl->constrained_intra_pred_flag);
-    if (lane * 32 < p.h.coeff_count) prefetch_l2(pic.stream + p.h.coeff_offset + lane * 32);
-}
-
-// Residual of one intra MB by one warp: scatter-dequantise the levels into the coefficient scratch, luma 4x4 / chroma
-// 2x2 DC Hadamards (transform_luma_dc :825-856, transform_chroma_dc :858-910), 4x4 / 8x8 inverse transforms only for
-// blocks that received a level (one instruction stream for the sixteen luma and eight chroma 4x4 blocks), int16 result
-// in sm.res (raster: Y 16x16 | Cb 8x8 | Cr 8x8).  MBs without levels get zeros.
-__device__ __forceinline__ void intra_residual_mb(const DevPicture& pic, IntraSmem& sm, const MbHdr& h, int lane, uint32_t* err)
-{
-    if (!h.has_resid()) {
-        reinterpret_cast<uint4*>(sm.res)[lane] = make_uint4(0, 0, 0, 0);
-        if (lane < 16) reinterpret_cast<uint4*>(sm.res)[32 + lane] = make_uint4(0, 0, 0, 0);
-        return;
-    }
-    int* const res = sm.cof;
-    const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
-    const bool t8 = h.t8();
-    const bool i16 = h.mb_type == H264R_MB_I16x16;
-    const int per = h.qp_y / 6, rem = h.qp_y - per * 6;
-#pragma unroll
-    for (int k = 0; k < (kResInts / 4 + 31) / 32; ++k)
-        if (lane + 32 * k < kResInts / 4) reinterpret_cast<int4*>(res)[lane + 32 * k] = make_int4(0, 0, 0, 0);
-    __syncwarp();
-    const uint32_t* __restrict__ lv = pic.stream + h.coeff_offset;
-    unsigned nz = 0;
-    const uint32_t ctl = scatter_ctl(h), mode = scatter_mode(h, 0);
-    for (int i = lane; i < h.coeff_count; i += 32) nz |= scatter_level(__ldg(lv + i), ctl, mode, sl, res, err);
-    nz = __reduce_or_sync(0xFFFFFFFFu, nz);
-    __syncwarp();
-
-    // DC transforms.  Luma (Intra16x16): lane j < 16 holds DC (j >> 2, j & 3); both Hadamard passes through shuffles.
-    // Chroma: lanes 16..23 = (plane, block); each evaluates the 2x2 Hadamard for its own block.
-    int dc = 0;
-    const bool cdc = h.cbp_chroma && (nz >> 16);
-    if (i16) {
-        const int j = lane & 15;
-        const int c = res[(j >> 2) * 4 * kResP + (j & 3) * 4];
-        // rows: e0 = c0+c1+c2+c3, e1 = c0+c1-c2-c3, e2 = c0-c1-c2+c3, e3 = c0-c1+c2-c3 (transform.cc:832-842)
-        const int base = lane & ~3, k = lane & 3;
-        const int c0 = __shfl_sync(0xFFFFFFFFu, c, base), c1 = __shfl_sync(0xFFFFFFFFu, c, base + 1),
-                  c2 = __shfl_sync(0xFFFFFFFFu, c, base + 2), c3 = __shfl_sync(0xFFFFFFFFu, c, base + 3);
-        const int e = k == 0 ? c0 + c1 + c2 + c3 : (k == 1 ? c0 + c1 - c2 - c3 : (k == 2 ? c0 - c1 - c2 + c3 : c0 - c1 + c2 - c3));
-        const int col = lane & 3, r = (lane >> 2) & 3, hb = lane & 16;
-        const int e0 = __shfl_sync(0xFFFFFFFFu, e, hb + col), e1 = __shfl_sync(0xFFFFFFFFu, e, hb + 4 + col),
-                  e2 = __shfl_sync(0xFFFFFFFFu, e, hb + 8 + col), e3 = __shfl_sync(0xFFFFFFFFu, e, hb + 12 + col);
-        const int f = r == 0 ? e0 + e1 + e2 + e3 : (r == 1 ? e0 + e1 - e2 - e3 : (r == 2 ? e0 - e1 - e2 + e3 : e0 - e1 + e2 - e3));
-        const int scale = (int)__ldg(&sl->level_scale_4x4[0][0][rem][0]);
-        dc = h.qp_y >= 36 ? (f * scale) * (1 << (per - 6)) : (f * scale + (1 << (5 - per))) >> (6 - per);
-        nz |= 0xFFFFu;                                       // the DC Hadamard spreads into every luma block
-    }
-    if (cdc) {
-        if (lane >= 16 && lane < 24) {
-            const int pl = (lane - 16) >> 2, qb = lane & 3;
-            const int qc = pl ? h.qp_c[1] : h.qp_c[0], cper = qc / 6, crem = qc - cper * 6;
-            const int* c = res + kResC + pl * kResCPlane;             // DC positions (0,0) (0,4) (4,0) (4,4)
-            dc = chroma_dc_of_block(qb, c[0], c[4], c[4 * kResCP], c[4 * kResCP + 4], (int)__ldg(&sl->level_scale_4x4[0][pl + 1][crem][0]), cper);
-        }
-        nz |= 0xFF0000u;
-    }
-    __syncwarp();                                            // every raw DC has been read
-    if (i16 && lane < 16) res[(lane >> 2) * 4 * kResP + (lane & 3) * 4] = dc;
-    if (cdc && lane >= 16 && lane < 24) {
-        const int pl = (lane - 16) >> 2, qb = lane & 3;
-        res[kResC + pl * kResCPlane + (qb >> 1) * 4 * kResCP + (qb & 1) * 4] = dc;
-    }
-    __syncwarp();
-
-    // inverse transforms, only where something is non-zero
-    if (t8) {
-        const int b8 = lane >> 3, i = lane & 7;
-        int* blk = res + (b8 >> 1) * 8 * kResP + (b8 & 1) * 8;
-        const unsigned m8 = 0x33u << ((b8 >> 1) * 8 + (b8 & 1) * 2);          // the four 4x4 blocks of 8x8 block b8
-        if (nz & m8) idct8_1d(blk + i * kResP, 1, false);
-        __syncwarp();
-        if (nz & m8) idct8_1d(blk + i, kResP, true);
-        if (lane < 8 && ((nz >> (16 + lane)) & 1)) {
-            int d[4][4];
-            int* cb = res + kResC + (lane >> 2) * kResCPlane + ((lane >> 1) & 1) * 4 * kResCP + (lane & 1) * 4;
-            load_block4(cb, kResCP, d); idct4_regs(d); store_block4(cb, kResCP, d);
-        }
-    } else if (lane < 24 && ((nz >> lane) & 1)) {
-        // one instruction stream for the sixteen luma blocks (lanes 0..15) and the eight chroma blocks (lanes 16..23)
-        const int c = lane - 16;
-        int* const blk = lane < 16 ? res + (lane >> 2) * 4 * kResP + (lane & 3) * 4
-                                   : res + kResC + (c >> 2) * kResCPlane + ((c >> 1) & 1) * 4 * kResCP + (c & 1) * 4;
-        const int pitch = lane < 16 ? kResP : kResCP;
-        int d[4][4];
-        load_block4(blk, pitch, d); idct4_regs(d); store_block4(blk, pitch, d);
-    }
-    __syncwarp();
-
-    // 384 x int16 = 48 x 16 B, clamped to [-255, 255]
-    auto pack8 = [&](const int* r, int v) {              // eight consecutive samples of a row -> one 16-byte store
-        reinterpret_cast<uint4*>(sm.res)[v] = make_uint4(pack_res2(r[0], r[1]), pack_res2(r[2], r[3]), pack_res2(r[4], r[5]), pack_res2(r[6], r[7]));
-    };
-    pack8(res + (lane >> 1) * kResP + (lane & 1) * 8, lane);                                       // luma row lane >> 1, half lane & 1
-    if (lane < 16) pack8(res + kResC + (lane >> 3) * kResCPlane + (lane & 7) * kResCP, 32 + lane);   // plane lane >> 3, row lane & 7
-}
-
-// Deblock descriptor of an intra MB (Deblock::strength for intra: 4 on MB edges, 3 inside, deblock.cc:78-289; thresholds
-// :469-474).  Lanes 0..8 compute the nine threshold words, lane 0 the strengths.
-__device__ __forceinline__ void intra_write_desc(const DevPicture& pic, const IntraPre& pre, int addr, int lane)
-{
-    if (!pic.run_deblock) return;
-    const MbHdr& h = pre.h;
-    const uint32_t wL = __shfl_sync(0xFFFFFFFFu, pre.nbw, 0), wT = __shfl_sync(0xFFFFFFFFu, pre.nbw, 1);
-    const uint32_t l1 = __shfl_sync(0xFFFFFFFFu, pre.nb1, 0), l2 = __shfl_sync(0xFFFFFFFFu, pre.nb2, 0);
-    const uint32_t t1 = __shfl_sync(0xFFFFFFFFu, pre.nb1, 1), t2 = __shfl_sync(0xFFFFFFFFu, pre.nb2, 1);
-    const int idc = (pre.sl0 >> 8) & 0xFF;
-    uint32_t* out = reinterpret_cast<uint32_t*>(pic.desc + addr);
-    if (idc == 1) { if (lane == 0) *reinterpret_cast<uint4*>(out) = make_uint4(0, 0, 0, 0); return; }
-    if (lane == 0) {
-        const bool left = wL != 0xFFFFFFFFu && !(idc == 2 && (wL >> 16) != (uint32_t)h.slice_idx);
-        const bool top  = wT != 0xFFFFFFFFu && !(idc == 2 && (wT >> 16) != (uint32_t)h.slice_idx);
-        const uint32_t odd = h.t8() ? 0u : 0x33330000u;                      // edges 1 and 3 do not exist with the 8x8 transform
-        *reinterpret_cast<uint4*>(out) = make_uint4((left ? 0x4444u : 0u) | odd, 0x3333u | odd, (top ? 0x4444u : 0u) | odd, 0x3333u | odd);
-    }
-    if (lane < 9) {
-        const int pl = lane / 3, t = lane - pl * 3;
-        const uint32_t q1 = (uint32_t)h.qp_y << 16 | (uint32_t)h.qp_c[0] << 24, q2 = (uint32_t)h.qp_c[1];
-        const uint32_t p1 = t == 0 ? (wL != 0xFFFFFFFFu ? l1 : q1) : (t == 2 ? (wT != 0xFFFFFFFFu ? t1 : q1) : q1);
-        const uint32_t p2 = t == 0 ? (wL != 0xFFFFFFFFu ? l2 : q2) : (t == 2 ? (wT != 0xFFFFFFFFu ? t2 : q2) : q2);
-        out[4 + lane] = deblock_threshold_word(qp_of_plane(p1, p2, pl), qp_of_plane(q1, q2, pl), (int)(int8_t)(pre.sl0 >> 16), (int)(int8_t)(pre.sl0 >> 24));
-    }
+    p.nbw = 0xFFFFFFFFu;
+    if (nx >= 0 && nx < W && ny >= 0) p.nbw = load_hdr_word0(pic.mbs, ny * W + nx);
+    const uint4* rsrc = reinterpret_cast<const uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB);
+    p.r0 = __ldg(rsrc + lane);
+    p.r1 = lane < 16 ? __ldg(rsrc + 32 + lane) : make_uint4(0, 0, 0, 0);
+    p.ci = (int)__ldg(&(pic.slices + p.h.slice_idx)->constrained_intra_pred_flag);
 }
 
 // Reconstruction of one intra macroblock by one warp (mb_pred_intra / mb_pred_ipcm, decoder.cc:149-215): neighbour
@@ -374,9 +245,6 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
         return;
     }
 
-    // residual of the MB (independent of the neighbours; the row wavefront has done it before its dependency wait)
-    if (!kRowMode) intra_residual_mb(pic, sm, h, lane, err);
-
     // availability of the four neighbouring MBs (neighbour.cc:123-175 + slice_nr + constrained intra): the neighbour
     // exists, belongs to the same slice and -- with constrained_intra_pred -- is an intra MB.  All four precede the MB
     // in raster order.
@@ -406,6 +274,11 @@ __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, cons
     if (!kRowMode && mbx > 0) {
         if (lane < 16) TY(-1, lane) = ldcg_u8(dY + (size_t)(py + lane) * g.pitch_y + px - 1);
         else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = ldcg_u8(dC[pl] + (size_t)(cy + y) * g.pitch_c + cx - 1); }
+    }
+    {   // residual plane written by residual_kernel (48 x 16 B), or zeros
+        const bool has = h.has_resid();
+        reinterpret_cast<uint4*>(sm.res)[lane] = has ? pre.r0 : make_uint4(0, 0, 0, 0);
+        if (lane < 16) reinterpret_cast<uint4*>(sm.res)[32 + lane] = has ? pre.r1 : make_uint4(0, 0, 0, 0);
     }
     __syncwarp();                                      // tiles and residual visible
 
@@ -622,9 +495,6 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
             if (lane < 16) TY(-1, lane) = TY(15, lane);
             else { const int c = lane - 16, pl = c >> 3, y = c & 7; TC(pl, -1, y) = TC(pl, 7, y); }
         }
-        // residual and deblock descriptor need nothing from the neighbours: they run before the dependency wait
-        if (cur.h.mb_type != H264R_MB_IPCM) intra_residual_mb(pic, sm, cur.h, lane, err);
-        intra_write_desc(pic, cur, mby * W + mbx, lane);
         if (mby > 0) {
             bool waiting = need && (uint32_t)(t >> 32) != tag;
             unsigned ns = 16;
@@ -668,7 +538,7 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
 #define H264R_SPARSE_WARPS 4
 #endif
 #ifndef H264R_SPARSE_CTAS
-#define H264R_SPARSE_CTAS (40 / H264R_SPARSE_WARPS)
+#define H264R_SPARSE_CTAS (48 / H264R_SPARSE_WARPS)
 #endif
 constexpr int kSparseWarps = H264R_SPARSE_WARPS;
 __global__ void __launch_bounds__(kSparseWarps * 32, H264R_SPARSE_CTAS)
@@ -703,7 +573,6 @@ recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int
             todo &= todo - 1;
             intra_prefetch(pic, g, addr % W, addr / W, lane, nxt, err);
         }
-        intra_write_desc(pic, pre, cur_addr, lane);
         if (lane < 4 && pre.nbw != 0xFFFFFFFFu && ((pre.nbw >> 8) & H264R_MB_FLAG_INTRA)) {
             const int nx = mbx + (lane == 3 ? 1 : (lane == 1 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // left, top, top-left, top-right
             const int* flag = reinterpret_cast<const int*>(pic.mb_done + ny * W + nx);

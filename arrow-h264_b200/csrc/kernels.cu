@@ -1,13 +1,16 @@
-// sm_100a kernels of the H.264 macroblock-reconstruction path (three per wave of pictures):
+// sm_100a kernels of the H.264 macroblock-reconstruction path, per wave of pictures:
 //
-//   recon_inter2_kernel       : kernel_inter.cuh   -- inter MBs: descriptor + MC + weighted prediction + residual
-//   recon_intra_kernel        : kernel_intra.cuh   -- all-intra pictures, row wavefront: residual + prediction + descriptor
-//   recon_intra_sparse_kernel : kernel_intra.cuh   -- intra MBs of P/B pictures
-//   deblock_kernel            : kernel_deblock.cuh -- deblocking filter, row wavefront
+//   residual_kernel           : kernel_residual.cuh -- dequantisation, DC Hadamards, inverse transforms -> int16 residual plane
+//   deblock_prep_kernel       : kernel_residual.cuh -- boundary strengths + thresholds -> 64-byte descriptor per MB
+//   recon_inter2_kernel       : kernel_inter.cuh    -- inter MBs: MC + weighted prediction + residual add
+//   recon_intra_kernel        : kernel_intra.cuh    -- all-intra pictures, row wavefront
+//   recon_intra_sparse_kernel : kernel_intra.cuh    -- intra MBs of P/B pictures
+//   deblock_kernel            : kernel_deblock.cuh  -- deblocking filter, row wavefront
 //
 // Arithmetic follows the reference (src/codec/h264/decoder/{transform,inter_prediction,intra_prediction,
 // deblock}.cc); the line-by-line citations live in the CPU restatement oracle/port_recon.c, whose structure
 // these kernels mirror.  All sample arithmetic is int32; results are bit-exact by construction.
+#include "kernel_residual.cuh"
 #include "kernel_inter.cuh"
 #include "kernel_intra.cuh"
 #include "kernel_deblock.cuh"
@@ -17,6 +20,8 @@ namespace h264r {
 const char* wave_kernel_name(int which)
 {
     switch (which) {
+    case KERNEL_RESID:   return "residual_kernel";
+    case KERNEL_DBPREP:  return "deblock_prep_kernel";
     case KERNEL_INTER:   return "recon_inter2_kernel";
     case KERNEL_INTRA:   return "recon_intra_kernel + recon_intra_sparse_kernel";
     case KERNEL_DEBLOCK: return "deblock_kernel";
@@ -29,6 +34,16 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     const int nmb = w.geom.width_mbs * w.geom.height_mbs;
     const int threads = kWarpsPerCta * 32;
     const int groups = (w.geom.height_mbs + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (which == KERNEL_RESID) {
+        residual_kernel<<<dim3((nmb + kResidWarps - 1) / kResidWarps, 1, w.num_pics), kResidWarps * 32, 0, stream>>>(w.pics, w.geom, w.err);
+        return 1;
+    }
+    if (which == KERNEL_DBPREP) {
+        if (!w.any_deblock) return 0;
+        const long long total = (long long)w.num_pics * nmb;
+        deblock_prep_kernel<<<(int)((total + 127) / 128), 128, 0, stream>>>(w.pics, w.num_pics, w.geom, w.err);
+        return 1;
+    }
     if (which == KERNEL_INTER) {
         if (!w.any_inter) return 0;
         const dim3 grid((w.geom.width_mbs + 2 * kInter2Warps - 1) / (2 * kInter2Warps), w.geom.height_mbs, w.num_pics);

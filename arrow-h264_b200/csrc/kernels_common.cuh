@@ -3,10 +3,11 @@
 // 597-733, 825-910) and the deblock-descriptor primitives (boundary strengths and thresholds: deblock.cc:35-289,
 // 469-474, tables :294-324).
 //
-// Round 2: there is no residual kernel, no residual plane and no descriptor pre-pass any more.  The kernel that
-// reconstructs a macroblock (recon_inter2_kernel, recon_intra_kernel, recon_intra_sparse_kernel) dequantises and
-// inverse-transforms the MB's levels itself, in shared memory / registers, right where the residual is added, and
-// writes the MB's 64-byte deblock descriptor from the header and motion it already holds.
+// Residual and deblock descriptors keep their own kernels (residual_kernel, deblock_prep_kernel).  Folding both into the
+// reconstruction kernels was built and measured in round 2 (git 43dfbcb, profiles/r2_fused_*): bit-exact, 47 % less DRAM
+// traffic, but 8 % MORE instructions (a half warp per MB does the per-MB residual work at 16 lanes, like the residual
+// kernel did) and 64 KB of straight-line inter-kernel code that stalls on instruction fetch (no_instruction 5-7 cycles
+// per issue): 2.4x slower.  The path is bound by instruction issue, not by HBM; the split keeps each kernel near 32 KB.
 #ifndef H264R_KERNELS_COMMON_CUH_
 #define H264R_KERNELS_COMMON_CUH_
 
@@ -156,7 +157,7 @@ __device__ __forceinline__ void store_block4(int* blk, int pitch, const int (&d)
 }
 
 // one 8-point pass of the 8x8 inverse transform (transform.cc:642-733) over p[0], p[stride], ...
-__device__ __noinline__ void idct8_1d(int* p, int stride, bool final_pass)
+__device__ __forceinline__ void idct8_1d(int* p, int stride, bool final_pass)
 {
     int d0 = p[0], d1 = p[stride], d2 = p[2 * stride], d3 = p[3 * stride];
     int d4 = p[4 * stride], d5 = p[5 * stride], d6 = p[6 * stride], d7 = p[7 * stride];
@@ -181,7 +182,7 @@ __device__ __noinline__ void idct8_1d(int* p, int stride, bool final_pass)
 
 // One transmitted level -> the scratch (transform.cc:394-456: the AC levels are dequantised when they are stored, the DC
 // levels of Intra16x16 luma and of chroma stay raw until their Hadamard).  Returns the bit of the 4x4 block that received
-// the level (0..15 luma raster, 16..23 chroma), 0 if the entry carries none.  Kept out of line (three kernels, code size):
+// the level (0..15 luma raster, 16..23 chroma), 0 if the entry carries none.
 //   ctl  = cbp_luma | cbp_chroma << 8 | QpC[0] << 16 | QpC[1] << 24
 //   mode = inter | t8 << 1 | i16 << 2 | (QpY / 6) << 8 | (QpY % 6) << 16
 __device__ __forceinline__ uint32_t scatter_ctl(const MbHdr& h) { return (uint32_t)h.cbp_luma | (uint32_t)h.cbp_chroma << 8 | (uint32_t)h.qp_c[0] << 16 | (uint32_t)h.qp_c[1] << 24; }
@@ -190,7 +191,7 @@ __device__ __forceinline__ uint32_t scatter_mode(const MbHdr& h, int inter)
     const int per = h.qp_y / 6, rem = h.qp_y - per * 6;
     return (uint32_t)inter | (h.t8() ? 2u : 0u) | (h.mb_type == H264R_MB_I16x16 ? 4u : 0u) | (uint32_t)per << 8 | (uint32_t)rem << 16;
 }
-__device__ __noinline__ unsigned scatter_level(uint32_t e, uint32_t ctl, uint32_t mode, const h264r_slice* __restrict__ sl, int* cof, uint32_t* err)
+__device__ __forceinline__ unsigned scatter_level(uint32_t e, uint32_t ctl, uint32_t mode, const h264r_slice* __restrict__ sl, int* cof, uint32_t* err)
 {
     const int p = (int)(e & 0xFFFFu), l = (int)(int16_t)(e >> 16);
     if (p >= H264R_COEFFS_PER_MB) { report_error(err, ERR_LEVEL); return 0u; }
@@ -280,7 +281,7 @@ __device__ __forceinline__ int mv_differs(uint32_t a, uint32_t b)
     return (abs(dx) >= 4) | (abs(dy) >= 4);
 }
 // bs_compare_mvs, deblock.cc:35-75, on two motion entries held in registers (mv[0], mv[1], ref_idx[0..1] | ref_pic[0..1] << 16)
-__device__ __noinline__ int bs_compare(uint32_t mp0, uint32_t mp1, uint32_t rp, uint32_t mq0, uint32_t mq1, uint32_t rq)
+__device__ __forceinline__ int bs_compare(uint32_t mp0, uint32_t mp1, uint32_t rp, uint32_t mq0, uint32_t mq1, uint32_t rq)
 {
     const int p0 = (int8_t)(rp >> 16), p1 = (int8_t)(rp >> 24), q0 = (int8_t)(rq >> 16), q1 = (int8_t)(rq >> 24);
     if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;

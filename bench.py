@@ -261,6 +261,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     out_host = eng.host_alloc(fbytes * npics)          # pinned destination of every reconstructed frame
     table = (pyapi.BenchPicture * npics)()
     acct = [0] * 8
+    total_levels = 0
     pics_by_type = {"P": 0, "B": 0, "I": 0}
     frames_of = [dict() for _ in range(streams)]
     frame_of_pic = {}
@@ -280,6 +281,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
             e.head, e.stream, e.stream_words = C.addressof(pk.head), C.addressof(pk.stream), pk.words
             e.pitch_y, e.out = eng.w, out_host + k * fbytes
             acct = [x + y for x, y in zip(acct, pk.acct)]
+            total_levels += pk.info.num_levels
             k += 1
     gen_s = time.time() - t0
     total_mb = npics * nmb
@@ -425,10 +427,12 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     value = world * total_mb * args.steps / t_dev
     e2e_value = world * total_mb * args.steps / t_e2e
     peak, peak_src = peaks()
-    names = ["inter", "intra", "deblock"]
-    # algorithmic bytes of each kernel's own pass (SURVEY 8d formula restricted to its MBs; deblock: 32 + 384 read, 384 written,
-    # + 192 motion for inter MBs)
-    k_bytes = [acct[1], acct[2], acct[3]]
+    names = ["residual", "inter", "intra", "deblock_prep", "deblock"]
+    assert len(names) == len(kernels)
+    # algorithmic bytes of each kernel's own pass: residual = levels in + 768 B residual plane out per coded MB;
+    # inter / intra = SURVEY 8d formula restricted to their MBs; deblock_prep = headers + motion in, 64 B out;
+    # deblock: 32 + 384 read, 384 written (+ 192 motion for inter MBs)
+    k_bytes = [4 * total_levels + acct[6] * (32 + 768), acct[1], acct[2], acct[7] * (32 + 64) + acct[4] * 192, acct[3]]
     nk = len(names)
     dom = max(range(nk), key=lambda i: kms[i + 1])
     dom_ms_per_launch = kms[dom + 1] / max(1, kn[dom + 1])
