@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 
+#include <emmintrin.h>
+
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -19,6 +21,25 @@ double now_s()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// What a parser thread does to the staging memory is WRITE it, once, front to back.  The stand-in copies a pre-parsed
+// picture there with streaming stores: the lines are written whole, so reading them into the cache first (the
+// read-for-ownership of an ordinary store) would only add host-memory traffic next to the two DMA directions.
+void stream_copy(void* dst, const void* src, size_t bytes)
+{
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    const uint8_t* s = static_cast<const uint8_t*>(src);
+    while (bytes && (reinterpret_cast<uintptr_t>(d) & 15)) { *d++ = *s++; --bytes; }
+    size_t n = bytes / 64;
+    for (; n; --n, d += 64, s += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16)),
+                      c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d), a); _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+    }
+    bytes &= 63;
+    memcpy(d, s, bytes);
+}
+
 struct FeedShared {
     std::mutex mu;
     std::condition_variable cv;
@@ -26,7 +47,6 @@ struct FeedShared {
     int total_submitted = 0;
     bool starving = false;               // a feeder found every staging slot filled or queued: flush now
     int error = 0;
-    std::atomic<int> steps_done{0};
 };
 
 } // namespace
@@ -60,8 +80,9 @@ double h264r_bench_feed(h264r_ctx* ctx, const h264r_bench_picture* pics, int num
                     std::this_thread::sleep_for(std::chrono::microseconds(50));
                 }
                 if (rc == H264R_OK) {
-                    memcpy(bufs.mbs, p.head, head_mbs + sizeof(h264r_slice) * (size_t)p.pp.num_slices);
-                    memcpy(bufs.stream, p.stream, sizeof(uint32_t) * (size_t)p.stream_words);
+                    stream_copy(bufs.mbs, p.head, head_mbs + sizeof(h264r_slice) * (size_t)p.pp.num_slices);
+                    stream_copy(bufs.stream, p.stream, sizeof(uint32_t) * (size_t)p.stream_words);
+                    _mm_sfence();                                // the streaming stores are globally visible before the submit
                     rc = h264r_picture_submit(ctx, bufs.picture, p.stream_words);
                 }
                 fill_s[(size_t)t] += now_s() - t0;

@@ -36,6 +36,8 @@ struct DevPicture {
     DeblockDesc*           desc;                      // [nmb], device only
     uint64_t*              mbox;                      // [nmb][24], device only: row-to-row mailboxes { 4 samples, epoch }
     uint32_t*              mb_done;                   // [nmb], device only: epoch stamp of the launch that reconstructed the intra MB
+    uint32_t*              intra_list;                // [nmb], device only: raster-ordered addresses of the intra MBs (intra_list_kernel)
+    uint32_t*              intra_count;               // device only: entries of intra_list
     uint32_t               stream_words;              // words of `stream` in use (bounds of coeff_offset / motion)
     int                    num_slices;
     int                    num_refs;
@@ -48,6 +50,7 @@ struct WaveLaunch {
     const DevPicture* pics;          // device array
     int   num_pics;
     int*  tickets;                   // device: work-ticket counters ([0] intra rows, [1] deblock, [2] sparse intra), zeroed per wave (64 ints)
+    uint32_t* wave_max;              // device word of this wave: largest intra_count of its pictures (intra_list_kernel)
     uint32_t* err;                   // host-mapped word: kernels OR in a bit when they meet a description outside its domain
     FrameGeom geom;
     int   any_inter, any_deblock;
@@ -56,8 +59,8 @@ struct WaveLaunch {
 };
 
 // Kernel launchers of one wave (kernels.cu).  Returns the number of kernels launched (0 when the wave has no work of that kind).
-// KERNEL_RESID and KERNEL_DBPREP need nothing but the picture description (side stream, a wave ahead).
-enum { KERNEL_RESID = 0, KERNEL_INTER = 1, KERNEL_INTRA = 2, KERNEL_DBPREP = 3, KERNEL_DEBLOCK = 4, KERNEL_KINDS = 5 };
+// KERNEL_RESID, KERNEL_DBPREP and KERNEL_LIST need nothing but the picture description (side stream, a wave ahead).
+enum { KERNEL_RESID = 0, KERNEL_INTER = 1, KERNEL_INTRA = 2, KERNEL_DBPREP = 3, KERNEL_DEBLOCK = 4, KERNEL_LIST = 5, KERNEL_KINDS = 6 };
 int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream);
 const char* wave_kernel_name(int which);
 

@@ -47,6 +47,7 @@ struct Slot {
     DeblockDesc* dev_desc = nullptr;          // device only: output of the deblock pre-pass
     int16_t* dev_resid = nullptr;             // device only: residual plane [nmb][384]
     uint32_t* dev_mb_done = nullptr;          // device only: per-MB epoch stamps of the sparse intra kernel
+    uint32_t* dev_intra_list = nullptr;       // device only: [nmb + 1] = count, then the addresses of the picture's intra MBs
     uint64_t* dev_mbox = nullptr;             // device only: row-to-row mailboxes [nmb][24]
     SlotState state = SLOT_FREE;
     h264r_pic_params pp;
@@ -103,6 +104,8 @@ struct h264r_ctx {
     size_t table_entries = 0, table_next = 0;
     std::deque<TableRegion> table_busy;       // regions of flushes that may still be running
     int* d_tickets = nullptr;                 // 64 ints, zeroed per wave on the compute stream
+    uint32_t* d_wave_words = nullptr;         // ring of per-wave device words (largest intra MB count of the wave)
+    size_t wave_word_next = 0;
     uint32_t* h_err = nullptr;                // host-mapped error word the kernels OR into
     uint32_t* d_err = nullptr;
     std::vector<WaveRecord> last_waves;
@@ -228,6 +231,8 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
             CU(cudaStreamWaitEvent(side, rec.ev_done, 0));
             for (const WaveCopy& c : rec.copies) if (c.prev_done) CU(cudaStreamWaitEvent(side, c.prev_done, 0));
         }
+        if (rec.launch.any_inter) CU(cudaMemsetAsync(rec.launch.wave_max, 0, sizeof(uint32_t), side));
+        { const int rc = launch(rec, KERNEL_LIST, side); if (rc != H264R_OK) return rc; }
         { const int rc = launch(rec, KERNEL_RESID, side); if (rc != H264R_OK) return rc; }
         { const int rc = launch(rec, KERNEL_DBPREP, side); if (rc != H264R_OK) return rc; }
         if (!time_kernels) {
@@ -320,12 +325,14 @@ void h264r_destroy(h264r_ctx* ctx)
         if (ctx->slots[0].dev_desc) cudaFree(ctx->slots[0].dev_desc);
         if (ctx->slots[0].dev_resid) cudaFree(ctx->slots[0].dev_resid);
         if (ctx->slots[0].dev_mb_done) cudaFree(ctx->slots[0].dev_mb_done);
+        if (ctx->slots[0].dev_intra_list) cudaFree(ctx->slots[0].dev_intra_list);
         if (ctx->slots[0].dev_mbox) cudaFree(ctx->slots[0].dev_mbox);
     }
     if (ctx->dummy_frame) cudaFree(ctx->dummy_frame);
     if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
     if (ctx->d_pics) cudaFree(ctx->d_pics);
     if (ctx->d_tickets) cudaFree(ctx->d_tickets);
+    if (ctx->d_wave_words) cudaFree(ctx->d_wave_words);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -373,7 +380,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
 
     // every CUDA failure below takes the one cleanup path (h264r_destroy frees whatever exists)
     uint8_t* h_arena = nullptr; uint8_t* d_arena = nullptr; DeblockDesc* d_desc = nullptr; int16_t* d_resid = nullptr;
-    uint32_t* d_done = nullptr; uint64_t* d_mbox = nullptr;
+    uint32_t* d_done = nullptr; uint64_t* d_mbox = nullptr; uint32_t* d_list = nullptr;
     const size_t mbox_words = (size_t)24 * nmb;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -394,6 +401,9 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_done, sizeof(uint32_t) * nmb * nslots);
     if (d_done) ctx->slots[0].dev_mb_done = d_done;
     if (e == cudaSuccess) e = cudaMemset(d_done, 0, sizeof(uint32_t) * nmb * nslots);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_list, sizeof(uint32_t) * (nmb + 1) * nslots);
+    if (d_list) ctx->slots[0].dev_intra_list = d_list;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_wave_words, sizeof(uint32_t) * kEventRing);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_mbox, sizeof(uint64_t) * mbox_words * nslots);
     if (d_mbox) ctx->slots[0].dev_mbox = d_mbox;
     if (e == cudaSuccess) e = cudaMemset(d_mbox, 0, sizeof(uint64_t) * mbox_words * nslots);   // epoch 0 is never used
@@ -417,6 +427,7 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
         s.dev_desc = d_desc + nmb * i;
         s.dev_resid = d_resid + (size_t)H264R_COEFFS_PER_MB * nmb * i;
         s.dev_mb_done = d_done + nmb * i;
+        s.dev_intra_list = d_list + (nmb + 1) * i;
         s.dev_mbox = d_mbox + mbox_words * i;
         ctx->free_slots.push_back((int)(nslots - 1 - i));          // slot 0 is handed out first
     }
@@ -598,6 +609,7 @@ int h264r_flush(h264r_ctx* ctx)
         p.resid = s.dev_resid;
         p.mbox = s.dev_mbox;
         p.mb_done = s.dev_mb_done;
+        p.intra_count = s.dev_intra_list; p.intra_list = s.dev_intra_list + 1;
         p.stream_words = s.stream_words;
         p.num_slices = s.pp.num_slices; p.num_refs = s.pp.num_ref_frames;
         p.run_deblock = s.pp.run_deblock; p.all_intra = s.all_intra;
@@ -615,6 +627,8 @@ int h264r_flush(h264r_ctx* ctx)
         WaveLaunch& L = rec.launch;
         L.pics = d_table + b; L.num_pics = e - b; L.tickets = ctx->d_tickets; L.err = ctx->d_err; L.geom = ctx->geom;
         L.any_inter = L.any_deblock = L.any_intra_rows = 0; L.epoch = 0;
+        L.wave_max = ctx->d_wave_words + ctx->wave_word_next;
+        ctx->wave_word_next = (ctx->wave_word_next + 1) % kEventRing;
         rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx); rec.ev_side = take_event(ctx);
         if (!rec.ev_h2d || !rec.ev_done || !rec.ev_side) return H264R_ERR_CUDA;
         for (int k = b; k < e; ++k) {

@@ -50,7 +50,7 @@ struct __align__(16) Inter2Smem {
 // whole 8x8 quadrant of the block.  Partition steps in 4x4 units per type 0..7 ({0,0},{4,4},{4,2},{2,4},{2,2},{2,1},
 // {1,2},{1,1}) are nibbles of two constants.
 __device__ __forceinline__ void partition_of_block2(const MbHdr& h, int is_b, int direct_spatial, const DevPicture& pic, int direct8x8,
-                                                    int blk, int& origin, int& dir, bool& covers8x8, uint32_t* err)
+                                                    int blk, int& origin, int& dir, bool& covers8x8)
 {
     const int bx = blk & 3, by = blk >> 2;
     int sh0 = (0x11222440u >> (4 * (h.mb_type & 7))) & 7, sv0 = (0x12124240u >> (4 * (h.mb_type & 7))) & 7;
@@ -62,10 +62,9 @@ __device__ __forceinline__ void partition_of_block2(const MbHdr& h, int is_b, in
     int sh4 = (0x11222440u >> (4 * (mode & 7))) & 7, sv4 = (0x12124240u >> (4 * (mode & 7))) & 7;
     if (mode == 0) sh4 = sv4 = direct8x8 ? 2 : 1;
     if (is_b && h.mb_type == H264R_MB_8x8 && direct_spatial) {
-        const uint32_t rw = __ldg(pic.stream + packed_entry_word(pic, h.packed, j0 * 4 + i0, err) + 2);
+        const uint32_t rw = __ldg(pic.stream + packed_entry_word(h.packed, j0 * 4 + i0) + 2);
         pd = (int8_t)(rw >> 8) < 0 ? 0 : ((int8_t)rw < 0 ? 1 : 2);
     }
-    if (pd > 2) { report_error(err, ERR_HEADER); pd = 2; }
     const int i = bx & ~(sh4 - 1), j = by & ~(sv4 - 1);   // partitions are aligned to their own size
     origin = j * 4 + i;
     dir = pd;
@@ -80,7 +79,7 @@ constexpr int kInter2Warps = H264R_INTER2_WARPS;       // warps per CTA (each wa
 // quadrant its four lanes share one 13x13 luma / 5x5 chroma window, otherwise every block has its own 9x9 / 3x3 window.
 // grid = (ceil(width_mbs / (2 * warps)), height_mbs, pictures of the wave)
 __global__ void __launch_bounds__(kInter2Warps * 32, H264R_INTER2_CTAS)
-recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* err)
+recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 {
     __shared__ __align__(16) Inter2Smem smem_all[kInter2Warps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,10 +90,9 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* 
     const int W = g.width_mbs;
     if ((blockIdx.x * kInter2Warps + warp) * 2 >= W) return;
     const int addr = mby * W + min(mbx, W - 1);
-    MbHdr h = load_hdr(pic.mbs, addr);
+    const MbHdr h = load_hdr(pic.mbs, addr);
     const bool valid = mbx < W && !h.intra();
     if (!__any_sync(0xFFFFFFFFu, valid)) return;
-    sanitize_hdr(h, pic, err);
     Inter2Smem& sm = smem_all[warp];
     const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
     const int wY = W * 16, hY = g.height_mbs * 16, wC = wY >> 1, hC = hY >> 1;
@@ -112,8 +110,8 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* 
     int origin = 0, pd = 0; bool uni = true;
     uint32_t mvw0 = 0, mvw1 = 0, rw = 0;                 // the motion entry of this block's partition
     if (valid) {
-        partition_of_block2(h, is_b, direct_spatial, pic, pic.direct8x8, b, origin, pd, uni, err);
-        const uint32_t* e = pic.stream + packed_entry_word(pic, h.packed, origin, err);
+        partition_of_block2(h, is_b, direct_spatial, pic, pic.direct8x8, b, origin, pd, uni);
+        const uint32_t* e = pic.stream + packed_entry_word(h.packed, origin);
         mvw0 = __ldg(e); mvw1 = __ldg(e + 1); rw = __ldg(e + 2);
     }
     const int q = (by >> 1) * 2 + (bx >> 1), sb = (by & 1) * 2 + (bx & 1);        // quadrant, block inside the quadrant
@@ -134,9 +132,10 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* 
         int loff = 2, coff = 0;
         if (active) {
             refidx = (int)(int8_t)(rw >> (8 * list));
-            int slot = (int)(int8_t)(rw >> (16 + 8 * list));
-            if ((unsigned)slot >= (unsigned)pic.num_refs) { report_error(err, ERR_MOTION); slot = 0; }
-            const uint8_t* __restrict__ rbase = pic.ref[slot];
+            // the entry names the reference picture itself (ref_pic = slot of pic_params.ref_frames, the identity the
+            // deblocking rule compares); slots the picture does not have point at a dummy frame
+            const int slot = (int)(int8_t)(rw >> (16 + 8 * list));
+            const uint8_t* __restrict__ rbase = pic.ref[slot & 31];
             const uint32_t mvw = list ? mvw1 : mvw0;
             const int mvx = (int)(int16_t)(mvw & 0xFFFF), mvy = (int)(int16_t)(mvw >> 16);
             vx = (mbx * 16 + bx * 4) * 4 + mvx; vy = (mby * 16 + by * 4) * 4 + mvy;       // this block's position

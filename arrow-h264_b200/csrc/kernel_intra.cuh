@@ -1,9 +1,8 @@
 // Intra reconstruction (intra_prediction.cc:137-904, decoder.cc:149-215); the residual comes from residual_kernel's plane:
 //   recon_intra_kernel        : all-intra pictures, one warp per MB ROW; rows form a 2:1 wavefront (MB(x,y) needs (x-1,y),
 //                               (x-1,y-1), (x,y-1), (x+1,y-1)) and talk through mailboxes
-//   recon_intra_sparse_kernel : the intra MBs of P/B pictures: one warp per 32 consecutive MB addresses, which finds its
-//                               intra MBs with one ballot over the headers (no list from the host); per-MB epoch stamps
-//                               between intra neighbours
+//   intra_list_kernel         : raster-ordered list of the intra MBs of every P/B picture of a wave (no list from the host)
+//   recon_intra_sparse_kernel : the intra MBs of P/B pictures, one warp each; per-MB epoch stamps between intra neighbours
 #ifndef H264R_KERNEL_INTRA_CUH_
 #define H264R_KERNEL_INTRA_CUH_
 
@@ -197,11 +196,10 @@ struct IntraPre {
     uint4 r0, r1;                   // residual chunks lane and 32 + lane (lanes 0..15) of the MB's 48 x 16 bytes
     int ci;
 };
-__device__ __forceinline__ void intra_prefetch(const DevPicture& pic, const FrameGeom& g, int mbx, int mby, int lane, IntraPre& p, uint32_t* err)
+__device__ __forceinline__ void intra_prefetch(const DevPicture& pic, const FrameGeom& g, int mbx, int mby, int lane, IntraPre& p)
 {
     const int W = g.width_mbs, addr = mby * W + mbx;
     p.h = load_hdr(pic.mbs, addr);
-    sanitize_hdr(p.h, pic, err);
     const int k = lane & 3;
     const int nx = mbx + (k == 3 ? 1 : (k == 1 ? 0 : -1)), ny = mby - (k == 0 ? 0 : 1);
     p.nbw = 0xFFFFFFFFu;
@@ -219,7 +217,7 @@ __device__ __forceinline__ void intra_prefetch(const DevPicture& pic, const Fram
 // left column (carried in the tile from the previous MB of the row) into the tiles; otherwise they are read from the frame.
 template <bool kRowMode>
 __device__ __forceinline__ void intra_reconstruct_mb(const DevPicture& pic, const FrameGeom& g, IntraSmem& sm, const IntraPre& pre,
-                                                     int mbx, int mby, int lane, uint32_t* err)
+                                                     int mbx, int mby, int lane)
 {
     const MbHdr& h = pre.h;
     const int W = g.width_mbs;
@@ -455,7 +453,7 @@ constexpr uint32_t kIntraEpochTag = 0x80000000u;
 // row of MB x, the first eight bottom samples of MB x+1 and the last bottom sample of MB x-1: 24 consecutive mailbox
 // words, polled by 24 lanes with one load each.  The left column never leaves the tile.  No fence, no progress counter.
 __global__ void __launch_bounds__(kWarpsPerCta * 32, H264R_INTRA_CTAS)
-recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g, uint32_t epoch, uint32_t* err)
+recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g, uint32_t epoch)
 {
     __shared__ __align__(16) IntraSmem smem_all[kWarpsPerCta];
     __shared__ int s_ticket;
@@ -479,7 +477,7 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
     const bool has_below = mby + 1 < H;
 
     IntraPre nxt;
-    intra_prefetch(pic, g, 0, mby, lane, nxt, err);
+    intra_prefetch(pic, g, 0, mby, lane, nxt);
     for (int mbx = 0; mbx < W; ++mbx) {
         const IntraPre cur = nxt;
         // the 24 words around MB mbx of the row above: lane j = word j & 7 of MB mbx - 1 + (j >> 3)
@@ -489,7 +487,7 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
         const bool need = mby > 0 && lane < 24 && bx >= 0 && bx < W &&
                           (lane < 8 ? (bw == 3 || bw == 5 || bw == 7) : (lane < 16 ? true : bw < 2));
         if (need) t = ld_mbox(box_in + (size_t)bx * kIntraBoxWords + bw);
-        if (mbx + 1 < W) intra_prefetch(pic, g, mbx + 1, mby, lane, nxt, err);   // lands while this MB is reconstructed
+        if (mbx + 1 < W) intra_prefetch(pic, g, mbx + 1, mby, lane, nxt);   // lands while this MB is reconstructed
         __syncwarp();                                      // the previous MB's tile has been stored and posted
         if (mbx > 0) {                                     // left column = the previous MB's last column, still in the tile
             if (lane < 16) TY(-1, lane) = TY(15, lane);
@@ -516,7 +514,7 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
                 else reinterpret_cast<uint32_t*>(sm.tc[(bw - 4) >> 1])[1 + (bw & 1)] = v;
             } else if (lane < 24 && bw < 2) reinterpret_cast<uint32_t*>(sm.ty)[5 + bw] = v;
         }
-        intra_reconstruct_mb<true>(pic, g, sm, cur, mbx, mby, lane, err);
+        intra_reconstruct_mb<true>(pic, g, sm, cur, mbx, mby, lane);
         // post the MB's bottom rows (the tile is final: the MB's own stores read it after a __syncwarp)
         if (has_below && lane < 8) {
             const uint32_t w = lane < 4 ? reinterpret_cast<const uint32_t*>(&TY(0, 15))[lane]
@@ -526,14 +524,54 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
     }
 }
 
-// Intra MBs of pictures that also have inter MBs (P/B pictures: a few percent of the MBs, mostly isolated).  One warp
-// per 32 consecutive MB addresses: lane i reads header word 0 of MB 32 w + i, one ballot gives the warp its intra MBs --
-// the host sends no list and does not look at the macroblocks at all.  The warp reconstructs them in raster order; an MB
-// waits only for those of its four neighbours (left, top-left, top, top-right) that are intra MBs themselves -- inter
-// neighbours were reconstructed by recon_inter2_kernel.  Completion is an epoch stamp per MB (no clearing between
-// launches).  Tickets interleave the pictures of the wave and run in raster order inside a picture, so a warp only ever
-// waits for warps that already hold a ticket.  Header, neighbour headers and levels of the warp's next intra MB are in
-// flight while the current one is reconstructed.
+// Intra MBs of pictures that also have inter MBs (P/B pictures: a few percent of the MBs, mostly isolated).  The host does
+// not look at the macroblocks at all: intra_list_kernel (side stream, one CTA per picture) compacts the addresses of the
+// intra MBs of a picture, in raster order, into the picture's device list.
+constexpr int kListThreads = 256;
+__global__ void __launch_bounds__(kListThreads)
+intra_list_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* wave_max)
+{
+    __shared__ uint32_t s_warp[kListThreads / 32];
+    __shared__ uint32_t s_base;
+    const DevPicture& pic = pics[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (pic.all_intra) { if (tid == 0) *pic.intra_count = 0; return; }
+    const int nmb = g.width_mbs * g.height_mbs, words = (nmb + 31) / 32;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int chunk = 0; chunk < words; chunk += kListThreads) {
+        // thread t: the intra mask of MBs 32 (chunk + t) .. + 31 (32 independent loads of header word 0)
+        const int first = (chunk + tid) * 32;
+        uint32_t mask = 0;
+        if (first < nmb) {
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i)
+                if (first + i < nmb && ((load_hdr_word0(pic.mbs, first + i) >> 8) & H264R_MB_FLAG_INTRA)) mask |= 1u << i;
+        }
+        // exclusive scan of the counts over the CTA
+        const uint32_t n = __popc(mask);
+        uint32_t incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t off = s_base + incl - n;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        uint32_t total = 0;
+        for (int w = 0; w < kListThreads / 32; ++w) total += s_warp[w];
+        while (mask) { pic.intra_list[off++] = (uint32_t)(first + __ffs(mask) - 1); mask &= mask - 1; }
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+    }
+    if (tid == 0) { *pic.intra_count = s_base; atomicMax(wave_max, s_base); }
+}
+
+// recon_intra_sparse_kernel: persistent CTAs; a CTA takes a ticket = four consecutive entries of one picture's list (one
+// warp per intra MB).  Tickets interleave the pictures of the wave and run in raster order inside a picture; an MB waits
+// only for those of its four neighbours (left, top-left, top, top-right) that are intra MBs themselves -- inter neighbours
+// were reconstructed by recon_inter2_kernel -- i.e. only for MBs of earlier tickets, which some running CTA already
+// holds: residency order cannot deadlock.  Completion is an epoch stamp per MB (no clearing between launches).
 #ifndef H264R_SPARSE_WARPS
 #define H264R_SPARSE_WARPS 4
 #endif
@@ -542,37 +580,30 @@ recon_intra_kernel(const DevPicture* __restrict__ pics, int num_pics, int* ticke
 #endif
 constexpr int kSparseWarps = H264R_SPARSE_WARPS;
 __global__ void __launch_bounds__(kSparseWarps * 32, H264R_SPARSE_CTAS)
-recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, FrameGeom g, uint32_t epoch, uint32_t* err)
+recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, const uint32_t* __restrict__ wave_max,
+                          FrameGeom g, uint32_t epoch)
 {
     __shared__ __align__(16) IntraSmem smem_all[kSparseWarps];
     __shared__ int s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[2], 1);
-    __syncthreads();
-    const int grp = s_ticket / num_pics, pic_i = s_ticket - grp * num_pics;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const DevPicture& pic = pics[pic_i];
-    if (pic.all_intra) return;
     const int W = g.width_mbs, nmb = W * g.height_mbs;
-    const int first = (grp * kSparseWarps + warp) * 32;
-    if (first >= nmb) return;
-    const int my = first + lane;
-    const uint32_t w0 = my < nmb ? load_hdr_word0(pic.mbs, my) : 0u;
-    unsigned todo = __ballot_sync(0xFFFFFFFFu, (w0 >> 8) & H264R_MB_FLAG_INTRA);
-    if (!todo) return;
-    IntraPre nxt;
-    int addr = first + __ffs(todo) - 1;
-    todo &= todo - 1;
-    intra_prefetch(pic, g, addr % W, addr / W, lane, nxt, err);     // header, neighbour headers, levels: all in flight at once
+    const int groups = ((int)__ldg(wave_max) + kSparseWarps - 1) / kSparseWarps;       // of the picture with the most intra MBs
 #pragma unroll 1
     for (;;) {
-        const IntraPre pre = nxt;
-        const int mby = addr / W, mbx = addr - mby * W, cur_addr = addr;
-        const bool more = todo != 0;
-        if (more) {
-            addr = first + __ffs(todo) - 1;
-            todo &= todo - 1;
-            intra_prefetch(pic, g, addr % W, addr / W, lane, nxt, err);
-        }
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[2], 1);
+        __syncthreads();
+        const int ticket = s_ticket;
+        __syncthreads();                                   // everybody has read the ticket before thread 0 takes the next one
+        const int grp = ticket / num_pics, pic_i = ticket - grp * num_pics;
+        if (grp >= groups) return;
+        const DevPicture& pic = pics[pic_i];
+        const int entry = grp * kSparseWarps + warp;
+        if (pic.all_intra || entry >= (int)__ldg(pic.intra_count)) continue;
+        const int addr = (int)__ldg(pic.intra_list + entry);
+        if (addr >= nmb) continue;
+        const int mby = addr / W, mbx = addr - mby * W;
+        IntraPre pre;
+        intra_prefetch(pic, g, mbx, mby, lane, pre);     // header, neighbour headers, residual: all in flight at once
         if (lane < 4 && pre.nbw != 0xFFFFFFFFu && ((pre.nbw >> 8) & H264R_MB_FLAG_INTRA)) {
             const int nx = mbx + (lane == 3 ? 1 : (lane == 1 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // left, top, top-left, top-right
             const int* flag = reinterpret_cast<const int*>(pic.mb_done + ny * W + nx);
@@ -580,10 +611,9 @@ recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int
             while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
         }
         __syncwarp();
-        intra_reconstruct_mb<false>(pic, g, smem_all[warp], pre, mbx, mby, lane, err);
+        intra_reconstruct_mb<false>(pic, g, smem_all[warp], pre, mbx, mby, lane);
         __syncwarp();
-        if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + cur_addr), (int)epoch);
-        if (!more) break;
+        if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + addr), (int)epoch);
     }
 }
 

@@ -1,6 +1,7 @@
 // residual_kernel: one warp per MB that received levels: scatter-dequantise the level list into shared memory, luma 4x4 /
 // chroma 2x2 DC Hadamards, 4x4 / 8x8 inverse transforms only for blocks that received a level, saturating pack to int16
 // -> the picture's residual plane [nmb][384] (transform.cc:394-456, 460-554, 597-733, 825-910).
+//                  It is also the one place where the description of a picture is checked (validate_and_repair).
 // deblock_prep_kernel: boundary strengths and alpha / beta / tc0 per MB (deblock.cc:35-289, 469-474), one thread per MB.
 // Both need nothing but the picture description: they run on the side stream, a wave ahead of the reconstruction.
 #ifndef H264R_KERNEL_RESIDUAL_CUH_
@@ -123,7 +124,7 @@ residual_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* err)
     if (addr >= nmb) return;
     const DevPicture& pic = pics[blockIdx.z];
     MbHdr h = load_hdr(pic.mbs, addr);
-    sanitize_hdr(h, pic, err);
+    validate_and_repair(h, pic, addr, lane, err);
     if (!h.has_resid()) return;
     residual_mb(pic, h, smem_all[warp].cof, reinterpret_cast<uint4*>(pic.resid + (size_t)addr * H264R_COEFFS_PER_MB), lane, err);
 }
@@ -145,7 +146,7 @@ __device__ __forceinline__ HdrLite load_hdr_lite(const h264r_mb* mbs, int addr)
 }
 
 __global__ void __launch_bounds__(128, H264R_PREP_CTAS)
-deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g, uint32_t* err)
+deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom g)
 {
     const int W = g.width_mbs, nmb = W * g.height_mbs;
     const long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,7 +156,7 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
     if (!pic.run_deblock) return;
     const int mbx = q % W, mby = q / W;
     const HdrLite Q = load_hdr_lite(pic.mbs, q);
-    const h264r_slice* sl = pic.slices + min(Q.slice_idx, pic.num_slices - 1);
+    const h264r_slice* sl = pic.slices + Q.slice_idx;
     const uint32_t s0 = __ldg(reinterpret_cast<const uint32_t*>(sl));      // slice_type | idc << 8 | FilterOffsetA << 16 | FilterOffsetB << 24
     const int idc = (s0 >> 8) & 0xFF;
     uint4* out = reinterpret_cast<uint4*>(pic.desc + q);
@@ -192,7 +193,7 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
                 uint32_t v = 0;
                 if (((Q.cbp_blks >> blkQ) & 1) || ((pcbp >> blkP) & 1)) v = 2;
                 else if (!same_part) {
-                    const uint32_t wp = packed_entry_word(pic, e ? Q.packed : PN.packed, blkP, err), wq = packed_entry_word(pic, Q.packed, blkQ, err);
+                    const uint32_t wp = packed_entry_word(e ? Q.packed : PN.packed, blkP), wq = packed_entry_word(Q.packed, blkQ);
                     if (wp != wq) {                              // the same entry: same pictures, same vectors
                         const uint32_t* ep = pic.stream + wp; const uint32_t* eq = pic.stream + wq;
                         v = bs_compare(__ldg(ep), __ldg(ep + 1), __ldg(ep + 2), __ldg(eq), __ldg(eq + 1), __ldg(eq + 2));

@@ -4,12 +4,15 @@
 //   deblock_prep_kernel       : kernel_residual.cuh -- boundary strengths + thresholds -> 64-byte descriptor per MB
 //   recon_inter2_kernel       : kernel_inter.cuh    -- inter MBs: MC + weighted prediction + residual add
 //   recon_intra_kernel        : kernel_intra.cuh    -- all-intra pictures, row wavefront
+//   intra_list_kernel         : kernel_intra.cuh    -- addresses of the intra MBs of P/B pictures (the host sends none)
 //   recon_intra_sparse_kernel : kernel_intra.cuh    -- intra MBs of P/B pictures
 //   deblock_kernel            : kernel_deblock.cuh  -- deblocking filter, row wavefront
 //
 // Arithmetic follows the reference (src/codec/h264/decoder/{transform,inter_prediction,intra_prediction,
 // deblock}.cc); the line-by-line citations live in the CPU restatement oracle/port_recon.c, whose structure
 // these kernels mirror.  All sample arithmetic is int32; results are bit-exact by construction.
+#include <algorithm>
+
 #include "kernel_residual.cuh"
 #include "kernel_inter.cuh"
 #include "kernel_intra.cuh"
@@ -22,6 +25,7 @@ const char* wave_kernel_name(int which)
     switch (which) {
     case KERNEL_RESID:   return "residual_kernel";
     case KERNEL_DBPREP:  return "deblock_prep_kernel";
+    case KERNEL_LIST:    return "intra_list_kernel";
     case KERNEL_INTER:   return "recon_inter2_kernel";
     case KERNEL_INTRA:   return "recon_intra_kernel + recon_intra_sparse_kernel";
     case KERNEL_DEBLOCK: return "deblock_kernel";
@@ -41,24 +45,31 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     if (which == KERNEL_DBPREP) {
         if (!w.any_deblock) return 0;
         const long long total = (long long)w.num_pics * nmb;
-        deblock_prep_kernel<<<(int)((total + 127) / 128), 128, 0, stream>>>(w.pics, w.num_pics, w.geom, w.err);
+        deblock_prep_kernel<<<(int)((total + 127) / 128), 128, 0, stream>>>(w.pics, w.num_pics, w.geom);
+        return 1;
+    }
+    if (which == KERNEL_LIST) {
+        if (!w.any_inter) return 0;
+        intra_list_kernel<<<w.num_pics, kListThreads, 0, stream>>>(w.pics, w.geom, w.wave_max);
         return 1;
     }
     if (which == KERNEL_INTER) {
         if (!w.any_inter) return 0;
         const dim3 grid((w.geom.width_mbs + 2 * kInter2Warps - 1) / (2 * kInter2Warps), w.geom.height_mbs, w.num_pics);
-        recon_inter2_kernel<<<grid, kInter2Warps * 32, 0, stream>>>(w.pics, w.geom, w.err);
+        recon_inter2_kernel<<<grid, kInter2Warps * 32, 0, stream>>>(w.pics, w.geom);
         return 1;
     }
     if (which == KERNEL_INTRA) {
         int n = 0;
         if (w.any_intra_rows) {
-            recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch, w.err);
+            recon_intra_kernel<<<w.num_pics * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
             ++n;
         }
         if (w.any_inter) {                                   // pictures with P / B slices may hold intra MBs anywhere
-            const int words = (nmb + 31) / 32, grps = (words + kSparseWarps - 1) / kSparseWarps;
-            recon_intra_sparse_kernel<<<w.num_pics * grps, kSparseWarps * 32, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch, w.err);
+            // persistent CTAs (the number of intra MBs is only known on the device): one round of resident CTAs, fewer for tiny waves
+            const long long most = ((long long)w.num_pics * nmb + kSparseWarps - 1) / kSparseWarps;
+            const int ctas = (int)std::min<long long>(most, 148LL * H264R_SPARSE_CTAS);
+            recon_intra_sparse_kernel<<<ctas, kSparseWarps * 32, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.wave_max, w.geom, w.epoch);
             ++n;
         }
         return n;

@@ -82,20 +82,45 @@ __device__ __forceinline__ uint32_t load_hdr_word0(const h264r_mb* mbs, int addr
     return __ldg(reinterpret_cast<const unsigned int*>(mbs + addr));
 }
 
-// The host no longer walks the macroblocks at submit time: whatever would lead a kernel out of bounds is clamped
-// here, by the warp that reads the header anyway, and reported.
-__device__ __forceinline__ void sanitize_hdr(MbHdr& h, const DevPicture& pic, uint32_t* err)
+// The host no longer walks the macroblocks at submit time.  residual_kernel, which reads every header of a picture before
+// any other kernel of the wave does, checks the description once and REPAIRS the HBM copy where a value would lead a
+// kernel out of bounds (slice index, QPs, level range, motion index); the other kernels read repaired headers and carry
+// no checks of their own beyond index masks.  One warp per MB; lanes share the work.
+__device__ __forceinline__ void validate_and_repair(MbHdr& h, const DevPicture& pic, int addr, int lane, uint32_t* err)
 {
     const bool intra = h.intra();
-    bool bad = h.slice_idx >= pic.num_slices;
-    bad |= ((unsigned)h.qp_y > 51u) | ((unsigned)h.qp_c[0] > 51u) | ((unsigned)h.qp_c[1] > 51u);
-    bad |= h.mb_type > H264R_MB_IPCM || h.mb_type == 11 || (intra ? h.mb_type < H264R_MB_I4x4 : h.mb_type > H264R_MB_8x8);
-    bad |= h.coeff_offset > pic.stream_words || (uint32_t)h.coeff_count > pic.stream_words - h.coeff_offset;
-    if (bad) {
-        h.slice_idx = min(h.slice_idx, pic.num_slices - 1);
-        h.qp_y = clip3i(0, 51, h.qp_y); h.qp_c[0] = clip3i(0, 51, h.qp_c[0]); h.qp_c[1] = clip3i(0, 51, h.qp_c[1]);
-        if (h.coeff_offset > pic.stream_words || (uint32_t)h.coeff_count > pic.stream_words - h.coeff_offset) h.coeff_count = 0;
-        report_error(err, ERR_HEADER);
+    bool bad_hdr = h.slice_idx >= pic.num_slices;
+    bad_hdr |= ((unsigned)h.qp_y > 51u) | ((unsigned)h.qp_c[0] > 51u) | ((unsigned)h.qp_c[1] > 51u);
+    const bool bad_levels = h.coeff_offset > pic.stream_words || (uint32_t)h.coeff_count > pic.stream_words - h.coeff_offset;
+    const bool bad_type = h.mb_type > H264R_MB_IPCM || h.mb_type == 11 || (intra ? h.mb_type < H264R_MB_I4x4 : h.mb_type > H264R_MB_8x8);
+    bool bad_motion = false, bad_ref = false;
+    if (!intra) {
+        const uint32_t code = h.packed & 15u, first = h.packed >> 4;
+        const uint32_t n = code == 1 ? 1u : (code == 2 || code == 3 ? 2u : (code == 4 ? 4u : (code == 5 ? 16u : 0u)));
+        bad_motion = n == 0 || first > pic.stream_words || 3u * n > pic.stream_words - first;
+        if (!bad_motion && (uint32_t)lane < n) {
+            const uint32_t rw = __ldg(pic.stream + first + 3u * lane + 2);      // ref_idx[0..1] | ref_pic[0..1] << 16
+            const int r0 = (int8_t)(rw >> 16), r1 = (int8_t)(rw >> 24);
+            bad_ref = r0 < -1 || r0 >= pic.num_refs || r1 < -1 || r1 >= pic.num_refs;
+        }
+        bad_ref = __any_sync(0xFFFFFFFFu, bad_ref);
+        const uint32_t pm = h.u1;                                               // sub_mb_pred_mode[0..3]
+        bad_hdr |= ((pm & 0xFF) > 2u) | (((pm >> 8) & 0xFF) > 2u) | (((pm >> 16) & 0xFF) > 2u) | ((pm >> 24) > 2u);
+    }
+    if (!(bad_hdr | bad_levels | bad_type | bad_motion | bad_ref)) return;
+    h.slice_idx = min(h.slice_idx, pic.num_slices - 1);
+    h.qp_y = clip3i(0, 51, h.qp_y); h.qp_c[0] = clip3i(0, 51, h.qp_c[0]); h.qp_c[1] = clip3i(0, 51, h.qp_c[1]);
+    if (bad_levels) { h.coeff_count = 0; h.coeff_offset = 0; }
+    if (bad_motion) h.packed = pic.stream_words >= 3u ? 1u : 0u;                // entry 0 of the stream, whatever it holds: in bounds
+    if (!intra) h.u1 = __vminu4(h.u1, 0x02020202u);
+    if (lane == 0) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(const_cast<h264r_mb*>(pic.mbs) + addr);
+        w[0] = (uint32_t)h.mb_type | (uint32_t)h.flags << 8 | (uint32_t)h.slice_idx << 16;
+        w[1] = (uint32_t)h.cbp_luma | (uint32_t)h.cbp_chroma << 8 | (uint32_t)h.qp_y << 16 | (uint32_t)h.qp_c[0] << 24;
+        w[2] = (uint32_t)h.qp_c[1] | (uint32_t)h.i16mode << 8 | (uint32_t)h.cmode << 16 | (w[2] & 0xFF000000u);
+        w[3] = (uint32_t)h.cbp_blks | (uint32_t)h.coeff_count << 16;
+        w[4] = h.coeff_offset; w[6] = h.u1; w[7] = h.packed;
+        report_error(err, (bad_hdr | bad_type ? ERR_HEADER : 0u) | (bad_levels ? ERR_LEVEL : 0u) | (bad_motion | bad_ref ? ERR_MOTION : 0u));
     }
 }
 
@@ -107,12 +132,10 @@ __device__ __forceinline__ int packed_entry_within(uint32_t packed, int b)
     const int code = packed & 15, row2 = b >> 3, col2 = (b >> 1) & 1;
     return code == 5 ? b : ((code == 2 || code == 4) ? row2 << (code == 4) : 0) + ((code == 3 || code == 4) ? col2 : 0);
 }
-// word index of the entry that covers block b; out-of-range descriptions read entry 0 of the stream
-__device__ __forceinline__ uint32_t packed_entry_word(const DevPicture& pic, uint32_t packed, int b, uint32_t* err)
+// word index of the entry that covers block b (in bounds: validate_and_repair)
+__device__ __forceinline__ uint32_t packed_entry_word(uint32_t packed, int b)
 {
-    uint32_t w = (packed >> 4) + 3u * (uint32_t)packed_entry_within(packed, b);
-    if (w + 3u > pic.stream_words) { report_error(err, ERR_MOTION); w = 0; }
-    return w;
+    return (packed >> 4) + 3u * (uint32_t)packed_entry_within(packed, b);
 }
 
 // ---------------------------------------------------------------------------------------------------

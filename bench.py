@@ -247,7 +247,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     st.close()
     npics = streams * frames
     cores = os.cpu_count() or 4
-    feeders = args.feeders or max(2, min(16, cores // max(1, min(world, 8))))
+    feeders = args.feeders or max(2, min(6, (cores - 2) // max(1, min(world, 8))))   # measured: 4-6 feeders saturate the host memory next to the two DMA directions
     max_levels = args.max_levels or nmb * 96
     eng = pyapi.Engine(seq, device=local_rank, max_frames=npics, max_pictures=npics, max_slices=4, max_levels=max_levels)
     kernels = eng.kernel_names()
@@ -255,6 +255,8 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     # ---- generate + pack (threads; the C helpers release the GIL) ----
     t0 = time.time()
     my_streams = pyapi.streams_of_rank(rank, world, streams)
+    if args.round1_mix:                               # diagnostic: only streams with direct_8x8_inference_flag = 1, as in round 1
+        my_streams = [s for s in range(rank * 2 * streams, (rank + 1) * 2 * streams) if s % 3 != 2][:streams]
     with ThreadPoolExecutor(max_workers=min(32, cores)) as ex:
         all_pics = list(ex.map(generate_and_pack, [(CONFIG_ID, sid, frames, nmb) for sid in my_streams]))
     fbytes = eng.w * eng.h * 3 // 2
@@ -312,7 +314,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     # the checker's answer for the sampled streams (CPU restatement; outside every timed region)
     sampled = {}
     if not args.no_parity_check:
-        for s in sorted({0, 2, streams - 1}):            # local stream 2 of every rank has direct_8x8_inference_flag = 0 (64 % 3 == 1: rank r starts at 64 r)
+        for s in sorted({0, 2, streams - 1} if not args.round1_mix else {0}):            # local stream 2 of every rank has direct_8x8_inference_flag = 0 (64 % 3 == 1: rank r starts at 64 r)
             if 0 <= s < streams:
                 sampled[s] = oracle_digests(CONFIG_ID, my_streams[s], frames)
 
@@ -356,7 +358,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     kms, kn = eng.replay(1, pyapi.Engine.REPLAY_TIME_KERNELS)
 
     # ---- K timed steps end to end through the public entry points ----
-    flush_every = args.flush_every or npics
+    flush_every = args.flush_every or min(npics, 4 * streams)      # four pictures of every stream per h264r_flush (measured best: 256)
     for _ in range(max(1, args.warmup // 2)):
         feed(1, flush_every)
     if sampled:
@@ -401,8 +403,8 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
         E2E = pyapi.Engine.REPLAY_H2D | pyapi.Engine.REPLAY_ASYNC
         print(f"[diag] kernels {timed(lambda: eng.replay(1, 0)):.1f} ms | h2d+kernels (replay) {timed(lambda: eng.replay(1, pyapi.Engine.REPLAY_H2D)):.1f} | "
               f"pipelined h2d+kernels (replay) {timed(lambda: eng.replay(1, E2E), 4):.1f}", file=sys.stderr)
-        for fe in (npics, max(streams, npics // 4), streams):
-            for th in sorted({1, 4, feeders}):
+        for fe in (npics, max(streams, npics // 4)):
+            for th in sorted({2, 4, 6, 8, 12, feeders}):
                 saved = feeders
                 feeders = th
                 t, f, fl = feed(2, fe)
@@ -427,12 +429,16 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     value = world * total_mb * args.steps / t_dev
     e2e_value = world * total_mb * args.steps / t_e2e
     peak, peak_src = peaks()
-    names = ["residual", "inter", "intra", "deblock_prep", "deblock"]
-    assert len(names) == len(kernels)
+    # short names in the engine's kernel-kind order (h264r_bench_kernel_name)
+    short = {"residual_kernel": "residual", "recon_inter2_kernel": "inter", "recon_intra_kernel + recon_intra_sparse_kernel": "intra",
+             "deblock_prep_kernel": "deblock_prep", "deblock_kernel": "deblock", "intra_list_kernel": "intra_list"}
+    names = [short[k] for k in kernels]
     # algorithmic bytes of each kernel's own pass: residual = levels in + 768 B residual plane out per coded MB;
     # inter / intra = SURVEY 8d formula restricted to their MBs; deblock_prep = headers + motion in, 64 B out;
-    # deblock: 32 + 384 read, 384 written (+ 192 motion for inter MBs)
-    k_bytes = [4 * total_levels + acct[6] * (32 + 768), acct[1], acct[2], acct[7] * (32 + 64) + acct[4] * 192, acct[3]]
+    # deblock: 32 + 384 read, 384 written (+ 192 motion for inter MBs); intra_list: one header word per MB in, 4 B per intra MB out
+    bytes_of = {"residual": 4 * total_levels + acct[6] * (32 + 768), "inter": acct[1], "intra": acct[2],
+                "deblock_prep": acct[7] * (32 + 64) + acct[4] * 192, "deblock": acct[3], "intra_list": 4 * total_mb + 4 * acct[5]}
+    k_bytes = [bytes_of[n] for n in names]
     nk = len(names)
     dom = max(range(nk), key=lambda i: kms[i + 1])
     dom_ms_per_launch = kms[dom + 1] / max(1, kn[dom + 1])
@@ -518,8 +524,9 @@ def main():
                     help="5: 64 x 1080p streams (the metric's workload); 3: 1080p single stream; 4: 4K single stream")
     ap.add_argument("--streams", type=int, default=0, help="independent streams per GPU (default 64, or 1 for --config 3/4)")
     ap.add_argument("--frames", type=int, default=0, help="pictures per stream (default: the config's own GOP)")
-    ap.add_argument("--feeders", type=int, default=0, help="feeder threads of the end-to-end path (default: host cores / ranks, 2..16)")
-    ap.add_argument("--flush-every", type=int, default=0, help="pictures per h264r_flush in the end-to-end path (default: one step)")
+    ap.add_argument("--feeders", type=int, default=0, help="feeder threads of the end-to-end path (default: (host cores - 2) / ranks, 2..6)")
+    ap.add_argument("--flush-every", type=int, default=0, help="pictures per h264r_flush in the end-to-end path (default: 4 per stream)")
+    ap.add_argument("--round1-mix", action="store_true", help="diagnostic: leave out the streams with direct_8x8_inference_flag = 0 (round-1 workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-ceiling", action="store_true")
