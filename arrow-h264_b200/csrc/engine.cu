@@ -81,6 +81,7 @@ struct h264r_ctx {
                                               // descriptors): they run ahead of, and underneath, the latency-bound
                                               // wavefront kernels of earlier waves
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t d2h_waited = nullptr;         // last event the D2H stream was made to wait for (frames of one wave share it)
     // events: a ring, taken in order; an event is reused only after kEventRing later takes, long after its work is done
     // (waiting for a re-recorded event is merely conservative)
     std::vector<cudaEvent_t> event_ring;
@@ -174,6 +175,7 @@ cudaEvent_t take_event(h264r_ctx* c)
     }
     cudaEvent_t ev = c->event_ring[c->event_next];
     c->event_next = (c->event_next + 1) % kEventRing;
+    if (ev == c->d2h_waited) c->d2h_waited = nullptr;      // the event gets a new meaning
     return ev;
 }
 
@@ -214,12 +216,20 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         cudaStream_t main = ctx->stream, side = time_kernels ? ctx->stream : ctx->s_side;
         if (h2d) {
             CU(cudaStreamWaitEvent(ctx->s_h2d, rec.ev_done, 0));          // replays: the previous run of this record; no-op the first time
+            cudaEvent_t waited = nullptr;                                  // the slots of a wave mostly share their previous wave
             for (const WaveCopy& c : rec.copies) {
                 Slot& s = ctx->slots[c.slot];
-                if (c.prev_done) CU(cudaStreamWaitEvent(ctx->s_h2d, c.prev_done, 0));
-                CU(cudaMemcpyAsync(s.dev, s.host, c.head_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
-                if (c.stream_bytes) CU(cudaMemcpyAsync(s.dev + ctx->off_stream, s.host + ctx->off_stream, c.stream_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
-                ctx->stats.h2d_bytes += c.head_bytes + c.stream_bytes;
+                if (c.prev_done && c.prev_done != waited) { CU(cudaStreamWaitEvent(ctx->s_h2d, c.prev_done, 0)); waited = c.prev_done; }
+                // [mbs | slices used] and [stream used]: one copy when the unused slice entries between them are small
+                const size_t gap = ctx->off_stream - c.head_bytes;
+                if (c.stream_bytes && gap <= 32768) {
+                    CU(cudaMemcpyAsync(s.dev, s.host, ctx->off_stream + c.stream_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+                    ctx->stats.h2d_bytes += ctx->off_stream + c.stream_bytes;
+                } else {
+                    CU(cudaMemcpyAsync(s.dev, s.host, c.head_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+                    if (c.stream_bytes) CU(cudaMemcpyAsync(s.dev + ctx->off_stream, s.host + ctx->off_stream, c.stream_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+                    ctx->stats.h2d_bytes += c.head_bytes + c.stream_bytes;
+                }
             }
             CU(cudaEventRecord(rec.ev_h2d, ctx->s_h2d));
             CU(cudaStreamWaitEvent(side, rec.ev_h2d, 0));
@@ -229,7 +239,9 @@ int run_waves(h264r_ctx* ctx, bool h2d, bool time_kernels, float* ms_kernel, int
         // slot's device buffers -- this record's previous run, or an earlier picture in the same slot -- must be done
         if (!time_kernels) {
             CU(cudaStreamWaitEvent(side, rec.ev_done, 0));
-            for (const WaveCopy& c : rec.copies) if (c.prev_done) CU(cudaStreamWaitEvent(side, c.prev_done, 0));
+            cudaEvent_t waited = nullptr;
+            for (const WaveCopy& c : rec.copies)
+                if (c.prev_done && c.prev_done != waited) { CU(cudaStreamWaitEvent(side, c.prev_done, 0)); waited = c.prev_done; }
         }
         if (rec.launch.any_inter) CU(cudaMemsetAsync(rec.launch.wave_max, 0, sizeof(uint32_t), side));
         { const int rc = launch(rec, KERNEL_LIST, side); if (rc != H264R_OK) return rc; }
@@ -747,7 +759,10 @@ int h264r_frame_download_async(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_
     const int w = g.width_mbs * 16, h = g.height_mbs * 16;
     if (pitch_y < w || pitch_c < w / 2) return H264R_ERR_INVALID;
     const uint8_t* d = ctx->frames[f].dev;
-    if (ctx->frames[f].ready) CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->frames[f].ready, 0));
+    if (ctx->frames[f].ready && ctx->frames[f].ready != ctx->d2h_waited) {
+        CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->frames[f].ready, 0));
+        ctx->d2h_waited = ctx->frames[f].ready;
+    }
     { const int rc = copy_frame_d2h(ctx, ctx->s_d2h, d, y, cb, cr, pitch_y, pitch_c); if (rc != H264R_OK) return rc; }
     Frame& fr = ctx->frames[f];
     if (!fr.read_done) CU(cudaEventCreateWithFlags(&fr.read_done, cudaEventDisableTiming));
