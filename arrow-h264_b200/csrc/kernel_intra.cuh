@@ -567,11 +567,13 @@ intra_list_kernel(const DevPicture* __restrict__ pics, FrameGeom g, uint32_t* wa
     if (tid == 0) { *pic.intra_count = s_base; atomicMax(wave_max, s_base); }
 }
 
-// recon_intra_sparse_kernel: persistent CTAs; a CTA takes a ticket = four consecutive entries of one picture's list (one
-// warp per intra MB).  Tickets interleave the pictures of the wave and run in raster order inside a picture; an MB waits
-// only for those of its four neighbours (left, top-left, top, top-right) that are intra MBs themselves -- inter neighbours
-// were reconstructed by recon_inter2_kernel -- i.e. only for MBs of earlier tickets, which some running CTA already
-// holds: residency order cannot deadlock.  Completion is an epoch stamp per MB (no clearing between launches).
+// recon_intra_sparse_kernel: persistent warps; a warp takes a ticket = one entry of one picture's list (one warp per intra
+// MB), and takes its next ticket before it starts on the current MB (the atomic's round trip hides behind the work; no
+// CTA-wide barrier couples the warps: the barrier version waited 15 cycles per issue on it).  Tickets interleave the
+// pictures of the wave and run in raster order inside a picture; an MB waits only for those of its four neighbours (left,
+// top-left, top, top-right) that are intra MBs themselves -- inter neighbours were reconstructed by recon_inter2_kernel --
+// i.e. only for MBs of earlier tickets, which some running warp already holds: residency order cannot deadlock.
+// Completion is an epoch stamp per MB (no clearing between launches).
 #ifndef H264R_SPARSE_WARPS
 #define H264R_SPARSE_WARPS 4
 #endif
@@ -584,36 +586,37 @@ recon_intra_sparse_kernel(const DevPicture* __restrict__ pics, int num_pics, int
                           FrameGeom g, uint32_t epoch)
 {
     __shared__ __align__(16) IntraSmem smem_all[kSparseWarps];
-    __shared__ int s_ticket;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = g.width_mbs, nmb = W * g.height_mbs;
-    const int groups = ((int)__ldg(wave_max) + kSparseWarps - 1) / kSparseWarps;       // of the picture with the most intra MBs
+    const int most = (int)__ldg(wave_max);                 // entries of the picture with the most intra MBs
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&tickets[2], 1);
+    ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
 #pragma unroll 1
     for (;;) {
-        if (threadIdx.x == 0) s_ticket = atomicAdd(&tickets[2], 1);
-        __syncthreads();
-        const int ticket = s_ticket;
-        __syncthreads();                                   // everybody has read the ticket before thread 0 takes the next one
-        const int grp = ticket / num_pics, pic_i = ticket - grp * num_pics;
-        if (grp >= groups) return;
+        const int entry = ticket / num_pics, pic_i = ticket - entry * num_pics;
+        if (entry >= most) return;
+        int next = 0;
+        if (lane == 0) next = atomicAdd(&tickets[2], 1);
         const DevPicture& pic = pics[pic_i];
-        const int entry = grp * kSparseWarps + warp;
-        if (pic.all_intra || entry >= (int)__ldg(pic.intra_count)) continue;
-        const int addr = (int)__ldg(pic.intra_list + entry);
-        if (addr >= nmb) continue;
-        const int mby = addr / W, mbx = addr - mby * W;
-        IntraPre pre;
-        intra_prefetch(pic, g, mbx, mby, lane, pre);     // header, neighbour headers, residual: all in flight at once
-        if (lane < 4 && pre.nbw != 0xFFFFFFFFu && ((pre.nbw >> 8) & H264R_MB_FLAG_INTRA)) {
-            const int nx = mbx + (lane == 3 ? 1 : (lane == 1 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // left, top, top-left, top-right
-            const int* flag = reinterpret_cast<const int*>(pic.mb_done + ny * W + nx);
-            unsigned ns = 16;
-            while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
+        int addr = nmb;
+        if (!pic.all_intra && entry < (int)__ldg(pic.intra_count)) addr = (int)__ldg(pic.intra_list + entry);
+        if (addr < nmb) {
+            const int mby = addr / W, mbx = addr - mby * W;
+            IntraPre pre;
+            intra_prefetch(pic, g, mbx, mby, lane, pre);       // header, neighbour headers, residual: all in flight at once
+            if (lane < 4 && pre.nbw != 0xFFFFFFFFu && ((pre.nbw >> 8) & H264R_MB_FLAG_INTRA)) {
+                const int nx = mbx + (lane == 3 ? 1 : (lane == 1 ? 0 : -1)), ny = mby - (lane == 0 ? 0 : 1);   // left, top, top-left, top-right
+                const int* flag = reinterpret_cast<const int*>(pic.mb_done + ny * W + nx);
+                unsigned ns = 16;
+                while ((uint32_t)ld_acquire(flag) != epoch) { __nanosleep(ns); if (ns < 256) ns *= 2; }
+            }
+            __syncwarp();
+            intra_reconstruct_mb<false>(pic, g, smem_all[warp], pre, mbx, mby, lane);
+            __syncwarp();
+            if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + addr), (int)epoch);
         }
-        __syncwarp();
-        intra_reconstruct_mb<false>(pic, g, smem_all[warp], pre, mbx, mby, lane);
-        __syncwarp();
-        if (lane == 0) st_release(reinterpret_cast<int*>(pic.mb_done + addr), (int)epoch);
+        ticket = __shfl_sync(0xFFFFFFFFu, next, 0);
     }
 }
 

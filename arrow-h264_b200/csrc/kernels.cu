@@ -67,7 +67,7 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
         }
         if (w.any_inter) {                                   // pictures with P / B slices may hold intra MBs anywhere
             // persistent CTAs (the number of intra MBs is only known on the device): one round of resident CTAs, fewer for tiny waves
-            const long long most = ((long long)w.num_pics * nmb + kSparseWarps - 1) / kSparseWarps;
+            const long long most = ((long long)w.num_pics * nmb + kSparseWarps - 1) / kSparseWarps;    // one warp per MB at the very most
             const int ctas = (int)std::min<long long>(most, 148LL * H264R_SPARSE_CTAS);
             recon_intra_sparse_kernel<<<ctas, kSparseWarps * 32, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.wave_max, w.geom, w.epoch);
             ++n;
