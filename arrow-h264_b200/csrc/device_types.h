@@ -4,6 +4,7 @@
 #define H264R_DEVICE_TYPES_H_
 
 #include "h264recon.h"
+#include <cuda.h>                    // CUtensorMap (type only; the encoder entry point is fetched through the runtime)
 #include <cuda_runtime.h>
 
 namespace h264r {
@@ -14,6 +15,16 @@ struct FrameGeom {
     int width_mbs, height_mbs;
     int pitch_y, pitch_c;            // bytes; tight: 16 * width_mbs and 8 * width_mbs
     size_t off_cb, off_cr, bytes;    // plane offsets inside the allocation
+};
+
+// TMA descriptors of one frame (the -DH264R_INTER_TMA=1 build of recon_inter2_kernel fetches interior reference windows
+// with cp.async.bulk.tensor): luma = 2-D uint8 {16 W, 16 H}, box 32 x 13; chroma = 3-D uint8 {8 W, 8 H, 2 planes}, box
+// 32 x 5 x 2.  The boxes are 32 bytes wide for 13 / 5 useful ones because a box must START on a 16-byte boundary (measured:
+// any other x origin raises "illegal instruction", scripts/probes/tma_probe3.cu), while a window starts at any sample.
+// Out-of-bounds bytes are zero-filled, so only windows inside the picture take this path.
+struct __align__(64) FrameMaps {
+    CUtensorMap luma, chroma;
+    int ok, pad[15];                 // 0: no descriptors (odd picture width: chroma pitch not a multiple of 16 bytes)
 };
 
 // Deblock descriptor of one MB, output of the parallel pre-pass (deblock_prep_kernel), input of the deblock wavefront: 64 bytes.
@@ -33,6 +44,7 @@ struct DevPicture {
     int16_t*               resid;                     // [nmb][384] residual plane, device only (residual_kernel)
     uint8_t*               dst;                       // frame base
     const uint8_t*         ref[H264R_MAX_REFS];       // frame bases of pic_params.ref_frames[]; unused slots: a dummy frame
+    const FrameMaps*       ref_maps[H264R_MAX_REFS];  // their TMA descriptors
     DeblockDesc*           desc;                      // [nmb], device only
     uint64_t*              mbox;                      // [nmb][24], device only: row-to-row mailboxes { 4 samples, epoch }
     uint32_t*              mb_done;                   // [nmb], device only: epoch stamp of the launch that reconstructed the intra MB

@@ -30,6 +30,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Frame {
     uint8_t* dev = nullptr;
+    FrameMaps* maps = nullptr;                // device: TMA descriptors of this frame (entry of h264r_ctx::d_maps)
     bool used = false;
     int write_wave = -1, read_wave = -1;      // bookkeeping inside one flush
     cudaEvent_t ready = nullptr;              // ev_done of the wave that last wrote this frame (owned by the event ring)
@@ -94,6 +95,8 @@ struct h264r_ctx {
     uint32_t stream_capacity = 0;             // words
     std::vector<Frame> frames;
     uint8_t* dummy_frame = nullptr;           // what unused reference slots point at (never written)
+    FrameMaps* d_maps = nullptr;              // [max_frames + 1] (the last one: the dummy frame)
+    void* encode_tiled = nullptr;             // cuTensorMapEncodeTiled, through cudaGetDriverEntryPoint (no libcuda link)
     std::mutex mu;                            // slots[].state, free_slots, inflight, queue
     std::vector<Slot> slots;
     std::vector<int> free_slots;
@@ -153,6 +156,32 @@ int copy_frame_d2h(h264r_ctx* ctx, cudaStream_t stream, const uint8_t* d, uint8_
     CU(cudaMemcpy2DAsync(y, pitch_y, d, g.pitch_y, w, h, cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpy2DAsync(cb, pitch_c, d + g.off_cb, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpy2DAsync(cr, pitch_c, d + g.off_cr, g.pitch_c, w / 2, h / 2, cudaMemcpyDeviceToHost, stream));
+    return H264R_OK;
+}
+
+// TMA descriptors of the frame at `dev` -> d_maps[index] (device memory; the kernels pass the address to cp.async.bulk.tensor)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int upload_frame_maps(h264r_ctx* ctx, uint8_t* dev, size_t index)
+{
+    alignas(64) FrameMaps m;
+    memset(&m, 0, sizeof(m));
+    const FrameGeom& g = ctx->geom;
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled);
+    if (enc && (g.pitch_c % 16) == 0) {
+        const cuuint64_t dimY[2] = { (cuuint64_t)g.pitch_y, (cuuint64_t)g.height_mbs * 16 }, strideY[1] = { (cuuint64_t)g.pitch_y };
+        const cuuint32_t boxY[2] = { 32, 13 }, one[3] = { 1, 1, 1 };
+        const cuuint64_t dimC[3] = { (cuuint64_t)g.pitch_c, (cuuint64_t)g.height_mbs * 8, 2 };
+        const cuuint64_t strideC[2] = { (cuuint64_t)g.pitch_c, (cuuint64_t)(g.off_cr - g.off_cb) };
+        const cuuint32_t boxC[3] = { 32, 5, 2 };
+        const CUresult r0 = enc(&m.luma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dev, dimY, strideY, boxY, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        const CUresult r1 = enc(&m.chroma, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, dev + g.off_cb, dimC, strideC, boxC, one, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        m.ok = r0 == CUDA_SUCCESS && r1 == CUDA_SUCCESS;
+    }
+    CU(cudaMemcpy(ctx->d_maps + index, &m, sizeof(m), cudaMemcpyHostToDevice));
     return H264R_OK;
 }
 
@@ -341,6 +370,7 @@ void h264r_destroy(h264r_ctx* ctx)
         if (ctx->slots[0].dev_mbox) cudaFree(ctx->slots[0].dev_mbox);
     }
     if (ctx->dummy_frame) cudaFree(ctx->dummy_frame);
+    if (ctx->d_maps) cudaFree(ctx->d_maps);
     if (ctx->h_pics) cudaFreeHost(ctx->h_pics);
     if (ctx->d_pics) cudaFree(ctx->d_pics);
     if (ctx->d_tickets) cudaFree(ctx->d_tickets);
@@ -421,6 +451,15 @@ int h264r_create(h264r_ctx** out, int device, const h264r_seq_params* sp)
     if (e == cudaSuccess) e = cudaMemset(d_mbox, 0, sizeof(uint64_t) * mbox_words * nslots);   // epoch 0 is never used
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->dummy_frame, g.bytes);
     if (e == cudaSuccess) e = cudaMemset(ctx->dummy_frame, 128, g.bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_maps, sizeof(FrameMaps) * ((size_t)sp->max_frames + 1));
+    if (e == cudaSuccess) {
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encode_tiled, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            ctx->encode_tiled = nullptr;                   // the TMA build then stays on its cp.async path
+            cudaGetLastError();
+        }
+        if (upload_frame_maps(ctx, ctx->dummy_frame, (size_t)sp->max_frames) != H264R_OK) e = cudaErrorUnknown;
+    }
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_pics, sizeof(DevPicture) * ctx->table_entries, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_pics, sizeof(DevPicture) * ctx->table_entries);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tickets, sizeof(int) * 64);
@@ -453,7 +492,12 @@ int h264r_frame_alloc(h264r_ctx* ctx, h264r_frame* out)
     cudaSetDevice(ctx->device);
     for (size_t i = 0; i < ctx->frames.size(); ++i)
         if (!ctx->frames[i].used) {
-            if (!ctx->frames[i].dev) CU(cudaMalloc((void**)&ctx->frames[i].dev, ctx->geom.bytes));
+            if (!ctx->frames[i].dev) {
+                CU(cudaMalloc((void**)&ctx->frames[i].dev, ctx->geom.bytes));
+                ctx->frames[i].maps = ctx->d_maps + i;
+                const int rc = upload_frame_maps(ctx, ctx->frames[i].dev, i);
+                if (rc != H264R_OK) return rc;
+            }
             ctx->frames[i].used = true;
             *out = (h264r_frame)i;
             return H264R_OK;
@@ -615,8 +659,11 @@ int h264r_flush(h264r_ctx* ctx)
         p.slices = reinterpret_cast<const h264r_slice*>(s.dev + ctx->off_slices);
         p.stream = reinterpret_cast<const uint32_t*>(s.dev + ctx->off_stream);
         p.dst = ctx->frames[s.dst].dev;
-        for (int i = 0; i < H264R_MAX_REFS; ++i)
-            p.ref[i] = i < s.pp.num_ref_frames ? ctx->frames[s.pp.ref_frames[i]].dev : ctx->dummy_frame;
+        for (int i = 0; i < H264R_MAX_REFS; ++i) {
+            const bool have = i < s.pp.num_ref_frames;
+            p.ref[i] = have ? ctx->frames[s.pp.ref_frames[i]].dev : ctx->dummy_frame;
+            p.ref_maps[i] = have ? ctx->frames[s.pp.ref_frames[i]].maps : ctx->d_maps + ctx->seq.max_frames;
+        }
         p.desc = s.dev_desc;
         p.resid = s.dev_resid;
         p.mbox = s.dev_mbox;

@@ -14,6 +14,13 @@ namespace h264r {
 #ifndef H264R_INTER2_CTAS
 #define H264R_INTER2_CTAS (28 / H264R_INTER2_WARPS)
 #endif
+// -DH264R_INTER_TMA=1: the windows of uniform 8x8 quadrants that lie inside the picture are fetched with TMA
+// (cp.async.bulk.tensor, one 32 x 13 luma box and one 32 x 5 x 2 chroma box per quadrant, completion on an mbarrier)
+// instead of 13 + 5 four-byte cp.async per lane.  A box must start on a 16-byte boundary, so it starts at x0 & ~15 and is 32
+// bytes wide.  Measured against the cp.async build in round 2: DESIGN.md section 3.
+#ifndef H264R_INTER_TMA
+#define H264R_INTER_TMA 0
+#endif
 
 // Reference windows in shared memory.  Interior windows are fetched as aligned 32-bit words: the first sample x0 of
 // a window row then sits at byte offset x0 & 3.  Windows touching the picture border (rare) are fetched sample by
@@ -39,11 +46,54 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // quadrant 4 blocks x (9 rows x 4 words), one row pitch for both so that row offsets are immediates; chroma 50 words =
 // uniform 2 planes x (5 rows x 2 words) | split 4 blocks x 2 planes x (3 rows x 2 words), + 1 word the funnel shifts
 // may touch.  146 = 2 (mod 8): the four quadrant groups of a warp read disjoint banks.
-constexpr int kLumaQ = 146, kChromaQ = 50;
+#if !H264R_INTER_TMA
+constexpr int kLumaQ = 146, kChromaQ = 50, kChromaUniPitch = 2, kLumaUniPitch = 4;
 struct __align__(16) Inter2Smem {
     uint32_t luma[2][4 * kLumaQ + 2];
     uint32_t chroma[2][4 * kChromaQ + 2];
 };
+#else
+// TMA destinations must be 128-byte aligned: a quadrant owns 640 bytes of luma (the 32 x 13 box = row pitch 8 words, or four
+// 9-row block windows of pitch 4) and 384 bytes of chroma (the 32 x 5 x 2 box = row pitch 8 words, or the split layout).  Every
+// quadrant therefore starts on bank 0: the eight quadrants of a warp read the same banks (the cp.async layout staggers
+// them by 146 words).
+constexpr int kLumaQ = 160, kChromaQ = 96, kChromaUniPitch = 8, kLumaUniPitch = 8;
+struct __align__(128) Inter2Smem {
+    uint32_t luma[2][4 * kLumaQ];
+    uint32_t chroma[2][4 * kChromaQ];
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar, uint32_t tx_bytes)
+{
+    if (tx_bytes) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(tx_bytes) : "memory");
+    else          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 // Decoder::mb_pred_inter partition walk (decoder.cc:217-262) for 4x4 block `blk`: returns the block whose motion
 // entry the reference reads (partition origin), the prediction direction, and whether the partition covers the
@@ -81,7 +131,12 @@ constexpr int kInter2Warps = H264R_INTER2_WARPS;       // warps per CTA (each wa
 __global__ void __launch_bounds__(kInter2Warps * 32, H264R_INTER2_CTAS)
 recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 {
+#if H264R_INTER_TMA
+    __shared__ Inter2Smem smem_all[kInter2Warps];
+    __shared__ __align__(8) uint64_t bar_all[kInter2Warps];
+#else
     __shared__ __align__(16) Inter2Smem smem_all[kInter2Warps];
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = lane >> 4, b = lane & 15, bx = b & 3, by = b >> 2;
     const int mbx = (blockIdx.x * kInter2Warps + warp) * 2 + m, mby = blockIdx.y;
@@ -94,6 +149,12 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
     const bool valid = mbx < W && !h.intra();
     if (!__any_sync(0xFFFFFFFFu, valid)) return;
     Inter2Smem& sm = smem_all[warp];
+#if H264R_INTER_TMA
+    uint64_t* const bar = &bar_all[warp];                 // one mbarrier per warp: 32 arrivals + the bytes of the warp's boxes per phase
+    if (lane == 0) mbar_init(bar, 32);
+    __syncwarp();
+    uint32_t phase = 0;
+#endif
     const h264r_slice* __restrict__ sl = pic.slices + h.slice_idx;
     const int wY = W * 16, hY = g.height_mbs * 16, wC = wY >> 1, hC = hY >> 1;
     const uint32_t s0 = __ldg(reinterpret_cast<const uint32_t*>(sl)), s1 = __ldg(reinterpret_cast<const uint32_t*>(sl) + 1),
@@ -130,6 +191,10 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
         int vx = 0, vy = 0, refidx = 0;
         const uint32_t* wl = lq; const uint32_t* wc0 = cq; const uint32_t* wc1 = cq;
         int loff = 2, coff = 0;
+        int cpitch = 2, lpitch = 4;                        // row pitches of this lane's chroma / luma windows, words
+#if H264R_INTER_TMA
+        uint32_t tx = 0;                                   // bytes this lane's TMA boxes will deliver
+#endif
         if (active) {
             refidx = (int)(int8_t)(rw >> (8 * list));
             // the entry names the reference picture itself (ref_pic = slot of pic_params.ref_frames, the identity the
@@ -145,24 +210,42 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
                 const int xa = x0 & ~3, cxa = cx0 & ~3;
                 const bool in_y = xa >= 0 && xa + 16 <= wY && y0 >= 0 && y0 + 13 <= hY;
                 const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 5 <= hC;
+#if H264R_INTER_TMA
+                const FrameMaps* __restrict__ maps = pic.ref_maps[slot & 31];
+                const bool tma = __ldg(&maps->ok) != 0;
+                const bool tma_y = tma && x0 >= 0 && x0 + 13 <= wY && y0 >= 0 && y0 + 13 <= hY;
+                const bool tma_c = tma && cx0 >= 0 && cx0 + 5 <= wC && cy0 >= 0 && cy0 + 5 <= hC;
+                if (tma_y) {                                    // one 32 x 13 box from the 16-byte boundary below x0: lane sb = 0 of the quadrant
+                    if (sb == 0) { tx += 32 * 13; mbar_arrive(bar, 32 * 13); tma_load_2d(lq, &maps->luma, x0 & ~15, y0, bar); }
+                } else
+#else
+                const bool tma_y = false, tma_c = false;
+#endif
                 if (in_y) {                                     // 13 rows x 4 words: lane = word column
                     const uint8_t* src = rbase + (uint32_t)(y0 * pitch_y + xa + sb * 4);
 #pragma unroll
-                    for (int i = 0; i < 13; ++i) cp_async4(lq + i * 4 + sb, src + (uint32_t)(i * pitch_y));
-                } else load_window_border(lq, 4, rbase, pitch_y, wY, hY, x0, y0, 13, 13, sb, 4);
-                {                                               // 2 planes x 5 rows x 2 words: lane = (plane, word column)
+                    for (int i = 0; i < 13; ++i) cp_async4(lq + i * kLumaUniPitch + sb, src + (uint32_t)(i * pitch_y));
+                } else load_window_border(lq, kLumaUniPitch, rbase, pitch_y, wY, hY, x0, y0, 13, 13, sb, 4);
+                {                                               // 2 planes x 5 rows x 2 (TMA build: 4) words: lane = (plane, word column)
                     const int pl = sb >> 1, col = sb & 1;
                     const uint8_t* cplane = rbase + (pl ? g.off_cr : g.off_cb);
+#if H264R_INTER_TMA
+                    if (tma_c) {                                // one 32 x 5 x 2 box (both planes): lane sb = 1 of the quadrant
+                        if (sb == 1) { tx += 32 * 5 * 2; mbar_arrive(bar, 32 * 5 * 2); tma_load_3d(cq, &maps->chroma, cx0 & ~15, cy0, 0, bar); }
+                    } else
+#endif
                     if (in_c) {
                         const uint8_t* src = cplane + (uint32_t)(cy0 * pitch_c + cxa + col * 4);
 #pragma unroll
-                        for (int i = 0; i < 5; ++i) cp_async4(cq + pl * 10 + i * 2 + col, src + (uint32_t)(i * pitch_c));
-                    } else load_window_border(cq + pl * 10, 2, cplane, pitch_c, wC, hC, cx0, cy0, 5, 5, col, 2);
+                        for (int i = 0; i < 5; ++i) cp_async4(cq + pl * 5 * kChromaUniPitch + i * kChromaUniPitch + col, src + (uint32_t)(i * pitch_c));
+                    } else load_window_border(cq + pl * 5 * kChromaUniPitch, kChromaUniPitch, cplane, pitch_c, wC, hC, cx0, cy0, 5, 5, col, 2);
                 }
-                wl = lq + (sb >> 1) * 4 * 4;
-                loff = 2 + (sb & 1) * 4 + (in_y ? x0 & 3 : 0);
-                wc0 = cq + (sb >> 1) * 2 * 2; wc1 = wc0 + 10;
-                coff = (sb & 1) * 2 + (in_c ? cx0 & 3 : 0);
+                lpitch = kLumaUniPitch;
+                wl = lq + (sb >> 1) * 4 * kLumaUniPitch;
+                loff = 2 + (sb & 1) * 4 + (tma_y ? x0 & 15 : (in_y ? x0 & 3 : 0));
+                cpitch = kChromaUniPitch;
+                wc0 = cq + (sb >> 1) * 2 * kChromaUniPitch; wc1 = wc0 + 5 * kChromaUniPitch;
+                coff = (sb & 1) * 2 + (tma_c ? cx0 & 15 : (in_c ? cx0 & 3 : 0));
             } else {
                 const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2, cx0 = vx >> 3, cy0 = vy >> 3;
                 const int xa = x0 & ~3, cxa = cx0 & ~3;
@@ -194,6 +277,11 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
         }
 
         cp_async_wait_all();                               // this lane's window copies have landed
+#if H264R_INTER_TMA
+        if (!tx) mbar_arrive(bar, 0);                      // (lanes that issued a box arrived with their expect_tx)
+        mbar_wait(bar, phase);                             // every box of the warp has landed
+        phase ^= 1;
+#endif
         __syncwarp();
         {
             const int xf = vx & 3, yf = vy & 3;
@@ -201,8 +289,8 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
             mc_luma_masks_r<4>(xf, yf, hm, cm);
             const unsigned whm = __reduce_or_sync(0xFFFFFFFFu, active ? hm : 0u), wcm = __reduce_or_sync(0xFFFFFFFFu, active ? cm : 0u);
             uint32_t y[4];
-            mc_luma_patch<4>(wl, loff, xf, yf, whm, wcm, y);
-            const uint32_t c0 = mc_chroma_patch_2x2(wc0, coff, vx & 7, vy & 7), c1 = mc_chroma_patch_2x2(wc1, coff, vx & 7, vy & 7);
+            mc_luma_patch<4>(wl, loff, xf, yf, whm, wcm, y, lpitch);
+            const uint32_t c0 = mc_chroma_patch_2x2(wc0, coff, vx & 7, vy & 7, cpitch), c1 = mc_chroma_patch_2x2(wc1, coff, vx & 7, vy & 7, cpitch);
             if (active) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { prevY[r] = curY[r]; curY[r] = y[r]; }
@@ -211,6 +299,9 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
             }
         }
         __syncwarp();
+#if H264R_INTER_TMA
+        fence_proxy_async();                               // the windows were read through the generic proxy; the next boxes arrive through the async proxy
+#endif
     }
 
     if (!valid) return;

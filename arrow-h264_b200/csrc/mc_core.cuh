@@ -139,9 +139,9 @@ MC_FN void mc_luma_masks(int xf, int yf, unsigned& hmask, unsigned& cmask) { mc_
 constexpr int kLumaPitchWords = 4;
 // 4 x R luma patch: one pass over the R + 5 window rows (sample rows -2 .. R + 2); out[r] = row r, four packed samples.
 template <int R>
-MC_FN void mc_luma_patch(const uint32_t* win, int off, int xf, int yf, unsigned hmask, unsigned cmask, uint32_t (&out)[R])
+MC_FN void mc_luma_patch(const uint32_t* win, int off, int xf, int yf, unsigned hmask, unsigned cmask, uint32_t (&out)[R],
+                         const int pitch_words = kLumaPitchWords)
 {
-    constexpr int pitch_words = kLumaPitchWords;
     const bool hasB = xf != 0 && yf != 2;                       // clipped horizontal half sample b (row + dy)
     const bool hasH = yf != 0 && xf != 2;                       // clipped vertical half sample h (column + dx)
     const bool hasJ = (xf == 2 && yf != 0) || (yf == 2 && xf != 0);
@@ -226,15 +226,16 @@ MC_FN void mc_luma_patch_4x2(const uint32_t* win, int off, int xf, int yf, unsig
     out0 = o[0]; out1 = o[1];
 }
 
-// Chroma 2x2 patch of one plane.  win: row pitch 2 words (8 bytes); off = byte offset of sample (0, 0), at most 5;
-// xf, yf = eighth-sample fractions.  Returns the four samples packed (row 0 in bytes 0-1, row 1 in bytes 2-3).
-MC_FN uint32_t mc_chroma_patch_2x2(const uint32_t* win, int off, int xf, int yf)
+// Chroma 2x2 patch of one plane.  win: row pitch `pitch` words (2 = 8 bytes; the TMA build stages uniform quadrants with 4);
+// off = byte offset of sample (0, 0), at most 5; xf, yf = eighth-sample fractions.  Returns the four samples packed (row 0
+// in bytes 0-1, row 1 in bytes 2-3).
+MC_FN uint32_t mc_chroma_patch_2x2(const uint32_t* win, int off, int xf, int yf, int pitch = 2)
 {
     const uint32_t* w = win + (off >> 2);
     const uint32_t sh = (uint32_t)(off & 3) * 8;
     uint32_t R[3];
 #pragma unroll
-    for (int y = 0; y < 3; ++y) R[y] = mc_shf_r(w[2 * y], w[2 * y + 1], sh);
+    for (int y = 0; y < 3; ++y) R[y] = mc_shf_r(w[pitch * y], w[pitch * y + 1], sh);
     const uint32_t wgt = (uint32_t)((8 - xf) * (8 - yf)) | (uint32_t)(xf * (8 - yf)) << 8 | (uint32_t)((8 - xf) * yf) << 16 | (uint32_t)(xf * yf) << 24;
     uint32_t v[4];
 #pragma unroll
