@@ -12,6 +12,13 @@ namespace h264r {
 #ifndef H264R_DEBLOCK_CTAS
 #define H264R_DEBLOCK_CTAS 4
 #endif
+// back-off of the mailbox poll, ns: first sleep and cap
+#ifndef H264R_POLL_NS0
+#define H264R_POLL_NS0 16
+#endif
+#ifndef H264R_POLL_NS1
+#define H264R_POLL_NS1 128
+#endif
 
 // One warp filters the SAME macroblock row of TWO pictures of the wave: lanes 0..15 picture A, lanes 16..31 picture B
 // (one instruction stream, independent data: the filter is a data-dependent scalar recipe per line, so a picture can
@@ -226,10 +233,10 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
         // ---- mailbox of the MB above: normally there already ----
         if (has_above) {
             bool waiting = enabled && ((uint32_t)(t0 >> 32) != epoch || (l < 8 && (uint32_t)(t1 >> 32) != epoch));
-            unsigned ns = 16;
+            unsigned ns = H264R_POLL_NS0;
             while (__any_sync(0xFFFFFFFFu, waiting)) {
                 if (waiting) {
-                    __nanosleep(ns); if (ns < 128) ns *= 2;
+                    __nanosleep(ns); if (ns < H264R_POLL_NS1) ns *= 2;
                     t0 = ld_mbox(box_in + mbx * kMboxWords + l);
                     if (l < 8) t1 = ld_mbox(box_in + mbx * kMboxWords + 16 + l);
                     waiting = (uint32_t)(t0 >> 32) != epoch || (l < 8 && (uint32_t)(t1 >> 32) != epoch);
