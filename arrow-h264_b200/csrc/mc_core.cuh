@@ -48,6 +48,10 @@ MC_FN uint32_t mc_dp4a_uu(uint32_t a, uint32_t b, uint32_t c)            // u8 x
     for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
     return c;
 }
+MC_FN int mc_dp2a_lo_su(uint32_t a, uint32_t b, int c)                  // s16 lanes of a x u8 bytes 0, 1 of b
+{
+    return c + (int)(int16_t)(a & 0xFFFF) * (int)(b & 0xFF) + (int)(int16_t)(a >> 16) * (int)((b >> 8) & 0xFF);
+}
 MC_FN uint32_t mc_pack_sat_u8(int a, int b, uint32_t c)                 // (c << 16) | sat_u8(a) << 8 | sat_u8(b)
 {
     const uint32_t sa = (uint32_t)(a < 0 ? 0 : (a > 255 ? 255 : a)), sb = (uint32_t)(b < 0 ? 0 : (b > 255 ? 255 : b));
@@ -85,6 +89,12 @@ MC_FN int mc_dp4a_us(uint32_t a, uint32_t b, int c)
     return d;
 }
 MC_FN uint32_t mc_dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
+MC_FN int mc_dp2a_lo_su(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 MC_FN uint32_t mc_pack_sat_u8(int a, int b, uint32_t c)
 {
     uint32_t d;
@@ -253,15 +263,15 @@ MC_FN uint32_t mc_chroma_patch_2x2(const uint32_t* win, int off, int xf, int yf,
 MC_FN uint32_t mc_weight4(int mode, uint32_t p0, uint32_t p1, int w0, int w1, int d, int o)
 {
     if (mode & 1) {
+        // one dot product per sample: (w0, w1) as 16-bit lanes (implicit weights reach 128) x (p0_i, p1_i) as bytes
         int v[4];
         const int sh = mode == 1 ? d : d + 1;
         const int rnd = sh > 0 ? 1 << (sh - 1) : 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int acc = (int)((p0 >> (8 * i)) & 0xFF) * w0 + rnd;
-            if (mode == 3) acc += (int)((p1 >> (8 * i)) & 0xFF) * w1;
-            v[i] = (acc >> sh) + o;
-        }
+        const uint32_t w = (uint32_t)(uint16_t)w0 | (mode == 3 ? (uint32_t)(uint16_t)w1 << 16 : 0u);
+        v[0] = (mc_dp2a_lo_su(w, mc_prmt(p0, p1, 0x0040u), rnd) >> sh) + o;
+        v[1] = (mc_dp2a_lo_su(w, mc_prmt(p0, p1, 0x0051u), rnd) >> sh) + o;
+        v[2] = (mc_dp2a_lo_su(w, mc_prmt(p0, p1, 0x0062u), rnd) >> sh) + o;
+        v[3] = (mc_dp2a_lo_su(w, mc_prmt(p0, p1, 0x0073u), rnd) >> sh) + o;
         return mc_pack4_sat(v[0], v[1], v[2], v[3]);              // clip1
     }
     return mode == 2 ? mc_avg_u8x4(p0, p1) : p0;
