@@ -29,10 +29,26 @@ namespace h264r {
 __device__ __noinline__ void load_window_border(uint32_t* win, int pitch_words, const uint8_t* __restrict__ plane, int pitch,
                                                 int W, int H, int x0, int y0, int ncols, int nrows, int first_row, int row_step)
 {
+    // word by word: four samples that lie inside the row are one unaligned 32-bit read (two aligned loads + funnel shift),
+    // only words that straddle or leave the row are clamped sample by sample (W is a multiple of 8: the second aligned
+    // word of an inside read is inside too)
+    const int nwords = (ncols + 3) >> 2;
     for (int row = first_row; row < nrows; row += row_step) {
         const uint8_t* src = plane + (uint32_t)(clip3i(0, H - 1, y0 + row) * pitch);
-        uint8_t* dst = reinterpret_cast<uint8_t*>(win + row * pitch_words);
-        for (int c = 0; c < ncols; ++c) dst[c] = __ldg(src + clip3i(0, W - 1, x0 + c));
+        uint32_t* dst = win + row * pitch_words;
+        for (int j = 0; j < nwords; ++j) {
+            const int xs = x0 + 4 * j;
+            uint32_t v;
+            if (xs >= 0 && xs + 3 < W) {
+                const uint32_t* p = reinterpret_cast<const uint32_t*>(src + (xs & ~3));
+                const uint32_t lo = __ldg(p), hi = (xs & 3) ? __ldg(p + 1) : 0u;
+                v = __funnelshift_r(lo, hi, (xs & 3) * 8);
+            } else {
+                v = (uint32_t)__ldg(src + clip3i(0, W - 1, xs)) | (uint32_t)__ldg(src + clip3i(0, W - 1, xs + 1)) << 8 |
+                    (uint32_t)__ldg(src + clip3i(0, W - 1, xs + 2)) << 16 | (uint32_t)__ldg(src + clip3i(0, W - 1, xs + 3)) << 24;
+            }
+            dst[j] = v;
+        }
     }
 }
 // 4-byte global -> shared copy that never touches a register (LDGSTS); completion: cp_async_wait_all()
