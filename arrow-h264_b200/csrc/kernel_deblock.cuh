@@ -12,6 +12,11 @@ namespace h264r {
 #ifndef H264R_DEBLOCK_CTAS
 #define H264R_DEBLOCK_CTAS 4
 #endif
+// 1: descriptor and samples of MB x + 1 are loaded while MB x is filtered (19 registers); 0: loaded at the start of their own
+// step -- for builds that trade the prefetch for more resident warps (H264R_DEBLOCK_CTAS 6 / 8)
+#ifndef H264R_DEBLOCK_PREFETCH
+#define H264R_DEBLOCK_PREFETCH 1
+#endif
 // back-off of the mailbox poll, ns: first sleep and cap
 #ifndef H264R_POLL_NS0
 #define H264R_POLL_NS0 16
@@ -164,6 +169,14 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
     uint32_t boxY = 0, boxC = 0;                          // this lane's mailbox words of the previous MB (after its horizontal pass)
 
     for (int mbx = 0; mbx < W; ++mbx) {
+#if !H264R_DEBLOCK_PREFETCH
+        if (mbx > 0 && enabled) {
+            n_bs = __ldg(desc + mbx * 4); n_pa = __ldg(desc + mbx * 4 + 1); n_pb = __ldg(desc + mbx * 4 + 2);
+            n_pz = __ldg(reinterpret_cast<const unsigned int*>(desc + mbx * 4) + 12);
+            n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y + mbx * 16)));
+            n_ownC = __ldcg(reinterpret_cast<const uint2*>(dC + (uint32_t)((cy + cl) * pitch_c + mbx * 8)));
+        }
+#endif
         const uint4 bs = n_bs, ownY = n_ownY; const uint2 ownC = n_ownC;
         const uint4 parY = make_uint4(n_pa.x, n_pa.y, n_pa.z, 0u);
         const uint4 parC = cpl ? make_uint4(n_pb.z, n_pb.w, n_pz, 0u) : make_uint4(n_pa.w, n_pb.x, n_pb.y, 0u);
@@ -180,7 +193,7 @@ deblock_kernel(const DevPicture* __restrict__ pics, int num_pics, int* tickets, 
         const uint32_t carryC = *reinterpret_cast<const uint32_t*>(TC + cl * 16 + 8 + 4);
 
         // prefetch the next MB: independent of every other MB of this kernel
-        if (mbx + 1 < W && enabled) {
+        if (H264R_DEBLOCK_PREFETCH && mbx + 1 < W && enabled) {
             n_bs = __ldg(desc + (mbx + 1) * 4); n_pa = __ldg(desc + (mbx + 1) * 4 + 1); n_pb = __ldg(desc + (mbx + 1) * 4 + 2);
             n_pz = __ldg(reinterpret_cast<const unsigned int*>(desc + (mbx + 1) * 4) + 12);
             n_ownY = __ldcg(reinterpret_cast<const uint4*>(dY + (uint32_t)((py + l) * pitch_y + px + 16)));

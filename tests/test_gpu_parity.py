@@ -271,3 +271,59 @@ def test_cropped_download_is_the_display_rectangle():
     with pytest.raises(pyapi.EngineError):
         eng.download_cropped(order[0], 1, 0, 0, 0)          # odd offsets do not exist in 4:2:0
     eng.close()
+
+
+def test_concurrent_fill_through_the_public_entry_points():
+    """Pictures of eight streams are filled CONCURRENTLY by four feeder threads (h264r_picture_begin -> write the staging
+    -> h264r_picture_submit, include/h264recon_bench.h h264r_bench_feed) while the calling thread flushes every five
+    submitted pictures and downloads asynchronously; two passes back to back (staging slots and frames are reused while
+    earlier pictures are still in flight).  Every frame must equal the oracle's."""
+    import ctypes as C
+    cfg, w, h, n, nstreams = 5, 9, 6, 7, 8
+    lib = pyapi.recon_lib()
+    streams = [pyapi.SynthStream(cfg, s, w, h, n) for s in range(nstreams)]
+    seq, nmb = streams[0].seq, streams[0].nmb
+    want = {}
+    for s in range(nstreams):
+        port = O.CpuDecoder("port", pyapi.SynthStream(cfg, s, w, h, n).seq)
+        want[s] = O.run_stream(port, cfg, s, w, h, n)
+        port.close()
+    npics = nstreams * n
+    eng = pyapi.Engine(seq, max_frames=npics, max_pictures=6, max_slices=4)     # far fewer staging slots than pictures
+    fbytes = eng.w * eng.h * 3 // 2
+    out_host = eng.host_alloc(fbytes * npics)
+    table = (pyapi.BenchPicture * npics)()
+    keep, where, frames = [], {}, [dict() for _ in range(nstreams)]
+    k = 0
+    for _ in range(n):
+        for s, st in enumerate(streams):
+            pic = st.next()
+            head = C.create_string_buffer(C.sizeof(pyapi.Mb) * nmb + C.sizeof(pyapi.Slice) * pic.pp.num_slices)
+            cap = pic.info.num_levels + 48 * nmb
+            stream = (C.c_uint32 * cap)()
+            words = lib.h264r_pack_picture(nmb, pic.mbs, pic.motion, pic.levels, pic.info.num_levels, head, stream, cap)
+            assert words >= 0
+            C.memmove(C.addressof(head) + C.sizeof(pyapi.Mb) * nmb, pic.slices, C.sizeof(pyapi.Slice) * pic.pp.num_slices)
+            keep.append((head, stream))
+            dst = eng.frame_alloc()
+            frames[s][pic.info.pic_index] = dst
+            e = table[k]
+            C.memmove(C.byref(e.pp), C.byref(pic.pp), C.sizeof(pyapi.PicParams))
+            for r in range(pic.info.num_refs):
+                e.pp.ref_frames[r] = frames[s][pic.info.ref_pic_index[r]]
+            e.dst, e.stream_id = dst, s
+            e.head, e.stream, e.stream_words = C.addressof(head), C.addressof(stream), int(words)
+            e.pitch_y, e.out = eng.w, out_host + k * fbytes
+            where[(s, pic.info.pic_index)] = k
+            k += 1
+    for st in streams:
+        st.close()
+    fill, flush = C.c_double(), C.c_double()
+    t = lib.h264r_bench_feed(eng.ctx, table, npics, nmb, 4, 5, 2, C.byref(fill), C.byref(flush))
+    assert t > 0, lib.h264r_strerror(int(t)).decode()
+    for (s, idx), kk in where.items():
+        d = hashlib.md5(C.string_at(out_host + kk * fbytes, fbytes)).hexdigest()
+        assert d == want[s][idx], f"stream {s} picture {idx} differs from the oracle"
+    assert eng.stats().pictures == 2 * npics
+    eng.host_free(out_host)
+    eng.close()
