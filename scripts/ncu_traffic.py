@@ -21,7 +21,6 @@ for r in rows[2:]:
     if not k:
         continue
     # the n-th launch of a kernel belongs to the n-th wave that launches it (the I wave has no inter / sparse / list kernels)
-    order = {"intra": None}
     n = seen.get(name, 0)
     seen[name] = n + 1
     if name in ("recon_inter2_kernel", "recon_intra_sparse_kernel", "intra_list_kernel"):
@@ -32,7 +31,6 @@ for r in rows[2:]:
         wave = waves[n] if n < 3 else None
     if wave is None:
         continue
-    dram = float(r[ix["dram__bytes_read.sum"]]) * (1e9 if float(r[ix["dram__bytes_read.sum"]]) < 50 else 1e6) if False else None
     rd, wr = float(r[ix["dram__bytes_read.sum"]]), float(r[ix["dram__bytes_write.sum"]])
     ru, wu = rows[1][ix["dram__bytes_read.sum"]], rows[1][ix["dram__bytes_write.sum"]]
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
