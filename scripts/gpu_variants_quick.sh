@@ -1,5 +1,7 @@
 #!/bin/bash
-# Runs on the GPU box: kernels-only bench (3 steps) of several engine builds.  Usage: scripts/gpu_variants_quick.sh <tag> <lib>...
+# Runs on the GPU box: bench (4 steps) of several engine builds.  Variants are built here with
+#   make -C arrow-h264_b200 OUT=variants/libx.so EXTRA="-DH264R_..." variants/libx.so
+# Usage: scripts/gpu_variants_quick.sh <tag> <lib>...
 tag=$1; shift
 mkdir -p gpurun_out
 for lib in "$@"; do
