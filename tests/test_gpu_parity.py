@@ -327,3 +327,32 @@ def test_concurrent_fill_through_the_public_entry_points():
     assert eng.stats().pictures == 2 * npics
     eng.host_free(out_host)
     eng.close()
+
+
+def test_long_run_wraps_the_event_and_table_rings():
+    """3000 pictures of a 2x1-MB stream, one h264r_flush per picture, two staging slots, three frames: the event ring (8192
+    events, three per wave), the picture-table ring and the staging slots wrap many times; every picture must still equal
+    the oracle's (a stale event or table entry would show up as a wrong or torn picture)."""
+    cfg, w, h, n = 1, 2, 1, 3000
+    st = pyapi.SynthStream(cfg, 0, w, h, n)
+    seq = st.seq
+    port = O.CpuDecoder("port", seq)
+    want = O.run_stream(port, cfg, 0, w, h, n)
+    port.close()
+    eng = pyapi.Engine(seq, max_frames=3, max_pictures=2)
+    frames, got = {}, []
+    for pic in st:
+        dst = eng.frame_alloc()
+        frames[pic.info.pic_index] = dst
+        eng.submit(pic, dst, [frames[pic.info.ref_pic_index[i]] for i in range(pic.info.num_refs)])
+        eng.flush()
+        for i in range(pic.info.num_refs):
+            if pic.info.last_use_of_ref[i]:
+                eng.frame_release(frames.pop(pic.info.ref_pic_index[i]))     # queued work keeps reading it: stream order
+        eng.wait(dst)
+        got.append(hashlib.md5(b"".join(eng.download(dst))).hexdigest())
+    st.close()
+    eng.wait()
+    eng.close()
+    bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
+    assert not bad, f"pictures {bad[:10]} differ"
