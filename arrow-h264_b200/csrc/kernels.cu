@@ -17,6 +17,14 @@
 #include "kernel_inter.cuh"
 #include "kernel_intra.cuh"
 #include "kernel_deblock.cuh"
+// -DH264R_DEBLOCK_PACKED=1: the deblocking of a wave runs in deblock4_kernel (two sample lines per lane in fp16x2, four pictures
+// per warp) instead of deblock_kernel.  Bit-exact, measured slower in round 2; not compiled by default.
+#ifndef H264R_DEBLOCK_PACKED
+#define H264R_DEBLOCK_PACKED 0
+#endif
+#if H264R_DEBLOCK_PACKED
+#include "kernel_deblock4.cuh"
+#endif
 
 namespace h264r {
 
@@ -28,7 +36,7 @@ const char* wave_kernel_name(int which)
     case KERNEL_LIST:    return "intra_list_kernel";
     case KERNEL_INTER:   return "recon_inter2_kernel";
     case KERNEL_INTRA:   return "recon_intra_kernel + recon_intra_sparse_kernel";
-    case KERNEL_DEBLOCK: return "deblock_kernel";
+    case KERNEL_DEBLOCK: return H264R_DEBLOCK_PACKED ? "deblock4_kernel" : "deblock_kernel";
     default:             return nullptr;
     }
 }
@@ -76,7 +84,11 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     }
     if (which == KERNEL_DEBLOCK) {
         if (!w.any_deblock) return 0;
+#if H264R_DEBLOCK_PACKED
+        deblock4_kernel<<<((w.num_pics + 3) / 4) * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
+#else
         deblock_kernel<<<((w.num_pics + 1) / 2) * groups, threads, 0, stream>>>(w.pics, w.num_pics, w.tickets, w.geom, w.epoch);
+#endif
         return 1;
     }
     return 0;

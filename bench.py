@@ -431,7 +431,7 @@ def run_gpu_arm(args, rank, world, local_rank, dist):
     peak, peak_src = peaks()
     # short names in the engine's kernel-kind order (h264r_bench_kernel_name)
     short = {"residual_kernel": "residual", "recon_inter2_kernel": "inter", "recon_intra_kernel + recon_intra_sparse_kernel": "intra",
-             "deblock_prep_kernel": "deblock_prep", "deblock_kernel": "deblock", "intra_list_kernel": "intra_list"}
+             "deblock_prep_kernel": "deblock_prep", "deblock_kernel": "deblock", "deblock4_kernel": "deblock", "intra_list_kernel": "intra_list"}
     names = [short[k] for k in kernels]
     # algorithmic bytes of each kernel's own pass: residual = levels in + 768 B residual plane out per coded MB;
     # inter / intra = SURVEY 8d formula restricted to their MBs; deblock_prep = headers + motion in, 64 B out;
