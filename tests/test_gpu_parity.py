@@ -356,3 +356,49 @@ def test_long_run_wraps_the_event_and_table_rings():
     eng.close()
     bad = [i for i, (a, b) in enumerate(zip(got, want)) if a != b]
     assert not bad, f"pictures {bad[:10]} differ"
+
+
+def test_resume_from_uploaded_reference_frames_and_statistics():
+    """A second context takes over a stream in the middle: the reference frames it needs are downloaded from the first
+    context and put into its frame pool with h264r_frame_upload (the way a decoder hands over pictures it reconstructed
+    elsewhere); the remaining pictures must still equal the oracle's.  h264r_get_stats must account for exactly the
+    pictures, macroblocks and copies that went through each context."""
+    cfg, sidx, w, h, n, split = 2, 1, 10, 6, 9, 4
+    st = pyapi.SynthStream(cfg, sidx, w, h, n)
+    seq = st.seq
+    port = O.CpuDecoder("port", seq)
+    want = O.run_stream(port, cfg, sidx, w, h, n)
+    port.close()
+    a = pyapi.Engine(seq, max_frames=n + 1, max_pictures=2)
+    b = pyapi.Engine(seq, max_frames=n + 1, max_pictures=2)
+    frames_a, frames_b, got = {}, {}, []
+    fbytes = w * h * 384
+    for pic in st:
+        i = pic.info.pic_index
+        refs_idx = [pic.info.ref_pic_index[k] for k in range(pic.info.num_refs)]
+        if len(got) < split:
+            eng, frames = a, frames_a
+        else:
+            eng, frames = b, frames_b
+            for r in refs_idx:                              # hand over the references context b does not have yet
+                if r not in frames_b:
+                    y, cb, cr = a.download(frames_a[r])
+                    frames_b[r] = b.frame_alloc()
+                    b.upload(frames_b[r], y, cb, cr)
+        frames[i] = eng.frame_alloc()
+        eng.submit(pic, frames[i], [frames[r] for r in refs_idx])
+        eng.flush()
+        eng.wait(frames[i])
+        got.append(hashlib.md5(b"".join(eng.download(frames[i]))).hexdigest())
+    st.close()
+    assert got == want, f"first difference at picture {first_diff(got, want)}"
+    sa, sb = a.stats(), b.stats()
+    assert (sa.pictures, sb.pictures) == (split, n - split)
+    assert (sa.macroblocks, sb.macroblocks) == (split * w * h, (n - split) * w * h)
+    assert sa.waves == split and sb.waves == n - split       # one flush per picture
+    assert sa.kernel_launches >= 3 * split and sb.kernel_launches >= 3 * (n - split)
+    uploads = len(frames_b) - (n - split)
+    assert uploads >= 1
+    assert sb.h2d_bytes > uploads * fbytes                   # the uploaded planes plus the picture descriptions
+    assert sa.d2h_bytes == (split + uploads) * fbytes and sb.d2h_bytes == (n - split) * fbytes
+    a.close(); b.close()
