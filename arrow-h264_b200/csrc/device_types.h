@@ -56,6 +56,10 @@ struct DevPicture {
     int                    run_deblock;
     int                    all_intra;                 // every slice is an I slice: row wavefront; otherwise inter + sparse intra kernels
     int                    direct8x8;                 // direct_8x8_inference_flag of the picture's stream
+    // field pictures (h264r_pic_params::structure != H264R_FRAME); all 0 for frame pictures
+    int                    field;                     // 1: mvlimit 2 and bS 3 on horizontal MB edges (deblock.cc:86, 106, 164, 188)
+    int                    chroma_dy;                 // -2 (top field) / +2 (bottom field): added to the vertical chroma vector ...
+    uint32_t               ref_opposite;              // ... for the reference slots of the other parity (inter_prediction.cc:352-354)
 };
 
 struct WaveLaunch {

@@ -137,6 +137,11 @@ bool pic_params_ok(const h264r_ctx* c, const h264r_pic_params* pp)
     if (pp->num_ref_frames < 0 || pp->num_ref_frames > H264R_MAX_REFS) return false;
     for (int i = 0; i < pp->num_ref_frames; ++i)
         if (pp->ref_frames[i] < 0 || pp->ref_frames[i] >= (int)c->frames.size() || !c->frames[pp->ref_frames[i]].dev) return false;
+    // frame pictures reference frames, field pictures reference fields (the context holds pictures of one kind)
+    if (pp->structure < H264R_FRAME || pp->structure > H264R_BOTTOM_FIELD) return false;
+    for (int i = 0; i < pp->num_ref_frames; ++i)
+        if (pp->structure == H264R_FRAME ? pp->ref_structure[i] != H264R_FRAME
+                                         : (pp->ref_structure[i] != H264R_TOP_FIELD && pp->ref_structure[i] != H264R_BOTTOM_FIELD)) return false;
     return true;
 }
 
@@ -673,6 +678,10 @@ int h264r_flush(h264r_ctx* ctx)
         p.num_slices = s.pp.num_slices; p.num_refs = s.pp.num_ref_frames;
         p.run_deblock = s.pp.run_deblock; p.all_intra = s.all_intra;
         p.direct8x8 = s.pp.direct_8x8_inference_flag != 0;
+        p.field = s.pp.structure != H264R_FRAME;
+        p.chroma_dy = s.pp.structure == H264R_TOP_FIELD ? -2 : (s.pp.structure == H264R_BOTTOM_FIELD ? 2 : 0);
+        for (int i = 0; i < s.pp.num_ref_frames; ++i)
+            if (p.field && s.pp.ref_structure[i] != s.pp.structure) p.ref_opposite |= 1u << i;
     }
     // on the H2D stream, ahead of the descriptions: every kernel of the flush (side and compute stream) follows its wave's ev_h2d
     CU(cudaMemcpyAsync(d_table, h_table, sizeof(DevPicture) * order.size(), cudaMemcpyHostToDevice, ctx->s_h2d));

@@ -55,13 +55,24 @@ inline int qpc_from_qpi(int qpi)
 }
 
 // Frame zig-zag scans, generated: idx -> (x, y).  4x4: Figure 8-8a; 8x8: Figure 8-8 (8x8 zig-zag).
+// Field scans (field pictures, transform.cc:344-382): H.264 Table 8-13 (4x4: down the first column, then column by column)
+// and Table 8-14 (8x8), one hex digit per index.
 struct ZigZag {
     uint8_t x4[16], y4[16], x8[64], y8[64];
+    uint8_t fx4[16], fy4[16], fx8[64], fy8[64];
     ZigZag()
     {
         gen(4, x4, y4);
         gen(8, x8, y8);
+        digits("0010011122223333", fx4); digits("0102312301230123", fy4);
+        digits("0001100121000123211123432222345433334565444456655556776666777777", fx8);
+        digits("0120134203567410256731024567310245673102456731245673014567234567", fy8);
     }
+    static void digits(const char* d, uint8_t* out) { for (int k = 0; d[k]; ++k) out[k] = (uint8_t)(d[k] - '0'); }
+    const uint8_t* sx4(bool field) const { return field ? fx4 : x4; }
+    const uint8_t* sy4(bool field) const { return field ? fy4 : y4; }
+    const uint8_t* sx8(bool field) const { return field ? fx8 : x8; }
+    const uint8_t* sy8(bool field) const { return field ? fy8 : y8; }
     static void gen(int n, uint8_t* xs, uint8_t* ys)
     {
         int x = 0, y = 0;

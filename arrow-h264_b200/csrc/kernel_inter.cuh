@@ -205,6 +205,7 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
         if (k == 1 && !__any_sync(0xFFFFFFFFu, active)) break;
         const int list = pd == 2 ? k : pd;
         int vx = 0, vy = 0, refidx = 0;
+        int cdy = 0;                                       // field pictures: vertical chroma offset towards a field of the other parity
         const uint32_t* wl = lq; const uint32_t* wc0 = cq; const uint32_t* wc1 = cq;
         int loff = 2, coff = 0;
         int cpitch = 2, lpitch = 4;                        // row pitches of this lane's chroma / luma windows, words
@@ -220,9 +221,10 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
             const uint32_t mvw = list ? mvw1 : mvw0;
             const int mvx = (int)(int16_t)(mvw & 0xFFFF), mvy = (int)(int16_t)(mvw >> 16);
             vx = (mbx * 16 + bx * 4) * 4 + mvx; vy = (mby * 16 + by * 4) * 4 + mvy;       // this block's position
+            cdy = ((pic.ref_opposite >> (slot & 31)) & 1) ? pic.chroma_dy : 0;         // get_block_chroma, inter_prediction.cc:352-354
             if (uni) {
                 const int qvx = (mbx * 16 + (bx >> 1) * 8) * 4 + mvx, qvy = (mby * 16 + (by >> 1) * 8) * 4 + mvy;
-                const int x0 = (qvx >> 2) - 2, y0 = (qvy >> 2) - 2, cx0 = qvx >> 3, cy0 = qvy >> 3;
+                const int x0 = (qvx >> 2) - 2, y0 = (qvy >> 2) - 2, cx0 = qvx >> 3, cy0 = (qvy + cdy) >> 3;
                 const int xa = x0 & ~3, cxa = cx0 & ~3;
                 const bool in_y = xa >= 0 && xa + 16 <= wY && y0 >= 0 && y0 + 13 <= hY;
                 const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 5 <= hC;
@@ -263,7 +265,7 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
                 wc0 = cq + (sb >> 1) * 2 * kChromaUniPitch; wc1 = wc0 + 5 * kChromaUniPitch;
                 coff = (sb & 1) * 2 + (tma_c ? cx0 & 15 : (in_c ? cx0 & 3 : 0));
             } else {
-                const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2, cx0 = vx >> 3, cy0 = vy >> 3;
+                const int x0 = (vx >> 2) - 2, y0 = (vy >> 2) - 2, cx0 = vx >> 3, cy0 = (vy + cdy) >> 3;
                 const int xa = x0 & ~3, cxa = cx0 & ~3;
                 const bool in_y = xa >= 0 && xa + 12 <= wY && y0 >= 0 && y0 + 9 <= hY;
                 const bool in_c = cxa >= 0 && cxa + 8 <= wC && cy0 >= 0 && cy0 + 3 <= hC;
@@ -306,7 +308,7 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
             const unsigned whm = __reduce_or_sync(0xFFFFFFFFu, active ? hm : 0u), wcm = __reduce_or_sync(0xFFFFFFFFu, active ? cm : 0u);
             uint32_t y[4];
             mc_luma_patch<4>(wl, loff, xf, yf, whm, wcm, y, lpitch);
-            const uint32_t c0 = mc_chroma_patch_2x2(wc0, coff, vx & 7, vy & 7, cpitch), c1 = mc_chroma_patch_2x2(wc1, coff, vx & 7, vy & 7, cpitch);
+            const uint32_t c0 = mc_chroma_patch_2x2(wc0, coff, vx & 7, (vy + cdy) & 7, cpitch), c1 = mc_chroma_patch_2x2(wc1, coff, vx & 7, (vy + cdy) & 7, cpitch);
             if (active) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { prevY[r] = curY[r]; curY[r] = y[r]; }

@@ -168,6 +168,7 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
     if (top)  { PT = load_hdr_lite(pic.mbs, q - W); if (idc == 2 && PT.slice_idx != Q.slice_idx) top = false; }
     const bool q_intra = Q.flags & H264R_MB_FLAG_INTRA, t8 = Q.flags & H264R_MB_FLAG_T8x8;
     const bool p_skip = (s0 & 0xFF) == H264R_P_SLICE && Q.mb_type == 0;
+    const int mvlimit = pic.field ? 2 : 4;
 
     // (loops kept rolled: unrolled, the kernel was 77 KB of code for a 32 KB instruction cache)
     uint32_t bs0 = 0, bs1 = 0, bs2 = 0, bs3 = 0;
@@ -183,7 +184,8 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
             if (e > 0 && p_skip) continue;
             const int wi = dir * 2 + (e >> 1), sh = (e & 1) * 16;
             const bool p_intra = e ? q_intra : (PN.flags & H264R_MB_FLAG_INTRA) != 0;
-            if (p_intra || q_intra) { bs_or(wi, (e == 0 ? 0x4444u : 0x3333u) << sh); continue; }
+            // bS 4 on MB edges -- in field pictures only on the vertical ones (cond_bS4, deblock.cc:106-107, 188-189)
+            if (p_intra || q_intra) { bs_or(wi, (e == 0 && !(pic.field && dir == 1) ? 0x4444u : 0x3333u) << sh); continue; }
             const int pcbp = e ? Q.cbp_blks : PN.cbp_blks;
             const bool same_part = e > 0 && (Q.mb_type == 1 || Q.mb_type == (dir == 0 ? 2 : 3));
 #pragma unroll
@@ -196,7 +198,7 @@ deblock_prep_kernel(const DevPicture* __restrict__ pics, int num_pics, FrameGeom
                     const uint32_t wp = packed_entry_word(e ? Q.packed : PN.packed, blkP), wq = packed_entry_word(Q.packed, blkQ);
                     if (wp != wq) {                              // the same entry: same pictures, same vectors
                         const uint32_t* ep = pic.stream + wp; const uint32_t* eq = pic.stream + wq;
-                        v = bs_compare(__ldg(ep), __ldg(ep + 1), __ldg(ep + 2), __ldg(eq), __ldg(eq + 1), __ldg(eq + 2));
+                        v = bs_compare(__ldg(ep), __ldg(ep + 1), __ldg(ep + 2), __ldg(eq), __ldg(eq + 1), __ldg(eq + 2), mvlimit);
                     }
                 }
                 bs_or(wi, v << (sh + k4 * 4));

@@ -297,22 +297,22 @@ __device__ __forceinline__ uint32_t deblock_threshold_word(int qp_p, int qp_q, i
     return __ldg(&c_thr_a[ia]) | (uint32_t)__ldg(&c_thr_beta[ib]) << 8;
 }
 
-// |mv_x| or |mv_y| differ by four quarter samples or more (mvlimit 4, frame pictures); a, b = packed int16 pairs
-__device__ __forceinline__ int mv_differs(uint32_t a, uint32_t b)
+// |mv_x| differs by four quarter samples or more, or |mv_y| by mvlimit (4; 2 in field pictures, deblock.cc:86, 164); a, b = packed int16 pairs
+__device__ __forceinline__ int mv_differs(uint32_t a, uint32_t b, int mvlimit)
 {
     const int dx = (int)(int16_t)(a & 0xFFFF) - (int)(int16_t)(b & 0xFFFF), dy = (int)(int16_t)(a >> 16) - (int)(int16_t)(b >> 16);
-    return (abs(dx) >= 4) | (abs(dy) >= 4);
+    return (abs(dx) >= 4) | (abs(dy) >= mvlimit);
 }
 // bs_compare_mvs, deblock.cc:35-75, on two motion entries held in registers (mv[0], mv[1], ref_idx[0..1] | ref_pic[0..1] << 16)
-__device__ __forceinline__ int bs_compare(uint32_t mp0, uint32_t mp1, uint32_t rp, uint32_t mq0, uint32_t mq1, uint32_t rq)
+__device__ __forceinline__ int bs_compare(uint32_t mp0, uint32_t mp1, uint32_t rp, uint32_t mq0, uint32_t mq1, uint32_t rq, int mvlimit)
 {
     const int p0 = (int8_t)(rp >> 16), p1 = (int8_t)(rp >> 24), q0 = (int8_t)(rq >> 16), q1 = (int8_t)(rq >> 24);
     if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;
     if (p0 != p1) {
-        if (p0 == q0) return mv_differs(mp0, mq0) | mv_differs(mp1, mq1);
-        return mv_differs(mp0, mq1) | mv_differs(mp1, mq0);
+        if (p0 == q0) return mv_differs(mp0, mq0, mvlimit) | mv_differs(mp1, mq1, mvlimit);
+        return mv_differs(mp0, mq1, mvlimit) | mv_differs(mp1, mq0, mvlimit);
     }
-    return (mv_differs(mp0, mq0) | mv_differs(mp1, mq1)) & (mv_differs(mp0, mq1) | mv_differs(mp1, mq0));
+    return (mv_differs(mp0, mq0, mvlimit) | mv_differs(mp1, mq1, mvlimit)) & (mv_differs(mp0, mq1, mvlimit) | mv_differs(mp1, mq0, mvlimit));
 }
 
 } // namespace h264r

@@ -587,7 +587,7 @@ void fill_slice_tables(h264s_stream* s, Gen& g, h264r_slice& sl, const PicPlan& 
     else if (cfg == H264S_CFG_CIF_BASELINE) { if (pic_idx % 4 == 3) sl.filter_offset_a = sl.filter_offset_b = -2; }
     else { sl.filter_offset_a = (int8_t)(2 * r.range(-3, 3)); sl.filter_offset_b = (int8_t)(2 * r.range(-3, 3)); }
 
-    sl.constrained_intra_pred_flag = (uint8_t)((cfg == H264S_CFG_1080P_HIGH || cfg == H264S_CFG_MULTI_1080P || cfg == H264S_CFG_4K_HIGH)
+    sl.constrained_intra_pred_flag = (uint8_t)((cfg == H264S_CFG_1080P_HIGH || cfg == H264S_CFG_MULTI_1080P || cfg == H264S_CFG_1080I_FIELDS || cfg == H264S_CFG_4K_HIGH)
                                                && plan.type == H264R_P_SLICE && (pic_idx % 3) == 1);
     sl.direct_spatial_mv_pred_flag = (uint8_t)r.chance(50);
     sl.num_ref[0] = (uint8_t)plan.n_l0; sl.num_ref[1] = (uint8_t)plan.n_l1;
@@ -646,10 +646,10 @@ extern "C" {
 
 h264s_stream* h264s_open(int config, int stream_idx, int width_mbs, int height_mbs, int num_frames)
 {
-    if (config < H264S_CFG_CIF_BASELINE || config > H264S_CFG_MULTI_1080P) return nullptr;
+    if (config < H264S_CFG_CIF_BASELINE || config > H264S_CFG_1080I_FIELDS) return nullptr;
     h264s_stream* s = new h264s_stream();
     s->config = config; s->stream_idx = stream_idx;
-    static const int dims[6][3] = { {0,0,0}, {22,18,30}, {80,45,24}, {120,68,16}, {240,135,8}, {120,68,16} };
+    static const int dims[7][3] = { {0,0,0}, {22,18,30}, {80,45,24}, {120,68,16}, {240,135,8}, {120,68,16}, {120,34,16} };
     s->W = width_mbs > 0 ? width_mbs : dims[config][0];
     s->H = height_mbs > 0 ? height_mbs : dims[config][1];
     s->num_frames = num_frames > 0 ? num_frames : dims[config][2];
@@ -658,7 +658,7 @@ h264s_stream* h264s_open(int config, int stream_idx, int width_mbs, int height_m
     // direct_8x8_inference_flag = 0 (direct motion per 4x4 block, decoder.cc:239-242) on every third stream with B pictures
     s->direct8x8 = !(s->allow_b && stream_idx % 3 == 2);
     s->transform8x8 = config >= H264S_CFG_1080P_HIGH;
-    s->default_matrices = (config == H264S_CFG_1080P_HIGH || config == H264S_CFG_MULTI_1080P) ? (stream_idx & 1)
+    s->default_matrices = (config == H264S_CFG_1080P_HIGH || config == H264S_CFG_MULTI_1080P || config == H264S_CFG_1080I_FIELDS) ? (stream_idx & 1)
                         : (config == H264S_CFG_4K_HIGH ? 1 : 0);
     s->chroma_qp_offset[0] = (config == H264S_CFG_CIF_BASELINE) ? ((stream_idx & 1) ? -2 : 0) : s->rng.range(-3, 3);
     s->chroma_qp_offset[1] = s->transform8x8 ? s->rng.range(-3, 3) : s->chroma_qp_offset[0];
@@ -714,6 +714,12 @@ int h264s_next(h264s_stream* s, h264s_pic_info* info, h264r_pic_params* pp, h264
     info->poc = plan.poc; info->num_refs = nref;
     pp->num_ref_frames = nref; pp->poc = plan.poc;
     pp->direct_8x8_inference_flag = s->direct8x8;
+    // field pictures (config 6): parities alternate in display order, so the references of a picture are fields of both
+    // parities (chroma vector offset, inter_prediction.cc:352-354)
+    if (s->config == H264S_CFG_1080I_FIELDS) {
+        pp->structure = ((plan.poc >> 1) & 1) ? H264R_BOTTOM_FIELD : H264R_TOP_FIELD;
+        for (int i = 0; i < nref; ++i) pp->ref_structure[i] = (uint8_t)(((pp->ref_poc[i] >> 1) & 1) ? H264R_BOTTOM_FIELD : H264R_TOP_FIELD);
+    }
 
     // slices: one, or two on odd pictures of the multi-slice configs (split not row aligned)
     g.num_slices = 1;

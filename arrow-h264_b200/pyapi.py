@@ -49,7 +49,8 @@ class Slice(C.Structure):
 class PicParams(C.Structure):
     _fields_ = [("num_slices", C.c_int32), ("num_ref_frames", C.c_int32), ("ref_frames", C.c_int32 * MAX_REFS),
                 ("run_deblock", C.c_int32), ("poc", C.c_int32), ("ref_poc", C.c_int32 * MAX_REFS),
-                ("ref_long_term", C.c_uint8 * MAX_REFS), ("direct_8x8_inference_flag", C.c_int32)]
+                ("ref_long_term", C.c_uint8 * MAX_REFS), ("direct_8x8_inference_flag", C.c_int32),
+                ("structure", C.c_int32), ("ref_structure", C.c_uint8 * MAX_REFS)]
 
 
 class SeqParams(C.Structure):

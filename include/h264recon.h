@@ -163,6 +163,7 @@ typedef struct h264r_slice {
 } h264r_slice;
 
 /* per-picture parameters */
+enum { H264R_FRAME = 0, H264R_TOP_FIELD = 1, H264R_BOTTOM_FIELD = 2 };   /* h264r_pic_params::structure */
 typedef int32_t h264r_frame;                     /* frame-pool id, >= 0                                */
 
 typedef struct h264r_pic_params {
@@ -176,6 +177,19 @@ typedef struct h264r_pic_params {
     uint8_t     ref_long_term[H264R_MAX_REFS];   /* informational                                      */
     int32_t     direct_8x8_inference_flag;       /* sps of THIS picture's stream (decoder.cc:239-242): streams
                                                     that share a context may differ                     */
+    int32_t     structure;                       /* shr.structure: H264R_FRAME, or H264R_TOP_FIELD / H264R_BOTTOM_FIELD
+                                                    for a field picture (field_pic_flag = 1, PAFF).  A field picture
+                                                    is a picture of its own of half the frame height (what the
+                                                    reference's storable_picture of a field is): the context is created
+                                                    with PicHeightInMbs = FrameHeightInMbs / 2 and every pool frame holds
+                                                    one field.  Differences on the path: field scans on the host side
+                                                    (transform.cc:344-382), the chroma vector offset between fields of
+                                                    different parity (inter_prediction.cc:352-354), mvlimit 2 and bS 3
+                                                    on horizontal MB edges in the deblocking rule (deblock.cc:86, 106,
+                                                    164, 188).  Frame and field pictures do not mix in one context
+                                                    (no field split / combine on the device yet); MBAFF is unsupported. */
+    uint8_t     ref_structure[H264R_MAX_REFS];   /* structure of ref_frames[i] (all H264R_FRAME for a frame picture,
+                                                    fields for a field picture)                            */
 } h264r_pic_params;
 
 /* context parameters (picture size = sps_t; every stream that shares the context has this size) */

@@ -25,7 +25,11 @@ enum {
     H264S_CFG_720P_MAIN    = 2,      /* 80x45, I B B P, bi-pred + explicit/implicit WP, 2 slices/odd    */
     H264S_CFG_1080P_HIGH   = 3,      /* 120x68, 8x8 transform, I8x8, scaling lists, constrained intra   */
     H264S_CFG_4K_HIGH      = 4,      /* 240x135, I/P/B, low QP, deblock offsets +-6, all-intra frames   */
-    H264S_CFG_MULTI_1080P  = 5       /* 64 x config 3 with distinct seeds                              */
+    H264S_CFG_MULTI_1080P  = 5,      /* 64 x config 3 with distinct seeds                              */
+    H264S_CFG_1080I_FIELDS = 6       /* 120x34: the FIELD pictures of a 1080i stream (field_pic_flag = 1 on every picture,
+                                        parities alternating in display order), otherwise the rules of config 3:
+                                        references of both parities, field deblocking rules (not in BASELINE.json:
+                                        SURVEY.md 8f-4, the PAFF part of the feature tail)                         */
 };
 
 typedef struct h264s_stream h264s_stream;

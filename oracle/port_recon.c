@@ -537,10 +537,15 @@ static void inter_mb(const pic_t* p, int cur, uint8_t pred[3][256])
                 if (k == 1 && pd != 2) break;
                 int list = pd == 2 ? k : pd;
                 refidx[k] = m->ref_idx[list][o];
-                const frame_t* rf = &p->d->fr[p->pp->ref_frames[sl->ref_pic_list[list][refidx[k]]]];
+                const int slot = sl->ref_pic_list[list][refidx[k]];
+                const frame_t* rf = &p->d->fr[p->pp->ref_frames[slot]];
                 /* absolute quarter-pel position of this 4x4 block's origin (:477-478) */
                 int vx = (mbx * 4 + bx) * 16 + m->mv[list][o][0];
                 int vy = (mby * 4 + by) * 16 + m->mv[list][o][1];
+                /* field pictures: a reference field of the other parity lies half a frame line off in chroma
+                 * (get_block_chroma, inter_prediction.cc:352-354) */
+                if (pl && p->pp->structure != H264R_FRAME && p->pp->ref_structure[slot] != p->pp->structure)
+                    vy += p->pp->structure == H264R_BOTTOM_FIELD ? 2 : -2;
                 for (int y = 0; y < n; ++y)
                     for (int x = 0; x < n; ++x)
                         smp[k][y * n + x] = pl == 0
@@ -651,20 +656,21 @@ static const uint8_t TAB_TC0[52][3] = {  /* Table 8-17 */
     {10,13,20},{11,15,23},{13,17,25} };
 
 /* bs_compare_mvs, deblock.cc:35-75.  (mp, bp) / (mq, bq): motion record + 4x4 block index of either side */
-static int mv_differs(const h264r_mb_motion* a, int ba, int la, const h264r_mb_motion* b, int bb, int lb)
+/* mvlimit (deblock.cc:86, 164): 4 quarter samples, 2 vertically in field pictures */
+static int mv_differs(int mvlimit, const h264r_mb_motion* a, int ba, int la, const h264r_mb_motion* b, int bb, int lb)
 {
-    return (iabs(a->mv[la][ba][0] - b->mv[lb][bb][0]) >= 4) | (iabs(a->mv[la][ba][1] - b->mv[lb][bb][1]) >= 4);
+    return (iabs(a->mv[la][ba][0] - b->mv[lb][bb][0]) >= 4) | (iabs(a->mv[la][ba][1] - b->mv[lb][bb][1]) >= mvlimit);
 }
-static int bs_compare(const h264r_mb_motion* mp, int bp, const h264r_mb_motion* mq, int bq)
+static int bs_compare(int mvlimit, const h264r_mb_motion* mp, int bp, const h264r_mb_motion* mq, int bq)
 {
     int p0 = mp->ref_pic[0][bp], p1 = mp->ref_pic[1][bp], q0 = mq->ref_pic[0][bq], q1 = mq->ref_pic[1][bq];
     if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;
     if (p0 != p1) {
-        if (p0 == q0) return mv_differs(mp, bp, 0, mq, bq, 0) | mv_differs(mp, bp, 1, mq, bq, 1);
-        return mv_differs(mp, bp, 0, mq, bq, 1) | mv_differs(mp, bp, 1, mq, bq, 0);
+        if (p0 == q0) return mv_differs(mvlimit, mp, bp, 0, mq, bq, 0) | mv_differs(mvlimit, mp, bp, 1, mq, bq, 1);
+        return mv_differs(mvlimit, mp, bp, 0, mq, bq, 1) | mv_differs(mvlimit, mp, bp, 1, mq, bq, 0);
     }
-    return (mv_differs(mp, bp, 0, mq, bq, 0) | mv_differs(mp, bp, 1, mq, bq, 1)) &
-           (mv_differs(mp, bp, 0, mq, bq, 1) | mv_differs(mp, bp, 1, mq, bq, 0));
+    return (mv_differs(mvlimit, mp, bp, 0, mq, bq, 0) | mv_differs(mvlimit, mp, bp, 1, mq, bq, 1)) &
+           (mv_differs(mvlimit, mp, bp, 0, mq, bq, 1) | mv_differs(mvlimit, mp, bp, 1, mq, bq, 0));
 }
 
 /* strength_vertical / strength_horizontal (deblock.cc:78-228) for frame pictures without SP/SI.
@@ -678,14 +684,15 @@ static void edge_strength(const pic_t* p, int q, int dir, int edge, uint8_t bS[1
     const h264r_slice* sl = &p->slices[Q->slice_idx];
     if (edge > 0 && sl->slice_type == H264R_P_SLICE && Q->mb_type == 0) { memset(bS, 0, 16); return; }
     const int intra = ((P->flags | Q->flags) & H264R_MB_FLAG_INTRA) != 0;
-    if (intra) { memset(bS, edge == 0 ? 4 : 3, 16); return; }
+    /* bS 4 on MB edges of frame pictures; in field pictures only on vertical MB edges (cond_bS4, deblock.cc:106-107, 188-189) */
+    if (intra) { memset(bS, edge == 0 && (p->pp->structure == H264R_FRAME || dir == 0) ? 4 : 3, 16); return; }
     for (int k4 = 0; k4 < 4; ++k4) {
         int blkQ = dir == 0 ? k4 * 4 + edge : edge * 4 + k4;
         int blkP = dir == 0 ? k4 * 4 + (edge ? edge - 1 : 3) : (edge ? edge - 1 : 3) * 4 + k4;
         int s;
         if (((Q->cbp_blks >> blkQ) & 1) || ((P->cbp_blks >> blkP) & 1)) s = 2;
         else if (edge > 0 && (Q->mb_type == 1 || Q->mb_type == (dir == 0 ? 2 : 3))) s = 0;
-        else s = bs_compare(&p->motion[pidx], blkP, &p->motion[q], blkQ);
+        else s = bs_compare(p->pp->structure != H264R_FRAME ? 2 : 4, &p->motion[pidx], blkP, &p->motion[q], blkQ);
         memset(bS + k4 * 4, s, 4);
     }
 }

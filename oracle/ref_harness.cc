@@ -134,6 +134,15 @@ int ref_reconstruct(ref_dec* d, int dst, const h264r_pic_params* pp, int used_fo
     VideoParameters* vid = d->vid;
     const int W = d->W, H = d->H, nmb = W * H;
     storable_picture* pic = d->frames[dst];
+    // A field picture (field_pic_flag = 1) is a picture of its own of half the frame height: d->H is the height of the
+    // field, every storable_picture of the pool holds one field (what the reference's own field pictures are).
+    const bool field = pp->structure != H264R_FRAME;
+    const PictureStructure structure = pp->structure == H264R_TOP_FIELD ? TOP_FIELD : (pp->structure == H264R_BOTTOM_FIELD ? BOTTOM_FIELD : FRAME);
+    d->sps.frame_mbs_only_flag = !field;
+    vid->structure = structure;
+    pic->slice.structure = structure;
+    const uint8_t* const X4 = d->zz.sx4(field); const uint8_t* const Y4 = d->zz.sy4(field);     // transform.cc:344-382
+    const uint8_t* const X8 = d->zz.sx8(field); const uint8_t* const Y8 = d->zz.sy8(field);
     pic->slice_headers.clear();
     pic->sps = &d->sps;
     pic->poc = pic->frame_poc = pic->top_poc = pic->bottom_poc = pp->poc;
@@ -189,7 +198,7 @@ int ref_reconstruct(ref_dec* d, int dst, const h264r_pic_params* pp, int used_fo
         s->layer_id = 0; s->view_id = 0;
         shr_t& shr = s->header;
         shr.slice_type = hs.slice_type;
-        shr.field_pic_flag = 0; shr.bottom_field_flag = 0; shr.MbaffFrameFlag = 0; shr.structure = FRAME;
+        shr.field_pic_flag = field; shr.bottom_field_flag = structure == BOTTOM_FIELD; shr.MbaffFrameFlag = 0; shr.structure = structure;
         shr.colour_plane_id = 0;
         shr.direct_spatial_mv_pred_flag = hs.direct_spatial_mv_pred_flag != 0;
         shr.disable_deblocking_filter_idc = hs.disable_deblocking_filter_idc;
@@ -280,7 +289,7 @@ int ref_reconstruct(ref_dec* d, int dst, const h264r_pic_params* pp, int used_fo
                 const bool i16 = hm.mb_type == H264R_MB_I16x16;
                 if (i16) {                                              // residual_luma, interpret_residual.cc:424-431
                     for (int k = 0; k < 16; ++k) {
-                        int bx = d->zz.x4[k], by = d->zz.y4[k];
+                        int bx = X4[k], by = Y4[k];
                         int lev = c[by * 4 * 16 + bx * 4];
                         if (lev) dec.coeff_luma_dc(&mb, PLANE_Y, 0, 0, k, lev);
                     }
@@ -291,14 +300,14 @@ int ref_reconstruct(ref_dec* d, int dst, const h264r_pic_params* pp, int used_fo
                     int bx0 = (i8 & 1) * 2, by0 = (i8 >> 1) * 2;
                     if (mb.transform_size_8x8_flag) {
                         for (int k = 0; k < 64; ++k) {
-                            int lev = c[(by0 * 4 + d->zz.y8[k]) * 16 + bx0 * 4 + d->zz.x8[k]];
+                            int lev = c[(by0 * 4 + Y8[k]) * 16 + bx0 * 4 + X8[k]];
                             if (lev) dec.coeff_luma_ac(&mb, PLANE_Y, bx0, by0, k, lev);
                         }
                     } else {
                         for (int i4 = 0; i4 < 4; ++i4) {
                             int bx = bx0 + (i4 & 1), by = by0 + (i4 >> 1);
                             for (int k = i16 ? 1 : 0; k < 16; ++k) {
-                                int lev = c[(by * 4 + d->zz.y4[k]) * 16 + bx * 4 + d->zz.x4[k]];
+                                int lev = c[(by * 4 + Y4[k]) * 16 + bx * 4 + X4[k]];
                                 if (lev) dec.coeff_luma_ac(&mb, PLANE_Y, bx, by, k, lev);
                             }
                         }
@@ -319,7 +328,7 @@ int ref_reconstruct(ref_dec* d, int dst, const h264r_pic_params* pp, int used_fo
                             for (int i4 = 0; i4 < 4; ++i4) {
                                 int bx = i4 & 1, by = i4 >> 1;
                                 for (int k = 1; k < 16; ++k) {
-                                    int lev = cc[(by * 4 + d->zz.y4[k]) * 8 + bx * 4 + d->zz.x4[k]];
+                                    int lev = cc[(by * 4 + Y4[k]) * 8 + bx * 4 + X4[k]];
                                     if (lev) dec.coeff_chroma_ac(&mb, (ColorPlane)(pl + 1), bx, by, k, lev);
                                 }
                             }

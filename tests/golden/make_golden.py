@@ -25,6 +25,9 @@ CASES = [
     # streams with stream % 3 == 2 carry direct_8x8_inference_flag = 0: direct sub-macroblocks / B_Skip / B_Direct_16x16
     # with motion per 4x4 block (decoder/decoder.cc:239-242); (2,2), (3,2) and (3,5) above are such streams too
     (2, 5, 20, 12, 12), (3, 8, 24, 14, 10), (4, 2, 30, 17, 8), (5, 2, 16, 10, 7), (5, 8, 16, 10, 7),
+    # field pictures (field_pic_flag = 1, h264r_pic_params::structure): field scans, chroma vector offset between parities,
+    # mvlimit 2 and bS 3 on horizontal MB edges; (6, 2) also has direct_8x8_inference_flag = 0; (6, 3) is a full 1080i field
+    (6, 0, 24, 14, 10), (6, 1, 11, 7, 16), (6, 2, 20, 12, 12), (6, 3, 120, 34, 3),
 ]
 
 if __name__ == "__main__":

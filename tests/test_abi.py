@@ -42,7 +42,8 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(pyapi.Slice) == 5216
     assert pyapi.Mb.coeff_offset.offset == 16 and pyapi.Mb.coeff_count.offset == 14 and pyapi.Mb.u.offset == 20 and pyapi.Mb.cbp_blks.offset == 12
     assert pyapi.Mb.motion.offset == 28
-    assert C.sizeof(pyapi.PicParams) == 8 + 4 * 32 + 8 + 4 * 32 + 32 + 4 and pyapi.PicParams.direct_8x8_inference_flag.offset == 304
+    assert C.sizeof(pyapi.PicParams) == 8 + 4 * 32 + 8 + 4 * 32 + 32 + 4 + 4 + 32 and pyapi.PicParams.direct_8x8_inference_flag.offset == 304
+    assert pyapi.PicParams.structure.offset == 308 and pyapi.PicParams.ref_structure.offset == 312
     assert C.sizeof(pyapi.PicBuffers) == 32 and pyapi.PicBuffers.picture.offset == 28
 
 

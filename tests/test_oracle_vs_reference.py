@@ -9,7 +9,8 @@ import pyapi
 
 needs_ref = pytest.mark.skipif(not os.path.exists(O.REF_PATH), reason="oracle/_ref not built (no /root/reference)")
 
-CASES = [(1, 2, 0, 0, 5), (2, 4, 24, 13, 9), (3, 8, 20, 11, 7), (3, 9, 20, 11, 7), (4, 2, 21, 12, 8), (5, 31, 15, 9, 7)]
+CASES = [(1, 2, 0, 0, 5), (2, 4, 24, 13, 9), (3, 8, 20, 11, 7), (3, 9, 20, 11, 7), (4, 2, 21, 12, 8), (5, 31, 15, 9, 7),
+         (6, 0, 20, 11, 9), (6, 1, 13, 6, 12), (6, 2, 20, 11, 9)]       # field pictures (PAFF)
 
 
 @needs_ref
