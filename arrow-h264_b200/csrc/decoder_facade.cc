@@ -4,9 +4,9 @@
 
 namespace h264r {
 
-void Decoder::init(const h264r_pic_buffers& bufs, int width_mbs, int height_mbs)
+void Decoder::init(const h264r_pic_buffers& bufs, int width_mbs, int height_mbs, bool field_pic_flag)
 {
-    bufs_ = bufs; width_mbs_ = width_mbs; height_mbs_ = height_mbs;
+    bufs_ = bufs; width_mbs_ = width_mbs; height_mbs_ = height_mbs; field_ = field_pic_flag;
     n_levels_ = 0; cur_mb_ = -1; cur_first_ = 0; overflow_ = false;
 }
 
@@ -25,7 +25,7 @@ void Decoder::append(FacadeMb* mb, int pos, int level)
 // Transform::coeff_luma_dc, transform.cc:425-429: cof[pos.y*4][pos.x*4] = level
 void Decoder::coeff_luma_dc(FacadeMb* mb, ColorPlane, int, int, int runarr, int levarr)
 {
-    append(mb, (zz_.y4[runarr] * 4) * 16 + zz_.x4[runarr] * 4, levarr);
+    append(mb, (zz_.sy4(field_)[runarr] * 4) * 16 + zz_.sx4(field_)[runarr] * 4, levarr);
 }
 
 // Transform::coeff_luma_ac, transform.cc:431-440
@@ -33,10 +33,10 @@ void Decoder::coeff_luma_ac(FacadeMb* mb, ColorPlane pl, int x0, int y0, int run
 {
     if (!mb->transform_size_8x8_flag) {
         mb->cbp_blks[pl] |= (uint64_t)0x01 << (y0 * 4 + x0);
-        append(mb, (y0 * 4 + zz_.y4[runarr]) * 16 + x0 * 4 + zz_.x4[runarr], levarr);
+        append(mb, (y0 * 4 + zz_.sy4(field_)[runarr]) * 16 + x0 * 4 + zz_.sx4(field_)[runarr], levarr);
     } else {
         mb->cbp_blks[pl] |= (uint64_t)0x33 << (y0 * 4 + x0);
-        append(mb, (y0 * 4 + zz_.y8[runarr]) * 16 + x0 * 4 + zz_.x8[runarr], levarr);
+        append(mb, (y0 * 4 + zz_.sy8(field_)[runarr]) * 16 + x0 * 4 + zz_.sx8(field_)[runarr], levarr);
     }
 }
 
@@ -49,7 +49,7 @@ void Decoder::coeff_chroma_dc(FacadeMb* mb, ColorPlane pl, int, int, int runarr,
 // Transform::coeff_chroma_ac, transform.cc:448-456
 void Decoder::coeff_chroma_ac(FacadeMb* mb, ColorPlane pl, int x0, int y0, int runarr, int levarr)
 {
-    append(mb, 256 + (pl - 1) * 64 + (y0 * 4 + zz_.y4[runarr]) * 8 + x0 * 4 + zz_.x4[runarr], levarr);
+    append(mb, 256 + (pl - 1) * 64 + (y0 * 4 + zz_.sy4(field_)[runarr]) * 8 + x0 * 4 + zz_.sx4(field_)[runarr], levarr);
 }
 
 void Decoder::pcm_sample(FacadeMb* mb, ColorPlane pl, int x, int y, int value)

@@ -44,8 +44,9 @@ struct FacadeMotion {
 
 class Decoder {
 public:
-    // Decoder::init (decoder.cc:52-57): bind to the buffers of the picture being parsed
-    void init(const h264r_pic_buffers& bufs, int width_mbs, int height_mbs);
+    // Decoder::init (decoder.cc:52-57): bind to the buffers of the picture being parsed.  field_pic_flag (shr.field_pic_flag)
+    // selects the field scans for the coefficient positions (Transform::inverse_scan_*, transform.cc:339-386)
+    void init(const h264r_pic_buffers& bufs, int width_mbs, int height_mbs, bool field_pic_flag = false);
 
     // Decoder::assign_quant_params (decoder.cc:59-62 -> Transform::init/set_quant): weightScale lists of slice
     // `slice_nr` in raster order, [0..5] 4x4 (Intra Y,Cb,Cr, Inter Y,Cb,Cr), [0..1] 8x8 (Intra Y, Inter Y)
@@ -82,6 +83,7 @@ private:
     int cur_mb_ = -1;
     uint32_t cur_first_ = 0;
     bool overflow_ = false;
+    bool field_ = false;
     ZigZag zz_;
 };
 

@@ -48,7 +48,7 @@ struct QuantLists { int q4[6][16]; int q8[2][64]; };
 // Engine frame of a decoded picture.  The map below is keyed by the storable_picture's ADDRESS, which is only an
 // identity: entries are never dereferenced (the DPB frees pictures behind our back), what the engine wants to know about a
 // reference (its POC) is cached here when the picture is decoded.
-struct GpuFrameEntry { h264r_frame frame; int poc; bool live; };
+struct GpuFrameEntry { h264r_frame frame; int poc; bool live; uint8_t structure; };
 
 struct GpuState {
     h264r_ctx* ctx = nullptr;
@@ -65,12 +65,18 @@ struct GpuState {
 
 const int kMaxGpuFrames = 40;        // > 16 DPB frames + the current picture + pictures waiting for output
 
-void open_engine(const sps_t& sps)
+// The engine context holds pictures of ONE size: frames, or -- for a stream coded in field pictures (PAFF with
+// field_pic_flag = 1 throughout) -- fields, which are pictures of their own of half the frame height exactly like the
+// reference's field storable_pictures.  A stream that switches between frame and field pictures would need the DPB's
+// dpb_split_field / dpb_combine_field on device frames: outside the supported subset, reported as such.
+void open_engine(const sps_t& sps, const shr_t& shr)
 {
-    const int W = (int)sps.PicWidthInMbs, H = (int)sps.FrameHeightInMbs;
+    const int W = (int)sps.PicWidthInMbs, H = (int)shr.PicHeightInMbs;
     if (g.ctx && W == g.width_mbs && H == g.height_mbs) return;
+    if (g.ctx && !g.frames.empty() && W == g.width_mbs)
+        error(500, "h264recon: frame and field pictures in one stream: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
     if (g.ctx) { h264r_destroy(g.ctx); g.ctx = nullptr; g.frames.clear(); }
-    if (sps.chroma_format_idc != 1 || sps.bit_depth_luma_minus8 != 0 || sps.bit_depth_chroma_minus8 != 0 || !sps.frame_mbs_only_flag)
+    if (sps.chroma_format_idc != 1 || sps.bit_depth_luma_minus8 != 0 || sps.bit_depth_chroma_minus8 != 0 || sps.mb_adaptive_frame_field_flag)
         error(500, "h264recon: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
     h264r_seq_params sp;
     memset(&sp, 0, sizeof(sp));
@@ -104,10 +110,17 @@ void sweep_dead_frames(VideoParameters* p_Vid, const storable_picture* current)
         for (unsigned i = 0; i < dpb->used_size; ++i) {
             const pic_t* fs = dpb->fs[i];
             if (!fs) continue;
-            auto it = g.frames.find(fs->frame);
-            if (it != g.frames.end()) it->second.live = true;
+            for (const storable_picture* p : { (const storable_picture*)fs->frame, (const storable_picture*)fs->top_field, (const storable_picture*)fs->bottom_field }) {
+                auto it = g.frames.find(p);
+                if (it != g.frames.end()) it->second.live = true;
+            }
         }
     }
+    if (p_Vid->out_buffer)                                  // fields waiting for their other half in direct_output (output_gpu.cc)
+        for (const storable_picture* p : { (const storable_picture*)p_Vid->out_buffer->top_field, (const storable_picture*)p_Vid->out_buffer->bottom_field }) {
+            auto it = g.frames.find(p);
+            if (it != g.frames.end()) it->second.live = true;
+        }
     for (auto it = g.frames.begin(); it != g.frames.end(); ) {
         if (it->second.live) { ++it; continue; }
         h264r_frame_release(g.ctx, it->second.frame);
@@ -116,14 +129,14 @@ void sweep_dead_frames(VideoParameters* p_Vid, const storable_picture* current)
 }
 
 // a new picture: its storable_picture may reuse the address of a freed one
-h264r_frame new_frame(const storable_picture* p, int poc)
+h264r_frame new_frame(const storable_picture* p, int poc, int structure)
 {
     auto it = g.frames.find(p);
     if (it != g.frames.end()) { h264r_frame_release(g.ctx, it->second.frame); g.frames.erase(it); }
     if ((int)g.frames.size() >= H264R_MAX_REFS) error(500, "h264recon: more than %d pictures alive in the decoded picture buffer", H264R_MAX_REFS);
     h264r_frame f;
     check(h264r_frame_alloc(g.ctx, &f), "h264r_frame_alloc");
-    g.frames[p] = GpuFrameEntry{ f, poc, true };
+    g.frames[p] = GpuFrameEntry{ f, poc, true, (uint8_t)structure };
     return f;
 }
 
@@ -137,11 +150,13 @@ int slot_of(h264r_frame f)
 // first slice of a picture (init_picture has run: core/slice_data.cc:149-313)
 void begin_picture(slice_t& slice)
 {
-    open_engine(*slice.active_sps);
+    open_engine(*slice.active_sps, slice.header);
     const storable_picture* pic = slice.dec_picture;
     sweep_dead_frames(slice.p_Vid, nullptr);
-    const h264r_frame dst = new_frame(pic, slice.header.PicOrderCnt);
+    const int structure = slice.header.structure == TOP_FIELD ? H264R_TOP_FIELD : (slice.header.structure == BOTTOM_FIELD ? H264R_BOTTOM_FIELD : H264R_FRAME);
+    const h264r_frame dst = new_frame(pic, slice.header.PicOrderCnt, structure);
     memset(&g.pp, 0, sizeof(g.pp));
+    g.pp.structure = structure;
     // reference table of the picture: every picture the DPB holds (later slices may list other references than the first
     // one).  POC and long-term state are informational for the engine (implicit weights are precomputed in fill_slice
     // from the pictures the slice lists, which are alive).
@@ -151,6 +166,7 @@ void begin_picture(slice_t& slice)
         g.pp.ref_frames[i] = kv.second.frame;
         g.pp.ref_poc[i] = kv.second.poc;
         g.pp.ref_long_term[i] = 0;
+        g.pp.ref_structure[i] = kv.second.structure;
     }
     g.pp.num_slices = 1;                     // grows with every slice; final value set before submit
     g.pp.poc = slice.header.PicOrderCnt;
@@ -159,7 +175,7 @@ void begin_picture(slice_t& slice)
     h264r_pic_params tmp = g.pp;
     tmp.num_slices = 64;                     // staging capacity check only; see end_picture
     check(h264r_picture_begin(g.ctx, dst, &tmp, &g.bufs), "h264r_picture_begin");
-    g.facade.init(g.bufs, g.width_mbs, g.height_mbs);
+    g.facade.init(g.bufs, g.width_mbs, g.height_mbs, slice.header.field_pic_flag != 0);      // field scans: transform.cc:339-386
     g.cur = pic;
     g.any_deblock = false;
 }
@@ -171,7 +187,7 @@ void fill_slice(slice_t& slice, const QuantLists& q)
     const pps_t& pps = *slice.active_pps;
     const int nr = slice.current_slice_nr;
     if (nr < 0 || nr >= 64) error(500, "h264recon: more than 64 slices in a picture");
-    if (shr.field_pic_flag || shr.MbaffFrameFlag || slice.active_sps->separate_colour_plane_flag ||
+    if (shr.MbaffFrameFlag || slice.active_sps->separate_colour_plane_flag ||
         (shr.slice_type != P_slice && shr.slice_type != B_slice && shr.slice_type != I_slice))
         error(500, "h264recon: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
     h264r_slice& s = g.bufs.slices[nr];
@@ -381,6 +397,7 @@ void Decoder::deblock_filter(slice_t& slice)
 // for output_gpu.cc
 h264r_ctx* gpu_engine() { return g.ctx; }
 h264r_frame gpu_frame_of_picture(const storable_picture* p) { return frame_of(p); }
+bool gpu_has_picture(const storable_picture* p) { return g.frames.find(p) != g.frames.end(); }
 // a picture that never entered the DPB is about to be deleted (direct_output): its engine frame goes back to the pool
 void gpu_picture_freed(const storable_picture* p)
 {

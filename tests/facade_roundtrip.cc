@@ -28,7 +28,10 @@ int main(int argc, char** argv)
     while (h264s_next(st, &info, &pp, mbs.data(), motion.data(), slices.data(), levels.data(), (uint32_t)levels.size()) == 1) {
         h264r_pic_buffers bufs = { fmbs.data(), fslices.data(), flevels.data(), (uint32_t)flevels.size(), 0 };
         Decoder dec;
-        dec.init(bufs, W, H);
+        const bool field = pp.structure != H264R_FRAME;       // field pictures: the parser's scan indexes are field-scan indexes
+        const uint8_t* const X4 = zz.sx4(field); const uint8_t* const Y4 = zz.sy4(field);
+        const uint8_t* const X8 = zz.sx8(field); const uint8_t* const Y8 = zz.sy8(field);
+        dec.init(bufs, W, H, field);
         for (int addr = 0; addr < nmb; ++addr) {
             const h264r_mb& hm = mbs[addr];
             FacadeMb mb; memset(&mb, 0, sizeof(mb));
@@ -50,17 +53,17 @@ int main(int argc, char** argv)
             } else if (hm.coeff_count) {
                 const bool i16 = hm.mb_type == H264R_MB_I16x16;
                 if (i16) {
-                    for (int k = 0; k < 16; ++k) { int lev = c[zz.y4[k] * 64 + zz.x4[k] * 4]; if (lev) dec.coeff_luma_dc(&mb, PLANE_Y, 0, 0, k, lev); }
+                    for (int k = 0; k < 16; ++k) { int lev = c[Y4[k] * 64 + X4[k] * 4]; if (lev) dec.coeff_luma_dc(&mb, PLANE_Y, 0, 0, k, lev); }
                     dec.transform_luma_dc(&mb, PLANE_Y);
                 }
                 for (int i8 = 0; i8 < 4; ++i8) {
                     if (!(hm.cbp_luma & (1 << i8))) continue;
                     int bx0 = (i8 & 1) * 2, by0 = (i8 >> 1) * 2;
                     if (mb.transform_size_8x8_flag) {
-                        for (int k = 0; k < 64; ++k) { int lev = c[(by0 * 4 + zz.y8[k]) * 16 + bx0 * 4 + zz.x8[k]]; if (lev) dec.coeff_luma_ac(&mb, PLANE_Y, bx0, by0, k, lev); }
+                        for (int k = 0; k < 64; ++k) { int lev = c[(by0 * 4 + Y8[k]) * 16 + bx0 * 4 + X8[k]]; if (lev) dec.coeff_luma_ac(&mb, PLANE_Y, bx0, by0, k, lev); }
                     } else for (int i4 = 0; i4 < 4; ++i4) {
                         int bx = bx0 + (i4 & 1), by = by0 + (i4 >> 1);
-                        for (int k = i16 ? 1 : 0; k < 16; ++k) { int lev = c[(by * 4 + zz.y4[k]) * 16 + bx * 4 + zz.x4[k]]; if (lev) dec.coeff_luma_ac(&mb, PLANE_Y, bx, by, k, lev); }
+                        for (int k = i16 ? 1 : 0; k < 16; ++k) { int lev = c[(by * 4 + Y4[k]) * 16 + bx * 4 + X4[k]]; if (lev) dec.coeff_luma_ac(&mb, PLANE_Y, bx, by, k, lev); }
                     }
                 }
                 if (hm.cbp_chroma & 3) {
@@ -73,7 +76,7 @@ int main(int argc, char** argv)
                         for (int pl = 1; pl <= 2; ++pl) {
                             const int16_t* cc = c + 256 + (pl - 1) * 64;
                             for (int i4 = 0; i4 < 4; ++i4) for (int k = 1; k < 16; ++k) {
-                                int lev = cc[((i4 >> 1) * 4 + zz.y4[k]) * 8 + (i4 & 1) * 4 + zz.x4[k]];
+                                int lev = cc[((i4 >> 1) * 4 + Y4[k]) * 8 + (i4 & 1) * 4 + X4[k]];
                                 if (lev) dec.coeff_chroma_ac(&mb, (ColorPlane)pl, i4 & 1, i4 >> 1, k, lev);
                             }
                         }

@@ -187,16 +187,20 @@ class Stream:
     LOG2_MAX_POC_LSB = 6
 
     def __init__(self, width_mbs, height_mbs, seed=1, profile="main", num_refs=2, weighted_pred=0, weighted_bipred=0,
-                 direct_8x8_inference=1, transform_8x8=False, scaling=None, constrained_intra=0, chroma_qp_offset=0):
+                 direct_8x8_inference=1, transform_8x8=False, scaling=None, constrained_intra=0, chroma_qp_offset=0, field=False):
         """profile: "main" (4x4 transform) or "high" (transform_8x8 / scaling allowed).  scaling = None, or a pair
         (sps_lists, pps_lists) where each is None (matrix not present) or a list of eight entries: None (list not present:
         fall-back rule A / B), "default" (useDefaultScalingMatrixFlag) or a list of 16 / 64 values in raster order."""
-        self.W, self.H = width_mbs, height_mbs
+        # field=True: every picture is a field (frame_mbs_only_flag = 0, field_pic_flag = 1); height_mbs is the height of the
+        # FRAME and must be even, the pictures this class writes are height_mbs / 2 high
+        self.field = field
+        assert not field or height_mbs % 2 == 0
+        self.W, self.H = width_mbs, height_mbs // 2 if field else height_mbs
         self.rng = random.Random(seed)
         self.profile = profile
         self.num_refs = num_refs
         self.weighted_pred, self.weighted_bipred = weighted_pred, weighted_bipred
-        self.direct8x8 = direct_8x8_inference
+        self.direct8x8 = 1 if field else direct_8x8_inference      # frame_mbs_only_flag = 0 requires direct_8x8_inference_flag = 1
         self.t8 = transform_8x8 and profile == "high"
         self.scaling = scaling if profile == "high" else None
         self.constrained_intra = constrained_intra
@@ -267,8 +271,10 @@ class Stream:
         w.ue(self.LOG2_MAX_POC_LSB - 4)
         w.ue(self.num_refs + 1)                   # max_num_ref_frames: one more than a slice lists, so that the picture a
         w.u(1, 0)                                 # co-located block of a temporal-direct MB refers to is still in the DPB
-        w.ue(self.W - 1); w.ue(self.H - 1)
-        w.u(1, 1)                                     # frame_mbs_only_flag
+        w.ue(self.W - 1); w.ue(self.H - 1)            # pic_height_in_map_units: the field height when frame_mbs_only_flag = 0
+        w.u(1, 0 if self.field else 1)                # frame_mbs_only_flag
+        if self.field:
+            w.u(1, 0)                                 # mb_adaptive_frame_field_flag
         w.u(1, self.direct8x8)
         w.u(1, 0)                                     # frame_cropping_flag
         w.u(1, 0)                                     # vui_parameters_present_flag
@@ -579,12 +585,15 @@ class Stream:
                     for _ in range(2):
                         w.se(self.rng.randint(-(1 << cd), (1 << cd) + (1 << cd) // 2 + 1)); w.se(self.rng.randint(-12, 12))
 
-    def _slice_header(self, w, first_mb, kind, is_ref, poc, qp, idc, off_a, off_b):
+    def _slice_header(self, w, first_mb, kind, is_ref, poc, qp, idc, off_a, off_b, bottom=False):
         """kind: "idr", "i", "p", "b".  Returns (n0, n1) = active reference counts."""
         w.ue(first_mb)
         w.ue({"idr": 2, "i": 2, "p": 0, "b": 1}[kind])
         w.ue(0)
         w.u(self.LOG2_MAX_FRAME_NUM, self.frame_num % (1 << self.LOG2_MAX_FRAME_NUM))
+        if self.field:
+            w.u(1, 1)                                 # field_pic_flag
+            w.u(1, 1 if bottom else 0)                # bottom_field_flag
         if kind == "idr":
             w.ue(self.idr_id)
         w.u(self.LOG2_MAX_POC_LSB, poc % (1 << self.LOG2_MAX_POC_LSB))
@@ -614,18 +623,24 @@ class Stream:
             w.se(off_a); w.se(off_b)
         return n0, n1
 
-    def picture(self, kind, poc, qp=30, idc=0, off_a=0, off_b=0, slices=2, intra_share=0.12, skip_share=0.2):
+    def picture(self, kind, poc, qp=30, idc=0, off_a=0, off_b=0, slices=2, intra_share=0.12, skip_share=0.2, bottom=False,
+                second_field=False):
+        """One picture; with field=True one FIELD: `bottom` its parity, `second_field` = it completes the frame the previous
+        call started (same frame_num; frame_num moves on after the second field of a reference frame).  The second field of
+        an IDR frame is a non-IDR P field (complementary reference field pair, H.264 3.30)."""
         is_ref = kind != "b"
         if kind == "idr":
             self.frame_num = 0
         self._new_picture()
-        self.direct_spatial = self.rng.randrange(2)
+        # field streams: spatial direct only (the co-located field of a temporal-direct MB may refer to a field that the two
+        # entries of this writer's list 0 do not hold)
+        self.direct_spatial = 1 if self.field else self.rng.randrange(2)
         n = self.W * self.H
         cuts = sorted(set([0] + ([self.rng.randrange(1, n)] if slices > 1 and n > 1 else [])))
         for si, first in enumerate(cuts):
             last = cuts[si + 1] if si + 1 < len(cuts) else n
             w = BitWriter()
-            n0, n1 = self._slice_header(w, first, kind, is_ref, poc, qp, idc, off_a, off_b)
+            n0, n1 = self._slice_header(w, first, kind, is_ref, poc, qp, idc, off_a, off_b, bottom)
             self.qp_running = qp
             skip_run = 0
             base = {"idr": 0, "i": 0, "p": 5, "b": 23}[kind]
@@ -655,12 +670,39 @@ class Stream:
             self.idr_id += 1
             self.refs_available = 1
         elif is_ref:
-            self.refs_available = min(self.num_refs + 1, self.refs_available + 1)
-        if is_ref:
+            self.refs_available = min((2 if self.field else 1) * (self.num_refs + 1) - (1 if self.field else 0), self.refs_available + 1)
+        if is_ref and (not self.field or second_field):
             self.frame_num += 1
 
     def data(self):
         return bytes(self.out)
+
+
+def make_field_stream(width_mbs=11, height_mbs=10, gops=2, seed=7, b_frames=True, **opts):
+    """The same GOP structure with every frame coded as two fields, top first: IDR frame = I field + P field, anchor frames
+    = P + P fields, B frames = B + B fields (not used for reference).  The fields of a frame share frame_num; POC = 2 x
+    display index of the frame (+ 1 for the bottom field).  Returns (bytes, number of FRAMES)."""
+    s = Stream(width_mbs, height_mbs, seed, field=True, **opts)
+    frames = 0
+    for g in range(gops):
+        disp = 0
+        s.picture("idr", 0, qp=28 + 2 * g, slices=1 + (g & 1))
+        s.picture("p", 1, qp=29, slices=2, bottom=True, second_field=True)
+        frames += 1
+        for k in range(3):
+            nb = 2 if b_frames else 0
+            disp_anchor = disp + nb + 1
+            for bottom in (False, True):
+                s.picture("p", 2 * disp_anchor + bottom, qp=(26, 32, 38)[k % 3] + bottom, idc=(0, 2, 0)[k % 3], off_a=(0, 2, -4)[k % 3],
+                          off_b=(2, 0, -2)[k % 3], slices=1 + (frames + bottom) % 2, bottom=bottom, second_field=bottom)
+            frames += 1
+            for b in range(nb):
+                for bottom in (False, True):
+                    s.picture("b", 2 * (disp + 1 + b) + bottom, qp=(30, 34)[b], idc=(0, 1)[(b + k + bottom) % 2], off_a=2 * b, off_b=-2 * b,
+                              slices=1 + b, bottom=bottom, second_field=bottom)
+                frames += 1
+            disp = disp_anchor
+    return s.data(), frames
 
 
 def make_stream(width_mbs=11, height_mbs=9, gops=2, seed=7, b_frames=True, **opts):

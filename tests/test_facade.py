@@ -19,7 +19,7 @@ def facade_binary(tmp_path_factory):
     return out
 
 
-@pytest.mark.parametrize("cfg,w,h,n", [(1, 22, 18, 4), (2, 9, 7, 9), (3, 12, 8, 6), (4, 7, 5, 8)])
+@pytest.mark.parametrize("cfg,w,h,n", [(1, 22, 18, 4), (2, 9, 7, 9), (3, 12, 8, 6), (4, 7, 5, 8), (6, 12, 8, 6)])
 def test_facade_reproduces_the_picture_description(facade_binary, cfg, w, h, n):
     r = subprocess.run([facade_binary, str(cfg), str(w), str(h), str(n)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr

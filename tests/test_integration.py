@@ -142,3 +142,57 @@ def test_reference_parser_on_the_gpu_engine_with_residual_b_pictures_and_scaling
             k = next(j for j in range(fsz) if a[j] != b[j])
             plane = "Y" if k < w * h * 256 else ("Cb" if k < w * h * 320 else "Cr")
             pytest.fail(f"{case}: output frame {i}: first difference in plane {plane} at byte {k} (reference {a[k]}, gpu {b[k]})")
+
+
+# ---- streams coded in FIELD pictures (field_pic_flag = 1 on every picture; SURVEY.md 8f-4, the PAFF part) ----
+
+FIELD_CASES = {
+    "field-main-ip":       dict(w=6, h=6, gops=1, seed=21, b_frames=False),
+    "field-main-ipb":      dict(w=11, h=10, gops=2, seed=22),
+    "field-main-explicit-wp": dict(w=7, h=4, gops=2, seed=23, weighted_pred=1, weighted_bipred=1),
+    "field-main-implicit-wp": dict(w=5, h=6, gops=2, seed=24, weighted_bipred=2, chroma_qp_offset=-2),
+    "field-high-t8-scaling": dict(w=6, h=8, gops=2, seed=25, profile="high", transform_8x8=True, scaling="both", constrained_intra=1),
+    "field-high-20x12":    dict(w=20, h=12, gops=1, seed=26, profile="high", transform_8x8=True, weighted_bipred=1),
+}
+
+
+def field_stream(case):
+    import h264_writer_cavlc
+    opts = dict(FIELD_CASES[case])
+    w, h = opts.pop("w"), opts.pop("h")
+    if "scaling" in opts:
+        sps, pps = _lists(opts["seed"])
+        opts["scaling"] = {"both": (sps, pps)}[opts["scaling"]]
+    data, frames = h264_writer_cavlc.make_field_stream(w, h, **opts)
+    return data, frames, w, h
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="integration/_build/ldecod_ref not built")
+@pytest.mark.parametrize("case", sorted(FIELD_CASES))
+def test_field_streams_are_decodable_by_the_reference(tmp_path, case):
+    stream, frames, w, h = field_stream(case)
+    yuv, log = decode(REF, stream, str(tmp_path), "ref")
+    assert len(yuv) == frames * w * h * 384, log[-1500:]
+    assert "rror" not in log, log[-1500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU)), reason="integration/_build binaries not built")
+@pytest.mark.parametrize("case", sorted(FIELD_CASES))
+def test_reference_parser_on_the_gpu_engine_with_field_pictures(tmp_path, case):
+    """Field pictures through the real parser: the reference's slice / MB parsing and DPB (field pairs, field reference lists),
+    field scans in the coefficient hand-off (transform.cc:339-386), references of both parities (chroma vector offset,
+    inter_prediction.cc:352-354), the field deblocking rules (deblock.cc:86-108), both fields interleaved on output:
+    byte-identical frames."""
+    stream, frames, w, h = field_stream(case)
+    want, _ = decode(REF, stream, str(tmp_path), "ref")
+    got, log = decode(GPU, stream, str(tmp_path), "gpu")
+    assert len(want) == frames * w * h * 384
+    assert len(got) == len(want), log[-1500:]
+    fsz = w * h * 384
+    for i in range(frames):
+        a, b = want[i * fsz:(i + 1) * fsz], got[i * fsz:(i + 1) * fsz]
+        if a != b:
+            k = next(j for j in range(fsz) if a[j] != b[j])
+            plane = "Y" if k < w * h * 256 else ("Cb" if k < w * h * 320 else "Cr")
+            pytest.fail(f"{case}: output frame {i}: first difference in plane {plane} at byte {k} (reference {a[k]}, gpu {b[k]})")
