@@ -16,7 +16,9 @@
  * (core/slice_data.cc:636-661).
  *
  * Supported stream subset (anything else returns H264R_ERR_UNSUPPORTED, there is NO CPU fallback):
- * 8-bit 4:2:0 frame pictures (no PAFF/MBAFF), no transform bypass, no SP/SI slices, no FMO/ASO.
+ * 8-bit 4:2:0 frame pictures, or the field pictures of a stream coded in fields throughout (h264r_pic_params::structure; a
+ * context holds pictures of one size); no MBAFF, no frame / field switching inside a stream, no transform bypass, no SP/SI
+ * slices, no FMO/ASO.
  *
  * Every struct below is also the HBM layout: the host fills pinned staging memory laid out exactly as
  * the device reads it, so submit is a handful of large cudaMemcpyAsync calls.
