@@ -884,6 +884,52 @@ int h264r_frame_upload(h264r_ctx* ctx, h264r_frame f, const uint8_t* y, const ui
     return H264R_OK;
 }
 
+// dpb_split_field / dpb_combine_field_yuv (framebuf/dpb.cc) between a context of frames and a context of fields
+int h264r_field_copy(h264r_ctx* frame_ctx, h264r_frame frame, h264r_ctx* field_ctx, h264r_frame field, int parity, int to_field)
+{
+    if (!frame_ctx || !field_ctx || frame_ctx == field_ctx || !frame_ok(frame_ctx, frame) || !frame_ok(field_ctx, field) ||
+        parity < 0 || parity > 1) return H264R_ERR_INVALID;
+    const FrameGeom& gf = frame_ctx->geom; const FrameGeom& gd = field_ctx->geom;
+    if (frame_ctx->device != field_ctx->device || gf.width_mbs != gd.width_mbs || gf.height_mbs != 2 * gd.height_mbs) return H264R_ERR_INVALID;
+    h264r_ctx* const sctx = to_field ? frame_ctx : field_ctx; h264r_ctx* const dctx = to_field ? field_ctx : frame_ctx;
+    const h264r_frame sf = to_field ? frame : field, df = to_field ? field : frame;
+    // The copy is enqueued now: pictures that were submitted but not flushed would run after it.  Neither picture may be
+    // named by a queued picture (as destination of the source, or in any role of the destination).
+    for (h264r_ctx* c : { sctx, dctx }) {
+        std::lock_guard<std::mutex> lock(c->mu);
+        for (int qi : c->queue) {
+            const Slot& s = c->slots[qi];
+            const h264r_frame f = c == sctx ? sf : df;
+            if (s.dst == f) return H264R_ERR_STATE;
+            if (c == dctx) for (int i = 0; i < s.pp.num_ref_frames; ++i) if (s.pp.ref_frames[i] == f) return H264R_ERR_STATE;
+        }
+    }
+    cudaSetDevice(dctx->device);
+    Frame& src = sctx->frames[sf]; Frame& dst = dctx->frames[df];
+    cudaStream_t st = dctx->stream;                           // the destination's compute stream: behind every kernel that reads or writes it
+    if (src.ready) { if (cudaStreamWaitEvent(st, src.ready, 0) != cudaSuccess) return cuda_fail(dctx, cudaGetLastError(), "h264r_field_copy"); }
+    if (dst.pending_read) { if (cudaStreamWaitEvent(st, dst.read_done, 0) != cudaSuccess) return cuda_fail(dctx, cudaGetLastError(), "h264r_field_copy"); dst.pending_read = false; }
+    const int w = gf.width_mbs * 16, hf = gd.height_mbs * 16;
+    uint8_t* const fb = frame_ctx->frames[frame].dev; uint8_t* const db = field_ctx->frames[field].dev;
+    struct Plane { size_t off_f, off_d; int pitch_f, pitch_d, width, rows; } planes[3] = {
+        { 0, 0, gf.pitch_y, gd.pitch_y, w, hf }, { gf.off_cb, gd.off_cb, gf.pitch_c, gd.pitch_c, w / 2, hf / 2 }, { gf.off_cr, gd.off_cr, gf.pitch_c, gd.pitch_c, w / 2, hf / 2 } };
+    for (const Plane& p : planes) {
+        uint8_t* const fl = fb + p.off_f + (size_t)parity * p.pitch_f;     // the field's lines inside the frame: every second line
+        uint8_t* const dl = db + p.off_d;
+        const cudaError_t e = to_field ? cudaMemcpy2DAsync(dl, p.pitch_d, fl, 2 * (size_t)p.pitch_f, p.width, p.rows, cudaMemcpyDeviceToDevice, st)
+                                       : cudaMemcpy2DAsync(fl, 2 * (size_t)p.pitch_f, dl, p.pitch_d, p.width, p.rows, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return cuda_fail(dctx, e, "h264r_field_copy");
+    }
+    // consumers of the destination wait for the copy; a later picture that overwrites the source waits for it too
+    cudaEvent_t done = take_event(dctx);
+    if (!done || cudaEventRecord(done, st) != cudaSuccess) return cuda_fail(dctx, cudaGetLastError(), "h264r_field_copy");
+    dst.ready = done;                                          // (combining: the second field's event covers the first, same stream)
+    if (!src.read_done && cudaEventCreateWithFlags(&src.read_done, cudaEventDisableTiming) != cudaSuccess) return cuda_fail(sctx, cudaGetLastError(), "h264r_field_copy");
+    if (cudaEventRecord(src.read_done, st) != cudaSuccess) return cuda_fail(sctx, cudaGetLastError(), "h264r_field_copy");
+    src.pending_read = true;
+    return H264R_OK;
+}
+
 int h264r_get_stats(h264r_ctx* ctx, h264r_stats* out)
 {
     if (!ctx || !out) return H264R_ERR_INVALID;

@@ -135,6 +135,7 @@ def recon_lib():
         L.h264r_wait.argtypes = [P, C.c_int32]
         L.h264r_frame_download.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.h264r_frame_upload.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.h264r_field_copy.argtypes = [P, C.c_int32, P, C.c_int32, C.c_int, C.c_int]
         L.h264r_replay_last_flush.argtypes = [P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         L.h264r_frame_download_async.argtypes = [P, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.h264r_frame_download_cropped.argtypes = [P, C.c_int32, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

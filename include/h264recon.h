@@ -17,8 +17,8 @@
  *
  * Supported stream subset (anything else returns H264R_ERR_UNSUPPORTED, there is NO CPU fallback):
  * 8-bit 4:2:0 frame pictures, or the field pictures of a stream coded in fields throughout (h264r_pic_params::structure; a
- * context holds pictures of one size); no MBAFF, no frame / field switching inside a stream, no transform bypass, no SP/SI
- * slices, no FMO/ASO.
+ * context holds pictures of one size; a stream that switches between the two uses a context of each kind and
+ * h264r_field_copy); no MBAFF, no transform bypass, no SP/SI slices, no FMO/ASO.
  *
  * Every struct below is also the HBM layout: the host fills pinned staging memory laid out exactly as
  * the device reads it, so submit is a handful of large cudaMemcpyAsync calls.
@@ -188,8 +188,8 @@ typedef struct h264r_pic_params {
                                                     (transform.cc:344-382), the chroma vector offset between fields of
                                                     different parity (inter_prediction.cc:352-354), mvlimit 2 and bS 3
                                                     on horizontal MB edges in the deblocking rule (deblock.cc:86, 106,
-                                                    164, 188).  Frame and field pictures do not mix in one context
-                                                    (no field split / combine on the device yet); MBAFF is unsupported. */
+                                                    164, 188).  Frame and field pictures do not mix in one context:
+                                                    see h264r_field_copy.  MBAFF is unsupported.            */
     uint8_t     ref_structure[H264R_MAX_REFS];   /* structure of ref_frames[i] (all H264R_FRAME for a frame picture,
                                                     fields for a field picture)                            */
 } h264r_pic_params;
@@ -267,6 +267,15 @@ int  h264r_frame_download(h264r_ctx* ctx, h264r_frame f, uint8_t* y, uint8_t* cb
 /* test/seed helper: set a frame's samples (e.g. an externally decoded reference picture)               */
 int  h264r_frame_upload(h264r_ctx* ctx, h264r_frame f, const uint8_t* y, const uint8_t* cb, const uint8_t* cr,
                         int pitch_y, int pitch_c);
+
+/* replaces: dpb_split_field / dpb_combine_field_yuv (framebuf/dpb.cc), for a stream that switches between frame and field
+ * pictures (PAFF).  Such a stream uses TWO contexts on one device: frame_ctx holds its frame pictures, field_ctx -- created
+ * with half the height -- its field pictures.  When the reference lists of a picture name a picture that exists in the other
+ * form only, the caller converts it: the lines of field `parity` (0 top, 1 bottom) of `frame` are copied to `field`
+ * (to_field != 0: one half of dpb_split_field) or from it (to_field == 0: one half of dpb_combine_field_yuv), device to
+ * device, asynchronously, ordered behind the picture that produces the source and ahead of every later use of both.
+ * H264R_ERR_STATE if a picture that was submitted but not flushed yet writes the source or names the destination. */
+int  h264r_field_copy(h264r_ctx* frame_ctx, h264r_frame frame, h264r_ctx* field_ctx, h264r_frame field, int parity, int to_field);
 
 /* Asynchronous variant: the copy is ordered after the wave that produces `f` and runs on the engine's D2H
  * stream, overlapping later waves; destination should be pinned (h264r_host_alloc).  h264r_wait(ctx, -1) joins. */

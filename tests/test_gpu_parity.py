@@ -402,3 +402,49 @@ def test_resume_from_uploaded_reference_frames_and_statistics():
     assert sb.h2d_bytes > uploads * fbytes                   # the uploaded planes plus the picture descriptions
     assert sa.d2h_bytes == (split + uploads) * fbytes and sb.d2h_bytes == (n - split) * fbytes
     a.close(); b.close()
+
+
+def test_field_copy_between_a_frame_context_and_a_field_context():
+    """h264r_field_copy (dpb_split_field / dpb_combine_field_yuv on the device): frames decoded in a frame context are split
+    into fields of a field context, which must equal the de-interleaved lines of the frame; combining the two fields into a
+    fresh frame must give the frame back.  The copies are enqueued right behind the flush, without waiting."""
+    import ctypes as C
+    cfg, sidx, w, h, n = 3, 1, 10, 6, 4
+    st = pyapi.SynthStream(cfg, sidx, w, h, n)
+    seq = st.seq
+    fa = pyapi.Engine(seq, max_frames=2 * n, max_pictures=n)
+    fseq = pyapi.SeqParams.from_buffer_copy(seq)
+    fseq.height_mbs = h // 2
+    fb = pyapi.Engine(fseq, max_frames=2 * n, max_pictures=n)
+    L = pyapi.recon_lib()
+    frames, order = {}, []
+    for pic in st:
+        dst = fa.frame_alloc()
+        frames[pic.info.pic_index] = dst
+        fa.submit(pic, dst, [frames[pic.info.ref_pic_index[i]] for i in range(pic.info.num_refs)])
+        order.append(dst)
+    st.close()
+    # not flushed yet: the source is still to be written by a queued picture
+    t0 = fb.frame_alloc()
+    assert L.h264r_field_copy(fa.ctx, order[0], fb.ctx, t0, 0, 1) == -5
+    fa.flush()
+    fields, back = [], []
+    for f in order:                                          # split every frame, then combine the fields into a new frame
+        top, bot, again = (t0 if f == order[0] else fb.frame_alloc()), fb.frame_alloc(), fa.frame_alloc()
+        for parity, fld in ((0, top), (1, bot)):
+            assert L.h264r_field_copy(fa.ctx, f, fb.ctx, fld, parity, 1) == 0
+        for parity, fld in ((0, top), (1, bot)):
+            assert L.h264r_field_copy(fa.ctx, again, fb.ctx, fld, parity, 0) == 0
+        fields.append((top, bot)); back.append(again)
+    W, H = w * 16, h * 16
+    for f, (top, bot), again in zip(order, fields, back):
+        y, cb, cr = fa.download(f)
+        for parity, fld in ((0, top), (1, bot)):
+            fy, fcb, fcr = fb.download(fld)
+            assert fy == b"".join(y[r * W:(r + 1) * W] for r in range(parity, H, 2))
+            assert fcb == b"".join(cb[r * (W // 2):(r + 1) * (W // 2)] for r in range(parity, H // 2, 2))
+            assert fcr == b"".join(cr[r * (W // 2):(r + 1) * (W // 2)] for r in range(parity, H // 2, 2))
+        assert fa.download(again) == (y, cb, cr)
+    assert L.h264r_field_copy(fa.ctx, order[0], fa.ctx, order[1], 0, 1) == -1      # one context is not a pair
+    assert L.h264r_field_copy(fa.ctx, order[0], fb.ctx, fields[0][0], 2, 1) == -1
+    fa.close(); fb.close()
