@@ -51,8 +51,12 @@ struct QuantLists { int q4[6][16]; int q8[2][64]; };
 struct GpuFrameEntry { h264r_frame frame; int poc; bool live; uint8_t structure; };
 
 struct GpuState {
-    h264r_ctx* ctx = nullptr;
-    int width_mbs = 0, height_mbs = 0;
+    // [0]: the context of the stream's frame pictures, [1]: of its field pictures (half the height; a field is a picture of
+    // its own, like the reference's field storable_pictures).  A PAFF stream uses both; references that exist in the other
+    // form only are converted on the device when a picture needs them (convert_references).
+    h264r_ctx* ctx[2] = { nullptr, nullptr };
+    int kind = 0;                          // context of the picture being parsed
+    int width_mbs = 0, height_mbs = 0;     // FrameHeightInMbs
     std::unordered_map<const storable_picture*, GpuFrameEntry> frames;   // engine frame of every decoded picture
     std::unordered_map<const Decoder*, QuantLists> quant;                 // assign_quant_params precedes init
     // picture being parsed
@@ -65,27 +69,27 @@ struct GpuState {
 
 const int kMaxGpuFrames = 40;        // > 16 DPB frames + the current picture + pictures waiting for output
 
-// The engine context holds pictures of ONE size: frames, or -- for a stream coded in field pictures (PAFF with
-// field_pic_flag = 1 throughout) -- fields, which are pictures of their own of half the frame height exactly like the
-// reference's field storable_pictures.  A stream that switches between frame and field pictures would need the DPB's
-// dpb_split_field / dpb_combine_field on device frames: outside the supported subset, reported as such.
+h264r_ctx* ctx_of(int structure) { return g.ctx[structure != H264R_FRAME]; }
+
 void open_engine(const sps_t& sps, const shr_t& shr)
 {
-    const int W = (int)sps.PicWidthInMbs, H = (int)shr.PicHeightInMbs;
-    if (g.ctx && W == g.width_mbs && H == g.height_mbs) return;
-    if (g.ctx && !g.frames.empty() && W == g.width_mbs)
-        error(500, "h264recon: frame and field pictures in one stream: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
-    if (g.ctx) { h264r_destroy(g.ctx); g.ctx = nullptr; g.frames.clear(); }
+    const int W = (int)sps.PicWidthInMbs, H = (int)sps.FrameHeightInMbs;
+    if (W != g.width_mbs || H != g.height_mbs) {
+        for (h264r_ctx*& c : g.ctx) if (c) { h264r_destroy(c); c = nullptr; }
+        g.frames.clear();
+        g.width_mbs = W; g.height_mbs = H;
+    }
+    g.kind = shr.field_pic_flag ? 1 : 0;
+    if (g.ctx[g.kind]) return;
     if (sps.chroma_format_idc != 1 || sps.bit_depth_luma_minus8 != 0 || sps.bit_depth_chroma_minus8 != 0 || sps.mb_adaptive_frame_field_flag)
         error(500, "h264recon: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
     h264r_seq_params sp;
     memset(&sp, 0, sizeof(sp));
-    sp.width_mbs = W; sp.height_mbs = H;
+    sp.width_mbs = W; sp.height_mbs = g.kind ? H / 2 : H;
     sp.direct_8x8_inference_flag = sps.direct_8x8_inference_flag;
     sp.max_frames = kMaxGpuFrames; sp.max_pictures_in_flight = 4; sp.max_slices_per_picture = 64;   // 4 staging slots: up to three pictures reconstruct while the next is parsed
     sp.max_levels_per_picture = 0;
-    check(h264r_create(&g.ctx, 0, &sp), "h264r_create");
-    g.width_mbs = W; g.height_mbs = H;
+    check(h264r_create(&g.ctx[g.kind], 0, &sp), "h264r_create");
 }
 
 // engine frame of a decoded picture
@@ -93,6 +97,7 @@ h264r_frame frame_of(const storable_picture* p)
 {
     auto it = g.frames.find(p);
     if (it == g.frames.end()) error(500, "h264recon: reference picture was not reconstructed by the GPU path");
+    if ((it->second.structure != H264R_FRAME) != (g.kind != 0)) error(500, "h264recon: reference picture is held in the other form (frame / field)");
     return it->second.frame;
 }
 
@@ -123,7 +128,7 @@ void sweep_dead_frames(VideoParameters* p_Vid, const storable_picture* current)
         }
     for (auto it = g.frames.begin(); it != g.frames.end(); ) {
         if (it->second.live) { ++it; continue; }
-        h264r_frame_release(g.ctx, it->second.frame);
+        h264r_frame_release(ctx_of(it->second.structure), it->second.frame);
         it = g.frames.erase(it);
     }
 }
@@ -132,10 +137,12 @@ void sweep_dead_frames(VideoParameters* p_Vid, const storable_picture* current)
 h264r_frame new_frame(const storable_picture* p, int poc, int structure)
 {
     auto it = g.frames.find(p);
-    if (it != g.frames.end()) { h264r_frame_release(g.ctx, it->second.frame); g.frames.erase(it); }
-    if ((int)g.frames.size() >= H264R_MAX_REFS) error(500, "h264recon: more than %d pictures alive in the decoded picture buffer", H264R_MAX_REFS);
+    if (it != g.frames.end()) { h264r_frame_release(ctx_of(it->second.structure), it->second.frame); g.frames.erase(it); }
+    int same_form = 0;
+    for (auto& kv : g.frames) same_form += (kv.second.structure != H264R_FRAME) == (structure != H264R_FRAME);
+    if (same_form >= H264R_MAX_REFS) error(500, "h264recon: more than %d pictures of one form alive in the decoded picture buffer", H264R_MAX_REFS);
     h264r_frame f;
-    check(h264r_frame_alloc(g.ctx, &f), "h264r_frame_alloc");
+    check(h264r_frame_alloc(ctx_of(structure), &f), "h264r_frame_alloc");
     g.frames[p] = GpuFrameEntry{ f, poc, true, (uint8_t)structure };
     return f;
 }
@@ -147,12 +154,47 @@ int slot_of(h264r_frame f)
     return -1;
 }
 
+// PAFF: the DPB keeps every complete frame in both forms (picture_t::insert_picture -> dpb_split_field / dpb_combine_field,
+// framebuf/picture.cc:408-745, on host arrays the GPU binding never fills).  On the device a picture exists in the form it was
+// decoded in; when the picture about to be decoded is of the other kind, the reference frames of the DPB are converted:
+// h264r_field_copy, device to device, asynchronous.
+void convert_references(VideoParameters* p_Vid)
+{
+    auto has = [](const storable_picture* p) { return p && g.frames.find(p) != g.frames.end(); };
+    for (int layer = 0; layer < MAX_NUM_DPB_LAYERS; ++layer) {
+        const decoded_picture_buffer_t* dpb = p_Vid->p_Dpb_layer[layer];
+        if (!dpb || !dpb->fs) continue;
+        for (unsigned i = 0; i < dpb->used_size; ++i) {
+            const pic_t* fs = dpb->fs[i];
+            if (!fs || fs->is_used != 3 || !fs->is_reference) continue;
+            if (g.kind == 1 && has(fs->frame)) {
+                const h264r_frame src = g.frames[fs->frame].frame;
+                for (int parity = 0; parity < 2; ++parity) {
+                    const storable_picture* fld = parity ? fs->bottom_field : fs->top_field;
+                    if (!fld || has(fld)) continue;
+                    h264r_frame f;
+                    check(h264r_frame_alloc(g.ctx[1], &f), "h264r_frame_alloc");
+                    check(h264r_field_copy(g.ctx[0], src, g.ctx[1], f, parity, 1), "h264r_field_copy");
+                    g.frames[fld] = GpuFrameEntry{ f, fld->poc, true, (uint8_t)(parity ? H264R_BOTTOM_FIELD : H264R_TOP_FIELD) };
+                }
+            } else if (g.kind == 0 && fs->frame && !has(fs->frame) && has(fs->top_field) && has(fs->bottom_field)) {
+                h264r_frame f;
+                check(h264r_frame_alloc(g.ctx[0], &f), "h264r_frame_alloc");
+                check(h264r_field_copy(g.ctx[0], f, g.ctx[1], g.frames[fs->top_field].frame, 0, 0), "h264r_field_copy");
+                check(h264r_field_copy(g.ctx[0], f, g.ctx[1], g.frames[fs->bottom_field].frame, 1, 0), "h264r_field_copy");
+                g.frames[fs->frame] = GpuFrameEntry{ f, fs->frame->poc, true, (uint8_t)H264R_FRAME };
+            }
+        }
+    }
+}
+
 // first slice of a picture (init_picture has run: core/slice_data.cc:149-313)
 void begin_picture(slice_t& slice)
 {
     open_engine(*slice.active_sps, slice.header);
     const storable_picture* pic = slice.dec_picture;
     sweep_dead_frames(slice.p_Vid, nullptr);
+    convert_references(slice.p_Vid);
     const int structure = slice.header.structure == TOP_FIELD ? H264R_TOP_FIELD : (slice.header.structure == BOTTOM_FIELD ? H264R_BOTTOM_FIELD : H264R_FRAME);
     const h264r_frame dst = new_frame(pic, slice.header.PicOrderCnt, structure);
     memset(&g.pp, 0, sizeof(g.pp));
@@ -161,7 +203,7 @@ void begin_picture(slice_t& slice)
     // one).  POC and long-term state are informational for the engine (implicit weights are precomputed in fill_slice
     // from the pictures the slice lists, which are alive).
     for (auto& kv : g.frames) {
-        if (kv.first == pic) continue;
+        if (kv.first == pic || (kv.second.structure != H264R_FRAME) != (g.kind != 0)) continue;      // pictures of this picture's form
         const int i = g.pp.num_ref_frames++;
         g.pp.ref_frames[i] = kv.second.frame;
         g.pp.ref_poc[i] = kv.second.poc;
@@ -174,8 +216,8 @@ void begin_picture(slice_t& slice)
     g.pp.direct_8x8_inference_flag = slice.active_sps->direct_8x8_inference_flag;
     h264r_pic_params tmp = g.pp;
     tmp.num_slices = 64;                     // staging capacity check only; see end_picture
-    check(h264r_picture_begin(g.ctx, dst, &tmp, &g.bufs), "h264r_picture_begin");
-    g.facade.init(g.bufs, g.width_mbs, g.height_mbs, slice.header.field_pic_flag != 0);      // field scans: transform.cc:339-386
+    check(h264r_picture_begin(g.ctx[g.kind], dst, &tmp, &g.bufs), "h264r_picture_begin");
+    g.facade.init(g.bufs, g.width_mbs, g.kind ? g.height_mbs / 2 : g.height_mbs, slice.header.field_pic_flag != 0);      // field scans: transform.cc:339-386
     g.cur = pic;
     g.any_deblock = false;
 }
@@ -385,9 +427,9 @@ void Decoder::deblock_filter(slice_t& slice)
     if (pic != g.cur) error(500, "h264recon: deblock_filter for a picture that was not begun");
     // Deblock::deblock (deblock.cc:622-656): runs unless every slice has disable_deblocking_filter_idc == 1
     g.pp.run_deblock = (g.any_deblock && (0x03 & (1 << pic->used_for_reference))) ? 1 : 0;
-    check(h264r_picture_update(g.ctx, g.bufs.picture, &g.pp), "h264r_picture_update");
-    check(h264r_picture_submit(g.ctx, g.bufs.picture, g.facade.stream_words()), "h264r_picture_submit");
-    check(h264r_flush(g.ctx), "h264r_flush");
+    check(h264r_picture_update(g.ctx[g.kind], g.bufs.picture, &g.pp), "h264r_picture_update");
+    check(h264r_picture_submit(g.ctx[g.kind], g.bufs.picture, g.facade.stream_words()), "h264r_picture_submit");
+    check(h264r_flush(g.ctx[g.kind]), "h264r_flush");
     // Nothing is copied back here: the picture stays in HBM (motion compensation of later pictures reads it there) and
     // reaches the host when the DPB outputs it (output_gpu.cc).  The call returns while the kernels run, so the parsing
     // of the next picture overlaps this one's reconstruction.
@@ -395,15 +437,25 @@ void Decoder::deblock_filter(slice_t& slice)
 }
 
 // for output_gpu.cc
-h264r_ctx* gpu_engine() { return g.ctx; }
-h264r_frame gpu_frame_of_picture(const storable_picture* p) { return frame_of(p); }
+h264r_ctx* gpu_engine_of(const storable_picture* p)
+{
+    auto it = g.frames.find(p);
+    if (it == g.frames.end()) error(500, "h264recon: picture was not reconstructed by the GPU path");
+    return ctx_of(it->second.structure);
+}
+h264r_frame gpu_frame_of_picture(const storable_picture* p)
+{
+    auto it = g.frames.find(p);
+    if (it == g.frames.end()) error(500, "h264recon: picture was not reconstructed by the GPU path");
+    return it->second.frame;
+}
 bool gpu_has_picture(const storable_picture* p) { return g.frames.find(p) != g.frames.end(); }
 // a picture that never entered the DPB is about to be deleted (direct_output): its engine frame goes back to the pool
 void gpu_picture_freed(const storable_picture* p)
 {
     auto it = g.frames.find(p);
     if (it == g.frames.end()) return;
-    h264r_frame_release(g.ctx, it->second.frame);
+    h264r_frame_release(ctx_of(it->second.structure), it->second.frame);
     g.frames.erase(it);
 }
 

@@ -24,7 +24,7 @@ using namespace vio::h264;
 
 // integration/decoder_gpu.cc
 namespace vio { namespace h264 {
-h264r_ctx*  gpu_engine();
+h264r_ctx*  gpu_engine_of(const storable_picture* p);
 h264r_frame gpu_frame_of_picture(const storable_picture* p);
 void        gpu_picture_freed(const storable_picture* p);
 bool        gpu_has_picture(const storable_picture* p);
@@ -62,7 +62,7 @@ void output_picture(VideoParameters* p_Vid, storable_picture* p, int p_out)
     const int w = (int)sps.PicWidthInMbs * 16 - left - right, h = (int)sps.FrameHeightInMbs * 16 - top - bottom;
     const size_t ny = (size_t)w * h, nc = ny / 4;
     g_out.resize(ny + 2 * nc);
-    const int rc = h264r_frame_download_cropped(gpu_engine(), gpu_frame_of_picture(p), left, right, top, bottom,
+    const int rc = h264r_frame_download_cropped(gpu_engine_of(p), gpu_frame_of_picture(p), left, right, top, bottom,
                                                 g_out.data(), g_out.data() + ny, g_out.data() + ny + nc, w, w / 2);
     if (rc != H264R_OK) error(500, "h264recon: h264r_frame_download_cropped: %s", h264r_strerror(rc));
     put(p_out, g_out.data(), ny);
@@ -83,7 +83,7 @@ void output_field_pair(VideoParameters* p_Vid, storable_picture* top_field, stor
     storable_picture* fields[2] = { top_field, bottom_field };
     for (int k = 0; k < 2; ++k) {
         g_field[k].resize(fy + 2 * fc);
-        const int rc = h264r_frame_download(gpu_engine(), gpu_frame_of_picture(fields[k]), g_field[k].data(), g_field[k].data() + fy,
+        const int rc = h264r_frame_download(gpu_engine_of(fields[k]), gpu_frame_of_picture(fields[k]), g_field[k].data(), g_field[k].data() + fy,
                                             g_field[k].data() + fy + fc, W, W / 2);
         if (rc != H264R_OK) error(500, "h264recon: h264r_frame_download: %s", h264r_strerror(rc));
     }
@@ -123,10 +123,9 @@ void write_stored_frame(VideoParameters* p_Vid, pic_t* fs, int p_out)
     if (!p_Vid->non_conforming_stream || p_Vid->recovery_flag) {
         // a frame store filled by two field pictures holds them as top_field / bottom_field; its `frame` is the host-side
         // combination the DPB made (dpb_combine_field), which no engine picture stands for
-        if (fs->top_field && fs->bottom_field && fs->top_field->slice.structure == TOP_FIELD && gpu_has_picture(fs->top_field))
-            output_field_pair(p_Vid, fs->top_field, fs->bottom_field, p_out);
-        else
-            output_picture(p_Vid, fs->frame, p_out);
+        // (a PAFF stream: the frame form exists on the device if the frame was decoded as one, or was needed as a reference of one)
+        if (fs->frame && gpu_has_picture(fs->frame)) output_picture(p_Vid, fs->frame, p_out);
+        else output_field_pair(p_Vid, fs->top_field, fs->bottom_field, p_out);
     }
     fs->is_output = 1;
 }

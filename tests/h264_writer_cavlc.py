@@ -191,16 +191,20 @@ class Stream:
         """profile: "main" (4x4 transform) or "high" (transform_8x8 / scaling allowed).  scaling = None, or a pair
         (sps_lists, pps_lists) where each is None (matrix not present) or a list of eight entries: None (list not present:
         fall-back rule A / B), "default" (useDefaultScalingMatrixFlag) or a list of 16 / 64 values in raster order."""
-        # field=True: every picture is a field (frame_mbs_only_flag = 0, field_pic_flag = 1); height_mbs is the height of the
-        # FRAME and must be even, the pictures this class writes are height_mbs / 2 high
-        self.field = field
+        # field=True: every picture is a field (frame_mbs_only_flag = 0, field_pic_flag = 1); field="adaptive": PAFF, picture()
+        # says per picture whether it is a frame or a field.  height_mbs is the height of the FRAME and must be even then.
+        self.interlaced = bool(field)
+        self.field = field is True                    # form of the picture being written
         assert not field or height_mbs % 2 == 0
-        self.W, self.H = width_mbs, height_mbs // 2 if field else height_mbs
+        self.Hframe, self.Hfield = height_mbs, height_mbs // 2
+        self.W, self.H = width_mbs, self.Hfield if self.field else self.Hframe
         self.rng = random.Random(seed)
         self.profile = profile
         self.num_refs = num_refs
         self.weighted_pred, self.weighted_bipred = weighted_pred, weighted_bipred
         self.direct8x8 = 1 if field else direct_8x8_inference      # frame_mbs_only_flag = 0 requires direct_8x8_inference_flag = 1
+        self.ref_frames = 0                           # complete reference frames in the DPB
+        self.first_field_is_ref = False               # the first field of the frame being written is a reference field
         self.t8 = transform_8x8 and profile == "high"
         self.scaling = scaling if profile == "high" else None
         self.constrained_intra = constrained_intra
@@ -271,9 +275,9 @@ class Stream:
         w.ue(self.LOG2_MAX_POC_LSB - 4)
         w.ue(self.num_refs + 1)                   # max_num_ref_frames: one more than a slice lists, so that the picture a
         w.u(1, 0)                                 # co-located block of a temporal-direct MB refers to is still in the DPB
-        w.ue(self.W - 1); w.ue(self.H - 1)            # pic_height_in_map_units: the field height when frame_mbs_only_flag = 0
-        w.u(1, 0 if self.field else 1)                # frame_mbs_only_flag
-        if self.field:
+        w.ue(self.W - 1); w.ue((self.Hfield if self.interlaced else self.Hframe) - 1)   # pic_height_in_map_units: the field height when frame_mbs_only_flag = 0
+        w.u(1, 0 if self.interlaced else 1)           # frame_mbs_only_flag
+        if self.interlaced:
             w.u(1, 0)                                 # mb_adaptive_frame_field_flag
         w.u(1, self.direct8x8)
         w.u(1, 0)                                     # frame_cropping_flag
@@ -591,9 +595,10 @@ class Stream:
         w.ue({"idr": 2, "i": 2, "p": 0, "b": 1}[kind])
         w.ue(0)
         w.u(self.LOG2_MAX_FRAME_NUM, self.frame_num % (1 << self.LOG2_MAX_FRAME_NUM))
-        if self.field:
-            w.u(1, 1)                                 # field_pic_flag
-            w.u(1, 1 if bottom else 0)                # bottom_field_flag
+        if self.interlaced:
+            w.u(1, 1 if self.field else 0)            # field_pic_flag
+            if self.field:
+                w.u(1, 1 if bottom else 0)            # bottom_field_flag
         if kind == "idr":
             w.ue(self.idr_id)
         w.u(self.LOG2_MAX_POC_LSB, poc % (1 << self.LOG2_MAX_POC_LSB))
@@ -601,7 +606,8 @@ class Stream:
         if kind == "b":
             w.u(1, self.direct_spatial)               # direct_spatial_mv_pred_flag
         if kind in ("p", "b"):
-            n0 = min(self.num_refs, self.refs_available)
+            avail = 2 * self.ref_frames + (1 if self.first_field_is_ref else 0) if self.field else self.ref_frames
+            n0 = min(self.num_refs, avail)
             n1 = 1
             override = n0 != self.num_refs
             w.u(1, 1 if override else 0)
@@ -624,17 +630,25 @@ class Stream:
         return n0, n1
 
     def picture(self, kind, poc, qp=30, idc=0, off_a=0, off_b=0, slices=2, intra_share=0.12, skip_share=0.2, bottom=False,
-                second_field=False):
+                second_field=False, field=None):
         """One picture; with field=True one FIELD: `bottom` its parity, `second_field` = it completes the frame the previous
         call started (same frame_num; frame_num moves on after the second field of a reference frame).  The second field of
-        an IDR frame is a non-IDR P field (complementary reference field pair, H.264 3.30)."""
+        an IDR frame is a non-IDR P field (complementary reference field pair, H.264 3.30).  field (PAFF streams only): this
+        picture is a field (True) or a frame (False)."""
         is_ref = kind != "b"
+        if field is not None:
+            assert self.interlaced
+            self.field = field
+        self.H = self.Hfield if self.field else self.Hframe
+        if not second_field:
+            self.first_field_is_ref = False
         if kind == "idr":
             self.frame_num = 0
+            self.ref_frames = 0
         self._new_picture()
-        # field streams: spatial direct only (the co-located field of a temporal-direct MB may refer to a field that the two
-        # entries of this writer's list 0 do not hold)
-        self.direct_spatial = 1 if self.field else self.rng.randrange(2)
+        # field / PAFF streams: spatial direct only (the co-located field of a temporal-direct MB may refer to a field that the
+        # two entries of this writer's list 0 do not hold)
+        self.direct_spatial = 1 if self.interlaced else self.rng.randrange(2)
         n = self.W * self.H
         cuts = sorted(set([0] + ([self.rng.randrange(1, n)] if slices > 1 and n > 1 else [])))
         for si, first in enumerate(cuts):
@@ -668,10 +682,10 @@ class Stream:
             self.out += nal(3 if kind == "idr" else (2 if is_ref else 0), 5 if kind == "idr" else 1, w.payload())
         if kind == "idr":
             self.idr_id += 1
-            self.refs_available = 1
-        elif is_ref:
-            self.refs_available = min((2 if self.field else 1) * (self.num_refs + 1) - (1 if self.field else 0), self.refs_available + 1)
+        if is_ref and self.field and not second_field:
+            self.first_field_is_ref = True
         if is_ref and (not self.field or second_field):
+            self.ref_frames = min(self.num_refs + 1, self.ref_frames + 1)
             self.frame_num += 1
 
     def data(self):
@@ -701,6 +715,37 @@ def make_field_stream(width_mbs=11, height_mbs=10, gops=2, seed=7, b_frames=True
                     s.picture("b", 2 * (disp + 1 + b) + bottom, qp=(30, 34)[b], idc=(0, 1)[(b + k + bottom) % 2], off_a=2 * b, off_b=-2 * b,
                               slices=1 + b, bottom=bottom, second_field=bottom)
                 frames += 1
+            disp = disp_anchor
+    return s.data(), frames
+
+
+def make_paff_stream(width_mbs=11, height_mbs=10, gops=2, seed=7, b_frames=True, pattern=(1, 0, 1, 1, 0, 0, 1, 0, 0, 1), **opts):
+    """Picture-adaptive frame / field coding: the GOP structure of make_stream, every frame coded as a frame (0) or as two
+    fields (1) following `pattern` in decode order, so that frames reference fields and fields reference frames.  Returns
+    (bytes, number of FRAMES)."""
+    s = Stream(width_mbs, height_mbs, seed, field="adaptive", **opts)
+    frames = 0
+
+    def frame(kind, disp, **kw):
+        nonlocal frames
+        as_field = bool(pattern[frames % len(pattern)])
+        if as_field:
+            s.picture(kind, 2 * disp, field=True, **kw)
+            kw2 = dict(kw); kw2["qp"] = kw.get("qp", 30) + 1
+            s.picture("p" if kind == "idr" else kind, 2 * disp + 1, field=True, bottom=True, second_field=True, **kw2)
+        else:
+            s.picture(kind, 2 * disp, field=False, **kw)
+        frames += 1
+
+    for g in range(gops):
+        disp = 0
+        frame("idr", 0, qp=28 + 2 * g, slices=1 + (g & 1))
+        for k in range(3):
+            nb = 2 if b_frames else 0
+            disp_anchor = disp + nb + 1
+            frame("p", disp_anchor, qp=(26, 32, 38)[k % 3], idc=(0, 2, 0)[k % 3], off_a=(0, 2, -4)[k % 3], off_b=(2, 0, -2)[k % 3], slices=1 + frames % 2)
+            for b in range(nb):
+                frame("b", disp + 1 + b, qp=(30, 34)[b], idc=(0, 1)[(b + k) % 2], off_a=2 * b, off_b=-2 * b, slices=1 + b)
             disp = disp_anchor
     return s.data(), frames
 

@@ -196,3 +196,55 @@ def test_reference_parser_on_the_gpu_engine_with_field_pictures(tmp_path, case):
             k = next(j for j in range(fsz) if a[j] != b[j])
             plane = "Y" if k < w * h * 256 else ("Cb" if k < w * h * 320 else "Cr")
             pytest.fail(f"{case}: output frame {i}: first difference in plane {plane} at byte {k} (reference {a[k]}, gpu {b[k]})")
+
+
+# ---- PAFF: frames and field pairs in one stream; references change form (dpb_split_field / dpb_combine_field on the device) ----
+
+PAFF_CASES = {
+    "paff-main-ipb":        dict(w=6, h=6, gops=2, seed=31),
+    "paff-main-ip":         dict(w=11, h=10, gops=2, seed=32, b_frames=False, pattern=(0, 1, 0, 0, 1, 1, 0)),
+    "paff-main-wp":         dict(w=7, h=4, gops=2, seed=33, weighted_pred=1, weighted_bipred=1, pattern=(1, 1, 0, 1, 0)),
+    "paff-high-t8-scaling": dict(w=6, h=8, gops=2, seed=35, profile="high", transform_8x8=True, scaling="both", weighted_bipred=2),
+    "paff-high-20x12":      dict(w=20, h=12, gops=1, seed=36, profile="high", transform_8x8=True, pattern=(0, 0, 1, 0, 1, 1)),
+}
+
+
+def paff_stream(case):
+    import h264_writer_cavlc
+    opts = dict(PAFF_CASES[case])
+    w, h = opts.pop("w"), opts.pop("h")
+    if "scaling" in opts:
+        sps, pps = _lists(opts["seed"])
+        opts["scaling"] = {"both": (sps, pps)}[opts["scaling"]]
+    data, frames = h264_writer_cavlc.make_paff_stream(w, h, **opts)
+    return data, frames, w, h
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="integration/_build/ldecod_ref not built")
+@pytest.mark.parametrize("case", sorted(PAFF_CASES))
+def test_paff_streams_are_decodable_by_the_reference(tmp_path, case):
+    stream, frames, w, h = paff_stream(case)
+    yuv, log = decode(REF, stream, str(tmp_path), "ref")
+    assert len(yuv) == frames * w * h * 384, log[-1500:]
+    assert "rror" not in log, log[-1500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF) and os.path.exists(GPU)), reason="integration/_build binaries not built")
+@pytest.mark.parametrize("case", sorted(PAFF_CASES))
+def test_reference_parser_on_the_gpu_engine_with_paff_streams(tmp_path, case):
+    """Picture-adaptive frame / field coding through the real parser: frame pictures live in one engine context, field
+    pictures in a second one of half the height; a reference that exists in the other form only is converted on the device
+    (h264r_field_copy = dpb_split_field / dpb_combine_field_yuv, framebuf/picture.cc:408-660).  Byte-identical frames."""
+    stream, frames, w, h = paff_stream(case)
+    want, _ = decode(REF, stream, str(tmp_path), "ref")
+    got, log = decode(GPU, stream, str(tmp_path), "gpu")
+    assert len(want) == frames * w * h * 384
+    assert len(got) == len(want), log[-1500:]
+    fsz = w * h * 384
+    for i in range(frames):
+        a, b = want[i * fsz:(i + 1) * fsz], got[i * fsz:(i + 1) * fsz]
+        if a != b:
+            k = next(j for j in range(fsz) if a[j] != b[j])
+            plane = "Y" if k < w * h * 256 else ("Cb" if k < w * h * 320 else "Cr")
+            pytest.fail(f"{case}: output frame {i}: first difference in plane {plane} at byte {k} (reference {a[k]}, gpu {b[k]})")
