@@ -1,5 +1,7 @@
 #!/bin/bash
 # Runs on the GPU box: (optionally) the parity tests, then the bench under several stream topologies.
+# The environment variables below are read by the stream-groups build only (profiles/r2_stream_groups_variant.diff applied
+# to arrow-h264_b200/csrc); the product build ignores them.
 # Usage: scripts/gpu_groups.sh <tag> <tests: 0|1> <G:M:K>...     G = stream groups, M = inter stream mode, K = wavefront CTAs per SM
 tag=$1; shift
 tests=$1; shift
