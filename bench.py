@@ -45,6 +45,9 @@ def workload_name(streams, frames):
     if CONFIG_ID == 4:
         return (f"{streams} 4K 3840x2160 (240x135 MB) High-profile I/P/B stream(s) x {frames} pictures (BASELINE configs[3]: low QP, "
                 "deblock offsets +-6, all-intra pictures); bound by the wavefront depth (508 MB steps per picture)")
+    if CONFIG_ID == 6:
+        return (f"{streams} independent 1080i streams coded in FIELD pictures (120x34 MB per field, field_pic_flag = 1, references "
+                f"of both parities) x {frames} fields per GPU; not a BASELINE config (SURVEY.md 8f-4)")
     return (f"{streams} independent 1080p (120x68 MB) High-profile I/P/B streams x {frames} pictures per GPU "
             "(BASELINE configs[4]; 8x8 transform, intra 8x8, bi-pred, weighted prediction, 2 slices on odd pictures; "
             "every third stream has direct_8x8_inference_flag = 0)")
@@ -520,8 +523,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=5, choices=[3, 4, 5],
-                    help="5: 64 x 1080p streams (the metric's workload); 3: 1080p single stream; 4: 4K single stream")
+    ap.add_argument("--config", type=int, default=5, choices=[3, 4, 5, 6],
+                    help="5: 64 x 1080p streams (the metric's workload); 3: 1080p single stream; 4: 4K single stream; "
+                         "6: 1080i field pictures (use --streams 64 for a throughput figure)")
     ap.add_argument("--streams", type=int, default=0, help="independent streams per GPU (default 64, or 1 for --config 3/4)")
     ap.add_argument("--frames", type=int, default=0, help="pictures per stream (default: the config's own GOP)")
     ap.add_argument("--feeders", type=int, default=0, help="feeder threads of the end-to-end path (default: (host cores - 2) / ranks, 2..6)")
