@@ -6,7 +6,8 @@
 // the picture, copied device->host when, and only when, the DPB releases the picture for output: one cropped 8-bit copy
 // (h264r_frame_download_cropped) that waits for the picture's own wave only, so pictures parsed after it keep
 // reconstructing underneath.  A frame coded as two field pictures lives in the engine as two pictures of half the height:
-// both come down and their lines are interleaved here.  Unpaired fields are outside the supported subset.
+// both come down and their lines are interleaved here; an unpaired field goes out with an empty (mid-grey) other field,
+// as write_unpaired_field does.
 #include "global.h"
 #include "input_parameters.h"
 #include "dpb.h"
@@ -83,6 +84,10 @@ void output_field_pair(VideoParameters* p_Vid, storable_picture* top_field, stor
     storable_picture* fields[2] = { top_field, bottom_field };
     for (int k = 0; k < 2; ++k) {
         g_field[k].resize(fy + 2 * fc);
+        if (!fields[k]) {                                          // unpaired field: the other one is "empty" (storable_picture::clear, framebuf/picture.cc:129-143)
+            memset(g_field[k].data(), 128, fy + 2 * fc);
+            continue;
+        }
         const int rc = h264r_frame_download(gpu_engine_of(fields[k]), gpu_frame_of_picture(fields[k]), g_field[k].data(), g_field[k].data() + fy,
                                             g_field[k].data() + fy + fc, W, W / 2);
         if (rc != H264R_OK) error(500, "h264recon: h264r_frame_download: %s", h264r_strerror(rc));
@@ -115,10 +120,37 @@ void release_and_delete(storable_picture*& p)
 
 } // namespace
 
+// write_unpaired_field (output.cc:228-267): a frame store that holds one field only is written with an empty other field.
+// The DPB's book-keeping is the reference's (the empty field object, the host-side combination, is_used = 3); the samples
+// come from the engine.
+static void write_unpaired(VideoParameters* p_Vid, pic_t* fs, int p_out)
+{
+    const bool have_top = (fs->is_used & 1) != 0;
+    storable_picture* p = have_top ? fs->top_field : fs->bottom_field;
+    storable_picture*& other = have_top ? fs->bottom_field : fs->top_field;
+    other = new storable_picture(p_Vid, have_top ? BOTTOM_FIELD : TOP_FIELD, p->size_x, p->size_y * 2, p->size_x_cr, p->size_y_cr * 2, 1);
+    other->clear();
+    fs->dpb_combine_field_yuv(p_Vid);
+    output_field_pair(p_Vid, have_top ? p : nullptr, have_top ? nullptr : p, p_out);
+    fs->is_used = 3;
+}
+
+// flush_direct_output (output.cc:269-287): a directly output field that is still waiting for its pair goes out unpaired
+static void flush_direct_output(VideoParameters* p_Vid, int p_out)
+{
+    pic_t* ob = p_Vid->out_buffer;
+    if (!ob->is_used) return;
+    write_unpaired(p_Vid, ob, p_out);
+    if (ob->frame) { delete ob->frame; ob->frame = nullptr; }
+    release_and_delete(ob->top_field);
+    release_and_delete(ob->bottom_field);
+    ob->is_used = 0;
+}
+
 void write_stored_frame(VideoParameters* p_Vid, pic_t* fs, int p_out)
 {
-    if (p_Vid->out_buffer->is_used || fs->is_used < 3)
-        error(500, "h264recon: unpaired field: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));      // not in the GPU subset
+    flush_direct_output(p_Vid, p_out);
+    if (fs->is_used < 3) { write_unpaired(p_Vid, fs, p_out); fs->is_output = 1; return; }
     if (fs->recovery_frame) p_Vid->recovery_flag = 1;
     if (!p_Vid->non_conforming_stream || p_Vid->recovery_flag) {
         // a frame store filled by two field pictures holds them as top_field / bottom_field; its `frame` is the host-side
@@ -135,7 +167,7 @@ void direct_output(VideoParameters* p_Vid, storable_picture* p, int p_out)
 {
     pic_t* ob = p_Vid->out_buffer;
     if (p->slice.structure == FRAME) {
-        if (ob->is_used) error(500, "h264recon: unpaired field: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
+        flush_direct_output(p_Vid, p_out);
         output_picture(p_Vid, p, p_out);
         p_Vid->calculate_frame_no(p);
         gpu_picture_freed(p);
@@ -143,10 +175,10 @@ void direct_output(VideoParameters* p_Vid, storable_picture* p, int p_out)
         return;
     }
     if (p->slice.structure == TOP_FIELD) {
-        if (ob->is_used & 1) error(500, "h264recon: unpaired field: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
+        if (ob->is_used & 1) flush_direct_output(p_Vid, p_out);
         ob->top_field = p; ob->is_used |= 1;
     } else {
-        if (ob->is_used & 2) error(500, "h264recon: unpaired field: %s", h264r_strerror(H264R_ERR_UNSUPPORTED));
+        if (ob->is_used & 2) flush_direct_output(p_Vid, p_out);
         ob->bottom_field = p; ob->is_used |= 2;
     }
     if (ob->is_used == 3) {

@@ -692,7 +692,7 @@ class Stream:
         return bytes(self.out)
 
 
-def make_field_stream(width_mbs=11, height_mbs=10, gops=2, seed=7, b_frames=True, **opts):
+def make_field_stream(width_mbs=11, height_mbs=10, gops=2, seed=7, b_frames=True, unpaired_tail=None, **opts):
     """The same GOP structure with every frame coded as two fields, top first: IDR frame = I field + P field, anchor frames
     = P + P fields, B frames = B + B fields (not used for reference).  The fields of a frame share frame_num; POC = 2 x
     display index of the frame (+ 1 for the bottom field).  Returns (bytes, number of FRAMES)."""
@@ -716,6 +716,9 @@ def make_field_stream(width_mbs=11, height_mbs=10, gops=2, seed=7, b_frames=True
                               slices=1 + b, bottom=bottom, second_field=bottom)
                 frames += 1
             disp = disp_anchor
+    if unpaired_tail is not None:                    # the stream ends with one field of a frame: "top" or "bottom"
+        s.picture("p", 2 * (disp + 1) + (unpaired_tail == "bottom"), qp=31, slices=2, bottom=unpaired_tail == "bottom")
+        frames += 1
     return s.data(), frames
 
 

@@ -153,6 +153,9 @@ FIELD_CASES = {
     "field-main-implicit-wp": dict(w=5, h=6, gops=2, seed=24, weighted_bipred=2, chroma_qp_offset=-2),
     "field-high-t8-scaling": dict(w=6, h=8, gops=2, seed=25, profile="high", transform_8x8=True, scaling="both", constrained_intra=1),
     "field-high-20x12":    dict(w=20, h=12, gops=1, seed=26, profile="high", transform_8x8=True, weighted_bipred=1),
+    # the stream ends with one field of a frame: written with an empty other field (write_unpaired_field, output.cc:228-267)
+    "field-unpaired-top":  dict(w=6, h=6, gops=1, seed=27, b_frames=False, unpaired_tail="top"),
+    "field-unpaired-bottom": dict(w=5, h=4, gops=1, seed=28, unpaired_tail="bottom"),
 }
 
 
