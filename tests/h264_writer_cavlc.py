@@ -187,12 +187,16 @@ class Stream:
     LOG2_MAX_POC_LSB = 6
 
     def __init__(self, width_mbs, height_mbs, seed=1, profile="main", num_refs=2, weighted_pred=0, weighted_bipred=0,
-                 direct_8x8_inference=1, transform_8x8=False, scaling=None, constrained_intra=0, chroma_qp_offset=0, field=False):
+                 direct_8x8_inference=1, transform_8x8=False, scaling=None, constrained_intra=0, chroma_qp_offset=0, field=False,
+                 claim_mbaff=False):
         """profile: "main" (4x4 transform) or "high" (transform_8x8 / scaling allowed).  scaling = None, or a pair
         (sps_lists, pps_lists) where each is None (matrix not present) or a list of eight entries: None (list not present:
         fall-back rule A / B), "default" (useDefaultScalingMatrixFlag) or a list of 16 / 64 values in raster order."""
         # field=True: every picture is a field (frame_mbs_only_flag = 0, field_pic_flag = 1); field="adaptive": PAFF, picture()
         # says per picture whether it is a frame or a field.  height_mbs is the height of the FRAME and must be even then.
+        # claim_mbaff: the SPS says mb_adaptive_frame_field_flag = 1 (the macroblock layer is NOT written as MBAFF: only good
+        # for checking that a decoder without MBAFF support stops at the slice header)
+        self.claim_mbaff = claim_mbaff
         self.interlaced = bool(field)
         self.field = field is True                    # form of the picture being written
         assert not field or height_mbs % 2 == 0
@@ -278,7 +282,7 @@ class Stream:
         w.ue(self.W - 1); w.ue((self.Hfield if self.interlaced else self.Hframe) - 1)   # pic_height_in_map_units: the field height when frame_mbs_only_flag = 0
         w.u(1, 0 if self.interlaced else 1)           # frame_mbs_only_flag
         if self.interlaced:
-            w.u(1, 0)                                 # mb_adaptive_frame_field_flag
+            w.u(1, 1 if self.claim_mbaff else 0)      # mb_adaptive_frame_field_flag
         w.u(1, self.direct8x8)
         w.u(1, 0)                                     # frame_cropping_flag
         w.u(1, 0)                                     # vui_parameters_present_flag

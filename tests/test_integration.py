@@ -251,3 +251,20 @@ def test_reference_parser_on_the_gpu_engine_with_paff_streams(tmp_path, case):
             k = next(j for j in range(fsz) if a[j] != b[j])
             plane = "Y" if k < w * h * 256 else ("Cb" if k < w * h * 320 else "Cr")
             pytest.fail(f"{case}: output frame {i}: first difference in plane {plane} at byte {k} (reference {a[k]}, gpu {b[k]})")
+
+
+@pytest.mark.skipif(not os.path.exists(GPU), reason="integration/_build/ldecod_gpu not built")
+def test_mbaff_stream_stops_with_unsupported_and_no_cpu_fallback(tmp_path):
+    """A stream whose SPS announces MBAFF is outside the supported subset: the GPU decoder must stop at the first slice with the
+    engine's own 'unsupported' status (no crash, no output, no silent CPU reconstruction).  Needs no GPU: the check precedes
+    every CUDA call."""
+    import h264_writer_cavlc
+    s = h264_writer_cavlc.Stream(6, 6, seed=41, field="adaptive", claim_mbaff=True)
+    s.picture("idr", 0, field=False)
+    src, out = str(tmp_path / "mbaff.264"), str(tmp_path / "mbaff.yuv")
+    with open(src, "wb") as f:
+        f.write(s.data())
+    r = subprocess.run([GPU, "-i", src, "-o", out], cwd=str(tmp_path), capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "h264recon" in (r.stdout + r.stderr) and "nsupported" in (r.stdout + r.stderr), (r.stdout + r.stderr)[-800:]
+    assert not os.path.exists(out) or os.path.getsize(out) == 0
