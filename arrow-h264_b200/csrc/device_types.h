@@ -71,6 +71,7 @@ struct WaveLaunch {
     FrameGeom geom;
     int   any_inter, any_deblock;
     int   any_intra_rows;            // some picture of the wave is all-intra: row wavefront kernel
+    int   any_field;                 // some picture of the wave is a field picture: recon_inter2_kernel<true>
     uint32_t epoch;                  // stamp of this launch sequence (mailboxes, DevPicture::mb_done)
 };
 

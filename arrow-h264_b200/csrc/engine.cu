@@ -694,7 +694,7 @@ int h264r_flush(h264r_ctx* ctx)
         WaveRecord rec;
         WaveLaunch& L = rec.launch;
         L.pics = d_table + b; L.num_pics = e - b; L.tickets = ctx->d_tickets; L.err = ctx->d_err; L.geom = ctx->geom;
-        L.any_inter = L.any_deblock = L.any_intra_rows = 0; L.epoch = 0;
+        L.any_inter = L.any_deblock = L.any_intra_rows = L.any_field = 0; L.epoch = 0;
         L.wave_max = ctx->d_wave_words + ctx->wave_word_next;
         ctx->wave_word_next = (ctx->wave_word_next + 1) % kEventRing;
         rec.ev_h2d = take_event(ctx); rec.ev_done = take_event(ctx); rec.ev_side = take_event(ctx);
@@ -704,6 +704,7 @@ int h264r_flush(h264r_ctx* ctx)
             rec.copies.push_back({ order[k], ctx->off_slices + sizeof(h264r_slice) * (size_t)s.pp.num_slices,
                                    sizeof(uint32_t) * (size_t)s.stream_words, s.ev_done });
             L.any_inter |= !s.all_intra; L.any_intra_rows |= s.all_intra; L.any_deblock |= s.pp.run_deblock;
+            L.any_field |= s.pp.structure != H264R_FRAME;
             Frame& d = ctx->frames[s.dst];
             d.ready = rec.ev_done;
             rec.dst_frames.push_back(s.dst);

@@ -144,6 +144,9 @@ constexpr int kInter2Warps = H264R_INTER2_WARPS;       // warps per CTA (each wa
 // partition walk, addressing, weights, loop control) is issued once for two MBs.  If one partition covers an 8x8
 // quadrant its four lanes share one 13x13 luma / 5x5 chroma window, otherwise every block has its own 9x9 / 3x3 window.
 // grid = (ceil(width_mbs / (2 * warps)), height_mbs, pictures of the wave)
+// kField: some picture of the wave is a field picture (the chroma vector offset between fields of different parity is compiled
+// in; waves of frame pictures run the instantiation without it)
+template <bool kField>
 __global__ void __launch_bounds__(kInter2Warps * 32, H264R_INTER2_CTAS)
 recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
 {
@@ -221,7 +224,7 @@ recon_inter2_kernel(const DevPicture* __restrict__ pics, FrameGeom g)
             const uint32_t mvw = list ? mvw1 : mvw0;
             const int mvx = (int)(int16_t)(mvw & 0xFFFF), mvy = (int)(int16_t)(mvw >> 16);
             vx = (mbx * 16 + bx * 4) * 4 + mvx; vy = (mby * 16 + by * 4) * 4 + mvy;       // this block's position
-            cdy = ((pic.ref_opposite >> (slot & 31)) & 1) ? pic.chroma_dy : 0;         // get_block_chroma, inter_prediction.cc:352-354
+            if (kField) cdy = ((pic.ref_opposite >> (slot & 31)) & 1) ? pic.chroma_dy : 0;     // get_block_chroma, inter_prediction.cc:352-354
             if (uni) {
                 const int qvx = (mbx * 16 + (bx >> 1) * 8) * 4 + mvx, qvy = (mby * 16 + (by >> 1) * 8) * 4 + mvy;
                 const int x0 = (qvx >> 2) - 2, y0 = (qvy >> 2) - 2, cx0 = qvx >> 3, cy0 = (qvy + cdy) >> 3;

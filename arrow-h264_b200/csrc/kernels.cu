@@ -64,7 +64,8 @@ int launch_wave_kernel(const WaveLaunch& w, int which, cudaStream_t stream)
     if (which == KERNEL_INTER) {
         if (!w.any_inter) return 0;
         const dim3 grid((w.geom.width_mbs + 2 * kInter2Warps - 1) / (2 * kInter2Warps), w.geom.height_mbs, w.num_pics);
-        recon_inter2_kernel<<<grid, kInter2Warps * 32, 0, stream>>>(w.pics, w.geom);
+        if (w.any_field) recon_inter2_kernel<true><<<grid, kInter2Warps * 32, 0, stream>>>(w.pics, w.geom);
+        else             recon_inter2_kernel<false><<<grid, kInter2Warps * 32, 0, stream>>>(w.pics, w.geom);
         return 1;
     }
     if (which == KERNEL_INTRA) {

@@ -3,7 +3,7 @@
 (waves: I x64, P x64, B+B x128): DRAM bytes and executed warp instructions per 1080p picture, by kernel and picture type.
 bench.py scales them to its workload for `roofline.traffic` and the issue-slot roofline.
 Usage: ncu_traffic.py <summary.csv> <source note> > profiles/r2_vNN_traffic.json"""
-import csv, json, sys
+import csv, json, re, sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[0]
@@ -16,7 +16,8 @@ waves = ["I", "P", "B"]
 pics = {"I": 64, "P": 64, "B": 128}
 bytes_pp, inst_pp, ms_pp = {}, {}, {}
 for r in rows[2:]:
-    name = r[ix["Kernel Name"]].split("(")[0]
+    m = re.search(r"(\w+)\s*(?:<[^(]*>)?\s*\(", r[ix["Kernel Name"]].replace("(bool)", ""))      # template arguments and return type dropped
+    name = m.group(1) if m else r[ix["Kernel Name"]].split("(")[0]
     k = short.get(name)
     if not k:
         continue

@@ -24,8 +24,8 @@ for l in dis.splitlines():
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: line = (os.path.basename(m.group(1)), int(m.group(2))); continue
     if cur and re.match(r'\s+/\*[0-9a-f]{4,}\*/', l): per[cur].append(line)
-base = kn.split('(')[0].split('::')[-1]
-fn = [f for f in per if ('%d%sE' % (len(base), base)) in f][0]
+base = re.sub(r'<.*', '', kn.split('(')[0].split('::')[-1]).split()[-1]
+fn = [f for f in per if ('%d%sE' % (len(base), base)) in f or ('%d%sI' % (len(base), base)) in f][0]
 lines = per[fn]
 if len(lines) != len(data): print('warning: cubin has %d instructions, report %d (different build: line mapping unreliable)' % (len(lines), len(data)))
 agg = {}; tw = te = 0
