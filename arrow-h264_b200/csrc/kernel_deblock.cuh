@@ -10,7 +10,7 @@
 namespace h264r {
 
 #ifndef H264R_DEBLOCK_CTAS
-#define H264R_DEBLOCK_CTAS 4
+#define H264R_DEBLOCK_CTAS (16 / H264R_WARPS_PER_CTA)      // 16 resident warps per SM (115 registers)
 #endif
 // 1: descriptor and samples of MB x + 1 are loaded while MB x is filtered (19 registers); 0: loaded at the start of their own
 // step -- for builds that trade the prefetch for more resident warps (H264R_DEBLOCK_CTAS 6 / 8)

@@ -20,7 +20,7 @@
 namespace h264r {
 
 #ifndef H264R_DEBLOCK4_CTAS
-#define H264R_DEBLOCK4_CTAS 4
+#define H264R_DEBLOCK4_CTAS (16 / H264R_WARPS_PER_CTA)
 #endif
 
 typedef __half2 h2;

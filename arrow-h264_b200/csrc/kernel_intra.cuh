@@ -11,7 +11,7 @@
 namespace h264r {
 
 #ifndef H264R_INTRA_CTAS
-#define H264R_INTRA_CTAS 4
+#define H264R_INTRA_CTAS (16 / H264R_WARPS_PER_CTA)        // 16 resident warps per SM (122 registers)
 #endif
 
 // ---------------------------------------------------------------------------------------------------

@@ -19,7 +19,12 @@
 
 namespace h264r {
 
-constexpr int kWarpsPerCta = 4;
+// Rows of one CTA of the wavefront kernels (row intra, deblock); the CTA takes one ticket for them.  Measured on the
+// 64-stream workload, deblock ms per step: 1 row (= a ticket per warp) 10.6, 2 rows 7.73, 4 rows 7.89, 8 rows 8.06.
+#ifndef H264R_WARPS_PER_CTA
+#define H264R_WARPS_PER_CTA 2
+#endif
+constexpr int kWarpsPerCta = H264R_WARPS_PER_CTA;
 
 // ---------------------------------------------------------------------------------------------------
 // small helpers
